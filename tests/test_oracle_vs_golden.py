@@ -1,0 +1,113 @@
+"""CPU: pin oracle/extract_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+made by oracle/make_golden.py) and its numpy restatements against OpenCV itself."""
+import numpy as np
+import pytest
+
+import extract_oracle as O
+from cases import CASE_NAMES, assert_close, case_inputs, golden
+
+cv2 = pytest.importorskip('cv2')
+
+
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_prep_matches_reference(name):
+    geom, chunk, roi, bg, cfg = case_inputs(name)
+    g = golden(name)
+    out = O.prep_frames(chunk.frames, bg, roi, cfg['min_height'], cfg['max_height'], fix_invalid=True)
+    assert out.dtype == np.uint8 and np.array_equal(out, g['prep'])
+    nofix = O.prep_frames(chunk.frames, bg, roi, cfg['min_height'], cfg['max_height'], fix_invalid=False)
+    assert np.array_equal(nofix, g['prep_nofix'])
+    if name == 'kinect_invalid':
+        assert not np.array_equal(g['prep'], g['prep_nofix'])    # the inpaint branch really ran
+
+
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_scale_matches_reference(name):
+    geom, chunk, roi, bg, cfg = case_inputs(name)
+    g = golden(name)
+    out = O.scale_frames(g['prep'][:4, :, :, None], cfg['min_height'], cfg['max_height'])
+    assert np.array_equal(out, g['scale'])
+    lut = O.scale_lut(cfg['min_height'], cfg['max_height'])
+    assert np.array_equal(lut[g['prep'][:4, :, :, None]], g['scale'])
+
+
+@pytest.mark.parametrize('name', CASE_NAMES)
+@pytest.mark.parametrize('use_cv2', [True, False])
+def test_extract_chunk_matches_reference(name, use_cv2):
+    if name == 'kinect_invalid' and not use_cv2:
+        pytest.skip('tiny case, covered with cv2')
+    geom, chunk, roi, bg, cfg = case_inputs(name)
+    g = golden(name)
+    res = O.extract_chunk(g['prep'], chunk.masks, chunk.keypoints, chunk.num_instances, cfg['min_height'],
+                          cfg['max_height'], cfg['true_depth'], cfg['crop_size'], use_cv2=use_cv2)
+    assert np.array_equal(res['cleaned_frames'], g['cleaned_frames'])
+    assert np.array_equal(res['masks'], g['masks'])
+    assert_close(res['features']['centroid'], g['centroid'], 1e-12, what='centroid')
+    assert_close(res['features']['axis_length'], g['axis_length'], 1e-11, what='axis_length')
+    assert_close(res['features']['orientation'], g['orientation'], 0, 1e-9, what='orientation (deg)')
+    assert np.array_equal(res['flips'], g['flips'])
+    for k in g.files:
+        if k.startswith('scalars/'):
+            assert_close(res['scalars'][k[8:]], g[k], 1e-9, 1e-9, what=k)
+        elif k.startswith('keypoints/'):
+            assert_close(res['keypoint_table'][k[10:]], g[k], 1e-9, 1e-9, what=k)
+    assert np.array_equal(res['depth_frames'], g['depth_frames'])
+    assert np.array_equal(res['mask_frames'], g['mask_frames'])
+
+
+def test_missing_case_has_nans_and_runs_all_passes():
+    geom, chunk, roi, bg, cfg = case_inputs('kinect_missing_holes')
+    g = golden('kinect_missing_holes')
+    assert np.isnan(g['centroid']).any() and (chunk.num_instances == 0).any()
+    res = O.extract_chunk(g['prep'], chunk.masks, chunk.keypoints, chunk.num_instances)
+    assert res['filter_passes'] == 1001                        # SURVEY trap 16: NaN defeats allclose
+
+
+def test_median_and_open_restatement_equals_opencv():
+    rng = np.random.default_rng(5)
+    for shape in [(1, 1), (1, 7), (9, 1), (5, 5), (31, 64), (57, 83), (240, 240)]:
+        fr = rng.integers(0, 256, size=(2,) + shape).astype(np.uint8)
+        fr[1] = (fr[1] > 128) * 200
+        assert np.array_equal(O.clean_frames_cv2(fr), O.clean_frames_np(fr)), shape
+
+
+def test_polygon_cells_equal_opencv_contour_moments():
+    rng = np.random.default_rng(6)
+    for t in range(150):
+        h, w = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+        if t % 3 == 0:
+            m = (rng.random((h, w)) < rng.uniform(0.2, 0.9)).astype(np.uint8)
+        else:
+            s = cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), float(rng.uniform(1, 3)))
+            m = (s > np.quantile(s, rng.uniform(0.2, 0.8))).astype(np.uint8)
+        if t % 10 == 0:
+            m[:] = 0
+        if t % 10 == 1:
+            m[:] = 1
+        cl = (m * 9).astype(np.uint8)[None]
+        a, b = O.frame_features_cv2(cl, m[None]), O.frame_features_np(cl, m[None])
+        for k in a:
+            assert_close(b[k], a[k], 1e-12, 1e-12, what=f'{k} trial {t}')
+
+
+def test_fixed_point_warp_restatement_equals_opencv():
+    rng = np.random.default_rng(7)
+    for t in range(120):
+        h, w = (240, 240) if t % 2 else (int(rng.integers(60, 200)), int(rng.integers(60, 200)))
+        fr = rng.integers(0, 101, size=(h, w)).astype(np.uint8)
+        c = np.array([rng.uniform(-2, w + 1), rng.uniform(-2, h + 1)])
+        if t % 7 == 0:
+            c = np.array([rng.uniform(0, 45), rng.uniform(0, 45)])
+        if t % 11 == 0:
+            c = np.array([float(rng.integers(0, w)), float(rng.integers(0, h))])
+        ang = float(rng.uniform(-10, 560)) if t % 13 else float(rng.integers(0, 8) * 45)
+        if t % 17 == 0:
+            ang = float('nan')
+        crop = (80, 80) if t % 3 else (128, 128)
+        assert np.array_equal(O.crop_rotate_cv2(fr, c, ang, crop), O.crop_rotate_np(fr, c, ang, crop)), (t, c, ang)
+
+
+def test_trailing_median_semantics():
+    a = np.array([1.0, np.nan, 5.0, 2.0, np.nan, np.nan, np.nan, 7.0])
+    m = O.trailing_median3(a)
+    assert np.array_equal(m, np.array([1.0, 1.0, 3.0, 3.5, 3.5, 2.0, np.nan, 7.0]), equal_nan=True)
