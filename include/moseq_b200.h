@@ -1,0 +1,179 @@
+/*
+ * moseq_b200.h -- C ABI of libmoseq_b200.so: the B200 (sm_100a) implementation of the per-frame
+ * extract hot path of tischfieldlab/moseq2-detectron-extract.
+ *
+ * The reference has NO FFI for this path: it is pure Python that calls NumPy/OpenCV
+ * (SURVEY.md section 8b).  Each entry point below therefore replaces one reference *Python function*
+ * (cited as `ref: file:line` relative to /root/reference/moseq2_detectron_extract/) and is what a
+ * ctypes stub in that function's place would bind (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch / C++ types; every image is dense row-major
+ *   - "dev" pointers are CUDA device pointers on the current device; "host" pointers are host memory
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - device entry points never allocate, never synchronise and are re-entrant per stream;
+ *     scratch memory is passed in by the caller (sizes from the *_scratch_bytes helpers)
+ *   - return 0 on success, a negative MSQ_E* code otherwise; msq_last_error() gives the message of
+ *     the last failure on the calling thread (Python raises from it)
+ *   - frames are counted in "n"; per-frame outputs are SoA arrays of length n
+ */
+#ifndef MOSEQ_B200_H
+#define MOSEQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MSQ_API __attribute__((visibility("default")))
+#else
+#define MSQ_API
+#endif
+
+#define MSQ_VERSION 100            /* major*10000 + minor*100 + patch */
+
+#define MSQ_OK            0
+#define MSQ_EINVAL      (-1)       /* bad argument (null pointer, non-positive size, bad enum) */
+#define MSQ_ECUDA       (-2)       /* a CUDA runtime call or kernel launch failed */
+#define MSQ_EUNSUPPORTED (-3)      /* valid request this build cannot serve (e.g. ROI wider than 4096 px) */
+#define MSQ_ENOMEM      (-4)       /* scratch buffer too small / allocation failed (engine only) */
+
+/* dtype codes for the background image (ref: SURVEY trap 8: float64 fresh, uint16 from TIFF cache) */
+#define MSQ_BG_NONE 0
+#define MSQ_BG_F32  1
+#define MSQ_BG_F64  2
+#define MSQ_BG_U16  3
+
+/* flags of msq_prep_frames */
+#define MSQ_PREP_HAS_VMIN 1
+#define MSQ_PREP_HAS_VMAX 2
+
+#define MSQ_NUM_KEYPOINTS 8        /* ref: io/annot.py:51-60 */
+#define MSQ_NUM_SCALARS  17        /* ref: proc/scalars.py:13-31 */
+#define MSQ_NUM_KPT_COLS 96        /* ref: proc/keypoints.py:147-163: 8 kpts x 2 systems x 6 */
+
+MSQ_API int         msq_version(void);
+MSQ_API const char *msq_last_error(void);
+/* number of SMs / name of the current device (host-side launch sizing, diagnostics) */
+MSQ_API int         msq_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* ---- a2  prep_raw_frames  (ref: proc/proc.py:129-172; apply_roi proc/roi.py:215-236; get_bbox :239-254;
+ *                            find_invalid_pixels proc/proc.py:175-186) ---------------------------------
+ * frames_dev  (n,H,W) int16 raw depth      bground_dev (H,W) of bg_dtype or NULL/MSQ_BG_NONE
+ * roi_dev     (H,W) uint8, nonzero = inside, or NULL (then the box must be the full frame)
+ * box         y0,x0 + h,w : the ROI bounding box, max-exclusive as the reference slices it
+ * out_dev     (n,h,w) uint8: ((bground - frame) * roi)[box], <vmin -> 0, >vmax -> vmax, truncated
+ * invalid_count_dev (n) int32 or NULL: number of raw==0 pixels inside roi&box per frame (the pixels the
+ *             reference in-paints, proc/proc.py:189-210); the caller decides what to do with flagged frames */
+MSQ_API int msq_prep_frames(const int16_t *frames_dev, int n, int H, int W,
+                    const void *bground_dev, int bg_dtype, const uint8_t *roi_dev,
+                    int y0, int x0, int h, int w, double vmin, double vmax, int flags,
+                    uint8_t *out_dev, int32_t *invalid_count_dev, void *stream);
+
+/* ---- a3  scale_raw_frames (ref: proc/proc.py:214-234, dtype uint8) --------------------------------------
+ * out = trunc((in - vmin) * (255 / (vmax - vmin)) + 0); vmin_is_int selects NumPy's uint8 wrap-around
+ * subtraction that applies when the reference is handed a Python int vmin. in/out may alias. */
+MSQ_API int msq_scale_frames(const uint8_t *in_dev, uint8_t *out_dev, size_t count,
+                     double vmin, double vmax, int vmin_is_int, void *stream);
+/* same map, written as 3 identical channel planes (n,3,h,w) of float32 for the R-CNN input
+ * (ref: model/predict.py:74-90 replicates the grey channel and moves it to CHW) */
+MSQ_API int msq_scale_frames_chw3_f32(const uint8_t *in_dev, float *out_dev, int n, int h, int w,
+                              double vmin, double vmax, int vmin_is_int, void *stream);
+
+/* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
+ * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
+MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);
+
+/* ---- a7  get_frame_features + im_moment_features (ref: proc/proc.py:237-302, 518-549) ----------------
+ * fm = (cleaned > frame_threshold) & (mask != 0); polygon moments of the largest outer contour.
+ * centroid_dev (n,2) f64 [x,y]; orientation_dev (n) f64 radians; axis_length_dev (n,2) f64;
+ * sums24_dev (n,6) int64 or NULL: exact 24x polygon integrals (1,x,y,xx,xy,yy) of the winning blob.
+ * scratch_dev: msq_frame_features_scratch_bytes(n,h,w) bytes. */
+MSQ_API size_t msq_frame_features_scratch_bytes(int n, int h, int w);
+MSQ_API int msq_frame_features(const uint8_t *cleaned_dev, const uint8_t *mask_dev, int n, int h, int w,
+                       double frame_threshold, double *centroid_dev, double *orientation_dev,
+                       double *axis_length_dev, int64_t *sums24_dev, void *scratch_dev, size_t scratch_bytes,
+                       void *stream);
+
+/* ---- a4  mask paste of detectron2's detector_postprocess (ref: model/util.py:45-62) -------------------
+ * soft_dev (n,M,M) f32 mask-head probabilities, boxes_dev (n,4) f32 [x0,y0,x1,y1] in frame px,
+ * out_dev (n,h,w) uint8 {0,1} = bilinear sample (align_corners=False, zeros outside) >= threshold */
+MSQ_API int msq_paste_masks(const float *soft_dev, const float *boxes_dev, int n, int M, int h, int w,
+                    float threshold, uint8_t *out_dev, void *stream);
+
+/* ---- a8-a10  angles, keypoint flips, iterative angle filter (ref: proc/proc.py:720-724, 827-839,
+ *              flips_from_keypoints :851-889, filter_angles :600-624, iterative_filter_angles :627-654)
+ * In : orientation_rad (n), axis_length (n,2), centroid (n,2), keypoints (n,8,3) f32 (NaN = no instance)
+ * Out: angle_deg (n) f64 final orientation in degrees, flips (n) u8, flip_conf (n) f64 or NULL,
+ *      filter_passes (n_chunks) int32 or NULL.
+ * The filter is chunk-local: frames [c*chunk, (c+1)*chunk) are filtered independently, which is how the
+ * reference behaves when each chunk goes through instances_to_features on its own. */
+MSQ_API int msq_angles_and_flips(const double *orientation_rad_dev, const double *axis_length_dev,
+                         const double *centroid_dev, const float *keypoints_dev, int n, int chunk,
+                         double *angle_deg_dev, uint8_t *flips_dev, double *flip_conf_dev,
+                         int32_t *filter_passes_dev, void *stream);
+
+/* the same pieces on their own, for callers that use the reference functions individually:
+ * flips_from_keypoints(keypoints, centroids, angles_deg, length) (ref: proc/proc.py:851-889) and
+ * iterative_filter_angles(angles, window, tolerance, max_iters) (ref: proc/proc.py:627-654; window <= 15) */
+MSQ_API int msq_flips_from_keypoints(const float *keypoints_dev, const double *centroid_dev,
+                                     const double *angles_deg_dev, const double *lengths_dev, int n,
+                                     uint8_t *flips_dev, double *flip_conf_dev, void *stream);
+MSQ_API int msq_iterative_filter_angles(const double *angles_deg_dev, int n, int chunk, int window,
+                                        double tolerance, int max_iters, double *out_dev, uint8_t *flips_dev,
+                                        int32_t *filter_passes_dev, void *stream);
+
+/* ---- a11 + a12  keypoints_to_dict and compute_scalars (ref: proc/keypoints.py:93-165,
+ *                 proc/scalars.py:36-120, proc/util.py:29-61) ---------------------------------------
+ * chunk_dev (n,h,w) u8 prepared frames, mask_dev (n,h,w) u8 or NULL (= ones), cleaned_dev (n,h,w) u8.
+ * scalars_dev  (17,n) f64 in the order of msq_scalar_name(i)   (area_px exact integer, height_ave_mm
+ *              rounded to float32 like the reference's array);
+ * kpt_cols_dev (96,n) f64 in the order of msq_keypoint_col_name(i).
+ * Either output may be NULL.  scratch_dev: msq_scalars_scratch_bytes(n) bytes, 8-byte aligned.
+ * Velocities are first-differences within each `chunk`-frame block (first frame of a block -> 0). */
+MSQ_API size_t msq_scalars_scratch_bytes(int n);
+MSQ_API int msq_scalars_and_keypoints(const uint8_t *chunk_dev, const uint8_t *mask_dev, const uint8_t *cleaned_dev,
+                              const double *centroid_dev, const double *angle_deg_dev,
+                              const double *axis_length_dev, const float *keypoints_dev,
+                              int n, int h, int w, int chunk, double min_height, double max_height,
+                              double true_depth, double *scalars_dev, double *kpt_cols_dev,
+                              void *scratch_dev, size_t scratch_bytes, void *stream);
+MSQ_API const char *msq_scalar_name(int i);
+MSQ_API const char *msq_keypoint_col_name(int i);
+
+/* ---- a13  crop_and_rotate_frame (ref: proc/proc.py:305-335; pipeline/process_features_step.py:190-195)
+ * For every frame i: OpenCV-exact fixed-point bilinear warp of src[i] (h,w) u8 about centroid[i] by
+ * angle_deg[i] into out[i] (crop_h,crop_w) u8; NaN / negative centre -> zeros.  src2/out2 optional
+ * second plane (the mask) warped with the same transform. */
+MSQ_API int msq_crop_rotate(const uint8_t *src_dev, const uint8_t *src2_dev, int n, int h, int w,
+                    const double *centroid_dev, const double *angle_deg_dev, int crop_w, int crop_h,
+                    uint8_t *out_dev, uint8_t *out2_dev, void *stream);
+
+/* ---- whole-chunk pipeline: everything ProcessFeaturesStep.process does (ref:
+ *      pipeline/process_features_step.py:56-60,163-199 with use_tracking=False), device buffers ------- */
+typedef struct msq_chunk_outputs {
+    uint8_t *cleaned;        /* (n,h,w)  */
+    double  *centroid;       /* (n,2)    */
+    double  *angle_deg;      /* (n)      */
+    double  *axis_length;    /* (n,2)    */
+    uint8_t *flips;          /* (n)      */
+    double  *scalars;        /* (17,n)   */
+    double  *kpt_cols;       /* (96,n)   */
+    uint8_t *depth_crops;    /* (n,crop_h,crop_w) */
+    uint8_t *mask_crops;     /* (n,crop_h,crop_w) */
+    int32_t *filter_passes;  /* (ceil(n/chunk)) or NULL */
+} msq_chunk_outputs;
+
+MSQ_API size_t msq_extract_scratch_bytes(int n, int h, int w);
+MSQ_API int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *keypoints_dev,
+                      int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
+                      int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch_dev,
+                      size_t scratch_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSEQ_B200_H */

@@ -1,0 +1,64 @@
+"""Device-memory plumbing: PyTorch owns device tensors and streams, nothing else.
+
+Every public function of this package accepts numpy arrays (host; copied to the current CUDA device,
+results copied back as numpy) or CUDA torch tensors (used in place; results stay on the device).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class CudaRequiredError(RuntimeError):
+    """Raised instead of silently computing on the CPU."""
+
+
+def require_cuda() -> None:
+    _lib.load()                                           # raises if the extension is not built
+    if not torch.cuda.is_available():
+        raise CudaRequiredError('moseq2_detectron_extract_b200 needs a CUDA device (B200, sm_100a); '
+                                'there is no CPU fallback for the extract hot path.')
+
+
+def is_device_tensor(x: Any) -> bool:
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def as_device(x: Any, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Contiguous CUDA tensor of `dtype` (no copy when `x` already is one)."""
+    require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x if x.is_cuda else x.cuda(non_blocking=True)
+    else:
+        arr = np.ascontiguousarray(x)
+        if arr.dtype == np.uint16:                        # torch has limited uint16 support: move the bits
+            t = torch.from_numpy(arr.view(np.int16)).cuda(non_blocking=True)
+            return t if dtype is None or dtype == torch.int16 else t.to(torch.int32).bitwise_and_(0xFFFF).to(dtype)
+        t = torch.from_numpy(arr).cuda(non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def empty(shape, dtype) -> torch.Tensor:
+    return torch.empty(shape, dtype=dtype, device='cuda')
+
+
+def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def give_back(t: torch.Tensor, like: Any):
+    """Return `t` in the same residency as the caller's input `like`."""
+    if is_device_tensor(like):
+        return t
+    return t.cpu().numpy()

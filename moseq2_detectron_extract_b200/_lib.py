@@ -1,0 +1,106 @@
+"""ctypes binding of libmoseq_b200.so (C ABI declared in include/moseq_b200.h).
+
+There is deliberately NO fallback: if the library cannot be loaded, or a call fails, an exception is
+raised.  Nothing in this package computes the hot path on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libmoseq_b200.so')
+
+MSQ_BG_NONE, MSQ_BG_F32, MSQ_BG_F64, MSQ_BG_U16 = 0, 1, 2, 3
+MSQ_PREP_HAS_VMIN, MSQ_PREP_HAS_VMAX = 1, 2
+NUM_SCALARS, NUM_KPT_COLS, NUM_KEYPOINTS = 17, 96, 8
+
+
+class MoseqB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+class ChunkOutputs(ctypes.Structure):
+    """struct msq_chunk_outputs"""
+    _fields_ = [(name, c_void_p) for name in (
+        'cleaned', 'centroid', 'angle_deg', 'axis_length', 'flips', 'scalars', 'kpt_cols', 'depth_crops',
+        'mask_crops', 'filter_passes')]
+
+
+# name -> (restype, argtypes); every symbol include/moseq_b200.h declares
+SIGNATURES = {
+    'msq_version': (c_int, []),
+    'msq_last_error': (c_char_p, []),
+    'msq_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), c_char_p, c_int]),
+    'msq_prep_frames': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    'msq_scale_frames': (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_double, c_int, c_void_p]),
+    'msq_scale_frames_chw3_f32': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int, c_void_p]),
+    'msq_clean_frames': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'msq_frame_features_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'msq_frame_features': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_paste_masks': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'msq_angles_and_flips': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    'msq_flips_from_keypoints': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'msq_iterative_filter_angles': (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]),
+    'msq_scalars_scratch_bytes': (c_size_t, [c_int]),
+    'msq_scalars_and_keypoints': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_scalar_name': (c_char_p, [c_int]),
+    'msq_keypoint_col_name': (c_char_p, [c_int]),
+    'msq_crop_rotate': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
+                                  c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- run
+    `python -m moseq2_detectron_extract_b200.build` or `__graft_entry__.build()`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MoseqB200Error(f'{LIB_PATH} is missing: the CUDA extension has not been built '
+                             '(python -m moseq2_detectron_extract_b200.build). There is no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().msq_last_error()
+    return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise MoseqB200Error(f'{what} failed with status {status}: {last_error()}')
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise on failure."""
+    check(getattr(load(), name)(*args), name)
+
+
+def scalar_names():
+    lib = load()
+    return [lib.msq_scalar_name(i).decode() for i in range(NUM_SCALARS)]
+
+
+def keypoint_col_names():
+    lib = load()
+    return [lib.msq_keypoint_col_name(i).decode() for i in range(NUM_KPT_COLS)]

@@ -1,0 +1,110 @@
+// Shared host/device helpers for libmoseq_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/moseq_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmoseq_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace msq {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);          // api.cu; thread-local message for msq_last_error()
+
+#define MSQ_REQUIRE(cond, code, ...)                                   \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            ::msq::set_error(__VA_ARGS__);                             \
+            return (code);                                             \
+        }                                                              \
+    } while (0)
+
+#define MSQ_CUDA_OK(expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::msq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                             __FILE__, __LINE__);                                         \
+            return MSQ_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+#define MSQ_LAUNCH_OK(name)                                                               \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            ::msq::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));    \
+            return MSQ_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+int sm_count();                                 // api.cu; cached per process (current device)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// streaming 128-bit global load / store that do not pollute L1 (inputs/outputs are touched once)
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u1(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_u4(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u2(void *p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u1(void *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__
+}  // namespace msq
+
+// ---- internal launchers shared with the whole-chunk pipeline (pipeline.cu) ---------------------
+namespace msq {
+int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);
+int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
+                          double *centroid, double *orientation, double *axis, int64_t *sums24, cudaStream_t st);
+int launch_angles_and_flips(const double *orientation, const double *axis, const double *centroid, const float *kpts,
+                            int n, int chunk, double *angle_out, uint8_t *flips, double *conf, int32_t *passes,
+                            cudaStream_t st);
+int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
+                                 const double *centroid, const double *angle_deg, const double *axis,
+                                 const float *kpts, int n, int h, int w, int chunk, double min_h, double max_h,
+                                 double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
+                                 cudaStream_t st);
+int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
+                       const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, cudaStream_t st);
+}  // namespace msq

@@ -1,0 +1,400 @@
+// a7 get_frame_features + im_moment_features: centroid / orientation / ellipse axes of the largest
+// outer contour of (cleaned > thr) & mask.   ref proc/proc.py:237-302 and :518-549.
+//
+// OpenCV's findContours + contourArea + moments(contour) are replaced by an exact, contour-free
+// formulation (SURVEY.md section 7 trap 1, pinned against OpenCV in tests/test_oracle_vs_golden.py):
+//   * the polygon traced around a hole-free 8-connected blob equals the union of unit squares
+//     (2x2 pixel-centre blocks with 4 corners set) and corner triangles (exactly 3 set);
+//   * its moments are sums of integer cell integrals (x24), accumulated in int64.
+// One WARP owns one frame, kept as bit rows in shared memory (lane k <-> 32-pixel word k of a row):
+//   phase 0  threshold+mask -> bit rows (coalesced 128-bit loads, the only HBM traffic)
+//   phase 1  4-connected flood of the background from outside, row sweeps with a warp-wide
+//            carry-lookahead run fill (ballot + integer add), gives the hole-filled set F
+//   phase 2  peel 8-connected blobs of F in raster order; per blob popcount-based cell sums
+//   phase 3  float64 epilogue in OpenCV's operation order (lane 0)
+#include "common.cuh"
+#include <algorithm>
+#include <math.h>
+
+namespace msq {
+namespace {
+
+constexpr int kFeatWarps = 4;            // frames per CTA
+
+__device__ __forceinline__ uint32_t fill_up(uint32_t seed, uint32_t open) {
+    return (((open + seed) ^ open) & open) | seed;
+}
+// all bits of every run of `open` that contains a seed bit, within one 32-bit word
+__device__ __forceinline__ uint32_t fill_local(uint32_t seed, uint32_t open) {
+    return fill_up(seed, open) | __brev(fill_up(__brev(seed), __brev(open)));
+}
+__device__ __forceinline__ uint32_t trailing_ones(uint32_t open) {
+    return open & ~(open + 1u);
+}
+__device__ __forceinline__ uint32_t leading_ones(uint32_t open) {
+    return __brev(trailing_ones(__brev(open)));
+}
+
+// Warp-wide: row = 32 lanes x 32 bits.  Returns, per lane, the bits of the runs of `open` (runs may
+// span words) that contain at least one bit of `seed`.
+__device__ __forceinline__ uint32_t fill_row(uint32_t seed, uint32_t open, int lane) {
+    uint32_t f = fill_local(seed & open, open);
+    const uint32_t full = __ballot_sync(0xffffffffu, open == 0xffffffffu);
+    const uint32_t g_up = __ballot_sync(0xffffffffu, (f >> 31) != 0u);     // word filled up to its top bit
+    const uint32_t g_dn = __ballot_sync(0xffffffffu, (f & 1u) != 0u);      // word filled down to bit 0
+    // carry-lookahead with one integer add: generate = g, propagate = word entirely open
+    const uint32_t xu = g_up | full;
+    const uint32_t cin_up = (xu + g_up) ^ xu ^ g_up;                       // bit k: carry enters word k from k-1
+    const uint32_t gr = __brev(g_dn), xr = gr | __brev(full);
+    const uint32_t cin_dn = __brev((xr + gr) ^ xr ^ gr);                   // bit k: carry enters word k from k+1
+    if ((cin_up >> lane) & 1u) f |= trailing_ones(open);
+    if ((cin_dn >> lane) & 1u) f |= leading_ones(open);
+    return f;
+}
+
+// x | x<<1 | x>>1 across the whole row (8-connected vertical neighbourhood)
+__device__ __forceinline__ uint32_t spread3(uint32_t x, int lane) {
+    uint32_t below = __shfl_up_sync(0xffffffffu, x, 1);
+    uint32_t above = __shfl_down_sync(0xffffffffu, x, 1);
+    if (lane == 0) below = 0u;
+    if (lane == 31) above = 0u;
+    return x | (x << 1) | (x >> 1) | (below >> 31) | (above << 31);
+}
+
+// sum of set-bit positions and of their squares in a 32-bit word
+__device__ __forceinline__ void bit_moments(uint32_t x, int &n, int &s1, int &s2) {
+    const int p0 = __popc(x & 0xAAAAAAAAu), p1 = __popc(x & 0xCCCCCCCCu), p2 = __popc(x & 0xF0F0F0F0u),
+              p3 = __popc(x & 0xFF00FF00u), p4 = __popc(x & 0xFFFF0000u);
+    n = __popc(x);
+    s1 = p0 + 2 * p1 + 4 * p2 + 8 * p3 + 16 * p4;
+    int cross = 0;
+    const uint32_t m[5] = {0xAAAAAAAAu, 0xCCCCCCCCu, 0xF0F0F0F0u, 0xFF00FF00u, 0xFFFF0000u};
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 5; ++b) cross += __popc(x & m[a] & m[b]) << (a + b + 1);
+    s2 = p0 + 4 * p1 + 16 * p2 + 64 * p3 + 256 * p4 + cross;
+}
+
+struct CellAcc {            // per-lane accumulators of one cell class
+    long long n, i, j, ii, ij, jj;
+};
+
+// 24 x (A, U, V, UU, UV, VV): area integrals of the covered part of a unit cell, cell-local coords
+__device__ __constant__ int kCell24[5][6] = {
+    {24, 12, 12, 8, 6, 8},    // all four corners
+    {12, 8, 8, 6, 5, 6},      // top-left missing
+    {12, 4, 8, 2, 3, 6},      // top-right missing
+    {12, 8, 4, 6, 3, 2},      // bottom-left missing
+    {12, 4, 4, 2, 1, 2},      // bottom-right missing
+};
+
+// OpenCV contourMoments/completeMomentState + ref proc/proc.py:529-547, float64, no contraction
+__device__ void moment_epilogue(const long long s[6], double *centroid, double *orientation, double *axis) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double a00 = (double)s[0] / 12.0;
+    if (!(fabs(a00) > 1.1920928955078125e-07)) {
+        centroid[0] = centroid[1] = nan; *orientation = nan; axis[0] = axis[1] = nan;
+        return;
+    }
+    const double a10 = (double)s[1] / 4.0, a01 = (double)s[2] / 4.0;
+    const double a20 = (double)s[3] / 2.0, a11 = (double)s[4], a02 = (double)s[5] / 2.0;
+    const double m00 = __dmul_rn(a00, 0.5);
+    const double m10 = __dmul_rn(a10, 0.16666666666666666666666666666667);
+    const double m01 = __dmul_rn(a01, 0.16666666666666666666666666666667);
+    const double m20 = __dmul_rn(a20, 0.083333333333333333333333333333333);
+    const double m11 = __dmul_rn(a11, 0.041666666666666666666666666666667);
+    const double m02 = __dmul_rn(a02, 0.083333333333333333333333333333333);
+    const double inv = __ddiv_rn(1.0, m00);
+    const double cx = __dmul_rn(m10, inv), cy = __dmul_rn(m01, inv);
+    const double mu20 = __dsub_rn(m20, __dmul_rn(m10, cx));
+    const double mu11 = __dsub_rn(m11, __dmul_rn(m10, cy));
+    const double mu02 = __dsub_rn(m02, __dmul_rn(m01, cy));
+    const double num = __dmul_rn(2.0, mu11);
+    const double den = __dsub_rn(mu20, mu02);
+    const double common = __dsqrt_rn(__dadd_rn(__dmul_rn(4.0, __dmul_rn(mu11, mu11)), __dmul_rn(den, den)));
+    *orientation = __dmul_rn(-0.5, atan2(num, den));
+    centroid[0] = __ddiv_rn(m10, m00);
+    centroid[1] = __ddiv_rn(m01, m00);
+    const double two_root2 = 2.8284271247461903;        // 2*np.sqrt(2)
+    const double tr = __dadd_rn(mu20, mu02);
+    axis[0] = __dmul_rn(two_root2, __dsqrt_rn(__ddiv_rn(__dadd_rn(tr, common), m00)));
+    axis[1] = __dmul_rn(two_root2, __dsqrt_rn(__ddiv_rn(__dsub_rn(tr, common), m00)));
+}
+
+// Build the bit word of pixels [32k, 32k+32) of one row: (cleaned >= ge) & (mask != 0), ge = floor(thr)+1
+__device__ __forceinline__ uint32_t threshold_word(const uint8_t *__restrict__ crow, const uint8_t *__restrict__ mrow,
+                                                   int k, int w, int ge, bool vec_ok) {
+    uint32_t bits = 0u;
+    const int x0 = k << 5;
+    if (ge > 255) return 0u;                             // nothing is above the threshold
+    if (vec_ok) {
+        const uint32_t t4 = (uint32_t)ge * 0x01010101u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int x = x0 + 16 * half;
+            if (x >= w) break;
+            const uint4 c = ldg_stream_u4(crow + x);
+            const uint4 m = ldg_stream_u4(mrow + x);
+            const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t on = __vcmpgeu4(cw[q], t4) & __vcmpne4(mw[q], 0u);     // 0xff per set pixel
+                const uint32_t nib = (((on & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+                bits |= nib << (16 * half + 4 * q);
+            }
+        }
+    } else {
+        for (int b = 0; b < 32 && x0 + b < w; ++b)
+            bits |= (uint32_t)(((int)crow[x0 + b] >= ge) && (mrow[x0 + b] != 0)) << b;
+    }
+    return bits;
+}
+
+template <int LPR>      // lanes per row: power of two >= words per row
+__global__ void __launch_bounds__(kFeatWarps * 32)
+features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__ mask, int n, int h, int w,
+                int ge, double *__restrict__ centroid, double *__restrict__ orientation,
+                double *__restrict__ axis_length, long long *__restrict__ sums24) {
+    extern __shared__ __align__(16) uint32_t smem_bits[];
+    constexpr int RPW = 32 / LPR;                       // rows handled per warp step in the parallel phases
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpr = (w + 31) >> 5;                      // words per row actually used
+    const int sub = lane / LPR, k = lane % LPR;         // (row within step, word) mapping of the parallel phases
+    uint32_t *P = smem_bits + (size_t)warp * 2 * h * LPR;   // fm, later the current blob
+    uint32_t *Q = P + (size_t)h * LPR;                       // reach, later the remaining set
+    const bool vec_ok = (w % 16 == 0) && ((uintptr_t)cleaned % 16 == 0) && ((uintptr_t)mask % 16 == 0);
+    const uint32_t lane_mask_row =                      // valid pixel bits of word `lane` (sequential phases)
+        lane < wpr - 1 ? 0xffffffffu : (lane == wpr - 1 ? ((w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu) : 0u);
+
+    for (int f = blockIdx.x * kFeatWarps + warp; f < n; f += gridDim.x * kFeatWarps) {
+        const uint8_t *cf = cleaned + (size_t)f * h * w;
+        const uint8_t *mf = mask + (size_t)f * h * w;
+
+        // ---------------- phase 0: bit rows ----------------
+        int r_lo = h, r_hi = -1;
+        for (int r = sub; r < h; r += RPW) {
+            uint32_t bits = 0u;
+            if (k < wpr) bits = threshold_word(cf + (size_t)r * w, mf + (size_t)r * w, k, w, ge, vec_ok);
+            P[r * LPR + k] = bits;
+            Q[r * LPR + k] = 0u;
+            if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r_lo = min(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, o));
+            r_hi = max(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, o));
+        }
+        __syncwarp();
+
+        long long best[6] = {0, 0, 0, 0, 0, 0};
+        bool have = false;
+
+        if (r_hi >= 0) {
+            // ---------------- phase 1: flood the background from outside (4-connected) ----------------
+            const uint32_t edge = (lane == 0 ? 1u : 0u) | (lane == ((w - 1) >> 5) ? (1u << ((w - 1) & 31)) : 0u);
+            const bool act = lane < LPR;
+            bool down = true;
+            for (int sweep = 0;; ++sweep) {
+                bool changed = false;
+                uint32_t prev = lane_mask_row;                      // the row outside [r_lo,r_hi] is all reached
+                const int r_begin = down ? r_lo : r_hi, r_end = down ? r_hi + 1 : r_lo - 1, dr = down ? 1 : -1;
+                for (int r = r_begin; r != r_end; r += dr) {
+                    const uint32_t open = act ? (~P[r * LPR + lane] & lane_mask_row) : 0u;
+                    const uint32_t old = act ? Q[r * LPR + lane] : 0u;
+                    const uint32_t now = fill_row((prev | old | edge) & open, open, lane);
+                    if (act) Q[r * LPR + lane] = now;
+                    changed |= (now != old);
+                    prev = now;
+                }
+                // a sweep that changes nothing after a sweep in the other direction means closure
+                if (!__any_sync(0xffffffffu, changed) && sweep > 0) break;
+                down = !down;
+            }
+            // F = everything not reached (foreground + enclosed holes); becomes the "remaining" set
+            for (int r = r_lo; r <= r_hi; ++r)
+                if (act) Q[r * LPR + lane] = ~Q[r * LPR + lane] & lane_mask_row;
+            __syncwarp();
+
+            // ---------------- phase 2: peel blobs in raster order ----------------
+            int scan = r_lo;
+            while (true) {
+                // raster-first remaining pixel
+                int r0 = -1; uint32_t seed = 0u;
+                for (int r = scan; r <= r_hi; ++r) {
+                    const uint32_t v = act ? Q[r * LPR + lane] : 0u;
+                    const uint32_t b = __ballot_sync(0xffffffffu, v != 0u);
+                    if (b) {
+                        const int kw = __ffs(b) - 1;
+                        const uint32_t word = __shfl_sync(0xffffffffu, v, kw);
+                        seed = (lane == kw) ? (1u << (__ffs(word) - 1)) : 0u;
+                        r0 = r;
+                        break;
+                    }
+                }
+                if (r0 < 0) break;
+                scan = r0;
+
+                // 8-connected flood of the blob inside the remaining set; blob rows are [r0, rmax]
+                int rmax = r0;
+                {
+                    const uint32_t rem0 = act ? Q[r0 * LPR + lane] : 0u;
+                    uint32_t prev = fill_row(seed, rem0, lane);
+                    if (act) P[r0 * LPR + lane] = prev;
+                    bool go_down = true;
+                    for (int sweep = 0;; ++sweep) {
+                        bool changed = false;
+                        if (go_down) {
+                            prev = act ? P[r0 * LPR + lane] : 0u;
+                            for (int r = r0 + 1; r <= r_hi; ++r) {
+                                const uint32_t rem = act ? Q[r * LPR + lane] : 0u;
+                                const uint32_t old = (act && r <= rmax) ? P[r * LPR + lane] : 0u;
+                                const uint32_t now = fill_row((spread3(prev, lane) | old) & rem, rem, lane);
+                                const bool any_now = __any_sync(0xffffffffu, now != 0u);
+                                if (!any_now && r > rmax) break;
+                                if (act) P[r * LPR + lane] = now;
+                                if (any_now) rmax = max(rmax, r);
+                                changed |= (now != old);
+                                prev = now;
+                            }
+                        } else {
+                            prev = act ? P[rmax * LPR + lane] : 0u;
+                            for (int r = rmax - 1; r >= r0; --r) {
+                                const uint32_t rem = act ? Q[r * LPR + lane] : 0u;
+                                const uint32_t old = act ? P[r * LPR + lane] : 0u;
+                                const uint32_t now = fill_row((spread3(prev, lane) | old) & rem, rem, lane);
+                                if (act) P[r * LPR + lane] = now;
+                                changed |= (now != old);
+                                prev = now;
+                            }
+                        }
+                        const bool any_change = __any_sync(0xffffffffu, changed);
+                        if (sweep > 0 && !any_change) break;
+                        if (sweep == 0 && rmax == r0) break;          // single-row blob
+                        go_down = !go_down;
+                    }
+                }
+                __syncwarp();
+
+                // exact cell sums of the blob (rows r0..rmax), lanes = (row-in-step, word)
+                CellAcc acc[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) acc[c] = {0, 0, 0, 0, 0, 0};
+                for (int r = r0 + sub; r < rmax; r += RPW) {
+                    if (k >= wpr) continue;
+                    const uint32_t a = P[r * LPR + k], b = P[(r + 1) * LPR + k];
+                    const uint32_t an = (k + 1 < wpr) ? P[r * LPR + k + 1] : 0u;
+                    const uint32_t bn = (k + 1 < wpr) ? P[(r + 1) * LPR + k + 1] : 0u;
+                    if ((a | b) == 0u) continue;
+                    const uint32_t a1 = (a >> 1) | (an << 31), b1 = (b >> 1) | (bn << 31);
+                    const uint32_t cls[5] = {a & a1 & b & b1, ~a & a1 & b & b1, a & ~a1 & b & b1,
+                                             a & a1 & ~b & b1, a & a1 & b & ~b1};
+                    const long long x0 = (long long)k << 5, y = r;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        if (cls[c] == 0u) continue;
+                        int cnt, s1, s2;
+                        bit_moments(cls[c], cnt, s1, s2);
+                        const long long si = x0 * cnt + s1;
+                        const long long sii = x0 * x0 * cnt + 2 * x0 * s1 + s2;
+                        acc[c].n += cnt;
+                        acc[c].i += si;
+                        acc[c].j += y * cnt;
+                        acc[c].ii += sii;
+                        acc[c].ij += y * si;
+                        acc[c].jj += y * y * cnt;
+                    }
+                }
+                long long s[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const long long A = kCell24[c][0], U = kCell24[c][1], V = kCell24[c][2], UU = kCell24[c][3],
+                                    UV = kCell24[c][4], VV = kCell24[c][5];
+                    s[0] += A * acc[c].n;
+                    s[1] += A * acc[c].i + U * acc[c].n;
+                    s[2] += A * acc[c].j + V * acc[c].n;
+                    s[3] += A * acc[c].ii + 2 * U * acc[c].i + UU * acc[c].n;
+                    s[4] += A * acc[c].ij + V * acc[c].i + U * acc[c].j + UV * acc[c].n;
+                    s[5] += A * acc[c].jj + 2 * V * acc[c].j + VV * acc[c].n;
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s[q] = warp_sum_ll(s[q]);
+                // OpenCV lists sibling contours in reverse raster order and np.argmax keeps the first
+                // maximum, so a later blob with an equal area replaces the current best
+                if (!have || s[0] >= best[0]) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) best[q] = s[q];
+                    have = true;
+                }
+                // remove the blob from the remaining set
+                for (int r = r0 + sub; r <= rmax; r += RPW)
+                    if (k < wpr) Q[r * LPR + k] &= ~P[r * LPR + k];
+                __syncwarp();
+            }
+        }
+
+        // ---------------- phase 3: float64 epilogue ----------------
+        if (lane == 0) {
+            double c[2], o, a[2];
+            moment_epilogue(best, c, &o, a);
+            centroid[2 * (size_t)f] = c[0];
+            centroid[2 * (size_t)f + 1] = c[1];
+            orientation[f] = o;
+            axis_length[2 * (size_t)f] = a[0];
+            axis_length[2 * (size_t)f + 1] = a[1];
+            if (sums24)
+                for (int q = 0; q < 6; ++q) sums24[6 * (size_t)f + q] = best[q];
+        }
+        __syncwarp();
+    }
+}
+
+template <int LPR>
+int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, int ge,
+                    double *centroid, double *orientation, double *axis, long long *sums24, cudaStream_t st) {
+    const size_t smem = (size_t)kFeatWarps * 2 * h * LPR * sizeof(uint32_t);
+    MSQ_REQUIRE(smem <= 227 * 1024, MSQ_EUNSUPPORTED,
+                "frame_features: %dx%d frames need %zu B of shared memory per CTA (max 232448)", h, w, smem);
+    MSQ_CUDA_OK(cudaFuncSetAttribute(features_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = std::max(1, std::min(16, (int)((227 * 1024) / (smem + 1024))));
+    const int ctas = (n + kFeatWarps - 1) / kFeatWarps;
+    const int grid = std::min(ctas, sm_count() * per_sm);
+    features_kernel<LPR><<<grid, kFeatWarps * 32, smem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
+                                                            axis, sums24);
+    MSQ_LAUNCH_OK("frame_features");
+    return MSQ_OK;
+}
+
+}  // namespace
+
+int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
+                          double *centroid, double *orientation, double *axis, int64_t *sums24, cudaStream_t st) {
+    MSQ_REQUIRE(w <= 1024, MSQ_EUNSUPPORTED, "frame_features: width %d > 1024 is not supported", w);
+    // pixel > thr on integers  <=>  pixel >= floor(thr) + 1; clamp to [0, 256] (0: all pass, 256: none)
+    int ge;
+    if (!(frame_threshold >= -1.0)) ge = 0;
+    else if (frame_threshold >= 255.0) ge = 256;
+    else ge = (int)floor(frame_threshold) + 1;
+    const int wpr = (w + 31) / 32;
+    long long *s24 = reinterpret_cast<long long *>(sums24);
+    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+}
+
+}  // namespace msq
+
+extern "C" size_t msq_frame_features_scratch_bytes(int, int, int) { return 0; }
+
+extern "C" int msq_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w,
+                                  double frame_threshold, double *centroid, double *orientation, double *axis,
+                                  int64_t *sums24, void * /*scratch*/, size_t /*scratch_bytes*/, void *stream) {
+    MSQ_REQUIRE(cleaned && mask && centroid && orientation && axis, MSQ_EINVAL, "msq_frame_features: null pointer");
+    MSQ_REQUIRE(n >= 0 && h > 0 && w > 0, MSQ_EINVAL, "msq_frame_features: bad sizes n=%d h=%d w=%d", n, h, w);
+    if (n == 0) return MSQ_OK;
+    return msq::launch_frame_features(cleaned, mask, n, h, w, frame_threshold, centroid, orientation, axis, sums24,
+                                      (cudaStream_t)stream);
+}

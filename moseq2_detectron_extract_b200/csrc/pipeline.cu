@@ -1,0 +1,43 @@
+// Whole-chunk pipeline: what ProcessFeaturesStep.process does per chunk with use_tracking=False and
+// <=1 instance per frame (ref pipeline/process_features_step.py:56-60, 163-199; proc/proc.py:700-848):
+//   clean -> moment features -> degrees/flips/angle filter -> scalars + keypoint table -> crops.
+// Pure sequencing on one stream; no allocation, no synchronisation.
+#include "common.cuh"
+
+using namespace msq;
+
+extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
+    const size_t nn = (size_t)(n > 0 ? n : 0);
+    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256);
+}
+
+extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,
+                                 int h, int w, int chunk, double min_height, double max_height, double true_depth,
+                                 int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch,
+                                 size_t scratch_bytes, void *stream) {
+    MSQ_REQUIRE(chunk_dev && mask_dev && kpts_dev && out, MSQ_EINVAL, "msq_extract_chunk: null input pointer");
+    MSQ_REQUIRE(out->cleaned && out->centroid && out->angle_deg && out->axis_length && out->flips && out->scalars &&
+                    out->kpt_cols && out->depth_crops && out->mask_crops,
+                MSQ_EINVAL, "msq_extract_chunk: null output pointer");
+    MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && chunk > 0 && crop_w > 0 && crop_h > 0, MSQ_EINVAL,
+                "msq_extract_chunk: bad sizes n=%d h=%d w=%d chunk=%d crop=%dx%d", n, h, w, chunk, crop_w, crop_h);
+    if (n == 0) return MSQ_OK;
+    MSQ_REQUIRE(scratch && (uintptr_t)scratch % 8 == 0 && scratch_bytes >= msq_extract_scratch_bytes(n, h, w), MSQ_ENOMEM,
+                "msq_extract_chunk: scratch must be 8-byte aligned and >= %zu bytes", msq_extract_scratch_bytes(n, h, w));
+    cudaStream_t st = (cudaStream_t)stream;
+    double *orientation = reinterpret_cast<double *>(scratch);
+    int2 *sums = reinterpret_cast<int2 *>(reinterpret_cast<char *>(scratch) + align_up((size_t)n * sizeof(double), 256));
+
+    int rc;
+    if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st)) != MSQ_OK) return rc;
+    // frame_threshold = 3 (ref proc/proc.py:716)
+    if ((rc = launch_frame_features(out->cleaned, mask_dev, n, h, w, 3.0, out->centroid, orientation, out->axis_length,
+                                    nullptr, st)) != MSQ_OK) return rc;
+    if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
+                                      out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
+    if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,
+                                           out->axis_length, kpts_dev, n, h, w, chunk, min_height, max_height,
+                                           true_depth, out->scalars, out->kpt_cols, sums, st)) != MSQ_OK) return rc;
+    return launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
+                              out->depth_crops, out->mask_crops, st);
+}

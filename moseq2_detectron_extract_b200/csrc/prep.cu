@@ -1,0 +1,290 @@
+// a2 prep_raw_frames and a3 scale_raw_frames as streaming HBM-bound kernels.
+//
+// prep: ref proc/proc.py:129-172.  out[n,r,c] = u8( clamp( (bg[y0+r,x0+c] - raw[n,y0+r,x0+c]) * roi ) ).
+// Only the ROI bounding box of the raw frame is ever read (apply_roi crops everything else away,
+// ref proc/roi.py:229-235), so the algorithmic traffic is 2 B in + 1 B out per box pixel.
+// Layout: a thread owns 8 horizontally adjacent box pixels at a FIXED (row, col) and walks over
+// frames, so the background and ROI values live in registers for the whole walk and every raw
+// access is one 128-bit streaming load (8 x int16) / one 64-bit store.
+#include "common.cuh"
+#include <type_traits>
+#include <algorithm>
+
+namespace msq {
+namespace {
+
+constexpr int kPrepThreads = 256;
+constexpr int kPrepUnroll = 4;
+
+template <typename T> struct PrepMath;
+
+// float32 background: NumPy computes float32 - int16 -> float32 and compares against the
+// (weak) Python scalars in float32.
+template <> struct PrepMath<float> {
+    using acc_t = float;
+    float lo, hi;
+    __host__ PrepMath(double vmin, double vmax) : lo((float)vmin), hi((float)vmax) {}
+    __device__ __forceinline__ uint32_t run(float bg, int raw, float roi, int flags) const {
+        float d = __fmul_rn(__fsub_rn(bg, (float)raw), roi);
+        if ((flags & MSQ_PREP_HAS_VMIN) && d < lo) d = 0.0f;
+        if ((flags & MSQ_PREP_HAS_VMAX) && d > hi) d = hi;
+        return (uint32_t)(int)d & 0xffu;
+    }
+};
+template <> struct PrepMath<double> {
+    using acc_t = double;
+    double lo, hi;
+    __host__ PrepMath(double vmin, double vmax) : lo(vmin), hi(vmax) {}
+    __device__ __forceinline__ uint32_t run(double bg, int raw, double roi, int flags) const {
+        double d = __dmul_rn(__dsub_rn(bg, (double)raw), roi);
+        if ((flags & MSQ_PREP_HAS_VMIN) && d < lo) d = 0.0;
+        if ((flags & MSQ_PREP_HAS_VMAX) && d > hi) d = hi;
+        return (uint32_t)(int)d & 0xffu;
+    }
+};
+// uint16 background (TIFF cache) or no background: integer arithmetic in int32.
+template <> struct PrepMath<int> {
+    using acc_t = int;
+    double lo, hi;
+    int hi_i;
+    __host__ PrepMath(double vmin, double vmax) : lo(vmin), hi(vmax), hi_i((int)vmax) {}
+    __device__ __forceinline__ uint32_t run(int bg_minus_raw, int /*raw*/, int roi, int flags) const {
+        int d = bg_minus_raw * roi;
+        if ((flags & MSQ_PREP_HAS_VMIN) && (double)d < lo) d = 0;
+        if ((flags & MSQ_PREP_HAS_VMAX) && (double)d > hi) d = hi_i;
+        return (uint32_t)d & 0xffu;
+    }
+};
+
+__device__ __forceinline__ int s16_lo(uint32_t v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int s16_hi(uint32_t v) { return (int)(short)(v >> 16); }
+
+// BG: element type of the background in global memory; ACC: arithmetic type (float/double/int)
+template <typename BG, typename ACC, bool HAS_BG>
+__global__ void __launch_bounds__(kPrepThreads)
+prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
+                 const BG *__restrict__ bground, const uint8_t *__restrict__ roi,
+                 int y0, int x0, int h, int w, PrepMath<ACC> math, int flags, int frames_per_group,
+                 uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count) {
+    const int w8 = w >> 3;
+    const int pos = blockIdx.x * kPrepThreads + threadIdx.x;
+    if (pos >= h * w8) return;
+    const int r = pos / w8;
+    const int c = (pos - r * w8) << 3;
+    const size_t in_off = (size_t)(y0 + r) * W + (x0 + c);
+    const size_t out_off = (size_t)r * w + c;
+
+    ACC bg[8], rm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        bg[k] = HAS_BG ? (ACC)bground[in_off + k] : (ACC)0;
+        rm[k] = roi ? (ACC)(roi[in_off + k] != 0) : (ACC)1;
+    }
+    const size_t in_stride = (size_t)H * W;
+    const size_t out_stride = (size_t)h * w;
+    const int f_begin = blockIdx.y * frames_per_group;
+    const int f_end = min(n, f_begin + frames_per_group);
+
+    for (int f = f_begin; f < f_end; f += kPrepUnroll) {
+        uint4 raw[kPrepUnroll];
+#pragma unroll
+        for (int u = 0; u < kPrepUnroll; ++u)
+            if (f + u < f_end) raw[u] = ldg_stream_u4(frames + (size_t)(f + u) * in_stride + in_off);
+#pragma unroll
+        for (int u = 0; u < kPrepUnroll; ++u) {
+            if (f + u >= f_end) break;
+            const uint32_t words[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            uint32_t packed[2] = {0u, 0u};
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int v = (k & 1) ? s16_hi(words[k >> 1]) : s16_lo(words[k >> 1]);
+                bad += (v == 0) && (rm[k] != (ACC)0);
+                uint32_t o;
+                if constexpr (std::is_same<ACC, int>::value)
+                    o = math.run(HAS_BG ? (int)bg[k] - v : v, v, (int)rm[k], flags);
+                else
+                    o = math.run(bg[k], v, rm[k], flags);
+                packed[k >> 2] |= o << ((k & 3) * 8);
+            }
+            stg_stream_u2(out + (size_t)(f + u) * out_stride + out_off, make_uint2(packed[0], packed[1]));
+            if (invalid_count && bad) atomicAdd(invalid_count + f + u, bad);
+        }
+    }
+}
+
+// any alignment / any box: one thread per output pixel
+template <typename BG, typename ACC, bool HAS_BG>
+__global__ void __launch_bounds__(kPrepThreads)
+prep_scalar_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
+                   const BG *__restrict__ bground, const uint8_t *__restrict__ roi,
+                   int y0, int x0, int h, int w, PrepMath<ACC> math, int flags,
+                   uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count) {
+    const size_t total = (size_t)n * h * w;
+    for (size_t i = (size_t)blockIdx.x * kPrepThreads + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * kPrepThreads) {
+        const int c = (int)(i % w);
+        const size_t t = i / w;
+        const int r = (int)(t % h);
+        const int f = (int)(t / h);
+        const size_t pix = (size_t)(y0 + r) * W + (x0 + c);
+        const int v = frames[(size_t)f * H * W + pix];
+        const ACC rm = roi ? (ACC)(roi[pix] != 0) : (ACC)1;
+        uint32_t o;
+        if constexpr (std::is_same<ACC, int>::value)
+            o = math.run(HAS_BG ? (int)bground[pix] - v : v, v, (int)rm, flags);
+        else
+            o = math.run((ACC)bground[pix], v, rm, flags);
+        out[i] = (uint8_t)o;
+        if (invalid_count && v == 0 && rm != (ACC)0) atomicAdd(invalid_count + f, 1);
+    }
+}
+
+template <typename BG, typename ACC, bool HAS_BG>
+int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground, const uint8_t *roi,
+                int y0, int x0, int h, int w, double vmin, double vmax, int flags, uint8_t *out,
+                int32_t *invalid, cudaStream_t st) {
+    PrepMath<ACC> math(vmin, vmax);
+    const bool vec_ok = (w % 8 == 0) && (x0 % 8 == 0) && (W % 8 == 0) &&
+                        ((uintptr_t)frames % 16 == 0) && ((uintptr_t)out % 8 == 0);
+    if (vec_ok) {
+        const int positions = h * (w / 8);
+        const int bx = (positions + kPrepThreads - 1) / kPrepThreads;
+        int groups = (sm_count() * 8 + bx - 1) / bx;
+        groups = max(1, min(groups, (n + kPrepUnroll - 1) / kPrepUnroll));
+        const int fpg = (n + groups - 1) / groups;
+        groups = (n + fpg - 1) / fpg;
+        dim3 grid(bx, groups);
+        prep_vec8_kernel<BG, ACC, HAS_BG><<<grid, kPrepThreads, 0, st>>>(
+            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, fpg, out, invalid);
+    } else {
+        const size_t total = (size_t)n * h * w;
+        const int blocks = (int)std::min<size_t>((total + kPrepThreads - 1) / kPrepThreads, (size_t)sm_count() * 16);
+        prep_scalar_kernel<BG, ACC, HAS_BG><<<blocks, kPrepThreads, 0, st>>>(
+            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, out, invalid);
+    }
+    MSQ_LAUNCH_OK("prep_frames");
+    return MSQ_OK;
+}
+
+// ------------------------------- scale ---------------------------------------------------------
+// ref proc/proc.py:214-234: float64 affine map then truncation.  256 possible inputs -> each CTA
+// builds the table in shared memory with the reference's exact float64 operation order.
+__device__ __forceinline__ void build_scale_lut(uint8_t *lut, double vmin, double vmax, int vmin_is_int) {
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) {
+        const double gain = __ddiv_rn(255.0 - 0.0, __dsub_rn(vmax, vmin));
+        double xv;
+        if (vmin_is_int) xv = (double)(uint8_t)(x - (int)vmin);   // uint8 array - Python int wraps in uint8
+        else xv = __dsub_rn((double)x, vmin);
+        const double v = __dadd_rn(__dmul_rn(xv, gain), 0.0);
+        lut[x] = (uint8_t)(long long)v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+scale_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t count, double vmin,
+                double vmax, int vmin_is_int, int vec_ok) {
+    __shared__ uint8_t lut[256];
+    build_scale_lut(lut, vmin, vmax, vmin_is_int);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (vec_ok) {
+        const size_t nvec = count / 16;
+        for (size_t i = tid; i < nvec; i += nthreads) {
+            uint4 v = ldg_stream_u4(in + i * 16);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = (uint32_t)lut[w[k] & 0xff] | ((uint32_t)lut[(w[k] >> 8) & 0xff] << 8) |
+                       ((uint32_t)lut[(w[k] >> 16) & 0xff] << 16) | ((uint32_t)lut[w[k] >> 24] << 24);
+            stg_stream_u4(out + i * 16, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+        done = nvec * 16;
+    }
+    for (size_t i = done + tid; i < count; i += nthreads) out[i] = lut[in[i]];
+}
+
+__global__ void __launch_bounds__(256)
+scale_chw3_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, int n, size_t plane, double vmin,
+                  double vmax, int vmin_is_int, int vec_ok) {
+    __shared__ uint8_t lut[256];
+    build_scale_lut(lut, vmin, vmax, vmin_is_int);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    if (vec_ok) {
+        const size_t q = plane / 4;
+        for (size_t i = tid; i < (size_t)n * q; i += nthreads) {
+            const size_t f = i / q, p = (i - f * q) * 4;
+            const uint32_t v = ldg_stream_u1(in + f * plane + p);
+            const float4 o = make_float4((float)lut[v & 0xff], (float)lut[(v >> 8) & 0xff],
+                                         (float)lut[(v >> 16) & 0xff], (float)lut[v >> 24]);
+            float *dst = out + f * 3 * plane + p;
+            *reinterpret_cast<float4 *>(dst) = o;
+            *reinterpret_cast<float4 *>(dst + plane) = o;
+            *reinterpret_cast<float4 *>(dst + 2 * plane) = o;
+        }
+    } else {
+        for (size_t i = tid; i < (size_t)n * plane; i += nthreads) {
+            const size_t f = i / plane, p = i - f * plane;
+            const float o = (float)lut[in[i]];
+            float *dst = out + f * 3 * plane + p;
+            dst[0] = o; dst[plane] = o; dst[2 * plane] = o;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const void *bground, int bg_dtype,
+                               const uint8_t *roi, int y0, int x0, int h, int w, double vmin, double vmax,
+                               int flags, uint8_t *out, int32_t *invalid, void *stream) {
+    MSQ_REQUIRE(n == 0 || (frames && out), MSQ_EINVAL, "msq_prep_frames: null frames/out pointer");
+    MSQ_REQUIRE(n >= 0 && H > 0 && W > 0 && h > 0 && w > 0, MSQ_EINVAL,
+                "msq_prep_frames: bad sizes n=%d H=%d W=%d h=%d w=%d", n, H, W, h, w);
+    MSQ_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + h <= H && x0 + w <= W, MSQ_EINVAL,
+                "msq_prep_frames: box (y0=%d,x0=%d,h=%d,w=%d) outside the %dx%d frame", y0, x0, h, w, H, W);
+    MSQ_REQUIRE(bg_dtype >= MSQ_BG_NONE && bg_dtype <= MSQ_BG_U16, MSQ_EINVAL, "msq_prep_frames: bad bg_dtype %d", bg_dtype);
+    MSQ_REQUIRE(bg_dtype == MSQ_BG_NONE || bground, MSQ_EINVAL, "msq_prep_frames: bground is null but bg_dtype=%d", bg_dtype);
+    if (n == 0) return MSQ_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (invalid) MSQ_CUDA_OK(cudaMemsetAsync(invalid, 0, sizeof(int32_t) * (size_t)n, st));
+    switch (bg_dtype) {
+        case MSQ_BG_F32: return launch_prep<float, float, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
+        case MSQ_BG_F64: return launch_prep<double, double, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
+        case MSQ_BG_U16: return launch_prep<uint16_t, int, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
+        default:         return launch_prep<uint16_t, int, false>(frames, n, H, W, nullptr, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
+    }
+}
+
+extern "C" int msq_scale_frames(const uint8_t *in, uint8_t *out, size_t count, double vmin, double vmax,
+                                int vmin_is_int, void *stream) {
+    MSQ_REQUIRE(count == 0 || (in && out), MSQ_EINVAL, "msq_scale_frames: null pointer");
+    MSQ_REQUIRE(vmax != vmin, MSQ_EINVAL, "msq_scale_frames: vmax == vmin");
+    if (count == 0) return MSQ_OK;
+    const int vec_ok = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const size_t work = (count + 15) / 16;
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 8);
+    scale_u8_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(in, out, count, vmin, vmax, vmin_is_int, vec_ok);
+    MSQ_LAUNCH_OK("scale_frames");
+    return MSQ_OK;
+}
+
+extern "C" int msq_scale_frames_chw3_f32(const uint8_t *in, float *out, int n, int h, int w, double vmin,
+                                         double vmax, int vmin_is_int, void *stream) {
+    MSQ_REQUIRE(in && out, MSQ_EINVAL, "msq_scale_frames_chw3_f32: null pointer");
+    MSQ_REQUIRE(n >= 0 && h > 0 && w > 0, MSQ_EINVAL, "msq_scale_frames_chw3_f32: bad sizes");
+    MSQ_REQUIRE(vmax != vmin, MSQ_EINVAL, "msq_scale_frames_chw3_f32: vmax == vmin");
+    if (n == 0) return MSQ_OK;
+    const size_t plane = (size_t)h * w;
+    const int vec_ok = (plane % 4 == 0) && ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 16 == 0);
+    const size_t work = (size_t)n * plane / 4 + 1;
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 8);
+    scale_chw3_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(in, out, n, plane, vmin, vmax, vmin_is_int, vec_ok);
+    MSQ_LAUNCH_OK("scale_frames_chw3_f32");
+    return MSQ_OK;
+}

@@ -575,7 +575,8 @@ def paste_masks_np(soft: np.ndarray, boxes: np.ndarray, height: int, width: int,
         x_lo = np.floor(px).astype(np.int64)
         wy1 = (py - y_lo.astype(np.float32)).astype(np.float32)
         wx1 = (px - x_lo.astype(np.float32)).astype(np.float32)
-        wy0, wx0 = np.float32(1) - wy1, np.float32(1) - wx1
+        wy0 = ((y_lo.astype(np.float32) + np.float32(1)) - py).astype(np.float32)     # torch: (iy_se - iy)
+        wx0 = ((x_lo.astype(np.float32) + np.float32(1)) - px).astype(np.float32)
         src = soft[i].astype(np.float32)
 
         def tap(yy, xx):
@@ -583,8 +584,11 @@ def paste_masks_np(soft: np.ndarray, boxes: np.ndarray, height: int, width: int,
             v = src[np.clip(yy, 0, M - 1)[:, None], np.clip(xx, 0, M - 1)[None, :]]
             return np.where(ok, v, np.float32(0))
 
-        val = (tap(y_lo, x_lo) * (wy0[:, None] * wx0[None, :]) + tap(y_lo, x_lo + 1) * (wy0[:, None] * wx1[None, :])
-               + tap(y_lo + 1, x_lo) * (wy1[:, None] * wx0[None, :]) + tap(y_lo + 1, x_lo + 1) * (wy1[:, None] * wx1[None, :]))
+        # torch's grid_sampler accumulates the four taps in the order nw, ne, sw, se
+        val = tap(y_lo, x_lo) * (wx0[None, :] * wy0[:, None])
+        val = val + tap(y_lo, x_lo + 1) * (wx1[None, :] * wy0[:, None])
+        val = val + tap(y_lo + 1, x_lo) * (wx0[None, :] * wy1[:, None])
+        val = val + tap(y_lo + 1, x_lo + 1) * (wx1[None, :] * wy1[:, None])
         out[i] = val >= np.float32(threshold)
     return out
 
