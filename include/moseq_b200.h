@@ -60,6 +60,15 @@ MSQ_API const char *msq_last_error(void);
 /* number of SMs / name of the current device (host-side launch sizing, diagnostics) */
 MSQ_API int         msq_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
 
+/* per-kernel device timing with CUDA events recorded on the launching stream (off by default; the
+ * equivalent of the reference's MOSEQ_DETECTRON_PROFILE switch, ref: io/util.py:239-255).  collect()
+ * synchronises on the recorded events and ADDS into total_ms[k] / timed[k] (k < msq_kernel_count()). */
+MSQ_API int msq_kernel_timing_enable(int enable);
+MSQ_API int msq_kernel_timing_collect(double *total_ms, long long *timed, int capacity);
+MSQ_API int msq_kernel_count(void);
+MSQ_API const char *msq_kernel_name(int id);
+MSQ_API long long msq_kernel_launches(int id);
+
 /* ---- a2  prep_raw_frames  (ref: proc/proc.py:129-172; apply_roi proc/roi.py:215-236; get_bbox :239-254;
  *                            find_invalid_pixels proc/proc.py:175-186) ---------------------------------
  * frames_dev  (n,H,W) int16 raw depth      bground_dev (H,W) of bg_dtype or NULL/MSQ_BG_NONE

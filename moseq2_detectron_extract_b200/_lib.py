@@ -33,6 +33,11 @@ SIGNATURES = {
     'msq_version': (c_int, []),
     'msq_last_error': (c_char_p, []),
     'msq_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), c_char_p, c_int]),
+    'msq_kernel_timing_enable': (c_int, [c_int]),
+    'msq_kernel_timing_collect': (c_int, [POINTER(c_double), POINTER(ctypes.c_longlong), c_int]),
+    'msq_kernel_count': (c_int, []),
+    'msq_kernel_name': (c_char_p, [c_int]),
+    'msq_kernel_launches': (ctypes.c_longlong, [c_int]),
     'msq_prep_frames': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                 c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     'msq_scale_frames': (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_double, c_int, c_void_p]),
@@ -104,3 +109,28 @@ def scalar_names():
 def keypoint_col_names():
     lib = load()
     return [lib.msq_keypoint_col_name(i).decode() for i in range(NUM_KPT_COLS)]
+
+
+def kernel_names():
+    lib = load()
+    return [lib.msq_kernel_name(i).decode() for i in range(lib.msq_kernel_count())]
+
+
+def kernel_launches() -> dict:
+    """Kernel launches issued by the library since it was loaded, per kernel."""
+    lib = load()
+    return {name: int(lib.msq_kernel_launches(i)) for i, name in enumerate(kernel_names())}
+
+
+def kernel_timing(enable: bool) -> None:
+    check(load().msq_kernel_timing_enable(int(enable)), 'msq_kernel_timing_enable')
+
+
+def kernel_timing_collect() -> dict:
+    """{kernel: (total_ms, launches_timed)} accumulated since the previous collect."""
+    lib = load()
+    k = lib.msq_kernel_count()
+    ms = (c_double * k)()
+    cnt = (ctypes.c_longlong * k)()
+    check(lib.msq_kernel_timing_collect(ms, cnt, k), 'msq_kernel_timing_collect')
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(kernel_names())}

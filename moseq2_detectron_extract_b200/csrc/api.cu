@@ -26,7 +26,71 @@ int sm_count() {
     return cached;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kernel timing: a fixed pool of event pairs, filled round-robin while enabled
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kTimerSlots = 4096;
+struct TimerState {
+    bool enabled = false;
+    int used = 0;
+    int dropped = 0;
+    long long launches[K_COUNT] = {0};
+    cudaEvent_t start[kTimerSlots], stop[kTimerSlots];
+    int kernel[kTimerSlots];
+    bool created = false;
+} g_timer;
+const char *const kKernelNames[K_COUNT] = {"prep_frames", "scale_frames", "clean_frames", "frame_features",
+                                           "angles_flips_filter", "masked_sums", "scalars_keypoints", "crop_rotate",
+                                           "paste_masks", "inpaint"};
+}  // namespace
+
+TimedLaunch::TimedLaunch(int kernel_id, cudaStream_t stream) : slot(-1), st(stream) {
+    g_timer.launches[kernel_id]++;
+    if (!g_timer.enabled) return;
+    if (g_timer.used >= kTimerSlots) { g_timer.dropped++; return; }
+    slot = g_timer.used++;
+    g_timer.kernel[slot] = kernel_id;
+    cudaEventRecord(g_timer.start[slot], st);
+}
+TimedLaunch::~TimedLaunch() {
+    if (slot >= 0) cudaEventRecord(g_timer.stop[slot], st);
+}
+
 }  // namespace msq
+
+extern "C" int msq_kernel_timing_enable(int enable) {
+    using namespace msq;
+    if (enable && !g_timer.created) {
+        for (int i = 0; i < kTimerSlots; ++i) {
+            MSQ_CUDA_OK(cudaEventCreate(&g_timer.start[i]));
+            MSQ_CUDA_OK(cudaEventCreate(&g_timer.stop[i]));
+        }
+        g_timer.created = true;
+    }
+    g_timer.enabled = enable != 0;
+    return MSQ_OK;
+}
+
+// Synchronises on the recorded events, ADDS their durations into total_ms[K]/timed[K], clears the pool.
+extern "C" int msq_kernel_timing_collect(double *total_ms, long long *timed, int capacity) {
+    using namespace msq;
+    MSQ_REQUIRE(total_ms && timed && capacity >= K_COUNT, MSQ_EINVAL, "msq_kernel_timing_collect: need %d slots", (int)K_COUNT);
+    for (int i = 0; i < g_timer.used; ++i) {
+        MSQ_CUDA_OK(cudaEventSynchronize(g_timer.stop[i]));
+        float ms = 0.f;
+        MSQ_CUDA_OK(cudaEventElapsedTime(&ms, g_timer.start[i], g_timer.stop[i]));
+        total_ms[g_timer.kernel[i]] += ms;
+        timed[g_timer.kernel[i]] += 1;
+    }
+    g_timer.used = 0;
+    return MSQ_OK;
+}
+
+extern "C" int msq_kernel_count(void) { return msq::K_COUNT; }
+extern "C" const char *msq_kernel_name(int id) { return (id >= 0 && id < msq::K_COUNT) ? msq::kKernelNames[id] : nullptr; }
+// number of kernel launches issued by this library since load (per kernel id), for `gpu_launches`
+extern "C" long long msq_kernel_launches(int id) { return (id >= 0 && id < msq::K_COUNT) ? msq::g_timer.launches[id] : -1; }
 
 extern "C" int msq_version(void) { return MSQ_VERSION; }
 

@@ -245,6 +245,7 @@ int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStrea
     const long long jobs = (long long)n * p.tiles_x * p.tiles_y;
     const int per_sm = std::max(1, (int)((227 * 1024) / (p.smem + 1024)));
     const int grid = (int)std::min<long long>(jobs, (long long)sm_count() * per_sm);
+    TimedLaunch timed(K_CLEAN, st);
     clean_kernel<<<grid, kCleanThreads, p.smem, st>>>(in, out, n, h, w, p.TW, p.TH, p.tiles_x, p.tiles_y);
     MSQ_LAUNCH_OK("clean_frames");
     return MSQ_OK;

@@ -45,6 +45,16 @@ void set_error(const char *fmt, ...);          // api.cu; thread-local message f
 
 int sm_count();                                 // api.cu; cached per process (current device)
 
+// ---- per-kernel device timing (CUDA events on the launching stream; off by default) ----------
+enum KernelId { K_PREP = 0, K_SCALE, K_CLEAN, K_FEATURES, K_ANGLES, K_MASKED_SUMS, K_SCALARS_KPTS, K_CROP, K_PASTE,
+                K_INPAINT, K_COUNT };
+struct TimedLaunch {                            // RAII: records an event pair around one kernel launch
+    int slot;
+    cudaStream_t st;
+    TimedLaunch(int kernel_id, cudaStream_t stream);
+    ~TimedLaunch();
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- device helpers -------------------------------------------------------------------------

@@ -98,6 +98,7 @@ crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__
 int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
                        const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, cudaStream_t st) {
     dim3 grid(n, (src2 && out2) ? 2 : 1);
+    TimedLaunch timed(K_CROP, st);
     crop_rotate_kernel<<<grid, 256, 0, st>>>(src, src2, n, h, w, centroid, angle_deg, cw, ch, out, out2);
     MSQ_LAUNCH_OK("crop_rotate");
     return MSQ_OK;

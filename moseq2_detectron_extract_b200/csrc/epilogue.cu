@@ -352,6 +352,7 @@ int launch_angles_and_flips(const double *orientation, const double *axis, const
     MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "angles_and_flips: chunk of %d frames is too large", chunk);
     if (smem > 48 * 1024)
         MSQ_CUDA_OK(cudaFuncSetAttribute(angles_flips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TimedLaunch timed(K_ANGLES, st);
     angles_flips_kernel<<<chunks, kAngleThreads, smem, st>>>(orientation, axis, centroid, kpts, n, chunk, angle_out,
                                                             flips, conf, passes);
     MSQ_LAUNCH_OK("angles_and_flips");
@@ -365,14 +366,18 @@ int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mas
                                  cudaStream_t st) {
     const size_t plane = (size_t)h * w;
     const int vec_ok = (plane % 16 == 0) && ((uintptr_t)chunk_frames % 16 == 0) && ((uintptr_t)mask % 16 == 0);   // NULL mask is "aligned"
-    masked_sums_kernel<<<std::min(n, sm_count() * 8), kSumThreads, 0, st>>>(chunk_frames, mask, n, plane, min_h, max_h,
-                                                                          vec_ok, sums_scratch);
+    {
+        TimedLaunch timed(K_MASKED_SUMS, st);
+        masked_sums_kernel<<<std::min(n, sm_count() * 8), kSumThreads, 0, st>>>(chunk_frames, mask, n, plane, min_h, max_h,
+                                                                              vec_ok, sums_scratch);
+    }
     MSQ_LAUNCH_OK("masked_sums");
     MmScale mm;
     // ref proc/util.py:53-54: f = resolution / (2 * deg2rad(fov / 2)), same float64 operation order
     mm.fw = 512 / (2 * ((70.6 / 2) * kPiOver180));
     mm.fh = 424 / (2 * ((60.0 / 2) * kPiOver180));
     mm.depth = true_depth;
+    TimedLaunch timed(K_SCALARS_KPTS, st);
     scalars_keypoints_kernel<<<(n + 127) / 128, 128, 0, st>>>(cleaned, centroid, angle_deg, axis, kpts, sums_scratch, n,
                                                             h, w, chunk, mm, scalars, kcols);
     MSQ_LAUNCH_OK("scalars_and_keypoints");
@@ -399,6 +404,7 @@ extern "C" int msq_flips_from_keypoints(const float *kpts, const double *centroi
     MSQ_REQUIRE(kpts && centroid && angles && lengths && flips, MSQ_EINVAL, "msq_flips_from_keypoints: null pointer");
     MSQ_REQUIRE(n >= 0, MSQ_EINVAL, "msq_flips_from_keypoints: bad n=%d", n);
     if (n == 0) return MSQ_OK;
+    TimedLaunch timed(K_ANGLES, (cudaStream_t)stream);
     flips_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kpts, centroid, angles, lengths, n, flips, conf);
     MSQ_LAUNCH_OK("flips_from_keypoints");
     return MSQ_OK;
@@ -414,6 +420,7 @@ extern "C" int msq_iterative_filter_angles(const double *angles, int n, int chun
     MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "iterative_filter_angles: chunk of %d frames is too large", chunk);
     if (smem > 48 * 1024)
         MSQ_CUDA_OK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TimedLaunch timed(K_ANGLES, (cudaStream_t)stream);
     filter_kernel<<<(n + chunk - 1) / chunk, kAngleThreads, smem, (cudaStream_t)stream>>>(angles, n, chunk, window,
                                                                                          tolerance, max_iters, out, flips, passes);
     MSQ_LAUNCH_OK("iterative_filter_angles");

@@ -359,6 +359,7 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
     const int per_sm = std::max(1, std::min(16, (int)((227 * 1024) / (smem + 1024))));
     const int ctas = (n + kFeatWarps - 1) / kFeatWarps;
     const int grid = std::min(ctas, sm_count() * per_sm);
+    TimedLaunch timed(K_FEATURES, st);
     features_kernel<LPR><<<grid, kFeatWarps * 32, smem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
                                                             axis, sums24);
     MSQ_LAUNCH_OK("frame_features");

@@ -59,6 +59,7 @@ extern "C" int msq_paste_masks(const float *soft, const float *boxes, int n, int
     MSQ_REQUIRE(n >= 0 && M > 0 && M <= 96 && h > 0 && w > 0, MSQ_EINVAL, "msq_paste_masks: bad sizes n=%d M=%d h=%d w=%d", n, M, h, w);
     if (n == 0) return MSQ_OK;
     dim3 grid((h + msq::kPasteRows - 1) / msq::kPasteRows, n);
+    msq::TimedLaunch timed(msq::K_PASTE, (cudaStream_t)stream);
     msq::paste_kernel<<<grid, msq::kPasteThreads, (size_t)M * M * sizeof(float), (cudaStream_t)stream>>>(
         soft, boxes, n, M, h, w, threshold, out);
     MSQ_LAUNCH_OK("paste_masks");

@@ -155,11 +155,13 @@ int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground,
         const int fpg = (n + groups - 1) / groups;
         groups = (n + fpg - 1) / fpg;
         dim3 grid(bx, groups);
+        TimedLaunch timed(K_PREP, st);
         prep_vec8_kernel<BG, ACC, HAS_BG><<<grid, kPrepThreads, 0, st>>>(
             frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, fpg, out, invalid);
     } else {
         const size_t total = (size_t)n * h * w;
         const int blocks = (int)std::min<size_t>((total + kPrepThreads - 1) / kPrepThreads, (size_t)sm_count() * 16);
+        TimedLaunch timed(K_PREP, st);
         prep_scalar_kernel<BG, ACC, HAS_BG><<<blocks, kPrepThreads, 0, st>>>(
             frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, out, invalid);
     }
@@ -269,6 +271,7 @@ extern "C" int msq_scale_frames(const uint8_t *in, uint8_t *out, size_t count, d
     const int vec_ok = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
     const size_t work = (count + 15) / 16;
     const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 8);
+    TimedLaunch timed(K_SCALE, (cudaStream_t)stream);
     scale_u8_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(in, out, count, vmin, vmax, vmin_is_int, vec_ok);
     MSQ_LAUNCH_OK("scale_frames");
     return MSQ_OK;
@@ -284,6 +287,7 @@ extern "C" int msq_scale_frames_chw3_f32(const uint8_t *in, float *out, int n, i
     const int vec_ok = (plane % 4 == 0) && ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 16 == 0);
     const size_t work = (size_t)n * plane / 4 + 1;
     const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 8);
+    TimedLaunch timed(K_SCALE, (cudaStream_t)stream);
     scale_chw3_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(in, out, n, plane, vmin, vmax, vmin_is_int, vec_ok);
     MSQ_LAUNCH_OK("scale_frames_chw3_f32");
     return MSQ_OK;

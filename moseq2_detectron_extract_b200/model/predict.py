@@ -1,0 +1,125 @@
+"""Predictor (mirrors reference model/predict.py:12-106).
+
+The R-CNN itself is a dense graph run by PyTorch (tensor cores via cuDNN/cuBLAS): either the repo's own
+TorchScript export (`from_torchscript`, ref: model/predict.py:47-51) or a randomly initialised
+Keypoint+Mask R-CNN R50-FPN built from torchvision parts with the reference's head layout
+(`from_random_init`; ref: model/config.py:21-94 -- 1 class, 8 keypoints, 240/250 px, no resize).
+Everything around it is ours: intensity scaling + channel replication (csrc/prep.cu), mask pasting
+(csrc/paste.cu) and the `Instances` container; detections never leave the GPU.
+"""
+from __future__ import annotations
+
+from contextlib import ExitStack
+from typing import Any, Dict, List
+
+import numpy as np
+import torch
+
+from .. import _dev, _lib
+from .util import outputs_to_instances
+
+
+def build_random_keypoint_mask_rcnn(num_keypoints: int = 8, image_size: int = 250, detections_per_img: int = 1,
+                                    rpn_post_nms_top_n: int = 100):
+    """Keypoint + Mask R-CNN with a ResNet-50-FPN backbone and random weights (no network access needed)."""
+    import torchvision
+    from torchvision.models.detection import MaskRCNN
+    from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
+    from torchvision.models.detection.keypoint_rcnn import KeypointRCNNHeads, KeypointRCNNPredictor
+    from torchvision.ops import MultiScaleRoIAlign
+
+    backbone = resnet_fpn_backbone(backbone_name='resnet50', weights=None, trainable_layers=5)
+    model = MaskRCNN(backbone, num_classes=2, min_size=image_size, max_size=image_size,
+                     image_mean=[103.53, 116.28, 123.675], image_std=[57.375, 57.12, 58.395],
+                     rpn_pre_nms_top_n_test=1000, rpn_post_nms_top_n_test=rpn_post_nms_top_n,
+                     box_detections_per_img=detections_per_img, box_score_thresh=0.0)
+    model.roi_heads.keypoint_roi_pool = MultiScaleRoIAlign(featmap_names=['0', '1', '2', '3'], output_size=14, sampling_ratio=2)
+    model.roi_heads.keypoint_head = KeypointRCNNHeads(backbone.out_channels, tuple(512 for _ in range(8)))
+    model.roi_heads.keypoint_predictor = KeypointRCNNPredictor(512, num_keypoints)
+
+    # keep the raw 28x28 mask probabilities: pasting is done by our kernel (detector_postprocess)
+    transform = model.transform
+    original_postprocess = transform.postprocess
+
+    def postprocess_keep_soft_masks(result, image_shapes, original_image_sizes):
+        soft = [r.pop('masks') if 'masks' in r else None for r in result]
+        result = original_postprocess(result, image_shapes, original_image_sizes)
+        for r, m in zip(result, soft):
+            if m is not None:
+                r['masks'] = m
+        return result
+
+    transform.postprocess = postprocess_keep_soft_masks
+    return model
+
+
+class _TorchvisionAdapter(torch.nn.Module):
+    """Gives a torchvision detector the I/O contract of the reference's TorchScript export
+    (ref: model/deploy.py:73-102): list of {'image': CHW} in, list of dicts with pred_* keys out."""
+
+    input_format = 'RGB'
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, inputs: List[Dict[str, torch.Tensor]]):
+        outs = self.model([i['image'] for i in inputs])
+        results = []
+        for o in outs:
+            results.append({'pred_boxes': o['boxes'], 'scores': o['scores'], 'pred_classes': o['labels'] - 1,
+                            'pred_masks': o['masks'], 'pred_keypoints': o['keypoints']})
+        return results
+
+
+class Predictor:
+    def __init__(self, model: Any, is_torchscript: bool = False):
+        self.model = model
+        self.is_torchscript = is_torchscript
+        self.exit_stack = ExitStack()
+        self.exit_stack.enter_context(torch.no_grad())
+
+    @property
+    def device(self):
+        return next(self.model.parameters()).device
+
+    @classmethod
+    def from_torchscript(cls, path: str):
+        _dev.require_cuda()
+        model = torch.jit.load(path, map_location='cuda')
+        model.eval()
+        return cls(model, is_torchscript=True)
+
+    @classmethod
+    def from_random_init(cls, device: str = 'cuda', seed: int = 0, **kwargs):
+        _dev.require_cuda()
+        torch.manual_seed(seed)
+        model = _TorchvisionAdapter(build_random_keypoint_mask_rcnn(**kwargs)).to(device).eval()
+        return cls(model, is_torchscript=True)
+
+    # ---- reference-shaped entry point (ref: model/predict.py:53-106) ---------------------------------
+    def __call__(self, original_image):
+        single = original_image.ndim == 3
+        if single:
+            original_image = original_image[None]
+        img = _dev.as_device(original_image)                     # (N, H, W, C) uint8
+        if img.shape[3] == 1:
+            img = img.expand(-1, -1, -1, 3)
+        chw = img.permute(0, 3, 1, 2).to(torch.float32).contiguous()
+        preds = self._forward(chw)
+        return preds[0] if single else preds
+
+    # ---- device fast path used by InferenceStep: scale + replicate + CHW in one kernel -----------------
+    def predict_prepared(self, chunk_u8: torch.Tensor, vmin, vmax) -> List[dict]:
+        n, h, w = (int(v) for v in chunk_u8.shape)
+        chw = _dev.empty((n, 3, h, w), torch.float32)
+        _lib.call('msq_scale_frames_chw3_f32', _dev.ptr(chunk_u8), _dev.ptr(chw), n, h, w, float(vmin), float(vmax),
+                  int(isinstance(vmin, (int, np.integer))), _dev.stream())
+        return self._forward(chw)
+
+    def _forward(self, chw: torch.Tensor) -> List[dict]:
+        with torch.no_grad():
+            inputs = [{'image': chw[i], 'height': torch.tensor(chw.shape[2]), 'width': torch.tensor(chw.shape[3])}
+                      for i in range(chw.shape[0])]
+            outputs = self.model(inputs)
+            return outputs_to_instances(inputs, outputs)

@@ -1,0 +1,61 @@
+"""Inference step (ref: pipeline/inference_step.py:16-72): intensity-scale the chunk batch by batch and run
+the Keypoint/Mask R-CNN.  Unlike the reference the Instances stay on the GPU (no `.to('cpu')`, :68)."""
+import os
+
+import torch
+
+from .. import _dev, _lib
+from ..model.instances import Boxes, Instances
+from ..model.predict import Predictor
+from .pipeline_step import ProcessPipelineStep
+
+
+class InferenceStep(ProcessPipelineStep):
+    def initialize(self):
+        model_path = self.config['model']
+        self.write_message('Loading model....')
+        if isinstance(model_path, str) and os.path.isfile(model_path) and model_path.endswith('.ts'):
+            self.predictor = Predictor.from_torchscript(model_path)
+        elif model_path is None or model_path == 'random':
+            self.predictor = Predictor.from_random_init(device=self.config.get('device', 'cuda'))
+        else:
+            raise NotImplementedError('InferenceStep: only TorchScript (.ts) models or model="random" are supported; '
+                                      'detectron2 checkpoints need detectron2 (not part of this build)')
+        self.write_message(f' -> Actually using device "{self.predictor.device}"')
+
+    def process(self, data):
+        raw = _dev.as_device(data['chunk'], torch.uint8)
+        n = int(raw.shape[0])
+        batch_size = min(self.config['batch_size'], n)
+        outputs = []
+        for i in range(0, n, batch_size):
+            pred = self.predictor.predict_prepared(raw[i:i + batch_size], self.config['min_height'], self.config['max_height'])
+            outputs.extend(pred)
+            self.update_progress(min(batch_size, n - i))
+        data['inference'] = outputs
+        return data
+
+
+class SyntheticInferenceStep(ProcessPipelineStep):
+    """Stand-in for InferenceStep in the no-R-CNN configuration (BASELINE.json configs[1]): turns the
+    synthetic session's ground-truth instances into the same `data['inference']` structure."""
+
+    def process(self, data):
+        gt = data['synthetic_instances']
+        masks = _dev.as_device(gt.masks).to(torch.bool)
+        kpts = _dev.as_device(gt.keypoints, torch.float32)
+        h, w = int(masks.shape[1]), int(masks.shape[2])
+        outputs = []
+        for i in range(int(masks.shape[0])):
+            if gt.num_instances[i] > 0:
+                inst = Instances((h, w), pred_boxes=Boxes(torch.tensor([[0., 0., float(w), float(h)]], device='cuda')),
+                                 scores=torch.ones((1,), device='cuda'), pred_classes=torch.zeros((1,), dtype=torch.int64, device='cuda'),
+                                 pred_masks=masks[i:i + 1], pred_keypoints=kpts[i:i + 1])
+            else:
+                from ..model.util import create_empty_instances
+                inst = create_empty_instances(w, h, _lib.NUM_KEYPOINTS, device='cuda')
+            outputs.append({'instances': inst})
+        data['inference'] = outputs
+        data['_dense_instances'] = (masks.to(torch.uint8), kpts, gt.num_instances)   # fast path for ProcessFeaturesStep
+        self.update_progress(int(masks.shape[0]))
+        return data
