@@ -58,8 +58,9 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_scalar_name': (c_char_p, [c_int]),
     'msq_keypoint_col_name': (c_char_p, [c_int]),
+    'msq_crop_scratch_bytes': (c_size_t, [c_int]),
     'msq_crop_rotate': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                                c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),

@@ -116,5 +116,5 @@ int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mas
                                  double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
                                  cudaStream_t st);
 int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
-                       const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, cudaStream_t st);
+                       const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch, cudaStream_t st);
 }  // namespace msq

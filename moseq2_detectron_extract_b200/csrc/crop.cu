@@ -6,31 +6,33 @@
 // and evaluates it in fixed point: coordinates with 10 fractional bits, rounded to 5 interpolation
 // bits, bilinear weights scaled to 2^15 (SURVEY.md section 7 trap 4; oracle/extract_oracle.py
 // crop_rotate_np is the same arithmetic and is pinned against cv2).  Here that is a gather straight
-// from the un-padded frame: one CTA per (frame, plane), one thread per output pixel.
+// from the un-padded frame: one CTA per frame warps both planes, one thread per output pixel.
 #include "common.cuh"
 #include <math.h>
 
 namespace msq {
 namespace {
 
-struct WarpCoeffs {
+struct __align__(16) WarpCoeffs {
     double i00, i01, b1, i10, i11, b2;   // inverse affine map (dst -> src sub-image)
-    int ox, oy, sw, sh;                  // sub-image origin in frame px and its size
-    int valid;
+    int ox, oy, sw, sh;                  // sub-image origin in frame px and its size (sw == 0: zero crop)
 };
+static_assert(sizeof(WarpCoeffs) == 64, "one coefficient record per frame, 64 bytes");
 
 __device__ void make_coeffs(double cx, double cy, double angle_deg, int cw, int ch, int W, int H, WarpCoeffs &k) {
-    k.valid = 0;
+    k.sw = k.sh = 0;
+    k.ox = k.oy = 0;
+    k.i00 = k.i01 = k.b1 = k.i10 = k.i11 = k.b2 = 0.0;
     if (angle_deg != angle_deg || cx != cx || cy != cy) return;     // NaN -> zeros (proc.py:317-318)
     if (cx < 0 || cy < 0) return;                                   // proc.py:320-322
     const int hx = cw / 2, hy = ch / 2;
-    k.ox = (int)(cx - (double)hx);                                   // Python int(): truncation
-    k.oy = (int)(cy - (double)hy);
-    k.sw = (int)(cx + (double)hx) - k.ox;
-    k.sh = (int)(cy + (double)hy) - k.oy;
-    k.sw = min(k.sw, W + cw - k.ox);                                 // NumPy slicing clips at the padded canvas
-    k.sh = min(k.sh, H + ch - k.oy);
-    if (k.sw <= 0 || k.sh <= 0) return;
+    const int ox = (int)(cx - (double)hx);                           // Python int(): truncation
+    const int oy = (int)(cy - (double)hy);
+    int sw = (int)(cx + (double)hx) - ox;
+    int sh = (int)(cy + (double)hy) - oy;
+    sw = min(sw, W + cw - ox);                                       // NumPy slicing clips at the padded canvas
+    sh = min(sh, H + ch - oy);
+    if (sw <= 0 || sh <= 0) return;
     // cv::getRotationMatrix2D(center=(hx,hy), angle, 1)
     const double rad = angle_deg * 0.017453292519943295;            // angle *= CV_PI/180
     const double alpha = cos(rad), beta = sin(rad);
@@ -46,71 +48,109 @@ __device__ void make_coeffs(double cx, double cy, double angle_deg, int cw, int 
     k.i11 = a22;
     k.b1 = -k.i00 * m02 - k.i01 * m12;
     k.b2 = -k.i10 * m02 - k.i11 * m12;
-    k.valid = 1;
+    k.ox = ox; k.oy = oy; k.sw = sw; k.sh = sh;
 }
 
 __device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
 
-__global__ void __launch_bounds__(256)
-crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int n, int H, int W,
-                   const double *__restrict__ centroid, const double *__restrict__ angle_deg, int cw, int ch,
-                   uint8_t *__restrict__ out0, uint8_t *__restrict__ out1) {
-    __shared__ WarpCoeffs k;
-    const int f = blockIdx.x;
-    const uint8_t *src = (blockIdx.y == 0 ? src0 : src1) + (size_t)f * H * W;
-    uint8_t *dst = (blockIdx.y == 0 ? out0 : out1) + (size_t)f * cw * ch;
-    if (threadIdx.x == 0) make_coeffs(centroid[2 * f], centroid[2 * f + 1], angle_deg[f], cw, ch, W, H, k);
-    __syncthreads();
-    const int total = cw * ch;
-    if (!k.valid) {
-        for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = 0;
+// one thread per frame: the float64 rotation coefficients
+__global__ void __launch_bounds__(128)
+crop_coeffs_kernel(const double *__restrict__ centroid, const double *__restrict__ angle_deg, int n, int cw, int ch,
+                   int W, int H, WarpCoeffs *__restrict__ coeffs) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    WarpCoeffs k;
+    make_coeffs(centroid[2 * f], centroid[2 * f + 1], angle_deg[f], cw, ch, W, H, k);
+    coeffs[f] = k;
+}
+
+constexpr int kCropThreads = 256;
+
+// one thread per output pixel, both planes (frame + mask) share the transform.  Per pixel: OpenCV's
+// fixed-point coordinates (AB_BITS 10, INTER_BITS 5, round_delta 16) and four gathered bytes per plane.
+__global__ void __launch_bounds__(kCropThreads)
+crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int H, int W,
+                   const WarpCoeffs *__restrict__ coeffs, int cw, int ch, uint8_t *__restrict__ out0,
+                   uint8_t *__restrict__ out1) {
+    // a CTA covers a 16x16 output tile; each warp an 8x4 patch, so that under rotation the 32 lanes of a
+    // gather touch a compact source footprint (a 32x1 line would hit up to 32 different source rows)
+    const int f = blockIdx.y;
+    const int tiles_x = (cw + 15) >> 4;
+    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = (tile_x << 4) + ((warp & 1) << 3) + (lane & 7);
+    const int y = (tile_y << 4) + ((warp >> 1) << 2) + (lane >> 3);
+    if (x >= cw || y >= ch) return;
+    const size_t crop_off = (size_t)f * cw * ch + (size_t)y * cw + x;
+    const int4 geo = __ldg(reinterpret_cast<const int4 *>(&coeffs[f].ox));
+    if (geo.z == 0) {
+        out0[crop_off] = 0;
+        if (out1) out1[crop_off] = 0;
         return;
     }
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int y = i / cw, x = i - y * cw;
-        // AB_BITS = 10, INTER_BITS = 5, round_delta = 16
-        const int adelta = __double2int_rn(k.i00 * (double)x * 1024.0);
-        const int bdelta = __double2int_rn(k.i10 * (double)x * 1024.0);
-        const int X0 = __double2int_rn((k.i01 * (double)y + k.b1) * 1024.0) + 16;
-        const int Y0 = __double2int_rn((k.i11 * (double)y + k.b2) * 1024.0) + 16;
-        const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-        const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-        const int fx = X & 31, fy = Y & 31;
-        int acc = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int dx = t & 1, dy = t >> 1;
-            const int px = sx + dx, py = sy + dy;
-            const int wgt = (dx ? fx : 32 - fx) * (dy ? fy : 32 - fy) * 32;     // sums to 2^15
-            int v = 0;
-            if (px >= 0 && px < k.sw && py >= 0 && py < k.sh) {
-                const int gx = px + k.ox, gy = py + k.oy;
-                if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = __ldg(src + (size_t)gy * W + gx);
-            }
-            acc += v * wgt;
-        }
-        dst[i] = (uint8_t)((acc + 16384) >> 15);
+    const double2 c0 = __ldg(reinterpret_cast<const double2 *>(&coeffs[f].i00));   // i00, i01
+    const double2 c1 = __ldg(reinterpret_cast<const double2 *>(&coeffs[f].b1));    // b1, i10
+    const double2 c2 = __ldg(reinterpret_cast<const double2 *>(&coeffs[f].i11));   // i11, b2
+    const int adelta = __double2int_rn(c0.x * (double)x * 1024.0);
+    const int bdelta = __double2int_rn(c1.y * (double)x * 1024.0);
+    const int X0 = __double2int_rn((c0.y * (double)y + c1.x) * 1024.0) + 16;
+    const int Y0 = __double2int_rn((c2.x * (double)y + c2.y) * 1024.0) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+    const int fx = X & 31, fy = Y & 31;
+    // a tap (px,py) of the sub-image is readable iff 0 <= px < sw and its frame pixel gx = px + ox lies in [0, W)
+    // (same in y): one interval per axis, evaluated once per axis instead of once per tap
+    const int lo_x = max(0, -geo.x), hi_x = min(geo.z, W - geo.x);
+    const int lo_y = max(0, -geo.y), hi_y = min(geo.w, H - geo.y);
+    const bool okx0 = sx >= lo_x && sx < hi_x, okx1 = sx + 1 >= lo_x && sx + 1 < hi_x;
+    const bool oky0 = sy >= lo_y && sy < hi_y, oky1 = sy + 1 >= lo_y && sy + 1 < hi_y;
+    // clamp the gather address into the frame so that every tap can be loaded unconditionally
+    const int gx0 = min(max(sx + geo.x, 0), W - 1), gx1 = min(max(sx + 1 + geo.x, 0), W - 1);
+    const int gy0 = min(max(sy + geo.y, 0), H - 1), gy1 = min(max(sy + 1 + geo.y, 0), H - 1);
+    const int w00 = (okx0 && oky0) ? (32 - fx) * (32 - fy) : 0, w01 = (okx1 && oky0) ? fx * (32 - fy) : 0;
+    const int w10 = (okx0 && oky1) ? (32 - fx) * fy : 0, w11 = (okx1 && oky1) ? fx * fy : 0;
+    const int o00 = gy0 * W + gx0, o01 = gy0 * W + gx1, o10 = gy1 * W + gx0, o11 = gy1 * W + gx1;
+    const uint8_t *p0 = src0 + (size_t)f * H * W;
+    // OpenCV: (sum of w*32*p + 2^14) >> 15 with weights summing to 2^15  ==  (sum of w*p + 2^9) >> 10
+    const int acc0 = (int)__ldg(p0 + o00) * w00 + (int)__ldg(p0 + o01) * w01 + (int)__ldg(p0 + o10) * w10 + (int)__ldg(p0 + o11) * w11;
+    out0[crop_off] = (uint8_t)((acc0 + 512) >> 10);
+    if (src1) {
+        const uint8_t *p1 = src1 + (size_t)f * H * W;
+        const int acc1 = (int)__ldg(p1 + o00) * w00 + (int)__ldg(p1 + o01) * w01 + (int)__ldg(p1 + o10) * w10 + (int)__ldg(p1 + o11) * w11;
+        out1[crop_off] = (uint8_t)((acc1 + 512) >> 10);
     }
 }
 
 }  // namespace
 
 int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
-                       const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, cudaStream_t st) {
-    dim3 grid(n, (src2 && out2) ? 2 : 1);
-    TimedLaunch timed(K_CROP, st);
-    crop_rotate_kernel<<<grid, 256, 0, st>>>(src, src2, n, h, w, centroid, angle_deg, cw, ch, out, out2);
+                       const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch,
+                       cudaStream_t st) {
+    WarpCoeffs *coeffs = reinterpret_cast<WarpCoeffs *>(scratch);
+    const bool two = src2 && out2;
+    TimedLaunch timed(K_CROP, st);          // the coefficient kernel is part of the crop step
+    crop_coeffs_kernel<<<(n + 127) / 128, 128, 0, st>>>(centroid, angle_deg, n, cw, ch, w, h, coeffs);
+    MSQ_LAUNCH_OK("crop_coeffs");
+    dim3 grid(((cw + 15) / 16) * ((ch + 15) / 16), n);
+    crop_rotate_kernel<<<grid, kCropThreads, 0, st>>>(src, two ? src2 : nullptr, h, w, coeffs, cw, ch, out,
+                                                      two ? out2 : nullptr);
     MSQ_LAUNCH_OK("crop_rotate");
     return MSQ_OK;
 }
 
 }  // namespace msq
 
+extern "C" size_t msq_crop_scratch_bytes(int n) { return (size_t)(n > 0 ? n : 0) * 64; }
+
 extern "C" int msq_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
-                               const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *stream) {
-    MSQ_REQUIRE(src && out && centroid && angle_deg, MSQ_EINVAL, "msq_crop_rotate: null pointer");
+                               const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch,
+                               size_t scratch_bytes, void *stream) {
+    MSQ_REQUIRE(n == 0 || (src && out && centroid && angle_deg), MSQ_EINVAL, "msq_crop_rotate: null pointer");
     MSQ_REQUIRE((src2 == nullptr) == (out2 == nullptr), MSQ_EINVAL, "msq_crop_rotate: src2/out2 must both be set or both be null");
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && cw > 0 && ch > 0, MSQ_EINVAL, "msq_crop_rotate: bad sizes");
     if (n == 0) return MSQ_OK;
-    return msq::launch_crop_rotate(src, src2, n, h, w, centroid, angle_deg, cw, ch, out, out2, (cudaStream_t)stream);
+    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_crop_rotate: at most 65535 frames per call (got %d)", n);
+    MSQ_REQUIRE(scratch && (uintptr_t)scratch % 16 == 0 && scratch_bytes >= msq_crop_scratch_bytes(n), MSQ_ENOMEM,
+                "msq_crop_rotate: scratch must be 16-byte aligned and >= %zu bytes", msq_crop_scratch_bytes(n));
+    return msq::launch_crop_rotate(src, src2, n, h, w, centroid, angle_deg, cw, ch, out, out2, scratch, (cudaStream_t)stream);
 }

@@ -122,32 +122,66 @@ __device__ void moment_epilogue(const long long s[6], double *centroid, double *
     axis[1] = __dmul_rn(two_root2, __dsqrt_rn(__ddiv_rn(__dsub_rn(tr, common), m00)));
 }
 
-// Build the bit word of pixels [32k, 32k+32) of one row: (cleaned >= ge) & (mask != 0), ge = floor(thr)+1
-__device__ __forceinline__ uint32_t threshold_word(const uint8_t *__restrict__ crow, const uint8_t *__restrict__ mrow,
-                                                   int k, int w, int ge, bool vec_ok) {
+// SWAR byte tests on 4 packed pixels, result in bit 7 of every byte, no cross-byte carries:
+//   c >= g  (1 <= g <= 255):  low 7 bits compared by adding (128 - (g & 127)); the top bit decides the rest
+//   m != 0
+struct ByteTest {
+    uint32_t k;        // (0x80 - (g & 0x7f)) replicated
+    uint32_t hi_or;    // g < 128: a set top bit alone passes;  g >= 128: the top bit is required
+    int mode;          // 0: everything passes (g <= 0), 1: g in 1..127, 2: g in 128..255, 3: nothing passes
+};
+__device__ __forceinline__ ByteTest make_byte_test(int ge) {
+    ByteTest t;
+    t.mode = ge <= 0 ? 0 : (ge > 255 ? 3 : (ge < 128 ? 1 : 2));
+    t.k = (uint32_t)(0x80 - (ge & 0x7f)) * 0x01010101u;
+    t.hi_or = 0u;
+    return t;
+}
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t c, const ByteTest &t) {
+    const uint32_t low = ((c & 0x7f7f7f7fu) + t.k);
+    if (t.mode == 1) return (low | c) & 0x80808080u;
+    if (t.mode == 2) return (low & c) & 0x80808080u;
+    return t.mode == 0 ? 0x80808080u : 0u;
+}
+__device__ __forceinline__ uint32_t bytes_nonzero(uint32_t m) {
+    return (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u;
+}
+// bits 7,15,23,31 -> bits 0..3
+__device__ __forceinline__ uint32_t gather_nibble(uint32_t on) {
+    return (((on >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+
+struct RowWordRaw { uint4 c0, m0, c1, m1; };     // the 32 pixels of one (row, word): two 16-byte halves of each image
+
+__device__ __forceinline__ void load_row_word(RowWordRaw &raw, const uint8_t *__restrict__ crow,
+                                              const uint8_t *__restrict__ mrow, int k, int w) {
+    const int x = k << 5;
+    raw.c0 = ldg_stream_u4(crow + x);
+    raw.m0 = ldg_stream_u4(mrow + x);
+    if (x + 16 < w) {
+        raw.c1 = ldg_stream_u4(crow + x + 16);
+        raw.m1 = ldg_stream_u4(mrow + x + 16);
+    } else {
+        raw.c1 = raw.m1 = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+__device__ __forceinline__ uint32_t threshold_raw(const RowWordRaw &raw, const ByteTest &t) {
+    const uint32_t cw[8] = {raw.c0.x, raw.c0.y, raw.c0.z, raw.c0.w, raw.c1.x, raw.c1.y, raw.c1.z, raw.c1.w};
+    const uint32_t mw[8] = {raw.m0.x, raw.m0.y, raw.m0.z, raw.m0.w, raw.m1.x, raw.m1.y, raw.m1.z, raw.m1.w};
+    uint32_t bits = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) bits |= gather_nibble(bytes_ge(cw[q], t) & bytes_nonzero(mw[q])) << (4 * q);
+    return bits;
+}
+
+// generic (unaligned) form: (cleaned >= ge) & (mask != 0) for pixels [32k, 32k+32) of one row
+__device__ __forceinline__ uint32_t threshold_word_scalar(const uint8_t *__restrict__ crow, const uint8_t *__restrict__ mrow,
+                                                          int k, int w, int ge) {
     uint32_t bits = 0u;
     const int x0 = k << 5;
-    if (ge > 255) return 0u;                             // nothing is above the threshold
-    if (vec_ok) {
-        const uint32_t t4 = (uint32_t)ge * 0x01010101u;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int x = x0 + 16 * half;
-            if (x >= w) break;
-            const uint4 c = ldg_stream_u4(crow + x);
-            const uint4 m = ldg_stream_u4(mrow + x);
-            const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t on = __vcmpgeu4(cw[q], t4) & __vcmpne4(mw[q], 0u);     // 0xff per set pixel
-                const uint32_t nib = (((on & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
-                bits |= nib << (16 * half + 4 * q);
-            }
-        }
-    } else {
-        for (int b = 0; b < 32 && x0 + b < w; ++b)
-            bits |= (uint32_t)(((int)crow[x0 + b] >= ge) && (mrow[x0 + b] != 0)) << b;
-    }
+    for (int b = 0; b < 32 && x0 + b < w; ++b)
+        bits |= (uint32_t)(((int)crow[x0 + b] >= ge) && (mrow[x0 + b] != 0)) << b;
     return bits;
 }
 
@@ -172,13 +206,36 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
         const uint8_t *mf = mask + (size_t)f * h * w;
 
         // ---------------- phase 0: bit rows ----------------
+        // The row loop is software-pipelined: the 4 x 128-bit loads of the NEXT row step are in flight while
+        // the current one is thresholded (ncu: the un-pipelined loop spent its time in long_scoreboard).
         int r_lo = h, r_hi = -1;
-        for (int r = sub; r < h; r += RPW) {
-            uint32_t bits = 0u;
-            if (k < wpr) bits = threshold_word(cf + (size_t)r * w, mf + (size_t)r * w, k, w, ge, vec_ok);
-            P[r * LPR + k] = bits;
-            Q[r * LPR + k] = 0u;
-            if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
+        if (vec_ok) {
+            const ByteTest bt = make_byte_test(ge);
+            const bool lane_on = k < wpr;
+            RowWordRaw cur, nxt;
+            if (lane_on && sub < h) load_row_word(cur, cf + (size_t)sub * w, mf + (size_t)sub * w, k, w);
+            for (int r = sub; r < h; r += RPW) {
+                const int rn = r + RPW;
+                if (lane_on && rn < h) load_row_word(nxt, cf + (size_t)rn * w, mf + (size_t)rn * w, k, w);
+                uint32_t bits = 0u;
+                if (lane_on) {
+                    bits = threshold_raw(cur, bt);
+                    const int x0 = k << 5;                                  // drop pixels beyond the row end
+                    if (x0 + 32 > w) bits &= (w - x0 >= 32) ? 0xffffffffu : ((1u << (w - x0)) - 1u);
+                }
+                P[r * LPR + k] = bits;
+                Q[r * LPR + k] = 0u;
+                if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
+                cur = nxt;
+            }
+        } else {
+            for (int r = sub; r < h; r += RPW) {
+                uint32_t bits = 0u;
+                if (k < wpr) bits = threshold_word_scalar(cf + (size_t)r * w, mf + (size_t)r * w, k, w, ge);
+                P[r * LPR + k] = bits;
+                Q[r * LPR + k] = 0u;
+                if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

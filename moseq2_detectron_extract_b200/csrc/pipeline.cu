@@ -8,7 +8,7 @@ using namespace msq;
 
 extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
     const size_t nn = (size_t)(n > 0 ? n : 0);
-    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256);
+    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256) + align_up(nn * 64, 256);
 }
 
 extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,
@@ -22,11 +22,14 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && chunk > 0 && crop_w > 0 && crop_h > 0, MSQ_EINVAL,
                 "msq_extract_chunk: bad sizes n=%d h=%d w=%d chunk=%d crop=%dx%d", n, h, w, chunk, crop_w, crop_h);
     if (n == 0) return MSQ_OK;
-    MSQ_REQUIRE(scratch && (uintptr_t)scratch % 8 == 0 && scratch_bytes >= msq_extract_scratch_bytes(n, h, w), MSQ_ENOMEM,
-                "msq_extract_chunk: scratch must be 8-byte aligned and >= %zu bytes", msq_extract_scratch_bytes(n, h, w));
+    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_extract_chunk: at most 65535 frames per call (got %d)", n);
+    MSQ_REQUIRE(scratch && (uintptr_t)scratch % 256 == 0 && scratch_bytes >= msq_extract_scratch_bytes(n, h, w), MSQ_ENOMEM,
+                "msq_extract_chunk: scratch must be 256-byte aligned and >= %zu bytes", msq_extract_scratch_bytes(n, h, w));
     cudaStream_t st = (cudaStream_t)stream;
     double *orientation = reinterpret_cast<double *>(scratch);
-    int2 *sums = reinterpret_cast<int2 *>(reinterpret_cast<char *>(scratch) + align_up((size_t)n * sizeof(double), 256));
+    char *base = reinterpret_cast<char *>(scratch);
+    int2 *sums = reinterpret_cast<int2 *>(base + align_up((size_t)n * sizeof(double), 256));
+    void *crop_scratch = base + align_up((size_t)n * sizeof(double), 256) + align_up((size_t)n * sizeof(int2), 256);
 
     int rc;
     if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st)) != MSQ_OK) return rc;
@@ -39,5 +42,5 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
                                            out->axis_length, kpts_dev, n, h, w, chunk, min_height, max_height,
                                            true_depth, out->scalars, out->kpt_cols, sums, st)) != MSQ_OK) return rc;
     return launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
-                              out->depth_crops, out->mask_crops, st);
+                              out->depth_crops, out->mask_crops, crop_scratch, st);
 }
