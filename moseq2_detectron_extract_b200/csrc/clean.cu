@@ -22,7 +22,6 @@ namespace {
 
 constexpr int kHX = 16;          // left/right halo columns kept in the planes (multiple of 8 >= 9)
 constexpr int kHY = 9;           // top/bottom halo rows (1 median + 4 erode + 4 dilate)
-constexpr int kCleanThreads = 512;
 
 struct MinOp {
     static __device__ __forceinline__ uint32_t op3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
@@ -51,7 +50,6 @@ struct Geometry {
     int groups;                    // 8-px column groups of the stencil passes: (PW - 16) / 8  (<= 32)
 };
 
-constexpr int kWarps = kCleanThreads / 32;
 
 // Thread mapping of every pass: lane <-> 8-pixel column group (one warp spans a full 256-pixel plane row with
 // 128-bit shared-memory accesses), warps stride over rows.  No per-item index arithmetic is left.
@@ -123,8 +121,8 @@ __device__ __forceinline__ uint4 load_group(const uint8_t *__restrict__ row, int
 // PWT: plane pitch as a compile-time constant (0 = runtime).  With a constant pitch every shared-memory
 // access of the stencil passes is base + immediate (ncu: with a runtime pitch the address arithmetic was as
 // many instructions as the min/max work).  VEC: the 8-aligned fast path (w % 8 == 0, aligned pointers).
-template <int PWT, bool VEC>
-__global__ void __launch_bounds__(kCleanThreads, 2)
+template <int PWT, bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 clean_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, Geometry G) {
     extern __shared__ __align__(16) uint16_t smem[];
     const int PW = PWT ? PWT : G.PW;
@@ -133,6 +131,7 @@ clean_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, G
     const int h = G.h, w = G.w, PH = G.PH;
     const int tiles_per_frame = G.tiles_x * G.tiles_y;
     constexpr bool vec_ok = VEC;
+    constexpr int kWarps = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool active = (PWT == 272) ? true : lane < G.groups;   // this lane owns a stencil column group
     const int col = 8 + (lane << 3);                // its first plane column
@@ -258,7 +257,7 @@ Geometry make_geometry(int h, int w) {
     G.h = h; G.w = w;
     const int w8 = (w + 7) & ~7;
     G.TW = std::min(w8, 240);                      // 240 + 2*16 halo = 272 plane columns = 34 groups; 32 stencil groups = one warp
-    int th = 30;                                   // 2 CTAs/SM with 272-px planes (104 KB each)
+    int th = 80;                                   // 98-row planes: 213 KB, one 1024-thread CTA per SM (fastest of 24..80 on B200)
     if (const char *e = getenv("MSQ_CLEAN_TH")) { int v = atoi(e); if (v >= 4 && v <= 256) th = v; }
     G.TH = std::min(th, h);
     G.PW = G.TW + 2 * kHX;
@@ -279,11 +278,14 @@ int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStrea
     const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
     const int grid = (int)std::min<long long>(jobs, (long long)sm_count() * per_sm);
     const bool vec = (w % 8 == 0) && ((uintptr_t)in % 8 == 0) && ((uintptr_t)out % 8 == 0);
-    void (*kernel)(const uint8_t *, uint8_t *, int, Geometry) =
-        (G.PW == 272 && vec) ? clean_kernel<272, true> : (vec ? clean_kernel<0, true> : clean_kernel<0, false>);
+    // strips that leave room for two CTAs per SM run 512 threads each, taller strips one CTA of 1024
+    const bool big = per_sm < 2;
+    void (*kernel)(const uint8_t *, uint8_t *, int, Geometry);
+    if (big) kernel = (G.PW == 272 && vec) ? clean_kernel<272, true, 1024> : (vec ? clean_kernel<0, true, 1024> : clean_kernel<0, false, 1024>);
+    else kernel = (G.PW == 272 && vec) ? clean_kernel<272, true, 512> : (vec ? clean_kernel<0, true, 512> : clean_kernel<0, false, 512>);
     MSQ_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TimedLaunch timed(K_CLEAN, st);
-    kernel<<<grid, kCleanThreads, smem, st>>>(in, out, n, G);
+    kernel<<<grid, big ? 1024 : 512, smem, st>>>(in, out, n, G);
     MSQ_LAUNCH_OK("clean_frames");
     return MSQ_OK;
 }

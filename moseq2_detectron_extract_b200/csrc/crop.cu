@@ -4,8 +4,8 @@
 // The reference pads the frame by the crop size, slices [int(c-crop/2), int(c+crop/2)) and warps the
 // slice with getRotationMatrix2D((crop/2, crop/2), angle, 1).  OpenCV inverts the matrix in float64
 // and evaluates it in fixed point: coordinates with 10 fractional bits, rounded to 5 interpolation
-// bits, bilinear weights scaled to 2^15 (SURVEY.md section 7 trap 4; oracle/extract_oracle.py
-// crop_rotate_np is the same arithmetic and is pinned against cv2).  Here that is a gather straight
+// bits, bilinear weights scaled to 2^15 (SURVEY.md section 7 trap 4; the test-side
+// numpy restatement of the same arithmetic is pinned against cv2).  Here that is a gather straight
 // from the un-padded frame: one CTA per frame warps both planes, one thread per output pixel.
 #include "common.cuh"
 #include <math.h>

@@ -1,0 +1,84 @@
+"""Chunk sharding across GPUs.
+
+The independent unit of the extract path is a chunk of `chunk_size` consecutive frames: with
+use_tracking=False and <=1 instance per frame there is no state across chunks (velocities restart per chunk,
+ref: proc/scalars.py:105-107; the angle filter is chunk-local, ref: proc/proc.py:837).  GPU g of G owns the
+contiguous chunk range [g*ceil(n/G), (g+1)*ceil(n/G)); background and ROI are replicated.  There is NO
+collective on the data path: every rank extracts its chunks and keeps (or writes) its results; an optional
+control-plane gather of the per-frame tables to rank 0 uses torch.distributed object gather.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def chunk_ranges(nframes: int, chunk_size: int, chunk_overlap: int = 0) -> List[range]:
+    """Frame ranges of the chunks of a session (ref: io/util.py:24-35 gen_batch_sequence)."""
+    out = []
+    for start in range(0, nframes, chunk_size):
+        out.append(range(max(start - chunk_overlap, 0), min(start + chunk_size, nframes)))
+    return out
+
+
+def shard_chunks(n_chunks: int, rank: int, world: int) -> range:
+    """Contiguous chunk indices owned by `rank` out of `world` ranks."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f'bad rank/world {rank}/{world}')
+    per = -(-n_chunks // world)
+    return range(min(rank * per, n_chunks), min((rank + 1) * per, n_chunks))
+
+
+def shard_frames(nframes: int, chunk_size: int, rank: int, world: int) -> range:
+    """Frame range owned by `rank` (whole chunks only)."""
+    chunks = chunk_ranges(nframes, chunk_size)
+    mine = shard_chunks(len(chunks), rank, world)
+    if len(mine) == 0:
+        return range(0, 0)
+    return range(chunks[mine.start].start, chunks[mine.stop - 1].stop)
+
+
+class ShardedExtractor:
+    """Runs `process_chunk(chunk_index, frame_range) -> dict of per-frame numpy arrays` over this rank's chunks.
+
+    `process_chunk` is the GPU pipeline on a real run (ProduceFramesStep -> InferenceStep ->
+    ProcessFeaturesStep on this rank's device); the CPU tests inject a stand-in so the partition / ordering /
+    gather logic is exercised under gloo without a GPU."""
+
+    def __init__(self, nframes: int, chunk_size: int, process_chunk: Callable[[int, range], Dict[str, np.ndarray]],
+                 rank: int = 0, world: int = 1):
+        self.nframes, self.chunk_size = int(nframes), int(chunk_size)
+        self.process_chunk = process_chunk
+        self.rank, self.world = int(rank), int(world)
+        self.chunks = chunk_ranges(self.nframes, self.chunk_size)
+        self.mine = shard_chunks(len(self.chunks), self.rank, self.world)
+
+    def run(self) -> Dict[str, np.ndarray]:
+        """Extract this rank's chunks; per-frame arrays are concatenated in frame order, plus `frame_idxs`."""
+        parts: List[Dict[str, np.ndarray]] = []
+        for ci in self.mine:
+            res = dict(self.process_chunk(ci, self.chunks[ci]))
+            res['frame_idxs'] = np.arange(self.chunks[ci].start, self.chunks[ci].stop)
+            parts.append(res)
+        return concat_results(parts)
+
+    def gather(self, local: Dict[str, np.ndarray]) -> Optional[Dict[str, np.ndarray]]:
+        """Control-plane gather of the per-frame tables to rank 0 (None elsewhere).  Not on the data path."""
+        if self.world == 1:
+            return local
+        import torch.distributed as dist
+        bucket = [None] * self.world if self.rank == 0 else None
+        dist.gather_object(local, bucket, dst=0)
+        if self.rank != 0:
+            return None
+        merged = concat_results([b for b in bucket if b])
+        order = np.argsort(merged['frame_idxs'], kind='stable')
+        return {k: v[order] for k, v in merged.items()}
+
+
+def concat_results(parts: Sequence[Dict[str, np.ndarray]]) -> Dict[str, np.ndarray]:
+    if not parts:
+        return {}
+    keys = parts[0].keys()
+    return {k: np.concatenate([np.asarray(p[k]) for p in parts], axis=0) for k in keys}

@@ -15,7 +15,7 @@ functions that are restated from OpenCV's published algorithms (3x3 median, flat
 opening, polygon moments of the outer contour, fixed-point bilinear warpAffine): each of those
 has a `*_cv2` twin that calls OpenCV exactly like the reference does and a `*_np` restatement,
 and the tests assert the two agree bit-for-bit on random inputs.  Third-party pieces that are not
-installed anywhere here (bottleneck.move_median, detectron2's paste_masks_in_image) are restated
+installed anywhere here XX
 from their published behaviour: "parity unpinned" for those two.
 
 Every function cites the reference lines it follows as `ref: <file>:<lines>`.

@@ -1,0 +1,103 @@
+"""GPU: the step classes end to end on a synthetic session, checked chunk by chunk against the oracle."""
+import numpy as np
+import pytest
+
+import extract_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+class Collect:
+    pass
+
+
+def _run_pipeline(nframes, chunk_size, **gen):
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.pipeline import (Pipeline, PipelineStep, ProcessFeaturesStep, ProduceFramesStep,
+                                                        SyntheticInferenceStep)
+    sess = synthetic.SyntheticSession(nframes, seed=4, **gen)
+    cfg = synthetic.default_config(sess.geom)
+    cfg.update(chunk_size=chunk_size, nframes=nframes)
+    results = []
+
+    class Sink(PipelineStep):
+        def process(self, data):
+            results.append(data)
+            return data
+
+    pipe = Pipeline()
+    steps = [pipe.add_step(ProduceFramesStep(sess, cfg, 'produce')), pipe.add_step(SyntheticInferenceStep(cfg, 'infer')),
+             pipe.add_step(ProcessFeaturesStep(cfg, 'features')), pipe.add_step(Sink(cfg, 'sink'))]
+    for a, b in zip(steps[:-1], steps[1:]):
+        pipe.link(a, b)
+    pipe.run()
+    return sess, cfg, results
+
+
+def test_steps_match_oracle_chunk_by_chunk():
+    from moseq2_detectron_extract_b200 import synthetic
+    sess, cfg, results = _run_pipeline(130, 50, missing_every=19, mask_holes=True)
+    assert [r['batch'] for r in results] == [0, 1, 2]
+    assert sum(len(r['frame_idxs']) for r in results) == 130
+    roi, bg = sess.roi, sess.bground_im
+    for r in results:
+        idxs = r['frame_idxs']
+        ch = synthetic.generate_chunk(len(idxs), seed=4, geom=sess.geom, t0=idxs[0], missing_every=19, mask_holes=True)
+        prep = O.prep_frames(ch.frames, bg, roi, cfg['min_height'], cfg['max_height'])
+        ref = O.extract_chunk(prep, ch.masks, ch.keypoints, ch.num_instances, cfg['min_height'], cfg['max_height'],
+                              cfg['true_depth'], cfg['crop_size'])
+        assert np.array_equal(r['chunk'].cpu().numpy(), prep)
+        f = r['features']
+        assert np.array_equal(f['cleaned_frames'], ref['cleaned_frames'])
+        assert np.array_equal(f['masks'], ch.masks)
+        assert np.allclose(f['features']['centroid'], ref['features']['centroid'], rtol=1e-12, atol=0, equal_nan=True)
+        assert np.allclose(f['features']['orientation'], ref['features']['orientation'], rtol=0, atol=1e-9, equal_nan=True)
+        assert np.array_equal(f['flips'], ref['flips'])
+        assert np.array_equal(f['num_instances'], ch.num_instances)
+        assert set(r['scalars']) == set(ref['scalars']) and set(r['keypoints']) == set(ref['keypoint_table'])
+        for k, v in ref['scalars'].items():
+            tol = 1e-4 if 'velocity' in k else 1e-9
+            assert np.allclose(r['scalars'][k], v, rtol=tol, atol=1e-9, equal_nan=True), k
+        assert r['scalars']['area_px'].dtype == np.int64 and r['scalars']['height_ave_mm'].dtype == np.float32
+        for k, v in ref['keypoint_table'].items():
+            assert np.allclose(r['keypoints'][k], v, rtol=1e-9, atol=1e-7, equal_nan=True), k
+        assert np.array_equal(r['depth_frames'], ref['depth_frames'])
+        assert np.array_equal(r['mask_frames'], ref['mask_frames'])
+
+
+def test_tracking_and_invalid_pixels_fail_loudly():
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.pipeline import Pipeline, ProcessFeaturesStep, WorkerError
+    cfg = synthetic.default_config()
+    cfg['use_tracking'] = True
+    step = ProcessFeaturesStep(cfg, 'features')
+    with pytest.raises(NotImplementedError):
+        step.initialize()
+    with pytest.raises(WorkerError):
+        _run_pipeline(20, 10, invalid_rate=0.01)        # produced frames contain invalid in-ROI pixels
+
+
+def test_predictor_random_init_smoke():
+    """R-CNN path (BASELINE configs[2]): random-init Keypoint+Mask R-CNN, outputs only checked for structure."""
+    pytest.importorskip('torchvision')
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.model.predict import Predictor
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(4, seed=9, geom=geom)
+    prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom),
+                           roi=synthetic.make_roi(geom), vmin=0, vmax=100)
+    pred = Predictor.from_random_init(detections_per_img=2)
+    out = pred.predict_prepared(prep, 0, 100)
+    assert len(out) == 4
+    for o in out:
+        inst = o['instances']
+        assert inst.image_size == (240, 240)
+        k = len(inst)
+        assert inst.pred_masks.shape == (k, 240, 240) and inst.pred_masks.dtype == torch.bool
+        assert inst.pred_keypoints.shape == (k, 8, 3) and inst.pred_boxes.tensor.shape == (k, 4)
+    # reference-shaped call: (N, H, W, 1) uint8 numpy, scaled like InferenceStep does
+    from moseq2_detectron_extract_b200.proc import scale_raw_frames
+    out2 = pred(scale_raw_frames(prep.cpu().numpy()[:, :, :, None], 0, 100))
+    assert len(out2) == 4 and out2[0]['instances'].image_size == (240, 240)

@@ -1,0 +1,208 @@
+"""CPU tests of the host-side logic: C-ABI surface, containers, pipeline runtime, sharding helpers."""
+import ctypes
+import os
+import queue
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from moseq2_detectron_extract_b200 import _lib, build
+    build.build()                     # nvcc cross-compiles for sm_100a without a GPU
+    return _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'moseq_b200.h')).read()
+    return sorted(set(re.findall(r'MSQ_API[^;(]*?\b(msq_\w+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    handle = ctypes.CDLL(lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, f'declared in include/moseq_b200.h but not exported: {missing}'
+    unbound = [s for s in declared if s not in lib.SIGNATURES]
+    assert not unbound, f'declared but not bound in _lib.SIGNATURES: {unbound}'
+    assert sorted(lib.SIGNATURES) == declared
+
+
+def test_library_metadata_without_gpu(lib):
+    l = lib.load()
+    assert l.msq_version() == 100
+    names = lib.scalar_names()
+    assert names[0] == 'centroid_x_px' and names[-1] == 'velocity_theta' and len(names) == 17
+    cols = lib.keypoint_col_names()
+    assert len(cols) == 96 and cols[0] == 'reference/Nose_x_px' and cols[-1] == 'rotated/TailTip_z_mm'
+    from moseq2_detectron_extract_b200.proc.keypoints import keypoint_attributes
+    from moseq2_detectron_extract_b200.proc.scalars import scalar_attributes
+    assert set(cols) == set(keypoint_attributes()) and set(names) == set(scalar_attributes())
+    assert lib.kernel_names()[0] == 'prep_frames'
+    assert l.msq_frame_features_scratch_bytes(10, 240, 240) == 0
+    assert l.msq_extract_scratch_bytes(1000, 240, 240) >= 1000 * (8 + 8 + 64)
+
+
+def test_argument_validation_returns_error_codes(lib):
+    l = lib.load()
+    assert l.msq_clean_frames(None, None, 5, 8, 8, None) == -1
+    assert 'null' in lib.last_error()
+    assert l.msq_prep_frames(None, 0, 8, 8, None, 0, None, 0, 0, 8, 8, 0.0, 1.0, 0, None, None, None) == 0   # n = 0 is a no-op
+    assert l.msq_prep_frames(None, 1, 8, 8, None, 0, None, 4, 4, 8, 8, 0.0, 1.0, 0, None, None, None) == -1
+    with pytest.raises(lib.MoseqB200Error):
+        lib.call('msq_scale_frames', None, None, 16, 1.0, 1.0, 0, None)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from moseq2_detectron_extract_b200 import _dev
+    import moseq2_detectron_extract_b200.proc as P
+    for call in (lambda: P.clean_frames(np.zeros((1, 8, 8), np.uint8), iters_tail=3),
+                 lambda: P.prep_raw_frames(np.zeros((1, 8, 8), np.int16)),
+                 lambda: P.scale_raw_frames(np.zeros((1, 8, 8), np.uint8), 0, 100),
+                 lambda: P.crop_and_rotate_frames_batch(np.zeros((1, 8, 8), np.uint8), np.zeros((1, 2)), np.zeros(1))):
+        with pytest.raises(_dev.CudaRequiredError):
+            call()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'moseq2_detectron_extract_b200')
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(base, f)).read()
+                assert 'extract_oracle' not in text and 'oracle/' not in text and 'import oracle' not in text, f
+
+
+def test_host_helpers_match_oracle():
+    import cv2
+    import extract_oracle as O
+    from moseq2_detectron_extract_b200.proc import convert_pxs_to_mm, im_moment_features, rotate_points, rotate_points_batch
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 240, (50, 2))
+    assert np.array_equal(convert_pxs_to_mm(pts, true_depth=673.0), O.px_to_mm(pts, 673.0))
+    kp = rng.uniform(0, 240, (6, 8, 3))
+    cen = rng.uniform(50, 200, (6, 2))
+    ang = rng.uniform(0, 360, 6)
+    ref = O.rotate_about(kp[..., :2], cen, ang)
+    got = rotate_points_batch(kp.copy(), cen, ang)
+    assert np.allclose(got[..., :2], ref, rtol=0, atol=1e-12) and np.array_equal(got[..., 2], kp[..., 2])
+    assert np.allclose(rotate_points(kp[0, :, :2], cen[0], ang[0]), ref[0], atol=1e-12)
+    m = np.zeros((40, 50), np.uint8)
+    cv2.ellipse(m, (25, 20), (15, 8), 30, 0, 360, 1, -1)
+    cnt, _ = cv2.findContours(m, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+    mine = im_moment_features(cnt[0])
+    mo = cv2.moments(cnt[0])
+    assert np.allclose(mine['centroid'], [mo['m10'] / mo['m00'], mo['m01'] / mo['m00']], rtol=1e-12)
+    ref_f = O.frame_features_cv2((m * 9)[None], m[None])
+    assert np.isclose(mine['orientation'], ref_f['orientation'][0], atol=1e-12)
+    assert np.allclose(mine['axis_length'], ref_f['axis_length'][0], rtol=1e-10)
+
+
+def test_instances_container():
+    import torch
+    from moseq2_detectron_extract_b200.model import Boxes, Instances, create_empty_instances
+    inst = Instances((240, 240), pred_boxes=Boxes(torch.tensor([[0., 0, 10, 10], [5, 5, 20, 30], [1, 1, 2, 2]])),
+                     scores=torch.tensor([0.9, 0.8, 0.1]), pred_masks=torch.zeros((3, 240, 240), dtype=torch.bool),
+                     pred_keypoints=torch.zeros((3, 8, 3)))
+    assert len(inst) == 3 and inst.image_size == (240, 240)
+    assert len(inst[1]) == 1 and torch.equal(inst[1].scores, torch.tensor([0.8]))
+    assert len(inst[torch.tensor([True, False, True])]) == 2
+    assert len(inst[[2, 0]]) == 2 and float(inst[[2, 0]].scores[0]) == pytest.approx(0.1)
+    assert torch.allclose(inst.pred_boxes.get_centers()[1], torch.tensor([12.5, 17.5]))
+    both = Instances.cat([inst[0], inst[2]])
+    assert len(both) == 2 and both.pred_masks.shape == (2, 240, 240)
+    empty = create_empty_instances(240, 240, 8)
+    assert len(empty) == 0 and empty.pred_keypoints.shape == (0, 8, 3) and empty.to('cpu').image_size == (240, 240)
+    with pytest.raises(AttributeError):
+        _ = inst.nonexistent
+
+
+def test_pipeline_runtime_propagates_data_sentinel_and_errors():
+    from moseq2_detectron_extract_b200.pipeline import Pipeline, PipelineStep, ProducerPipelineStep, WorkerError
+
+    class Source(ProducerPipelineStep):
+        def initialize(self):
+            self.i = 0
+
+        def process(self, data):
+            self.i += 1
+            return {'batch': self.i, 'x': self.i * 2} if self.i <= 5 else None
+
+    class Double(PipelineStep):
+        def process(self, data):
+            data['x'] *= 2
+            self.update_progress(1)
+            return data
+
+    class Sink(PipelineStep):
+        def initialize(self):
+            self.seen = []
+
+        def process(self, data):
+            self.seen.append((data['batch'], data['x']))
+            return data
+
+    cfg = {'nframes': 5}
+    pipe = Pipeline()
+    src, dbl, sink = pipe.add_step(Source(cfg, 'src')), pipe.add_step(Double(cfg, 'dbl')), pipe.add_step(Sink(cfg, 'sink'))
+    pipe.link(src, dbl)
+    pipe.link(dbl, sink)
+    pipe.run()
+    assert sink.seen == [(i, i * 4) for i in range(1, 6)]
+    assert all(s.is_complete.is_set() for s in (src, dbl, sink))
+
+    class Boom(PipelineStep):
+        def process(self, data):
+            raise RuntimeError('boom')
+
+    pipe = Pipeline()
+    src, boom = pipe.add_step(Source(cfg, 'src')), pipe.add_step(Boom(cfg, 'boom'))
+    pipe.link(src, boom)
+    with pytest.raises(WorkerError, match='boom'):
+        pipe.run()
+    msgs = []
+    while True:
+        try:
+            msgs.append(pipe.progress.get_nowait())
+        except queue.Empty:
+            break
+    assert any(m.get('raise') for m in msgs if 'message' in m)
+
+
+def test_synthetic_session_iterator_and_chunking():
+    from moseq2_detectron_extract_b200 import shard, synthetic
+    sess = synthetic.SyntheticSession(25, seed=3)
+    it = sess.iterate(10, 0)
+    seen = []
+    it.attach_filter(filterer=lambda f: f[:, :2, :2])
+    for idxs, frames in it:
+        seen.append((idxs[0], idxs[-1], frames.shape))
+    assert seen == [(0, 9, (10, 2, 2)), (10, 19, (10, 2, 2)), (20, 24, (5, 2, 2))]
+    a = synthetic.generate_chunk(6, seed=1, t0=100)
+    b = synthetic.generate_chunk(6, seed=1, t0=100)
+    assert np.array_equal(a.frames, b.frames) and np.array_equal(a.keypoints, b.keypoints, equal_nan=True)
+    assert [list(r) for r in shard.chunk_ranges(25, 10)] == [list(range(0, 10)), list(range(10, 20)), list(range(20, 25))]
+    assert shard.chunk_ranges(25, 10, 3)[1] == range(7, 20)
+    roi = synthetic.make_roi(synthetic.SessionGeometry())
+    y0, x0, y1, x1 = synthetic.roi_bbox(roi)
+    assert (y1 - y0, x1 - x0) == (240, 240) and x0 % 8 == 0
+
+
+@pytest.mark.parametrize('n_chunks,world', [(54, 1), (54, 2), (54, 4), (54, 8), (5, 8), (0, 3), (864, 8)])
+def test_shard_chunks_partition(n_chunks, world):
+    from moseq2_detectron_extract_b200.shard import shard_chunks
+    owned = [shard_chunks(n_chunks, r, world) for r in range(world)]
+    flat = [c for rng in owned for c in rng]
+    assert flat == list(range(n_chunks))                 # contiguous, ordered, exactly once
+    sizes = [len(r) for r in owned]
+    assert max(sizes) - min(s for s in sizes if s or True) <= -(-n_chunks // world)
+    with pytest.raises(ValueError):
+        shard_chunks(10, 3, 3)

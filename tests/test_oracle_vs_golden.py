@@ -111,3 +111,44 @@ def test_trailing_median_semantics():
     a = np.array([1.0, np.nan, 5.0, 2.0, np.nan, np.nan, np.nan, 7.0])
     m = O.trailing_median3(a)
     assert np.array_equal(m, np.array([1.0, 1.0, 3.0, 3.5, 3.5, 2.0, np.nan, 7.0]), equal_nan=True)
+
+
+def test_paste_restatement_equals_torch_grid_sample():
+    """detectron2 is not installed; its _do_paste_mask is grid_sample on pixel centres mapped into the box.
+    Pin the numpy restatement (what csrc/paste.cu follows) against torch's own grid_sample arithmetic."""
+    torch = pytest.importorskip('torch')
+    F = torch.nn.functional
+    rng = np.random.default_rng(3)
+    n, M, h, w = 6, 28, 120, 150
+    soft = torch.sigmoid(torch.from_numpy(rng.normal(0, 2, (n, M, M)).astype(np.float32)))
+    soft = F.avg_pool2d(soft[:, None], 3, 1, 1)[:, 0]
+    boxes = np.stack([rng.uniform(-5, 60, n), rng.uniform(-5, 50, n), rng.uniform(70, 155, n), rng.uniform(60, 125, n)], 1).astype(np.float32)
+    bt = torch.from_numpy(boxes)
+    x0, y0, x1, y1 = torch.split(bt, 1, dim=1)
+    img_y = (torch.arange(0, h, dtype=torch.float32) + 0.5 - y0) / (y1 - y0) * 2 - 1
+    img_x = (torch.arange(0, w, dtype=torch.float32) + 0.5 - x0) / (x1 - x0) * 2 - 1
+    gx = img_x[:, None, :].expand(n, h, w)
+    gy = img_y[:, :, None].expand(n, h, w)
+    ref = F.grid_sample(soft[:, None], torch.stack([gx, gy], dim=3), align_corners=False)[:, 0] >= 0.5
+    got = O.paste_masks_np(soft.numpy(), boxes, h, w)
+    assert np.array_equal(got, ref.numpy())
+
+
+def test_warp_emulation_of_feature_kernel_matches_oracle():
+    """Lane-level emulation of csrc/features.cu (bit-row flood with carry-lookahead, blob peeling, popcount cell
+    sums) against the oracle's exact integer sums -- algorithm check that runs without a GPU."""
+    from warp_emulation import emulate_frame
+    rng = np.random.default_rng(11)
+    for t in range(60):
+        h, w = int(rng.integers(3, 50)), int(rng.integers(3, 110))
+        if t % 3 == 0:
+            m = rng.random((h, w)) < rng.uniform(0.2, 0.9)
+        else:
+            s = cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), float(rng.uniform(1, 4)))
+            m = s > np.quantile(s, rng.uniform(0.2, 0.8))
+        if t % 20 == 0:
+            m[:] = True
+        if t % 20 == 1:
+            m[:] = False
+        ref = O.frame_features_np((m * 9).astype(np.uint8)[None], m.astype(np.uint8)[None], return_sums=True)['sums24'][0]
+        assert list(ref) == list(emulate_frame(m)), (t, h, w)
