@@ -179,6 +179,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     _dev.require_cuda()
     if world > 1:
+        # NCCL carries only the barrier and the max-over-ranks of two timing scalars (no data-path collective);
+        # keep its banner off stdout so that the single JSON line is the only output
+        os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     def barrier():
@@ -340,9 +343,12 @@ def run_ours(args):
         h2d_bytes, d2h_bytes = h2d_chunk * n_e2e_chunks, d2h_chunk * n_e2e_chunks
     # ---- reduce over ranks (max time) --------------------------------------------------------------------
     times = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device='cuda')
+    launches_all = torch.tensor([float(gpu_launches)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches_all, op=dist.ReduceOp.SUM)
     ms, e2e_ms_max = float(times[0]), float(times[1])
+    gpu_launches = int(launches_all[0])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
