@@ -227,7 +227,7 @@ def run_ours(args):
             n = min(launch, n_frames - s)
             _lib.call('msq_prep_frames', _dev.ptr(frames[s:s + n]), n, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32, _dev.ptr(roi_d),
                       y0, x0, h, w, float(cfg['min_height']), float(cfg['max_height']), flags, _dev.ptr(prep_buf),
-                      _dev.ptr(invalid), st)
+                      _dev.ptr(invalid), None, st)
             engine.extract(prep_buf[:n], masks[s:s + n], kpts[s:s + n], **kw)
 
     # ---- device-resident throughput ------------------------------------------------------------------
@@ -305,7 +305,7 @@ def run_ours(args):
                     src = pool_frames[:chunk] if zero_copy else in_f[b]
                     _lib.call('msq_prep_frames', _dev.ptr(src), chunk, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32,
                               _dev.ptr(roi_d), y0, x0, h, w, float(cfg['min_height']), float(cfg['max_height']), flags,
-                              _dev.ptr(preps[b]), _dev.ptr(invs[b]), _dev.stream())
+                              _dev.ptr(preps[b]), _dev.ptr(invs[b]), None, _dev.stream())
                     res = engines[b].extract(preps[b], in_m[b], in_k[b], **kw)
                     ev_comp[b] = torch.cuda.Event()
                     ev_comp[b].record(compute)

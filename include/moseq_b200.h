@@ -76,11 +76,22 @@ MSQ_API long long msq_kernel_launches(int id);
  * box         y0,x0 + h,w : the ROI bounding box, max-exclusive as the reference slices it
  * out_dev     (n,h,w) uint8: ((bground - frame) * roi)[box], <vmin -> 0, >vmax -> vmax, truncated
  * invalid_count_dev (n) int32 or NULL: number of raw==0 pixels inside roi&box per frame (the pixels the
- *             reference in-paints, proc/proc.py:189-210); the caller decides what to do with flagged frames */
+ *             reference in-paints, proc/proc.py:189-210)
+ * invalid_bits_dev (n, h, ceil(w/8)) bytes or NULL, 4-byte aligned and padded to a multiple of 4 bytes: the same
+ *             pixels as a packed mask (bit b of byte B of a row = pixel 8B+b), the input of msq_inpaint_frames */
 MSQ_API int msq_prep_frames(const int16_t *frames_dev, int n, int H, int W,
                     const void *bground_dev, int bg_dtype, const uint8_t *roi_dev,
                     int y0, int x0, int h, int w, double vmin, double vmax, int flags,
-                    uint8_t *out_dev, int32_t *invalid_count_dev, void *stream);
+                    uint8_t *out_dev, int32_t *invalid_count_dev, uint8_t *invalid_bits_dev, void *stream);
+
+/* ---- a2  fill_invalid_pixels (ref: proc/proc.py:189-210): cv2.inpaint(frame, mask, radius, INPAINT_NS), bit-exact.
+ * frames_dev (n_total,h,w) u8 updated IN PLACE; invalid_bits_dev as written by msq_prep_frames; frame_idx_dev (m) int32
+ * indices of the frames to in-paint (NULL = frames 0..m-1); radius 1..4 (the reference uses 3).
+ * scratch_dev: msq_inpaint_scratch_bytes(m,h,w) bytes, 8-byte aligned (per-frame distance map + spill space of the
+ * priority queue). One warp per frame runs OpenCV's fast-marching order exactly. */
+MSQ_API size_t msq_inpaint_scratch_bytes(int m, int h, int w);
+MSQ_API int msq_inpaint_frames(uint8_t *frames_dev, const uint8_t *invalid_bits_dev, const int32_t *frame_idx_dev,
+                       int m, int h, int w, int radius, void *scratch_dev, size_t scratch_bytes, void *stream);
 
 /* ---- a3  scale_raw_frames (ref: proc/proc.py:214-234, dtype uint8) --------------------------------------
  * out = trunc((in - vmin) * (255 / (vmax - vmin)) + 0); vmin_is_int selects NumPy's uint8 wrap-around

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
                  const BG *__restrict__ bground, const uint8_t *__restrict__ roi,
                  int y0, int x0, int h, int w, PrepMath<ACC> math, int flags, int frames_per_group,
-                 uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count) {
+                 uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint8_t *__restrict__ invalid_bits) {
     const int w8 = w >> 3;
     const int pos = blockIdx.x * kPrepThreads + threadIdx.x;
     if (pos >= h * w8) return;
@@ -96,10 +96,13 @@ prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
             const uint32_t words[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
             uint32_t packed[2] = {0u, 0u};
             int bad = 0;
+            uint32_t bad_bits = 0u;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int v = (k & 1) ? s16_hi(words[k >> 1]) : s16_lo(words[k >> 1]);
-                bad += (v == 0) && (rm[k] != (ACC)0);
+                const bool is_bad = (v == 0) && (rm[k] != (ACC)0);
+                bad += is_bad;
+                bad_bits |= (uint32_t)is_bad << k;
                 uint32_t o;
                 if constexpr (std::is_same<ACC, int>::value)
                     o = math.run(HAS_BG ? (int)bg[k] - v : v, v, (int)rm[k], flags);
@@ -109,6 +112,7 @@ prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
             }
             stg_stream_u2(out + (size_t)(f + u) * out_stride + out_off, make_uint2(packed[0], packed[1]));
             if (invalid_count && bad) atomicAdd(invalid_count + f + u, bad);
+            if (invalid_bits) invalid_bits[((size_t)(f + u) * h + r) * w8 + (c >> 3)] = (uint8_t)bad_bits;
         }
     }
 }
@@ -119,8 +123,9 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_scalar_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
                    const BG *__restrict__ bground, const uint8_t *__restrict__ roi,
                    int y0, int x0, int h, int w, PrepMath<ACC> math, int flags,
-                   uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count) {
+                   uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint32_t *__restrict__ invalid_bits_words) {
     const size_t total = (size_t)n * h * w;
+    const int bytes_per_row = (w + 7) >> 3;
     for (size_t i = (size_t)blockIdx.x * kPrepThreads + threadIdx.x; i < total;
          i += (size_t)gridDim.x * kPrepThreads) {
         const int c = (int)(i % w);
@@ -136,14 +141,20 @@ prep_scalar_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
         else
             o = math.run((ACC)bground[pix], v, rm, flags);
         out[i] = (uint8_t)o;
-        if (invalid_count && v == 0 && rm != (ACC)0) atomicAdd(invalid_count + f, 1);
+        if (v == 0 && rm != (ACC)0) {
+            if (invalid_count) atomicAdd(invalid_count + f, 1);
+            if (invalid_bits_words) {           // byte-packed mask, set with word atomics (buffer zeroed by the launcher)
+                const size_t byte = ((size_t)f * h + r) * bytes_per_row + (c >> 3);
+                atomicOr(invalid_bits_words + (byte >> 2), 1u << ((byte & 3) * 8 + (c & 7)));
+            }
+        }
     }
 }
 
 template <typename BG, typename ACC, bool HAS_BG>
 int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground, const uint8_t *roi,
                 int y0, int x0, int h, int w, double vmin, double vmax, int flags, uint8_t *out,
-                int32_t *invalid, cudaStream_t st) {
+                int32_t *invalid, uint8_t *invalid_bits, cudaStream_t st) {
     PrepMath<ACC> math(vmin, vmax);
     const bool vec_ok = (w % 8 == 0) && (x0 % 8 == 0) && (W % 8 == 0) &&
                         ((uintptr_t)frames % 16 == 0) && ((uintptr_t)out % 8 == 0);
@@ -157,13 +168,18 @@ int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground,
         dim3 grid(bx, groups);
         TimedLaunch timed(K_PREP, st);
         prep_vec8_kernel<BG, ACC, HAS_BG><<<grid, kPrepThreads, 0, st>>>(
-            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, fpg, out, invalid);
+            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, fpg, out, invalid, invalid_bits);
     } else {
         const size_t total = (size_t)n * h * w;
+        if (invalid_bits) {
+            MSQ_REQUIRE((uintptr_t)invalid_bits % 4 == 0, MSQ_EINVAL, "msq_prep_frames: invalid_bits must be 4-byte aligned");
+            const size_t bytes = align_up((size_t)n * h * ((w + 7) / 8), 4);
+            MSQ_CUDA_OK(cudaMemsetAsync(invalid_bits, 0, bytes, st));
+        }
         const int blocks = (int)std::min<size_t>((total + kPrepThreads - 1) / kPrepThreads, (size_t)sm_count() * 16);
         TimedLaunch timed(K_PREP, st);
         prep_scalar_kernel<BG, ACC, HAS_BG><<<blocks, kPrepThreads, 0, st>>>(
-            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, out, invalid);
+            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, out, invalid, reinterpret_cast<uint32_t *>(invalid_bits));
     }
     MSQ_LAUNCH_OK("prep_frames");
     return MSQ_OK;
@@ -244,7 +260,7 @@ using namespace msq;
 
 extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const void *bground, int bg_dtype,
                                const uint8_t *roi, int y0, int x0, int h, int w, double vmin, double vmax,
-                               int flags, uint8_t *out, int32_t *invalid, void *stream) {
+                               int flags, uint8_t *out, int32_t *invalid, uint8_t *invalid_bits, void *stream) {
     MSQ_REQUIRE(n == 0 || (frames && out), MSQ_EINVAL, "msq_prep_frames: null frames/out pointer");
     MSQ_REQUIRE(n >= 0 && H > 0 && W > 0 && h > 0 && w > 0, MSQ_EINVAL,
                 "msq_prep_frames: bad sizes n=%d H=%d W=%d h=%d w=%d", n, H, W, h, w);
@@ -256,10 +272,10 @@ extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const
     cudaStream_t st = (cudaStream_t)stream;
     if (invalid) MSQ_CUDA_OK(cudaMemsetAsync(invalid, 0, sizeof(int32_t) * (size_t)n, st));
     switch (bg_dtype) {
-        case MSQ_BG_F32: return launch_prep<float, float, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
-        case MSQ_BG_F64: return launch_prep<double, double, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
-        case MSQ_BG_U16: return launch_prep<uint16_t, int, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
-        default:         return launch_prep<uint16_t, int, false>(frames, n, H, W, nullptr, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, st);
+        case MSQ_BG_F32: return launch_prep<float, float, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
+        case MSQ_BG_F64: return launch_prep<double, double, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
+        case MSQ_BG_U16: return launch_prep<uint16_t, int, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
+        default:         return launch_prep<uint16_t, int, false>(frames, n, H, W, nullptr, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
     }
 }
 

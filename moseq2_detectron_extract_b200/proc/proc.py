@@ -30,11 +30,8 @@ _ELLIPSE9 = np.array([[0, 0, 0, 0, 1, 0, 0, 0, 0],
 
 
 class InvalidPixelsError(NotImplementedError):
-    """Frames contain Kinect invalid pixels (raw value 0) inside the ROI and in-painting was requested.
-
-    The reference fills them with cv2.inpaint (Navier-Stokes fast marching, ref: proc/proc.py:189-210), which has no
-    GPU implementation in this build yet.  Rather than silently computing
-    on the CPU the call fails; pass fix_invalid_pixels=False to get the un-filled frames."""
+    """Kept for API compatibility with earlier builds: invalid pixels are now in-painted on the GPU
+    (csrc/inpaint.cu), so `prep_raw_frames` no longer raises this."""
 
 
 # --------------------------------------------------------------------------------------------
@@ -56,8 +53,9 @@ def _bg_code(bground) -> Tuple[int, Optional[torch.Tensor]]:
     return _lib.MSQ_BG_F64, _dev.as_device(arr.astype(np.float64))
 
 
-def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, out_dtype_u8: bool = True):
-    """Launch the fused prep kernel; returns (out_u8 (n,h,w), invalid_count (n) int32 or None)."""
+def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, want_bits: bool = False):
+    """Launch the fused prep kernel; returns (out_u8 (n,h,w), invalid_count (n) int32 or None) and, with
+    want_bits, additionally the packed invalid-pixel mask (n, h, ceil(w/8)) uint8."""
     raw = _dev.as_device(frames, torch.int16)
     if raw.dim() != 3:
         raise ValueError(f'frames must be (nframes, height, width); got shape {tuple(raw.shape)}')
@@ -75,14 +73,36 @@ def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, out_dt
         if box is not None:      # max-exclusive slicing, ref: proc/roi.py:233-235
             y0, x0, h, w = int(box[0, 0]), int(box[0, 1]), int(box[1, 0] - box[0, 0]), int(box[1, 1] - box[0, 1])
     if h <= 0 or w <= 0:
-        return _dev.empty((n, max(h, 0), max(w, 0)), torch.uint8), None
+        empty = _dev.empty((n, max(h, 0), max(w, 0)), torch.uint8)
+        return (empty, None, None) if want_bits else (empty, None)
     flags = (_lib.MSQ_PREP_HAS_VMIN if vmin is not None else 0) | (_lib.MSQ_PREP_HAS_VMAX if vmax is not None else 0)
     out = _dev.empty((n, h, w), torch.uint8)
     invalid = _dev.empty((n,), torch.int32) if want_invalid else None
+    bits = None
+    if want_bits:
+        row_bytes = (w + 7) // 8
+        bits = torch.zeros(((n * h * row_bytes + 3) // 4 * 4,), dtype=torch.uint8, device='cuda')
     _lib.call('msq_prep_frames', _dev.ptr(raw), n, H, W, _dev.ptr(bg), code, _dev.ptr(roi_dev), y0, x0, h, w,
               float(vmin if vmin is not None else 0.0), float(vmax if vmax is not None else 0.0), flags,
-              _dev.ptr(out), _dev.ptr(invalid), _dev.stream())
+              _dev.ptr(out), _dev.ptr(invalid), _dev.ptr(bits), _dev.stream())
+    if want_bits:
+        return out, invalid, bits
     return out, invalid
+
+
+def fill_invalid_pixels_device(frames_u8: torch.Tensor, invalid_count: torch.Tensor, invalid_bits: torch.Tensor,
+                               radius: int = 3) -> int:
+    """In-paint, in place, every frame whose invalid count is non-zero (ref: proc/proc.py:189-210,
+    cv2.inpaint(..., 3, cv2.INPAINT_NS) bit-exact; csrc/inpaint.cu).  Returns the number of frames touched."""
+    flagged = torch.nonzero(invalid_count, as_tuple=False).flatten().to(torch.int32)
+    m = int(flagged.numel())
+    if m == 0:
+        return 0
+    n, h, w = (int(v) for v in frames_u8.shape)
+    scratch = _dev.empty((int(_lib.load().msq_inpaint_scratch_bytes(m, h, w)) + 8,), torch.uint8)
+    _lib.call('msq_inpaint_frames', _dev.ptr(frames_u8), _dev.ptr(invalid_bits), _dev.ptr(flagged), m, h, w, int(radius),
+              _dev.ptr(scratch), scratch.numel(), _dev.stream())
+    return m
 
 
 def prep_raw_frames(frames, bground_im=None, roi=None, vmin: Optional[float] = None, vmax: Optional[float] = None,
@@ -93,12 +113,12 @@ def prep_raw_frames(frames, bground_im=None, roi=None, vmin: Optional[float] = N
     the two fancy-index clamps + astype.  Returns (nframes, roi_height, roi_width) uint8."""
     if np.dtype(dtype) != np.uint8:
         raise NotImplementedError('prep_raw_frames: only dtype=uint8 (the extract path) is implemented')
-    out, invalid = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=fix_invalid_pixels)
-    if fix_invalid_pixels and invalid is not None:
-        bad = int(torch.count_nonzero(invalid).item())
-        if bad:
-            raise InvalidPixelsError(f'{bad} of {out.shape[0]} frames have invalid (raw == 0) pixels inside the ROI; '
-                                     'GPU in-painting is not implemented yet (pass fix_invalid_pixels=False)')
+    if not fix_invalid_pixels:
+        out, _ = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=False)
+        return _dev.give_back(out, frames)
+    out, invalid, bits = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=True, want_bits=True)
+    if invalid is not None and out.numel() > 0:
+        fill_invalid_pixels_device(out, invalid, bits)
     return _dev.give_back(out, frames)
 
 

@@ -31,12 +31,10 @@ def test_prep_matches_reference(P, name):
     out = P.prep_raw_frames(chunk.frames, bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'],
                             fix_invalid_pixels=False)
     assert out.dtype == np.uint8 and np.array_equal(out, g['prep_nofix'])
+    out = P.prep_raw_frames(chunk.frames, bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'])
+    assert np.array_equal(out, g['prep'])               # includes cv2.inpaint of the invalid pixels, bit-exact
     if name == 'kinect_invalid':
-        with pytest.raises(P.InvalidPixelsError):
-            P.prep_raw_frames(chunk.frames, bground_im=bg, roi=roi, vmin=0, vmax=100)
-    else:
-        out = P.prep_raw_frames(chunk.frames, bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'])
-        assert np.array_equal(out, g['prep'])
+        assert not np.array_equal(g['prep'], g['prep_nofix'])
 
 
 def test_prep_invalid_counts_and_device_tensors(P):
@@ -72,6 +70,46 @@ def test_prep_background_dtypes_and_unaligned_boxes(P, bg_kind, aligned):
         ref = O.prep_frames(f, bg, roi, vmin, vmax, fix_invalid=False)
         out = P.prep_raw_frames(f, bground_im=bg, roi=roi, vmin=vmin, vmax=vmax, fix_invalid_pixels=False)
         assert np.array_equal(out, ref), (bg_kind, aligned, vmin, vmax)
+
+
+@pytest.mark.parametrize('rate', [0.0005, 0.01, 0.1, 0.5])
+@pytest.mark.parametrize('aligned', [True, False])
+def test_inpaint_matches_opencv(P, rate, aligned):
+    """fill_invalid_pixels (ref proc/proc.py:189-210): GPU fast-marching Navier-Stokes vs cv2.inpaint, bit-exact."""
+    rng = np.random.default_rng(int(rate * 1e4) + aligned)
+    H, W = 70, 112
+    n = 6
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames = (650 - 40 * np.exp(-((xx - 50) ** 2 + (yy - 35) ** 2) / 300.0)[None] + rng.normal(0, 1.5, (n, H, W))).astype(np.int16)
+    frames[rng.random(frames.shape) < rate] = 0
+    frames[1, 20:26, 30:37] = 0                      # a solid invalid block
+    frames[2, :, :] = np.where(rng.random((H, W)) < 0.9, 0, frames[2])    # nearly everything invalid
+    frames[3] = np.maximum(frames[3], 1)             # one frame without invalid pixels
+    roi = np.zeros((H, W), dtype=bool)
+    if aligned:
+        roi[3:60, 16:97] = True                      # x0 = 16, w = 80
+    else:
+        roi[2:66, 11:100] = True                     # x0 = 11, w = 88 -> scalar prep path, atomically packed mask
+    roi[30, 40] = False
+    bg = np.full((H, W), 673.0, dtype=np.float32)
+    ref = O.prep_frames(frames, bg, roi, 0, 100, fix_invalid=True)
+    got = P.prep_raw_frames(frames, bground_im=bg, roi=roi, vmin=0, vmax=100)
+    assert np.array_equal(got, ref), (rate, aligned, int((got != ref).sum()))
+    assert not np.array_equal(ref, O.prep_frames(frames, bg, roi, 0, 100, fix_invalid=False))
+
+
+def test_inpaint_edge_cases(P):
+    rng = np.random.default_rng(77)
+    for (H, W) in [(9, 9), (12, 40), (33, 17)]:
+        frames = rng.integers(580, 673, size=(4, H, W)).astype(np.int16)
+        frames[0, 0, 0] = 0; frames[0, -1, -1] = 0; frames[0, 0, W // 2] = 0      # corners / borders
+        frames[1, :, 0] = 0; frames[1, 0, :] = 0                                    # whole border row + column
+        frames[2] = 0                                                               # everything invalid
+        roi = np.ones((H, W), dtype=bool)                                           # box = [0:H-1, 0:W-1)
+        bg = np.full((H, W), 673.0, dtype=np.float32)
+        ref = O.prep_frames(frames, bg, roi, 0, 100, fix_invalid=True)
+        got = P.prep_raw_frames(frames, bground_im=bg, roi=roi, vmin=0, vmax=100)
+        assert np.array_equal(got, ref), (H, W, int((got != ref).sum()))
 
 
 def test_prep_empty_and_errors(P):

@@ -66,16 +66,23 @@ def test_steps_match_oracle_chunk_by_chunk():
         assert np.array_equal(r['mask_frames'], ref['mask_frames'])
 
 
-def test_tracking_and_invalid_pixels_fail_loudly():
+def test_tracking_fails_loudly_and_invalid_pixels_are_inpainted():
     from moseq2_detectron_extract_b200 import synthetic
-    from moseq2_detectron_extract_b200.pipeline import Pipeline, ProcessFeaturesStep, WorkerError
+    from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
     cfg = synthetic.default_config()
     cfg['use_tracking'] = True
     step = ProcessFeaturesStep(cfg, 'features')
     with pytest.raises(NotImplementedError):
         step.initialize()
-    with pytest.raises(WorkerError):
-        _run_pipeline(20, 10, invalid_rate=0.01)        # produced frames contain invalid in-ROI pixels
+    sess, cfg, results = _run_pipeline(20, 10, invalid_rate=0.002)     # Kinect-like invalid pixels inside the ROI
+    for r in results:
+        idxs = r['frame_idxs']
+        ch = synthetic.generate_chunk(len(idxs), seed=4, geom=sess.geom, t0=idxs[0], invalid_rate=0.002)
+        prep = O.prep_frames(ch.frames, sess.bground_im, sess.roi, cfg['min_height'], cfg['max_height'])   # cv2.inpaint inside
+        assert np.array_equal(r['chunk'].cpu().numpy(), prep)
+        ref = O.extract_chunk(prep, ch.masks, ch.keypoints, ch.num_instances, cfg['min_height'], cfg['max_height'],
+                              cfg['true_depth'], cfg['crop_size'])
+        assert np.array_equal(r['depth_frames'], ref['depth_frames'])
 
 
 def test_predictor_random_init_smoke():

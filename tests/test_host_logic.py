@@ -52,8 +52,11 @@ def test_argument_validation_returns_error_codes(lib):
     l = lib.load()
     assert l.msq_clean_frames(None, None, 5, 8, 8, None) == -1
     assert 'null' in lib.last_error()
-    assert l.msq_prep_frames(None, 0, 8, 8, None, 0, None, 0, 0, 8, 8, 0.0, 1.0, 0, None, None, None) == 0   # n = 0 is a no-op
-    assert l.msq_prep_frames(None, 1, 8, 8, None, 0, None, 4, 4, 8, 8, 0.0, 1.0, 0, None, None, None) == -1
+    assert l.msq_prep_frames(None, 0, 8, 8, None, 0, None, 0, 0, 8, 8, 0.0, 1.0, 0, None, None, None, None) == 0   # n = 0 is a no-op
+    assert l.msq_prep_frames(None, 1, 8, 8, None, 0, None, 4, 4, 8, 8, 0.0, 1.0, 0, None, None, None, None) == -1
+    assert l.msq_inpaint_frames(None, None, None, 0, 8, 8, 3, None, 0, None) == 0
+    assert l.msq_inpaint_frames(None, None, None, 2, 8, 8, 9, None, 0, None) == -1
+    assert l.msq_inpaint_scratch_bytes(3, 240, 240) >= 3 * 240 * 240 * 16
     with pytest.raises(lib.MoseqB200Error):
         lib.call('msq_scale_frames', None, None, 16, 1.0, 1.0, 0, None)
 

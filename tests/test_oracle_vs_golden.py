@@ -152,3 +152,22 @@ def test_warp_emulation_of_feature_kernel_matches_oracle():
             m[:] = False
         ref = O.frame_features_np((m * 9).astype(np.uint8)[None], m.astype(np.uint8)[None], return_sums=True)['sums24'][0]
         assert list(ref) == list(emulate_frame(m)), (t, h, w)
+
+
+def test_inpaint_restatement_equals_opencv():
+    """oracle/inpaint_ns.py (the algorithm csrc/inpaint.cu follows) against cv2.inpaint(.., 3, INPAINT_NS)."""
+    from inpaint_ns import inpaint_ns
+    rng = np.random.default_rng(5)
+    for t in range(40):
+        h, w = int(rng.integers(6, 30)), int(rng.integers(6, 30))
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8) if t % 3 else cv2.GaussianBlur(rng.integers(0, 101, (h, w)).astype(np.uint8), (0, 0), 1.5)
+        m = (rng.random((h, w)) < [0.002, 0.02, 0.1, 0.3, 0.6][t % 5]).astype(np.uint8)
+        if t % 4 == 0:
+            y, x = int(rng.integers(0, h - 3)), int(rng.integers(0, w - 3))
+            m[y:y + int(rng.integers(2, 6)), x:x + int(rng.integers(2, 6))] = 1
+        if t % 11 == 0:
+            m[:] = 1
+        if t % 13 == 0:
+            m[0, :] = 1
+            m[:, 0] = 1
+        assert np.array_equal(inpaint_ns(img, m, 3), cv2.inpaint(img, m, 3, cv2.INPAINT_NS)), t

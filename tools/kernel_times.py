@@ -40,7 +40,7 @@ ang = _dev.empty((n,), torch.float64); fl = _dev.empty((n,), torch.uint8); ps = 
 sc = _dev.empty((17, n), torch.float64); kc = _dev.empty((96, n), torch.float64); scr = _dev.empty((16 * n + 512,), torch.uint8)
 cscr = _dev.empty((64 * n,), torch.uint8); dc = _dev.empty((n, 80, 80), torch.uint8); mc = _dev.empty((n, 80, 80), torch.uint8)
 out = {}
-out['prep'] = timeit(lambda: _lib.call('msq_prep_frames', _dev.ptr(frames), n, geom.height, geom.width, _dev.ptr(bgd), 1, _dev.ptr(roid), y0, x0, h, w, 0.0, 100.0, 3, _dev.ptr(prep), _dev.ptr(inv), st))
+out['prep'] = timeit(lambda: _lib.call('msq_prep_frames', _dev.ptr(frames), n, geom.height, geom.width, _dev.ptr(bgd), 1, _dev.ptr(roid), y0, x0, h, w, 0.0, 100.0, 3, _dev.ptr(prep), _dev.ptr(inv), None, st))
 out['clean'] = timeit(lambda: _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, st))
 out['features'] = timeit(lambda: _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(cen), _dev.ptr(ori), _dev.ptr(ax), None, None, 0, st))
 out['angles'] = timeit(lambda: _lib.call('msq_angles_and_flips', _dev.ptr(ori), _dev.ptr(ax), _dev.ptr(cen), _dev.ptr(kpts), n, 1000, _dev.ptr(ang), _dev.ptr(fl), None, _dev.ptr(ps), st))
