@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument('--cpu-frames-per-worker', type=int, default=250)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--rcnn-frames', type=int, default=2000, help='frames for the secondary full-extract (R-CNN) figure; 0 = skip')
+    ap.add_argument('--rcnn-batch', type=int, default=50)
     return ap.parse_args()
 
 
@@ -341,6 +343,14 @@ def run_ours(args):
         else:
             e2e_ms, e2e_mode, h2d_chunk = e2e_copy_ms, 'copy', pool_frames[:chunk].numel() * 2 + small_chunk
         h2d_bytes, d2h_bytes = h2d_chunk * n_e2e_chunks, d2h_chunk * n_e2e_chunks
+    # ---- secondary figures (rank 0, not part of `value`): in-painting cost and the full extract with the R-CNN ------
+    extras = {}
+    if rank == 0 and world == 1:
+        try:
+            extras.update(secondary_figures(args, geom, cfg, roi, bg))
+        except Exception as exc:       # never let a secondary figure break the contract line
+            extras['secondary_error'] = repr(exc)[:300]
+
     # ---- reduce over ranks (max time) --------------------------------------------------------------------
     times = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device='cuda')
     launches_all = torch.tensor([float(gpu_launches)], dtype=torch.float64, device='cuda')
@@ -411,9 +421,59 @@ def run_ours(args):
                 if e2e_ms is not None else None),
         'roofline': roofline, 'cpu_baseline': cpu_base,
     }
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_figures(args, geom, cfg, roi, bg):
+    """(1) prep with Kinect-like invalid pixels (rate 0.002) incl. the GPU in-paint, (2) BASELINE configs[2]: the full
+    extract path with a random-init Keypoint+Mask R-CNN R50-FPN (torchvision graph, bf16 autocast) between our kernels."""
+    import numpy as np
+    import torch
+    from moseq2_detectron_extract_b200 import _dev, synthetic
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    out = {}
+
+    def timed(fn, iters=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    small = synthetic.generate_chunk(200, seed=11, geom=geom, invalid_rate=0.002)
+    fr = torch.from_numpy(np.tile(small.frames, (5, 1, 1))).cuda()
+    ms_fix = timed(lambda: prep_raw_frames(fr, bground_im=bg, roi=roi, vmin=0, vmax=100, fix_invalid_pixels=True))
+    ms_raw = timed(lambda: prep_raw_frames(fr, bground_im=bg, roi=roi, vmin=0, vmax=100, fix_invalid_pixels=False))
+    out['prep_with_invalid_pixels'] = {'frames': int(fr.shape[0]), 'invalid_rate': 0.002, 'ms_prep_only': ms_raw,
+                                       'ms_prep_plus_inpaint': ms_fix, 'frames_per_s': fr.shape[0] / (ms_fix * 1e-3)}
+    del fr
+    if args.rcnn_frames > 0:
+        from moseq2_detectron_extract_b200.pipeline import InferenceStep, ProcessFeaturesStep
+        n = args.rcnn_frames
+        cfg2 = dict(cfg, batch_size=args.rcnn_batch, model='random', nframes=n, results_to_host=False, amp=True)
+        infer, feats = InferenceStep(cfg2, 'infer'), ProcessFeaturesStep(cfg2, 'features')
+        infer.initialize()
+        feats.initialize()
+        ch = synthetic.generate_chunk(min(n, 500), seed=12, geom=geom)
+        raw = torch.from_numpy(np.tile(ch.frames, ((n + len(ch.frames) - 1) // len(ch.frames), 1, 1))[:n]).cuda()
+
+        def full():
+            chunk = prep_raw_frames(raw, bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'])
+            data = {'batch': 0, 'chunk': chunk, 'frame_idxs': list(range(n)), 'offset': 0}
+            feats.process(infer.process(data))
+        ms_full = timed(full, iters=2)
+        out['full_extract_rcnn'] = {
+            'workload': 'configs[2]: prep -> scale -> Keypoint+Mask R-CNN R50-FPN (random init, torchvision graph, bf16 autocast, '
+                        f'batch {args.rcnn_batch}, 100 proposals, 1 detection/frame) -> paste -> features -> crops',
+            'frames': n, 'ms': ms_full, 'frames_per_s': n / (ms_full * 1e-3)}
+    return out
 
 
 def main():

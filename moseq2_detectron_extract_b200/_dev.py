@@ -58,7 +58,7 @@ def stream() -> ctypes.c_void_p:
 
 
 def give_back(t: torch.Tensor, like: Any):
-    """Return `t` in the same residency as the caller's input `like`."""
-    if is_device_tensor(like):
+    """numpy in -> numpy out; torch tensor in (CUDA, or host/pinned) -> the result stays on the device."""
+    if isinstance(like, torch.Tensor):
         return t
     return t.cpu().numpy()

@@ -1,0 +1,136 @@
+"""Raw depth decode-to-tensor (mirrors reference io/video.py:33-127).
+
+The wire format is headerless little-endian int16, `width*height*2` bytes per frame, optionally a member of a
+tar archive.  "Decoding" is therefore a byte reinterpretation: frames are read with `readinto` straight into ONE
+destination buffer -- optionally page-locked, so that the prep kernel can consume the ROI box of the frames
+directly from host memory (zero-copy, see bench.py e2e) or a single cudaMemcpyAsync can move them.
+"""
+from __future__ import annotations
+
+import os
+import tarfile
+from typing import Iterable, List, Optional, Tuple, Union
+
+import numpy as np
+
+
+def get_raw_info(filename: Union[str, tarfile.TarInfo], bit_depth: int = 16, frame_dims: Tuple[int, int] = (512, 424)) -> dict:
+    """Size bookkeeping of a raw depth file (ref: io/video.py:33-58)."""
+    bytes_per_frame = int(frame_dims[0] * frame_dims[1] * bit_depth / 8)
+    file_bytes = filename.size if isinstance(filename, tarfile.TarInfo) else os.stat(filename).st_size
+    return {'bytes': file_bytes, 'nframes': int(file_bytes / bytes_per_frame), 'dims': frame_dims,
+            'bytes_per_frame': bytes_per_frame}
+
+
+def _consecutive_runs(values: List[int]) -> List[Tuple[int, int]]:
+    """[(start, count)] of runs of consecutive integers in a sorted list (ref: io/video.py:130-150)."""
+    runs: List[Tuple[int, int]] = []
+    for v in values:
+        if runs and v == runs[-1][0] + runs[-1][1]:
+            runs[-1] = (runs[-1][0], runs[-1][1] + 1)
+        else:
+            runs.append((v, 1))
+    return runs
+
+
+def read_frames_raw(filename: Union[str, tarfile.TarInfo], frames: Optional[Union[int, Iterable[int]]] = None,
+                    frame_dims: Tuple[int, int] = (512, 424), bit_depth: int = 16, dtype="<i2",
+                    tar_object: Optional[tarfile.TarFile] = None, pinned: bool = False, as_tensor: bool = False):
+    """Read frames of a raw binary depth file into a `(nframes, height, width)` array (ref: io/video.py:67-127).
+
+    Same arguments as the reference plus `pinned`: allocate the result in page-locked host memory (a numpy view of a
+    pinned torch tensor); with `as_tensor` the pinned torch tensor itself is returned, which `prep_raw_frames` consumes
+    zero-copy.  Requested indices may be unordered or repeated: like the reference, runs of consecutive frames are read
+    with one seek + one read each."""
+    info = get_raw_info(filename, frame_dims=frame_dims, bit_depth=bit_depth)
+    if isinstance(frames, (int, np.integer)):
+        frames = [int(frames)]
+    elif frames is not None:
+        frames = [int(i) for i in frames]
+    if frames is None or len(frames) == 0:
+        frames = list(range(info['nframes']))
+    dt = np.dtype(dtype)
+    shape = (len(frames), frame_dims[1], frame_dims[0])
+    if pinned:
+        import torch
+        holder = torch.empty(shape, dtype=torch.int16).pin_memory()
+        out = holder.numpy().view(dt)
+    else:
+        out = np.empty(shape, dtype=dt)
+    first_slot = {}
+    for slot, idx in enumerate(frames):
+        first_slot.setdefault(idx, slot)
+
+    if isinstance(tar_object, tarfile.TarFile):
+        handle = tar_object.extractfile(filename)
+        if handle is None:
+            name = filename.name if isinstance(filename, tarfile.TarInfo) else filename
+            raise FileNotFoundError(f'Could not open tar member: {name}')
+    elif isinstance(filename, str):
+        handle = open(filename, 'rb')
+    else:
+        raise ValueError('Could not read!')
+    contiguous = frames == list(range(frames[0], frames[0] + len(frames)))
+    with handle:
+        if contiguous:                                  # the chunk iterator's case: one read into the destination
+            handle.seek(max(0, frames[0] * info['bytes_per_frame']))
+            got = handle.readinto(memoryview(out).cast('B'))
+            if got != out.nbytes:
+                raise EOFError(f'{filename}: wanted {out.nbytes} bytes, got {got}')
+        else:
+            for start, count in _consecutive_runs(sorted(set(frames))):
+                handle.seek(max(0, start * info['bytes_per_frame']))
+                block = np.empty((count, frame_dims[1], frame_dims[0]), dtype=dt)
+                got = handle.readinto(memoryview(block).cast('B'))
+                if got != block.nbytes:
+                    raise EOFError(f'{filename}: wanted {block.nbytes} bytes, got {got}')
+                for k in range(count):
+                    out[first_slot[start + k]] = block[k]
+            for slot, idx in enumerate(frames):          # repeated indices
+                if first_slot[idx] != slot:
+                    out[slot] = out[first_slot[idx]]
+    return holder if (pinned and as_tensor) else out
+
+
+class RawDepthSession:
+    """The slice of `io.session.Session` that ProduceFramesStep uses (ref: io/session.py:24, :352-466), backed by a raw
+    `.dat` depth file: `.bground_im`, `.roi`, `.nframes`, `.iterate(chunk_size, chunk_overlap)`.  Background and ROI
+    are supplied by the caller (their estimation, ref proc/roi.py:14/:293, is per-session set-up, not the hot path)."""
+
+    def __init__(self, depth_file: str, bground_im: np.ndarray, roi: np.ndarray, true_depth: float,
+                 frame_dims: Tuple[int, int] = (512, 424), pinned: bool = True):
+        self.depth_file, self.frame_dims, self.pinned = depth_file, frame_dims, pinned
+        self.bground_im, self.roi, self.true_depth = bground_im, roi, float(true_depth)
+        self.nframes = get_raw_info(depth_file, frame_dims=frame_dims)['nframes']
+
+    def iterate(self, chunk_size: int = 1000, chunk_overlap: int = 0):
+        return _RawIterator(self, chunk_size, chunk_overlap)
+
+
+class _RawIterator:
+    def __init__(self, session: RawDepthSession, chunk_size: int, chunk_overlap: int):
+        from ..shard import chunk_ranges
+        self.session = session
+        self.batches = chunk_ranges(session.nframes, chunk_size, chunk_overlap)
+        self.filters = []
+        self._pos = 0
+
+    def attach_filter(self, stream=None, filterer=None):
+        self.filters.append(filterer)
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._pos >= len(self.batches):
+            raise StopIteration
+        idxs = self.batches[self._pos]
+        self._pos += 1
+        frames = read_frames_raw(self.session.depth_file, idxs, frame_dims=self.session.frame_dims, pinned=self.session.pinned,
+                                 as_tensor=self.session.pinned)
+        for f in self.filters:
+            frames = f(frames)
+        return list(idxs), frames

@@ -73,9 +73,10 @@ class _TorchvisionAdapter(torch.nn.Module):
 
 
 class Predictor:
-    def __init__(self, model: Any, is_torchscript: bool = False):
+    def __init__(self, model: Any, is_torchscript: bool = False, amp: bool = False):
         self.model = model
         self.is_torchscript = is_torchscript
+        self.amp = amp                      # bf16 autocast for the dense graph (tensor cores)
         self.exit_stack = ExitStack()
         self.exit_stack.enter_context(torch.no_grad())
 
@@ -91,11 +92,13 @@ class Predictor:
         return cls(model, is_torchscript=True)
 
     @classmethod
-    def from_random_init(cls, device: str = 'cuda', seed: int = 0, **kwargs):
+    def from_random_init(cls, device: str = 'cuda', seed: int = 0, amp: bool = False, **kwargs):
         _dev.require_cuda()
         torch.manual_seed(seed)
         model = _TorchvisionAdapter(build_random_keypoint_mask_rcnn(**kwargs)).to(device).eval()
-        return cls(model, is_torchscript=True)
+        if amp:
+            model = model.to(memory_format=torch.channels_last)
+        return cls(model, is_torchscript=True, amp=amp)
 
     # ---- reference-shaped entry point (ref: model/predict.py:53-106) ---------------------------------
     def __call__(self, original_image):
@@ -121,5 +124,7 @@ class Predictor:
         with torch.no_grad():
             inputs = [{'image': chw[i], 'height': torch.tensor(chw.shape[2]), 'width': torch.tensor(chw.shape[3])}
                       for i in range(chw.shape[0])]
-            outputs = self.model(inputs)
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
+                outputs = self.model(inputs)
+            outputs = [{k: (v.float() if v.is_floating_point() else v) for k, v in o.items()} for o in outputs]
             return outputs_to_instances(inputs, outputs)

@@ -17,7 +17,7 @@ class InferenceStep(ProcessPipelineStep):
         if isinstance(model_path, str) and os.path.isfile(model_path) and model_path.endswith('.ts'):
             self.predictor = Predictor.from_torchscript(model_path)
         elif model_path is None or model_path == 'random':
-            self.predictor = Predictor.from_random_init(device=self.config.get('device', 'cuda'))
+            self.predictor = Predictor.from_random_init(device=self.config.get('device', 'cuda'), amp=bool(self.config.get('amp', False)))
         else:
             raise NotImplementedError('InferenceStep: only TorchScript (.ts) models or model="random" are supported; '
                                       'detectron2 checkpoints need detectron2 (not part of this build)')

@@ -16,8 +16,10 @@ class ProduceFramesStep(ProducerPipelineStep):
 
     def initialize(self):
         def prep_on_device(frames, **kw):
-            return prep_raw_frames(torch.from_numpy(frames).cuda(non_blocking=True) if not isinstance(frames, torch.Tensor)
-                                   else frames, **kw)
+            if isinstance(frames, torch.Tensor):
+                out = prep_raw_frames(frames, **kw)          # CUDA tensor, or pinned host tensor consumed zero-copy
+                return out if out.is_cuda else out.cuda()
+            return prep_raw_frames(torch.from_numpy(frames).cuda(non_blocking=True), **kw)
         self.prep_frames = partial(prep_on_device, bground_im=self.session.bground_im, roi=self.session.roi,
                                    vmin=self.config['min_height'], vmax=self.config['max_height'])
         self.iterator = self.session.iterate(self.config['chunk_size'], self.config['chunk_overlap'])

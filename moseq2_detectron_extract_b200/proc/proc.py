@@ -56,7 +56,12 @@ def _bg_code(bground) -> Tuple[int, Optional[torch.Tensor]]:
 def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, want_bits: bool = False):
     """Launch the fused prep kernel; returns (out_u8 (n,h,w), invalid_count (n) int32 or None) and, with
     want_bits, additionally the packed invalid-pixel mask (n, h, ceil(w/8)) uint8."""
-    raw = _dev.as_device(frames, torch.int16)
+    if isinstance(frames, torch.Tensor) and not frames.is_cuda and frames.dtype == torch.int16 and frames.is_pinned() \
+            and frames.is_contiguous():
+        _dev.require_cuda()
+        raw = frames          # zero-copy: the kernel reads the ROI box straight from page-locked host memory (UVA)
+    else:
+        raw = _dev.as_device(frames, torch.int16)
     if raw.dim() != 3:
         raise ValueError(f'frames must be (nframes, height, width); got shape {tuple(raw.shape)}')
     n, H, W = (int(v) for v in raw.shape)

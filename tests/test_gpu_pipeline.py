@@ -108,3 +108,36 @@ def test_predictor_random_init_smoke():
     from moseq2_detectron_extract_b200.proc import scale_raw_frames
     out2 = pred(scale_raw_frames(prep.cpu().numpy()[:, :, :, None], 0, 100))
     assert len(out2) == 4 and out2[0]['instances'].image_size == (240, 240)
+
+
+def test_raw_file_session_zero_copy_prep(tmp_path):
+    """a1 + a2: raw .dat file -> pinned host buffer -> prep kernel reading host memory directly -> oracle parity."""
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.io import RawDepthSession, read_frames_raw
+    from moseq2_detectron_extract_b200.pipeline import Pipeline, PipelineStep, ProduceFramesStep
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(45, seed=6, geom=geom, invalid_rate=0.001)
+    path = str(tmp_path / 'depth.dat')
+    ch.frames.astype('<i2').tofile(path)
+    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+    ref = O.prep_frames(ch.frames, bg, roi, 0, 100)
+    pinned = read_frames_raw(path, frame_dims=(geom.width, geom.height), pinned=True, as_tensor=True)
+    assert pinned.is_pinned() and np.array_equal(pinned.numpy(), ch.frames)
+    out = prep_raw_frames(pinned, bground_im=bg, roi=roi, vmin=0, vmax=100)           # zero-copy path
+    assert np.array_equal(out.cpu().numpy() if hasattr(out, 'cpu') else out, ref)
+    sess = RawDepthSession(path, bg, roi, geom.floor_depth, frame_dims=(geom.width, geom.height))
+    cfg = synthetic.default_config(geom)
+    cfg.update(chunk_size=20, nframes=45)
+    got = []
+
+    class Sink(PipelineStep):
+        def process(self, data):
+            got.append(data['chunk'].cpu().numpy())
+            return data
+
+    pipe = Pipeline()
+    a, b = pipe.add_step(ProduceFramesStep(sess, cfg, 'produce')), pipe.add_step(Sink(cfg, 'sink'))
+    pipe.link(a, b)
+    pipe.run()
+    assert np.array_equal(np.concatenate(got), ref)

@@ -209,3 +209,34 @@ def test_shard_chunks_partition(n_chunks, world):
     assert max(sizes) - min(s for s in sizes if s or True) <= -(-n_chunks // world)
     with pytest.raises(ValueError):
         shard_chunks(10, 3, 3)
+
+
+def test_read_frames_raw_matches_reference_semantics(tmp_path):
+    """a1 decode-to-tensor (ref io/video.py:67-127): headerless little-endian int16, plain file and tar member,
+    contiguous / unordered / repeated indices."""
+    import tarfile
+    from moseq2_detectron_extract_b200.io import RawDepthSession, get_raw_info, read_frames_raw
+    rng = np.random.default_rng(0)
+    W, H, N = 32, 20, 17
+    frames = rng.integers(-5, 4000, size=(N, H, W)).astype('<i2')
+    path = tmp_path / 'depth.dat'
+    frames.tofile(path)
+    info = get_raw_info(str(path), frame_dims=(W, H))
+    assert info == {'bytes': N * H * W * 2, 'nframes': N, 'dims': (W, H), 'bytes_per_frame': H * W * 2}
+    assert np.array_equal(read_frames_raw(str(path), frame_dims=(W, H)), frames)
+    assert np.array_equal(read_frames_raw(str(path), range(3, 11), frame_dims=(W, H)), frames[3:11])
+    assert np.array_equal(read_frames_raw(str(path), 5, frame_dims=(W, H)), frames[5:6])
+    pick = [9, 2, 3, 4, 16, 2, 0]
+    got = read_frames_raw(str(path), pick, frame_dims=(W, H))
+    assert got.dtype == np.dtype('<i2') and np.array_equal(got, frames[pick])
+    with tarfile.open(tmp_path / 'session.tar.gz', 'w:gz') as tar:
+        tar.add(path, arcname='depth.dat')
+    with tarfile.open(tmp_path / 'session.tar.gz', 'r:gz') as tar:
+        member = tar.getmember('depth.dat')
+        assert np.array_equal(read_frames_raw(member, range(4, 9), frame_dims=(W, H), tar_object=tar), frames[4:9])
+        assert np.array_equal(read_frames_raw(member, [8, 1], frame_dims=(W, H), tar_object=tar), frames[[8, 1]])
+    sess = RawDepthSession(str(path), np.zeros((H, W), np.float32), np.ones((H, W), bool), 673.0, frame_dims=(W, H), pinned=False)
+    chunks = list(sess.iterate(7, 0))
+    assert [c[0][0] for c in chunks] == [0, 7, 14] and np.array_equal(np.concatenate([c[1] for c in chunks]), frames)
+    with pytest.raises(EOFError):
+        read_frames_raw(str(path), range(10, 30), frame_dims=(W, H))
