@@ -264,7 +264,7 @@ def run_ours(args):
     e2e_mode = None
     if not args.no_e2e:
         n_e2e_chunks = (n_frames + chunk - 1) // chunk
-        copy_in, compute, copy_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        copy_in, compute, copy_out, prep_st = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         slots = 2
         in_f = [_dev.empty((chunk, H, W), torch.int16) for _ in range(slots)]
         in_m = [_dev.empty((chunk, h, w), torch.uint8) for _ in range(slots)]
@@ -300,14 +300,24 @@ def run_ours(args):
                     in_k[b].copy_(pool_kpts[:chunk], non_blocking=True)
                     ev_h2d[b] = torch.cuda.Event()
                     ev_h2d[b].record(copy_in)
-                with torch.cuda.stream(compute):
-                    compute.wait_event(ev_h2d[b])
-                    if ev_d2h[b] is not None:
-                        compute.wait_event(ev_d2h[b])           # output slot drained
+                # prep is PCIe-bound in zero-copy mode (it pulls the ROI box from host memory) and needs few SMs; on its
+                # own stream it overlaps the SM-bound extract kernels of the previous chunk
+                with torch.cuda.stream(prep_st):
+                    if not zero_copy:
+                        prep_st.wait_event(ev_h2d[b])
+                    if ev_comp[b] is not None:
+                        prep_st.wait_event(ev_comp[b])          # preps[b] consumed by the previous user of the slot
                     src = pool_frames[:chunk] if zero_copy else in_f[b]
                     _lib.call('msq_prep_frames', _dev.ptr(src), chunk, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32,
                               _dev.ptr(roi_d), y0, x0, h, w, float(cfg['min_height']), float(cfg['max_height']), flags,
                               _dev.ptr(preps[b]), _dev.ptr(invs[b]), None, _dev.stream())
+                    ev_prep = torch.cuda.Event()
+                    ev_prep.record(prep_st)
+                with torch.cuda.stream(compute):
+                    compute.wait_event(ev_h2d[b])
+                    compute.wait_event(ev_prep)
+                    if ev_d2h[b] is not None:
+                        compute.wait_event(ev_d2h[b])           # output slot drained
                     res = engines[b].extract(preps[b], in_m[b], in_k[b], **kw)
                     ev_comp[b] = torch.cuda.Event()
                     ev_comp[b].record(compute)
@@ -320,6 +330,7 @@ def run_ours(args):
                     ev_d2h[b].record(copy_out)
             torch.cuda.current_stream().wait_stream(copy_out)
             torch.cuda.current_stream().wait_stream(compute)
+            torch.cuda.current_stream().wait_stream(prep_st)
 
         def time_e2e(zero_copy):
             for _ in range(min(args.warmup, 3)):
@@ -416,7 +427,7 @@ def run_ours(args):
                  'frames_per_s_full_frame_copy': n_frames * args.steps / (e2e_copy_ms * 1e-3),
                  'frames_per_s_zero_copy_roi': n_frames * args.steps / (e2e_zc_ms * 1e-3),
                  'path': 'pinned host int16 frames + u8 masks + f32 keypoints -> msq_prep_frames + msq_extract_chunk -> '
-                         'pinned host crops/scalars/keypoint table/flips; 3-stream double-buffered pipeline; in zero-copy '
+                         'pinned host crops/scalars/keypoint table/flips; 4-stream (H2D, prep, extract, D2H) double-buffered pipeline; in zero-copy '
                          'mode the prep kernel reads the ROI box of the raw frames directly from pinned host memory'}
                 if e2e_ms is not None else None),
         'roofline': roofline, 'cpu_baseline': cpu_base,

@@ -271,6 +271,13 @@ Geometry make_geometry(int h, int w) {
 }  // namespace
 
 int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st) {
+    // fast path: the streaming warp-per-strip kernel (clean_stream.cu); the tiled kernel below serves widths that are
+    // not a multiple of 8 / unaligned pointers, and MSQ_CLEAN_TILED=1 forces it for A/B comparisons
+    static const bool force_tiled = getenv("MSQ_CLEAN_TILED") != nullptr;
+    if (!force_tiled) {
+        const int rc = launch_clean_stream(in, out, n, h, w, st);
+        if (rc != -100) return rc;
+    }
     const Geometry G = make_geometry(h, w);
     const size_t smem = (size_t)4 * G.PW * G.PH * sizeof(uint16_t);
     MSQ_REQUIRE(smem <= 227 * 1024, MSQ_EUNSUPPORTED, "clean_frames: tile needs %zu B of shared memory", smem);

@@ -1,0 +1,251 @@
+// a6 clean_frames, streaming formulation (the fast path; clean.cu keeps the tiled kernel for odd widths).
+// ref proc/proc.py:480-515: 3x3 median (replicate border) + one opening by the 9x9 ellipse.
+//
+// One WARP owns a full-width strip of a frame (32 lanes x 8 pixels = 256 plane columns: 240 output columns plus
+// an 8-pixel halo lane on either side) and walks down its rows.  Per input row, in registers:
+//   raw row  --3x3 median-->  M[m]  --row min 7/9-->  H7[m], H9[m]
+//   V7[m-1] = min(H7[m-1], H7[m])            T3[m-1] = min(H9[m-2], H9[m-1], H9[m])
+//   E[e]  = min(M[e-4], M[e+4], V7[e-3], V7[e+2], T3[e])        e = m-4     (the 9x9 ellipse is rows of width 1,7,7,9,9,9,7,7,1)
+//   ... and the same chain with max on E for the dilation, d = e-4.
+// Horizontal neighbours come from warp shuffles (lane +-1); vertical history is a set of per-lane delay lines in
+// shared memory (each lane only ever touches its own 16-byte slots, so there is no synchronisation at all), and the
+// pair/triple pre-combination (V7, T3) means every delay line is written once and read at most twice per row.
+// ncu on the tiled kernel showed 52 M shared-memory wavefronts / 1000 frames (LSU pipe 68 % busy) next to a 53 %
+// busy ALU pipe; this formulation needs ~3x fewer wavefronts, no block barriers and no second pass over the raw tile.
+#include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
+
+namespace msq {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kOutCols = 240;              // output columns per warp-row (lanes 1..30)
+constexpr int kDelay = 8;                  // rows in the M delay line   (M[m-8] is read, then M[m] overwrites it)
+constexpr int kDelayV = 6;                 // rows in the V7 delay line  (V7[m-7] is read, then V7[m-1] overwrites it)
+constexpr int kDelayT = 3;                 // rows in the T3 delay line  (T3[m-4] is read, then T3[m-1] overwrites it)
+constexpr int kPrefetch = 4;               // raw rows requested ahead of use
+constexpr int kWarpsPerCta = 1;
+
+struct MinOp {
+    static __device__ __forceinline__ uint32_t op3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+};
+struct MaxOp {
+    static __device__ __forceinline__ uint32_t op3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+};
+
+// (p[k],p[k+1]),(p[k+2],p[k+3]) -> (p[k+1],p[k+2])   (moving this to the FMA pipe as IMAD.HI + IMAD was measured: no gain)
+__device__ __forceinline__ uint32_t mid_pair(uint32_t a, uint32_t b) { return __funnelshift_r(a, b, 16); }
+__device__ __forceinline__ uint32_t med3(uint32_t a, uint32_t b, uint32_t c) {
+    return __vmaxu2(__vminu2(a, b), __vminu2(__vmaxu2(a, b), c));
+}
+__device__ __forceinline__ uint4 splat(uint32_t v) { return make_uint4(v, v, v, v); }
+
+struct RawRow {            // 8 pixels of one row as 16-bit lanes + the pixel just left / right of them
+    uint4 c;
+    uint32_t left;         // high lane = pixel -1
+    uint32_t right;        // low lane  = pixel  8
+};
+
+// 7- and 9-wide row extrema of one row held in registers; neighbours by shuffle.  Lane 0 / 31 receive their own
+// values as "neighbours": that only reaches the outer 4 columns of the halo lanes, which nothing consumes.
+template <class OP>
+__device__ __forceinline__ void row_extrema(const uint4 &b, uint4 &h7, uint4 &h9) {
+    const uint32_t ax = __shfl_up_sync(kFull, b.z, 1), ay = __shfl_up_sync(kFull, b.w, 1);      // px -4..-1
+    const uint32_t cx = __shfl_down_sync(kFull, b.x, 1), cy = __shfl_down_sync(kFull, b.y, 1);  // px  8..11
+    const uint32_t s_a = mid_pair(ax, ay), s_ab = mid_pair(ay, b.x), s_b0 = mid_pair(b.x, b.y), s_b1 = mid_pair(b.y, b.z),
+                   s_b2 = mid_pair(b.z, b.w), s_bc = mid_pair(b.w, cx), s_c = mid_pair(cx, cy);
+    const uint32_t t1 = OP::op3(s_ab, b.x, s_b0), t2 = OP::op3(b.y, s_b1, b.z), t3 = OP::op3(s_b2, b.w, s_bc);
+    h7.x = OP::op3(OP::op3(t1, s_a, ay), b.y, s_b1);
+    h7.y = OP::op3(t1, t2, s_b2);
+    h7.z = OP::op3(s_b0, t2, t3);
+    h7.w = OP::op3(OP::op3(s_b1, b.z, t3), cx, s_c);
+    h9.x = OP::op3(h7.x, ax, b.z);
+    h9.y = OP::op3(h7.y, ay, b.w);
+    h9.z = OP::op3(h7.z, b.x, cx);
+    h9.w = OP::op3(h7.w, b.y, cy);
+}
+
+template <class OP> __device__ __forceinline__ uint4 op2_4(const uint4 &a, const uint4 &b) {
+    return make_uint4(OP::op2(a.x, b.x), OP::op2(a.y, b.y), OP::op2(a.z, b.z), OP::op2(a.w, b.w));
+}
+template <class OP> __device__ __forceinline__ uint4 op3_4(const uint4 &a, const uint4 &b, const uint4 &c) {
+    return make_uint4(OP::op3(a.x, b.x, c.x), OP::op3(a.y, b.y, c.y), OP::op3(a.z, b.z, c.z), OP::op3(a.w, b.w, c.w));
+}
+
+struct StreamGeom {
+    int h, w, tiles_x, strips, strip_rows;
+};
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, StreamGeom G) {
+    // per-lane delay lines: [row slot][lane] uint4
+    __shared__ uint4 ring_m[kDelay][32], ring_v[kDelayV][32], ring_t[kDelayT][32];
+    __shared__ uint4 ring_e[kDelay][32], ring_w[kDelayV][32], ring_u[kDelayT][32];
+    const int lane = threadIdx.x & 31;
+    const int h = G.h, w = G.w;
+    const long long tasks = (long long)n * G.tiles_x * G.strips;
+
+    for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
+        const int f = (int)(task / (G.tiles_x * G.strips));
+        const int rem = (int)(task - (long long)f * G.tiles_x * G.strips);
+        const int tx = rem / G.strips, sy = rem - tx * G.strips;
+        const int y_out0 = sy * G.strip_rows, y_out1 = min(h, y_out0 + G.strip_rows);
+        const int x_lane = tx * kOutCols - 8 + (lane << 3);            // image column of this lane's first pixel
+        const bool col_in = (unsigned)x_lane < (unsigned)w;            // groups are 8-aligned: all in or all out
+        const bool writes = lane >= 1 && lane <= 30 && col_in;
+        const uint8_t *src = in + (size_t)f * h * w;
+        uint8_t *dst = out + (size_t)f * h * w;
+        // column addressing of the raw loads (replicate border): nearest in-image group + which byte to splat
+        const int xg = min(max(x_lane, 0), w - 8);
+        const int x_left = min(max(x_lane - 1, 0), w - 1), x_right = min(max(x_lane + 8, 0), w - 1);
+
+        auto issue = [&](int y, uint2 &v, uint32_t &edge) {           // raw bytes of input row y (clamped)
+            const uint8_t *row = src + (size_t)min(max(y, 0), h - 1) * w;
+            v = __ldg(reinterpret_cast<const uint2 *>(row + xg));
+            // pixel -1 / pixel 8 come from the neighbouring lane except at the two ends of the warp-row
+            edge = (lane == 0) ? (uint32_t)__ldg(row + x_left) : ((lane == 31) ? (uint32_t)__ldg(row + x_right) : 0u);
+        };
+        auto decode = [&](uint2 v, uint32_t edge) {
+            if (x_lane < 0) { v.x = (v.x & 0xffu) * 0x01010101u; v.y = v.x; }
+            else if (x_lane >= w) { v.y = (v.y >> 24) * 0x01010101u; v.x = v.y; }
+            RawRow r;
+            r.c = make_uint4(__byte_perm(v.x, 0, 0x4140), __byte_perm(v.x, 0, 0x4342), __byte_perm(v.y, 0, 0x4140),
+                             __byte_perm(v.y, 0, 0x4342));
+            const uint32_t from_left = __shfl_up_sync(kFull, r.c.w, 1), from_right = __shfl_down_sync(kFull, r.c.x, 1);
+            r.left = (lane == 0) ? (edge << 16) : from_left;
+            r.right = (lane == 31) ? edge : from_right;
+            return r;
+        };
+
+        const int y_first = y_out0 - 9;                                // first input row of the strip
+        // The three stages are software-pipelined across iterations: iteration s computes the median row s-1, the
+        // erosion from the median row of iteration s-1 and the dilation from the erosion row of iteration s-2, so the
+        // stages inside one iteration are mutually independent instruction streams (ILP for the ~10 resident warps).
+        const int steps = (y_out1 - y_out0) + 20;
+        uint2 pf_v[kPrefetch];
+        uint32_t pf_e[kPrefetch];
+#pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) issue(y_first + k, pf_v[k], pf_e[k]);
+
+        RawRow r0, r1, r2;                                             // the three newest raw rows (r2 newest)
+        r0.c = r1.c = r2.c = splat(0u); r0.left = r1.left = r2.left = 0u; r0.right = r1.right = r2.right = 0u;
+        uint4 h7_prev = splat(0u), h9_prev = splat(0u), h9_prev2 = splat(0u), v7_prev = splat(0u);
+        uint4 g7_prev = splat(0u), g9_prev = splat(0u), g9_prev2 = splat(0u), w7_prev = splat(0u);
+        uint4 M_cur = splat(0u), E_cur = splat(0u);                    // M[s-2] and E[s-7] entering iteration s
+        int slot6 = 0, slot3 = 0;                                      // s mod 6, s mod 3: both stages advance one row per iteration
+
+#pragma unroll 2
+        for (int s = 0; s < steps; ++s) {
+            // ================= stage 3: dilation row d = e-4 from E_cur = E[e], e = s-7 =================
+            {
+                const int e = s - 7;
+                uint4 g7, g9;
+                row_extrema<MaxOp>(E_cur, g7, g9);
+                const uint4 w7 = op2_4<MaxOp>(g7_prev, g7);                 // W7[e-1]
+                const uint4 u3 = op3_4<MaxOp>(g9_prev2, g9_prev, g9);       // U3[e-1]
+                const uint4 e_old = ring_e[e & (kDelay - 1)][lane];         // E[e-8]: read before the slot is overwritten
+                ring_e[e & (kDelay - 1)][lane] = E_cur;
+                const uint4 w_old = ring_w[slot6][lane];                    // W7[e-7], then W7[e-1] takes its slot
+                ring_w[slot6][lane] = w7;
+                const uint4 u_old = ring_u[slot3][lane];                    // U3[e-4], then U3[e-1] takes its slot
+                ring_u[slot3][lane] = u3;
+                const uint4 D = op3_4<MaxOp>(op3_4<MaxOp>(e_old, E_cur, w_old), w7_prev, u_old);    // w7_prev = W7[e-2]
+                g7_prev = g7; g9_prev2 = g9_prev; g9_prev = g9; w7_prev = w7;
+                const int yd = y_first + e - 4;
+                if (writes && yd >= y_out0 && yd < y_out1) {
+                    const uint2 packed = make_uint2(__byte_perm(D.x, D.y, 0x6420), __byte_perm(D.z, D.w, 0x6420));
+                    *reinterpret_cast<uint2 *>(dst + ((size_t)yd * w + x_lane)) = packed;
+                }
+            }
+            // ================= stage 2: erosion row e = m-4 from M_cur = M[m], m = s-2 =================
+            uint4 E_next;
+            {
+                const int m = s - 2;
+                uint4 h7, h9;
+                row_extrema<MinOp>(M_cur, h7, h9);
+                const uint4 v7 = op2_4<MinOp>(h7_prev, h7);                 // V7[m-1]
+                const uint4 t3 = op3_4<MinOp>(h9_prev2, h9_prev, h9);       // T3[m-1]
+                const uint4 m_old = ring_m[m & (kDelay - 1)][lane];         // M[m-8]
+                ring_m[m & (kDelay - 1)][lane] = M_cur;
+                const uint4 v_old = ring_v[slot6][lane];                    // V7[m-7], then V7[m-1] takes its slot
+                ring_v[slot6][lane] = v7;
+                const uint4 t_old = ring_t[slot3][lane];                    // T3[m-4], then T3[m-1] takes its slot
+                ring_t[slot3][lane] = t3;
+                E_next = op3_4<MinOp>(op3_4<MinOp>(m_old, M_cur, v_old), v7_prev, t_old);      // v7_prev = V7[m-2]
+                h7_prev = h7; h9_prev2 = h9_prev; h9_prev = h9; v7_prev = v7;
+                const int ye = y_first + m - 4;
+                if (!(col_in && (unsigned)ye < (unsigned)h)) E_next = splat(0u);               // dilation identity outside the image
+            }
+            // ================= stage 1: median row m = s-1 (image row y_first + s - 1), centre row r1 =================
+            uint4 M_next;
+            {
+                r0 = r1; r1 = r2;
+                r2 = decode(pf_v[0], pf_e[0]);                              // raw row y_first + s
+#pragma unroll
+                for (int k = 0; k + 1 < kPrefetch; ++k) { pf_v[k] = pf_v[k + 1]; pf_e[k] = pf_e[k + 1]; }
+                issue(y_first + s + kPrefetch, pf_v[kPrefetch - 1], pf_e[kPrefetch - 1]);     // rows are clamped: always in bounds
+                uint32_t lo[6], mi[6], hi[6];
+                const uint32_t a0[6] = {r0.left, r0.c.x, r0.c.y, r0.c.z, r0.c.w, r0.right};
+                const uint32_t a1[6] = {r1.left, r1.c.x, r1.c.y, r1.c.z, r1.c.w, r1.right};
+                const uint32_t a2[6] = {r2.left, r2.c.x, r2.c.y, r2.c.z, r2.c.w, r2.right};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    lo[q] = __vimin3_u16x2(a0[q], a1[q], a2[q]);
+                    hi[q] = __vimax3_u16x2(a0[q], a1[q], a2[q]);
+                    mi[q] = med3(a0[q], a1[q], a2[q]);
+                }
+                uint32_t res[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t max_lo = __vimax3_u16x2(mid_pair(lo[q], lo[q + 1]), lo[q + 1], mid_pair(lo[q + 1], lo[q + 2]));
+                    const uint32_t min_hi = __vimin3_u16x2(mid_pair(hi[q], hi[q + 1]), hi[q + 1], mid_pair(hi[q + 1], hi[q + 2]));
+                    const uint32_t med_mi = med3(mid_pair(mi[q], mi[q + 1]), mi[q + 1], mid_pair(mi[q + 1], mi[q + 2]));
+                    res[q] = med3(max_lo, med_mi, min_hi);
+                }
+                const int ym = y_first + s - 1;
+                const bool in_img = col_in && (unsigned)ym < (unsigned)h;   // the erosion must ignore pixels outside the image
+                M_next = in_img ? make_uint4(res[0], res[1], res[2], res[3]) : splat(0x00ff00ffu);
+            }
+            M_cur = M_next;
+            E_cur = E_next;
+            slot6 = (slot6 == kDelayV - 1) ? 0 : slot6 + 1;
+            slot3 = (slot3 == kDelayT - 1) ? 0 : slot3 + 1;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// returns MSQ_EUNSUPPORTED-like negative hint (-100) when the streaming kernel cannot serve the shape
+int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st) {
+    const bool vec = (w % 8 == 0) && w >= 8 && ((uintptr_t)in % 8 == 0) && ((uintptr_t)out % 8 == 0);
+    if (!vec) return -100;
+    StreamGeom G;
+    G.h = h; G.w = w;
+    G.tiles_x = (w + kOutCols - 1) / kOutCols;
+    // strips: enough warp tasks for ~3 waves of 11 warps/SM, but at least ~40 rows per strip (18 rows of halo each)
+    static thread_local int resident = 0;          // co-resident CTAs per SM (shared-memory limited, ~10)
+    if (resident == 0) {
+        int r = 0;
+        MSQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, clean_stream_kernel, 32 * kWarpsPerCta, 0));
+        resident = std::max(1, r);
+    }
+    const long long want = (long long)sm_count() * resident * 3;
+    int strips = (int)std::min<long long>(std::max<long long>(1, (want + (long long)n * G.tiles_x - 1) / ((long long)n * G.tiles_x)),
+                                          std::max(1, h / 40));
+    if (const char *e = getenv("MSQ_CLEAN_STRIPS")) { int v = atoi(e); if (v >= 1 && v <= h) strips = v; }
+    G.strip_rows = (h + strips - 1) / strips;
+    G.strips = (h + G.strip_rows - 1) / G.strip_rows;
+    const long long tasks = (long long)n * G.tiles_x * G.strips;
+    const int grid = (int)std::min<long long>(tasks, (long long)sm_count() * resident);   // persistent: every CTA is resident
+    TimedLaunch timed(K_CLEAN, st);
+    clean_stream_kernel<<<grid, 32 * kWarpsPerCta, 0, st>>>(in, out, n, G);
+    MSQ_LAUNCH_OK("clean_frames (streaming)");
+    return MSQ_OK;
+}
+
+}  // namespace msq

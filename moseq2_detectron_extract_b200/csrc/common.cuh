@@ -105,6 +105,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // ---- internal launchers shared with the whole-chunk pipeline (pipeline.cu) ---------------------
 namespace msq {
 int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);
+int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);   // -100: shape not served
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
                           double *centroid, double *orientation, double *axis, int64_t *sums24, cudaStream_t st);
 int launch_angles_and_flips(const double *orientation, const double *axis, const double *centroid, const float *kpts,
