@@ -168,7 +168,8 @@ MSQ_API const char *msq_keypoint_col_name(int i);
  * For every frame i: OpenCV-exact fixed-point bilinear warp of src[i] (h,w) u8 about centroid[i] by
  * angle_deg[i] into out[i] (crop_h,crop_w) u8; NaN / negative centre -> zeros.  src2/out2 optional
  * second plane (the mask) warped with the same transform.  scratch_dev: msq_crop_scratch_bytes(n) bytes,
- * 16-byte aligned (per-frame float64 rotation coefficients).  n <= 65535 per call. */
+ * 16-byte aligned (per-frame float64 rotation coefficients + OpenCV's fixed-point row/column tables).
+ * n <= 65535 per call, crops up to 512x512. */
 MSQ_API size_t msq_crop_scratch_bytes(int n);
 MSQ_API int msq_crop_rotate(const uint8_t *src_dev, const uint8_t *src2_dev, int n, int h, int w,
                     const double *centroid_dev, const double *angle_deg_dev, int crop_w, int crop_h,

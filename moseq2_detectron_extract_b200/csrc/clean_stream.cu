@@ -24,7 +24,8 @@ constexpr int kOutCols = 240;              // output columns per warp-row (lanes
 constexpr int kDelay = 8;                  // rows in the M delay line   (M[m-8] is read, then M[m] overwrites it)
 constexpr int kDelayV = 6;                 // rows in the V7 delay line  (V7[m-7] is read, then V7[m-1] overwrites it)
 constexpr int kDelayT = 3;                 // rows in the T3 delay line  (T3[m-4] is read, then T3[m-1] overwrites it)
-constexpr int kPrefetch = 4;               // raw rows requested ahead of use
+constexpr int kPrefetch = 3;               // raw rows requested ahead of use (divides kUnroll: the queue rotates by renaming)
+constexpr int kUnroll = 6;                 // lcm of the delay-line / history periods (6, 3, 2): no register moves, static slots
 constexpr int kWarpsPerCta = 1;
 
 struct MinOp {
@@ -38,8 +39,19 @@ struct MaxOp {
 
 // (p[k],p[k+1]),(p[k+2],p[k+3]) -> (p[k+1],p[k+2])   (moving this to the FMA pipe as IMAD.HI + IMAD was measured: no gain)
 __device__ __forceinline__ uint32_t mid_pair(uint32_t a, uint32_t b) { return __funnelshift_r(a, b, 16); }
-__device__ __forceinline__ uint32_t med3(uint32_t a, uint32_t b, uint32_t c) {
-    return __vmaxu2(__vminu2(a, b), __vminu2(__vmaxu2(a, b), c));
+// med3(a,b,c) = max(min(a,b), min(max(a,b),c)) is 4 ALU ops; the same median as a sum, a+b+c-min-max:  Lanes hold values <= 255, so neither the 16-bit sums nor the differences carry
+// across lanes.  `one`/`neg1` are kernel parameters (1, -1) so that the adds are IMADs on the otherwise idle FMA pipe:
+// measured (tools/microbench/pipe_mix): in mixed code every ALU-pipe op (2- or 3-input VIMNMX, SHF, IADD3) costs
+// 0.5 cycle/SM, IMAD runs beside them.
+__device__ __forceinline__ uint32_t med3_of_sorted(uint32_t a, uint32_t b, uint32_t c, uint32_t lo, uint32_t hi, uint32_t one,
+                                                   uint32_t neg1) {
+    uint32_t s = a * one + b;
+    s = c * one + s;
+    s = lo * neg1 + s;
+    return hi * neg1 + s;
+}
+__device__ __forceinline__ uint32_t med3_sum(uint32_t a, uint32_t b, uint32_t c, uint32_t one, uint32_t neg1) {
+    return med3_of_sorted(a, b, c, __vimin3_u16x2(a, b, c), __vimax3_u16x2(a, b, c), one, neg1);
 }
 __device__ __forceinline__ uint4 splat(uint32_t v) { return make_uint4(v, v, v, v); }
 
@@ -77,6 +89,7 @@ template <class OP> __device__ __forceinline__ uint4 op3_4(const uint4 &a, const
 
 struct StreamGeom {
     int h, w, tiles_x, strips, strip_rows;
+    uint32_t one, neg1;        // 1 and -1, opaque to the compiler (see med3_of_sorted)
 };
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
@@ -101,12 +114,16 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
         // column addressing of the raw loads (replicate border): nearest in-image group + which byte to splat
         const int xg = min(max(x_lane, 0), w - 8);
         const int x_left = min(max(x_lane - 1, 0), w - 1), x_right = min(max(x_lane + 8, 0), w - 1);
+        const bool need_edge = G.tiles_x > 1;
 
         auto issue = [&](int y, uint2 &v, uint32_t &edge) {           // raw bytes of input row y (clamped)
             const uint8_t *row = src + (size_t)min(max(y, 0), h - 1) * w;
             v = __ldg(reinterpret_cast<const uint2 *>(row + xg));
             // pixel -1 / pixel 8 come from the neighbouring lane except at the two ends of the warp-row
-            edge = (lane == 0) ? (uint32_t)__ldg(row + x_left) : ((lane == 31) ? (uint32_t)__ldg(row + x_right) : 0u);
+            // (only when the image is wider than one warp-row: otherwise lanes 0 / 31 lie outside the image and the
+            //  pixel beyond them reaches nothing that is consumed -- a warp-uniform test, no divergence in the common case)
+            edge = 0u;
+            if (need_edge) edge = (lane == 0) ? (uint32_t)__ldg(row + x_left) : ((lane == 31) ? (uint32_t)__ldg(row + x_right) : 0u);
         };
         auto decode = [&](uint2 v, uint32_t edge) {
             if (x_lane < 0) { v.x = (v.x & 0xffu) * 0x01010101u; v.y = v.x; }
@@ -125,6 +142,7 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
         // erosion from the median row of iteration s-1 and the dilation from the erosion row of iteration s-2, so the
         // stages inside one iteration are mutually independent instruction streams (ILP for the ~10 resident warps).
         const int steps = (y_out1 - y_out0) + 20;
+        const uint32_t one = G.one, neg1 = G.neg1;
         uint2 pf_v[kPrefetch];
         uint32_t pf_e[kPrefetch];
 #pragma unroll
@@ -135,84 +153,88 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
         uint4 h7_prev = splat(0u), h9_prev = splat(0u), h9_prev2 = splat(0u), v7_prev = splat(0u);
         uint4 g7_prev = splat(0u), g9_prev = splat(0u), g9_prev2 = splat(0u), w7_prev = splat(0u);
         uint4 M_cur = splat(0u), E_cur = splat(0u);                    // M[s-2] and E[s-7] entering iteration s
-        int slot6 = 0, slot3 = 0;                                      // s mod 6, s mod 3: both stages advance one row per iteration
 
-#pragma unroll 2
-        for (int s = 0; s < steps; ++s) {
-            // ================= stage 3: dilation row d = e-4 from E_cur = E[e], e = s-7 =================
-            {
-                const int e = s - 7;
-                uint4 g7, g9;
-                row_extrema<MaxOp>(E_cur, g7, g9);
-                const uint4 w7 = op2_4<MaxOp>(g7_prev, g7);                 // W7[e-1]
-                const uint4 u3 = op3_4<MaxOp>(g9_prev2, g9_prev, g9);       // U3[e-1]
-                const uint4 e_old = ring_e[e & (kDelay - 1)][lane];         // E[e-8]: read before the slot is overwritten
-                ring_e[e & (kDelay - 1)][lane] = E_cur;
-                const uint4 w_old = ring_w[slot6][lane];                    // W7[e-7], then W7[e-1] takes its slot
-                ring_w[slot6][lane] = w7;
-                const uint4 u_old = ring_u[slot3][lane];                    // U3[e-4], then U3[e-1] takes its slot
-                ring_u[slot3][lane] = u3;
-                const uint4 D = op3_4<MaxOp>(op3_4<MaxOp>(e_old, E_cur, w_old), w7_prev, u_old);    // w7_prev = W7[e-2]
-                g7_prev = g7; g9_prev2 = g9_prev; g9_prev = g9; w7_prev = w7;
-                const int yd = y_first + e - 4;
-                if (writes && yd >= y_out0 && yd < y_out1) {
-                    const uint2 packed = make_uint2(__byte_perm(D.x, D.y, 0x6420), __byte_perm(D.z, D.w, 0x6420));
-                    *reinterpret_cast<uint2 *>(dst + ((size_t)yd * w + x_lane)) = packed;
-                }
-            }
-            // ================= stage 2: erosion row e = m-4 from M_cur = M[m], m = s-2 =================
-            uint4 E_next;
-            {
-                const int m = s - 2;
-                uint4 h7, h9;
-                row_extrema<MinOp>(M_cur, h7, h9);
-                const uint4 v7 = op2_4<MinOp>(h7_prev, h7);                 // V7[m-1]
-                const uint4 t3 = op3_4<MinOp>(h9_prev2, h9_prev, h9);       // T3[m-1]
-                const uint4 m_old = ring_m[m & (kDelay - 1)][lane];         // M[m-8]
-                ring_m[m & (kDelay - 1)][lane] = M_cur;
-                const uint4 v_old = ring_v[slot6][lane];                    // V7[m-7], then V7[m-1] takes its slot
-                ring_v[slot6][lane] = v7;
-                const uint4 t_old = ring_t[slot3][lane];                    // T3[m-4], then T3[m-1] takes its slot
-                ring_t[slot3][lane] = t3;
-                E_next = op3_4<MinOp>(op3_4<MinOp>(m_old, M_cur, v_old), v7_prev, t_old);      // v7_prev = V7[m-2]
-                h7_prev = h7; h9_prev2 = h9_prev; h9_prev = h9; v7_prev = v7;
-                const int ye = y_first + m - 4;
-                if (!(col_in && (unsigned)ye < (unsigned)h)) E_next = splat(0u);               // dilation identity outside the image
-            }
-            // ================= stage 1: median row m = s-1 (image row y_first + s - 1), centre row r1 =================
-            uint4 M_next;
-            {
-                r0 = r1; r1 = r2;
-                r2 = decode(pf_v[0], pf_e[0]);                              // raw row y_first + s
+        // kUnroll iterations per trip: every rotation below (raw rows 3, prefetch queue 3, H9 history 3, V7 history 2, the
+        // 6- and 3-slot delay lines) has a period dividing 6, so after unrolling the compiler renames instead of moving and
+        // the V/T slot indices are literals.  Trips past `steps` only touch clamped rows and store nothing.
+        for (int s0 = 0; s0 < steps; s0 += kUnroll) {
 #pragma unroll
-                for (int k = 0; k + 1 < kPrefetch; ++k) { pf_v[k] = pf_v[k + 1]; pf_e[k] = pf_e[k + 1]; }
-                issue(y_first + s + kPrefetch, pf_v[kPrefetch - 1], pf_e[kPrefetch - 1]);     // rows are clamped: always in bounds
-                uint32_t lo[6], mi[6], hi[6];
-                const uint32_t a0[6] = {r0.left, r0.c.x, r0.c.y, r0.c.z, r0.c.w, r0.right};
-                const uint32_t a1[6] = {r1.left, r1.c.x, r1.c.y, r1.c.z, r1.c.w, r1.right};
-                const uint32_t a2[6] = {r2.left, r2.c.x, r2.c.y, r2.c.z, r2.c.w, r2.right};
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    lo[q] = __vimin3_u16x2(a0[q], a1[q], a2[q]);
-                    hi[q] = __vimax3_u16x2(a0[q], a1[q], a2[q]);
-                    mi[q] = med3(a0[q], a1[q], a2[q]);
+            for (int u = 0; u < kUnroll; ++u) {
+                const int s = s0 + u;
+                const int slot6 = u % kDelayV, slot3 = u % kDelayT;
+                // ================= stage 3: dilation row d = e-4 from E_cur = E[e], e = s-7 =================
+                {
+                    const int e = s - 7;
+                    uint4 g7, g9;
+                    row_extrema<MaxOp>(E_cur, g7, g9);
+                    const uint4 w7 = op2_4<MaxOp>(g7_prev, g7);                 // W7[e-1]
+                    const uint4 u3 = op3_4<MaxOp>(g9_prev2, g9_prev, g9);       // U3[e-1]
+                    const uint4 e_old = ring_e[e & (kDelay - 1)][lane];         // E[e-8]: read before the slot is overwritten
+                    ring_e[e & (kDelay - 1)][lane] = E_cur;
+                    const uint4 w_old = ring_w[slot6][lane];                    // W7[e-7], then W7[e-1] takes its slot
+                    ring_w[slot6][lane] = w7;
+                    const uint4 u_old = ring_u[slot3][lane];                    // U3[e-4], then U3[e-1] takes its slot
+                    ring_u[slot3][lane] = u3;
+                    const uint4 D = op3_4<MaxOp>(op3_4<MaxOp>(e_old, E_cur, w_old), w7_prev, u_old);    // w7_prev = W7[e-2]
+                    g7_prev = g7; g9_prev2 = g9_prev; g9_prev = g9; w7_prev = w7;
+                    const int yd = y_first + e - 4;
+                    if (writes && yd >= y_out0 && yd < y_out1) {
+                        const uint2 packed = make_uint2(__byte_perm(D.x, D.y, 0x6420), __byte_perm(D.z, D.w, 0x6420));
+                        *reinterpret_cast<uint2 *>(dst + ((size_t)yd * w + x_lane)) = packed;
+                    }
                 }
-                uint32_t res[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t max_lo = __vimax3_u16x2(mid_pair(lo[q], lo[q + 1]), lo[q + 1], mid_pair(lo[q + 1], lo[q + 2]));
-                    const uint32_t min_hi = __vimin3_u16x2(mid_pair(hi[q], hi[q + 1]), hi[q + 1], mid_pair(hi[q + 1], hi[q + 2]));
-                    const uint32_t med_mi = med3(mid_pair(mi[q], mi[q + 1]), mi[q + 1], mid_pair(mi[q + 1], mi[q + 2]));
-                    res[q] = med3(max_lo, med_mi, min_hi);
+                // ================= stage 2: erosion row e = m-4 from M_cur = M[m], m = s-2 =================
+                uint4 E_next;
+                {
+                    const int m = s - 2;
+                    uint4 h7, h9;
+                    row_extrema<MinOp>(M_cur, h7, h9);
+                    const uint4 v7 = op2_4<MinOp>(h7_prev, h7);                 // V7[m-1]
+                    const uint4 t3 = op3_4<MinOp>(h9_prev2, h9_prev, h9);       // T3[m-1]
+                    const uint4 m_old = ring_m[m & (kDelay - 1)][lane];         // M[m-8]
+                    ring_m[m & (kDelay - 1)][lane] = M_cur;
+                    const uint4 v_old = ring_v[slot6][lane];                    // V7[m-7], then V7[m-1] takes its slot
+                    ring_v[slot6][lane] = v7;
+                    const uint4 t_old = ring_t[slot3][lane];                    // T3[m-4], then T3[m-1] takes its slot
+                    ring_t[slot3][lane] = t3;
+                    E_next = op3_4<MinOp>(op3_4<MinOp>(m_old, M_cur, v_old), v7_prev, t_old);      // v7_prev = V7[m-2]
+                    h7_prev = h7; h9_prev2 = h9_prev; h9_prev = h9; v7_prev = v7;
+                    const int ye = y_first + m - 4;
+                    if (!(col_in && (unsigned)ye < (unsigned)h)) E_next = splat(0u);               // dilation identity outside the image
                 }
-                const int ym = y_first + s - 1;
-                const bool in_img = col_in && (unsigned)ym < (unsigned)h;   // the erosion must ignore pixels outside the image
-                M_next = in_img ? make_uint4(res[0], res[1], res[2], res[3]) : splat(0x00ff00ffu);
+                // ================= stage 1: median row m = s-1 (image row y_first + s - 1), centre row r1 =================
+                uint4 M_next;
+                {
+                    r0 = r1; r1 = r2;
+                    r2 = decode(pf_v[0], pf_e[0]);                              // raw row y_first + s
+#pragma unroll
+                    for (int k = 0; k + 1 < kPrefetch; ++k) { pf_v[k] = pf_v[k + 1]; pf_e[k] = pf_e[k + 1]; }
+                    issue(y_first + s + kPrefetch, pf_v[kPrefetch - 1], pf_e[kPrefetch - 1]);     // rows are clamped: always in bounds
+                    uint32_t lo[6], mi[6], hi[6];
+                    const uint32_t a0[6] = {r0.left, r0.c.x, r0.c.y, r0.c.z, r0.c.w, r0.right};
+                    const uint32_t a1[6] = {r1.left, r1.c.x, r1.c.y, r1.c.z, r1.c.w, r1.right};
+                    const uint32_t a2[6] = {r2.left, r2.c.x, r2.c.y, r2.c.z, r2.c.w, r2.right};
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        lo[q] = __vimin3_u16x2(a0[q], a1[q], a2[q]);
+                        hi[q] = __vimax3_u16x2(a0[q], a1[q], a2[q]);
+                        mi[q] = med3_of_sorted(a0[q], a1[q], a2[q], lo[q], hi[q], one, neg1);
+                    }
+                    uint32_t res[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t max_lo = __vimax3_u16x2(mid_pair(lo[q], lo[q + 1]), lo[q + 1], mid_pair(lo[q + 1], lo[q + 2]));
+                        const uint32_t min_hi = __vimin3_u16x2(mid_pair(hi[q], hi[q + 1]), hi[q + 1], mid_pair(hi[q + 1], hi[q + 2]));
+                        const uint32_t med_mi = med3_sum(mid_pair(mi[q], mi[q + 1]), mi[q + 1], mid_pair(mi[q + 1], mi[q + 2]), one, neg1);
+                        res[q] = med3_sum(max_lo, med_mi, min_hi, one, neg1);
+                    }
+                    const int ym = y_first + s - 1;
+                    const bool in_img = col_in && (unsigned)ym < (unsigned)h;   // the erosion must ignore pixels outside the image
+                    M_next = in_img ? make_uint4(res[0], res[1], res[2], res[3]) : splat(0x00ff00ffu);
+                }
+                M_cur = M_next;
+                E_cur = E_next;
             }
-            M_cur = M_next;
-            E_cur = E_next;
-            slot6 = (slot6 == kDelayV - 1) ? 0 : slot6 + 1;
-            slot3 = (slot3 == kDelayT - 1) ? 0 : slot3 + 1;
         }
         __syncwarp();
     }
@@ -225,7 +247,7 @@ int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cu
     const bool vec = (w % 8 == 0) && w >= 8 && ((uintptr_t)in % 8 == 0) && ((uintptr_t)out % 8 == 0);
     if (!vec) return -100;
     StreamGeom G;
-    G.h = h; G.w = w;
+    G.h = h; G.w = w; G.one = 1u; G.neg1 = 0xffffffffu;
     G.tiles_x = (w + kOutCols - 1) / kOutCols;
     // strips: enough warp tasks for ~3 waves of 11 warps/SM, but at least ~40 rows per strip (18 rows of halo each)
     static thread_local int resident = 0;          // co-resident CTAs per SM (shared-memory limited, ~10)

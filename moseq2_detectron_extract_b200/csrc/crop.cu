@@ -53,15 +53,29 @@ __device__ void make_coeffs(double cx, double cy, double angle_deg, int cw, int 
 
 __device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
 
-// one thread per frame: the float64 rotation coefficients
+// One CTA per frame: the float64 rotation coefficients, then -- like OpenCV's WarpAffineInvoker -- the fixed-point
+// column terms adelta[x], bdelta[x] and row terms X0[y], Y0[y] (AB_BITS 10, round_delta 16), so that the per-pixel
+// kernel is integer-only.  Table layout per frame: [adelta(cw) | bdelta(cw) | X0(ch) | Y0(ch)] int32.
 __global__ void __launch_bounds__(128)
 crop_coeffs_kernel(const double *__restrict__ centroid, const double *__restrict__ angle_deg, int n, int cw, int ch,
-                   int W, int H, WarpCoeffs *__restrict__ coeffs) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n) return;
-    WarpCoeffs k;
-    make_coeffs(centroid[2 * f], centroid[2 * f + 1], angle_deg[f], cw, ch, W, H, k);
-    coeffs[f] = k;
+                   int W, int H, WarpCoeffs *__restrict__ coeffs, int *__restrict__ tables) {
+    __shared__ WarpCoeffs k;
+    const int f = blockIdx.x;
+    if (threadIdx.x == 0) {
+        make_coeffs(centroid[2 * f], centroid[2 * f + 1], angle_deg[f], cw, ch, W, H, k);
+        coeffs[f] = k;
+    }
+    __syncthreads();
+    if (k.sw == 0) return;
+    int *t = tables + (size_t)f * 2 * (cw + ch);
+    for (int x = threadIdx.x; x < cw; x += blockDim.x) {
+        t[x] = __double2int_rn(k.i00 * (double)x * 1024.0);
+        t[cw + x] = __double2int_rn(k.i10 * (double)x * 1024.0);
+    }
+    for (int y = threadIdx.x; y < ch; y += blockDim.x) {
+        t[2 * cw + y] = __double2int_rn((k.i01 * (double)y + k.b1) * 1024.0) + 16;
+        t[2 * cw + ch + y] = __double2int_rn((k.i11 * (double)y + k.b2) * 1024.0) + 16;
+    }
 }
 
 constexpr int kCropThreads = 256;
@@ -70,8 +84,8 @@ constexpr int kCropThreads = 256;
 // fixed-point coordinates (AB_BITS 10, INTER_BITS 5, round_delta 16) and four gathered bytes per plane.
 __global__ void __launch_bounds__(kCropThreads)
 crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int H, int W,
-                   const WarpCoeffs *__restrict__ coeffs, int cw, int ch, uint8_t *__restrict__ out0,
-                   uint8_t *__restrict__ out1) {
+                   const WarpCoeffs *__restrict__ coeffs, const int *__restrict__ tables, int cw, int ch,
+                   uint8_t *__restrict__ out0, uint8_t *__restrict__ out1) {
     // a CTA covers a 16x16 output tile; each warp an 8x4 patch, so that under rotation the 32 lanes of a
     // gather touch a compact source footprint (a 32x1 line would hit up to 32 different source rows)
     const int f = blockIdx.y;
@@ -88,13 +102,9 @@ crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__
         if (out1) out1[crop_off] = 0;
         return;
     }
-    const double2 c0 = __ldg(reinterpret_cast<const double2 *>(&coeffs[f].i00));   // i00, i01
-    const double2 c1 = __ldg(reinterpret_cast<const double2 *>(&coeffs[f].b1));    // b1, i10
-    const double2 c2 = __ldg(reinterpret_cast<const double2 *>(&coeffs[f].i11));   // i11, b2
-    const int adelta = __double2int_rn(c0.x * (double)x * 1024.0);
-    const int bdelta = __double2int_rn(c1.y * (double)x * 1024.0);
-    const int X0 = __double2int_rn((c0.y * (double)y + c1.x) * 1024.0) + 16;
-    const int Y0 = __double2int_rn((c2.x * (double)y + c2.y) * 1024.0) + 16;
+    const int *t = tables + (size_t)f * 2 * (cw + ch);
+    const int adelta = __ldg(t + x), bdelta = __ldg(t + cw + x);
+    const int X0 = __ldg(t + 2 * cw + y), Y0 = __ldg(t + 2 * cw + ch + y);
     const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
     const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
     const int fx = X & 31, fy = Y & 31;
@@ -127,12 +137,13 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
                        const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch,
                        cudaStream_t st) {
     WarpCoeffs *coeffs = reinterpret_cast<WarpCoeffs *>(scratch);
+    int *tables = reinterpret_cast<int *>(reinterpret_cast<char *>(scratch) + (size_t)n * sizeof(WarpCoeffs));
     const bool two = src2 && out2;
     TimedLaunch timed(K_CROP, st);          // the coefficient kernel is part of the crop step
-    crop_coeffs_kernel<<<(n + 127) / 128, 128, 0, st>>>(centroid, angle_deg, n, cw, ch, w, h, coeffs);
+    crop_coeffs_kernel<<<n, 128, 0, st>>>(centroid, angle_deg, n, cw, ch, w, h, coeffs, tables);
     MSQ_LAUNCH_OK("crop_coeffs");
     dim3 grid(((cw + 15) / 16) * ((ch + 15) / 16), n);
-    crop_rotate_kernel<<<grid, kCropThreads, 0, st>>>(src, two ? src2 : nullptr, h, w, coeffs, cw, ch, out,
+    crop_rotate_kernel<<<grid, kCropThreads, 0, st>>>(src, two ? src2 : nullptr, h, w, coeffs, tables, cw, ch, out,
                                                       two ? out2 : nullptr);
     MSQ_LAUNCH_OK("crop_rotate");
     return MSQ_OK;
@@ -140,7 +151,8 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
 
 }  // namespace msq
 
-extern "C" size_t msq_crop_scratch_bytes(int n) { return (size_t)(n > 0 ? n : 0) * 64; }
+// per frame: one 64-byte coefficient record + the 2*(cw+ch) int32 fixed-point tables (sized for crops up to 512x512)
+extern "C" size_t msq_crop_scratch_bytes(int n) { return (size_t)(n > 0 ? n : 0) * (64 + 2 * (512 + 512) * sizeof(int)); }
 
 extern "C" int msq_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
                                const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch,
@@ -150,6 +162,7 @@ extern "C" int msq_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, i
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && cw > 0 && ch > 0, MSQ_EINVAL, "msq_crop_rotate: bad sizes");
     if (n == 0) return MSQ_OK;
     MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_crop_rotate: at most 65535 frames per call (got %d)", n);
+    MSQ_REQUIRE(cw <= 512 && ch <= 512, MSQ_EUNSUPPORTED, "msq_crop_rotate: crop %dx%d exceeds 512x512", cw, ch);
     MSQ_REQUIRE(scratch && (uintptr_t)scratch % 16 == 0 && scratch_bytes >= msq_crop_scratch_bytes(n), MSQ_ENOMEM,
                 "msq_crop_rotate: scratch must be 16-byte aligned and >= %zu bytes", msq_crop_scratch_bytes(n));
     return msq::launch_crop_rotate(src, src2, n, h, w, centroid, angle_deg, cw, ch, out, out2, scratch, (cudaStream_t)stream);

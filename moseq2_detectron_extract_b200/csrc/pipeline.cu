@@ -8,7 +8,7 @@ using namespace msq;
 
 extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
     const size_t nn = (size_t)(n > 0 ? n : 0);
-    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256) + align_up(nn * 64, 256);
+    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256) + align_up(msq_crop_scratch_bytes((int)nn), 256);
 }
 
 extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,

@@ -262,7 +262,7 @@ def crop_and_rotate_frames_batch(frames, centers, angles, crop_size: Tuple[int, 
     if frames2 is not None:
         src2 = _dev.as_device(frames2, torch.uint8)
         out2 = _dev.empty((n, ch, cw), torch.uint8)
-    scratch = _dev.empty((max(n, 1) * 64,), torch.uint8)
+    scratch = _dev.empty((int(_lib.load().msq_crop_scratch_bytes(max(n, 1))) + 16,), torch.uint8)
     _lib.call('msq_crop_rotate', _dev.ptr(src), _dev.ptr(src2), n, h, w, _dev.ptr(cen), _dev.ptr(ang), cw, ch,
               _dev.ptr(out), _dev.ptr(out2), _dev.ptr(scratch), scratch.numel(), _dev.stream())
     if frames2 is None:

@@ -38,7 +38,7 @@ y0, x0, y1, x1 = synthetic.roi_bbox(roi)
 cleaned = torch.empty_like(prep); cen = _dev.empty((n, 2), torch.float64); ori = _dev.empty((n,), torch.float64); ax = _dev.empty((n, 2), torch.float64)
 ang = _dev.empty((n,), torch.float64); fl = _dev.empty((n,), torch.uint8); ps = _dev.empty((64,), torch.int32)
 sc = _dev.empty((17, n), torch.float64); kc = _dev.empty((96, n), torch.float64); scr = _dev.empty((16 * n + 512,), torch.uint8)
-cscr = _dev.empty((64 * n,), torch.uint8); dc = _dev.empty((n, 80, 80), torch.uint8); mc = _dev.empty((n, 80, 80), torch.uint8)
+cscr = _dev.empty((int(_lib.load().msq_crop_scratch_bytes(n)) + 16,), torch.uint8); dc = _dev.empty((n, 80, 80), torch.uint8); mc = _dev.empty((n, 80, 80), torch.uint8)
 out = {}
 out['prep'] = timeit(lambda: _lib.call('msq_prep_frames', _dev.ptr(frames), n, geom.height, geom.width, _dev.ptr(bgd), 1, _dev.ptr(roid), y0, x0, h, w, 0.0, 100.0, 3, _dev.ptr(prep), _dev.ptr(inv), None, st))
 out['clean'] = timeit(lambda: _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, st))

@@ -10,7 +10,7 @@ __device__ __forceinline__ uint32_t hmin2u(uint32_t a, uint32_t b) {
     x = __hmin2(x, y); return *reinterpret_cast<uint32_t *>(&x);
 }
 template <int MODE>
-__global__ void bench(uint32_t *out, uint32_t seed) {
+__global__ void bench(uint32_t *out, uint32_t seed, uint32_t one, uint32_t neg1) {
     uint32_t a[ILP], b[ILP], c[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; ++i) { a[i] = seed * (threadIdx.x + 1 + i); b[i] = seed ^ (0x9e3779b9u * (i + 1 + threadIdx.x)); c[i] = a[i] ^ b[i]; }
@@ -34,6 +34,13 @@ __global__ void bench(uint32_t *out, uint32_t seed) {
             if (MODE == 13) { a[i] = __funnelshift_r(a[i], b[i], 16); }
             if (MODE == 14) { a[i] = a[i] + b[i] + c[i]; }     // IADD3
             if (MODE == 15) { a[i] = a[i] + b[i] + 3; c[i] = __vimin3_u16x2(c[i], b[i], b[i]+1); }
+            if (MODE == 16) { a[i] = __vmaxu2(__vminu2(a[i], b[i]), __vminu2(__vmaxu2(a[i], b[i]), c[i])); }   // med3, 4 x VIMNMX2
+            if (MODE == 17) { uint32_t lo = __vimin3_u16x2(a[i], b[i], c[i]), hi = __vimax3_u16x2(a[i], b[i], c[i]);
+                              a[i] = (a[i] + b[i] + c[i]) - lo - hi; }                                        // med3, 2 x VIMNMX3 + 2 x IADD3
+            if (MODE == 18) { uint32_t lo = __vimin3_u16x2(a[i], b[i], c[i]), hi = __vimax3_u16x2(a[i], b[i], c[i]);
+                              uint32_t s = a[i] * one + b[i]; s = c[i] * one + s; s = lo * neg1 + s; a[i] = hi * neg1 + s; }  // 2 x VIMNMX3 + 4 x IMAD
+            if (MODE == 19) { a[i] = a[i] * one + b[i]; }                                                      // IMAD alone
+            if (MODE == 20) { a[i] = a[i] * one + b[i]; c[i] = __vminu2(c[i], b[i]); }
             asm volatile("" : "+r"(a[i]), "+r"(c[i]));
         }
     }
@@ -47,11 +54,11 @@ void run(const char *name, int instr_per_op) {
     uint32_t *out;
     const int threads = 1024, blocks = 148 * 2;
     cudaMalloc(&out, blocks * threads * 4);
-    bench<MODE><<<blocks, threads>>>(out, 12345u);
+    bench<MODE><<<blocks, threads>>>(out, 12345u, 1u, 0xffffffffu);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    bench<MODE><<<blocks, threads>>>(out, 12345u);
+    bench<MODE><<<blocks, threads>>>(out, 12345u, 1u, 0xffffffffu);
     cudaEventRecord(e1); cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     int clk_khz; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
@@ -77,5 +84,10 @@ int main() {
     run<10>("HMNMX2 + VIMNMX2", 2);
     run<11>("SHF + IMAD", 2);
     run<15>("IADD + VIMNMX3 + VIADD", 3);
+    run<16>("med3 = 4 x VIMNMX2 (per med3)", 1);
+    run<17>("med3 = 2 x VIMNMX3 + 2 x IADD3 (per med3)", 1);
+    run<18>("med3 = 2 x VIMNMX3 + 4 x IMAD (per med3)", 1);
+    run<19>("IMAD", 1);
+    run<20>("IMAD + VIMNMX2", 2);
     return 0;
 }
