@@ -164,6 +164,15 @@ MSQ_API int msq_scalars_and_keypoints(const uint8_t *chunk_dev, const uint8_t *m
 MSQ_API const char *msq_scalar_name(int i);
 MSQ_API const char *msq_keypoint_col_name(int i);
 
+/* float64-keypoint variants (the tracking branch writes smoothed float64 keypoints back, proc/proc.py:752) */
+MSQ_API int msq_flips_from_keypoints_f64(const double *kpts_dev, const double *centroid_dev, const double *angles_dev,
+                                 const double *lengths_dev, int n, uint8_t *flips_dev, double *conf_dev, void *stream);
+MSQ_API int msq_scalars_and_keypoints_f64(const uint8_t *chunk_dev, const uint8_t *mask_dev, const uint8_t *cleaned_dev,
+                                  const double *centroid_dev, const double *angle_deg_dev, const double *axis_dev,
+                                  const double *kpts_dev, int n, int h, int w, int chunk, double min_height,
+                                  double max_height, double true_depth, double *scalars_dev, double *kpt_cols_dev,
+                                  void *scratch_dev, size_t scratch_bytes, void *stream);
+
 /* ---- a13  crop_and_rotate_frame (ref: proc/proc.py:305-335; pipeline/process_features_step.py:190-195)
  * For every frame i: OpenCV-exact fixed-point bilinear warp of src[i] (h,w) u8 about centroid[i] by
  * angle_deg[i] into out[i] (crop_h,crop_w) u8; NaN / negative centre -> zeros.  src2/out2 optional
@@ -174,6 +183,47 @@ MSQ_API size_t msq_crop_scratch_bytes(int n);
 MSQ_API int msq_crop_rotate(const uint8_t *src_dev, const uint8_t *src2_dev, int n, int h, int w,
                     const double *centroid_dev, const double *angle_deg_dev, int crop_w, int crop_h,
                     uint8_t *out_dev, uint8_t *out2_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
+
+/* ---- a14  Kalman tracking branch ------------------------------------------------------------
+ * Replaces pykalman.KalmanFilter as driven by the reference's KalmanTracker (proc/kalman.py:281-418:
+ * initialize -> em(n_iter=10) :322-338, smooth_update :386-401, filter_update :408-418, sample :370-377)
+ * and the per-frame angle heuristic of instances_to_features (proc/proc.py:771-796).
+ * Time-invariant model x' = A x + N(0,Q), z = H x + N(0,R): A (S,S), H (O,S), Q (S,S), R (O,O), m0 (S),
+ * P0 (S,S), all float64 row-major on the device; obs (T,O) float64, a row with any non-finite entry is a
+ * missing observation (pykalman skips it entirely).  1 <= O <= 32, O <= S <= 64.
+ * workspace: msq_kalman_workspace_bytes(T,S,O,for_em) bytes, 256-byte aligned.
+ *
+ * msq_kalman_smooth: forward filter (the first prediction is (m0,P0) itself unless predict_first != 0,
+ *   which is KalmanFilter.filter_update's "predict, then correct") and, when smooth != 0, the RTS smoother.
+ *   means_out (T,S) smoothed (or filtered) state means; last_mean (S) / last_cov (S,S) = the filtered state
+ *   at T-1, which the reference carries into the next chunk (kalman.py:399-400).  Outputs may be NULL.
+ * msq_kalman_em: n_iter EM iterations for transition_covariance, observation_covariance and
+ *   initial_state_covariance (the em_vars of kalman.py:326); Q, R, P0 are updated in place.  T >= 2.
+ * msq_keypoint_alignment_scores: compute_keypoint_alignment_scores(rotate_points_batch(kpts[:, :7, :2], ...))
+ *   (proc/proc.py:762-763, 936-958); kpts (n,8,kp_stride) float64, kp_stride 2 or 3.
+ * msq_track_angles: the sequential loop of proc/proc.py:771-796 on the angle tracker (state = (sin,cos) x order,
+ *   S = 2*order <= 8): per frame read the tracked angle from `mean`, replace / flip the observed angle
+ *   (alignment score < 0.4 -> tracked angle; |difference| > 140 deg -> +180 deg and toggle flips[i]), then
+ *   filter_update with it.  angles (n) and flips (n) are updated in place, mean/cov hold the last state. */
+MSQ_API size_t msq_kalman_workspace_bytes(int T, int S, int O, int for_em);
+MSQ_API int msq_kalman_smooth(const double *A_dev, const double *H_dev, const double *Q_dev, const double *R_dev,
+                      const double *m0_dev, const double *P0_dev, const double *obs_dev, int T, int S, int O,
+                      int predict_first, int smooth, double *means_out_dev, double *last_mean_dev,
+                      double *last_cov_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+MSQ_API int msq_kalman_em(const double *A_dev, const double *H_dev, double *Q_dev, double *R_dev, const double *m0_dev,
+                  double *P0_dev, const double *obs_dev, int T, int S, int O, int n_iter, void *workspace_dev,
+                  size_t workspace_bytes, void *stream);
+MSQ_API int msq_keypoint_alignment_scores(const double *kpts_dev, int kp_stride, const double *centroid_dev,
+                                  const double *angles_deg_dev, int n, double *scores_dev, void *stream);
+/* a8 + a9 of the tracking branch (proc/proc.py:720-724, 756-763): orientation (rad) -> clamped degrees, keypoint flip
+ * votes on float64 (smoothed) keypoints (n,8,3), angles[flips] = clamp(angles + 180), alignment scores of the
+ * keypoints rotated by the result.  conf may be NULL. */
+MSQ_API int msq_tracking_prepare(const double *orientation_rad_dev, const double *axis_length_dev, const double *centroid_dev,
+                         const double *kpts_dev, int n, double *angles_deg_dev, uint8_t *flips_dev, double *conf_dev,
+                         double *scores_dev, void *stream);
+MSQ_API int msq_track_angles(const double *A_dev, const double *H_dev, const double *Q_dev, const double *R_dev,
+                     double *mean_dev, double *cov_dev, int S, double *angles_deg_dev, uint8_t *flips_dev,
+                     const double *scores_dev, int n, void *stream);
 
 /* ---- whole-chunk pipeline: everything ProcessFeaturesStep.process does (ref:
  *      pipeline/process_features_step.py:56-60,163-199 with use_tracking=False), device buffers ------- */

@@ -63,6 +63,20 @@ SIGNATURES = {
     'msq_crop_scratch_bytes': (c_size_t, [c_int]),
     'msq_crop_rotate': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_kalman_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'msq_kalman_smooth': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_kalman_em': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_int, c_void_p, c_size_t, c_void_p]),
+    'msq_keypoint_alignment_scores': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'msq_tracking_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    'msq_flips_from_keypoints_f64': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'msq_scalars_and_keypoints_f64': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_void_p,
+                                              c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_track_angles': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_void_p]),
     'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),

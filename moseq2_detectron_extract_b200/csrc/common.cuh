@@ -47,7 +47,7 @@ int sm_count();                                 // api.cu; cached per process (c
 
 // ---- per-kernel device timing (CUDA events on the launching stream; off by default) ----------
 enum KernelId { K_PREP = 0, K_SCALE, K_CLEAN, K_FEATURES, K_ANGLES, K_MASKED_SUMS, K_SCALARS_KPTS, K_CROP, K_PASTE,
-                K_INPAINT, K_COUNT };
+                K_INPAINT, K_KALMAN, K_COUNT };
 struct TimedLaunch {                            // RAII: records an event pair around one kernel launch
     int slot;
     cudaStream_t st;
@@ -113,8 +113,8 @@ int launch_angles_and_flips(const double *orientation, const double *axis, const
                             cudaStream_t st);
 int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
                                  const double *centroid, const double *angle_deg, const double *axis,
-                                 const float *kpts, int n, int h, int w, int chunk, double min_h, double max_h,
-                                 double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
+                                 const void *kpts, bool kpts_f64, int n, int h, int w, int chunk, double min_h,
+                                 double max_h, double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
                                  cudaStream_t st);
 int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
                        const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch, cudaStream_t st);

@@ -5,55 +5,12 @@
 //   a11     keypoints_to_dict       ref proc/keypoints.py:93-165, proc/util.py:29-61
 // All floating point is float64 in NumPy's operation order (compiled with --fmad=false).
 #include "common.cuh"
+#include "angles.cuh"
 #include <algorithm>
 #include <math.h>
 
 namespace msq {
 namespace {
-
-constexpr double kPiOver180 = 0.017453292519943295;     // np.pi / 180
-constexpr double k180OverPi = 57.29577951308232;        // 180 / np.pi
-
-__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000LL); }
-__device__ __forceinline__ double np_max2(double a, double b) { return (a != a || b != b) ? nan_f64() : (a > b ? a : b); }
-__device__ __forceinline__ double np_min2(double a, double b) { return (a != a || b != b) ? nan_f64() : (a < b ? a : b); }
-
-// rotate_points (ref proc/keypoints.py:11-39): R(-angle) @ (p - o) + o
-__device__ __forceinline__ void rotate_about(double px, double py, double ox, double oy, double c, double s,
-                                             double &rx, double &ry) {
-    const double dx = px - ox, dy = py - oy;
-    rx = (c * dx + (-s) * dy) + ox;
-    ry = (s * dx + c * dy) + oy;
-}
-
-// ---------------------------------------------------------------------------------------------
-// flips_from_keypoints for one frame (ref proc/proc.py:851-889): front (0..3) and rear (4..6)
-// keypoints, rotated by -angle about the centroid, vote for the nearer end of the body box
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool keypoint_flip_vote(const float *__restrict__ kp, double cx, double cy, double angle,
-                                                   double length, double *conf) {
-    const double t = (-angle) * kPiOver180;
-    const double c = cos(t), s = sin(t);
-    const double lo = cx - length / 2, hi = cx + length / 2;
-    int votes[MSQ_NUM_KEYPOINTS - 1];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        double rx, ry;
-        rotate_about((double)kp[k * 3], (double)kp[k * 3 + 1], cx, cy, c, s, rx, ry);
-        votes[k] = (fabs(lo - rx) < fabs(hi - rx)) ? -1 : 1;
-    }
-    const int front = votes[0] + votes[1] + votes[2] + votes[3];
-    const int rear = votes[4] + votes[5] + votes[6];
-    const bool flip = 3 * front < 4 * rear;              // mean(front) < mean(rear)
-    const int want_front = flip ? -1 : 1;
-    int agree = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) agree += votes[k] == want_front;
-#pragma unroll
-    for (int k = 4; k < 7; ++k) agree += votes[k] == -want_front;
-    if (conf) *conf = (double)agree / 7.0;
-    return flip;
-}
 
 // ---------------------------------------------------------------------------------------------
 // iterative_filter_angles on one chunk held in shared memory (ref proc/proc.py:600-654).
@@ -156,8 +113,9 @@ angles_flips_kernel(const double *__restrict__ orientation, const double *__rest
     if (passes_out && threadIdx.x == 0) passes_out[blockIdx.x] = passes;
 }
 
+template <class KP>
 __global__ void __launch_bounds__(128)
-flips_kernel(const float *__restrict__ kpts, const double *__restrict__ centroid, const double *__restrict__ angles,
+flips_kernel(const KP *__restrict__ kpts, const double *__restrict__ centroid, const double *__restrict__ angles,
              const double *__restrict__ lengths, int n, uint8_t *__restrict__ flips, double *__restrict__ conf) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
@@ -264,10 +222,11 @@ enum ScalarRow {
     S_V3D_MM, S_WIDTH_MM, S_LENGTH_MM, S_AREA_MM, S_HEIGHT, S_ANGLE, S_VTHETA
 };
 
+template <class KP>
 __global__ void __launch_bounds__(128)
 scalars_keypoints_kernel(const uint8_t *__restrict__ cleaned, const double *__restrict__ centroid,
                          const double *__restrict__ angle_deg, const double *__restrict__ axis,
-                         const float *__restrict__ kpts, const int2 *__restrict__ sums, int n, int h, int w,
+                         const KP *__restrict__ kpts, const int2 *__restrict__ sums, int n, int h, int w,
                          int chunk, MmScale mm, double *__restrict__ scalars, double *__restrict__ kcols) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
@@ -361,8 +320,8 @@ int launch_angles_and_flips(const double *orientation, const double *axis, const
 
 int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
                                  const double *centroid, const double *angle_deg, const double *axis,
-                                 const float *kpts, int n, int h, int w, int chunk, double min_h, double max_h,
-                                 double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
+                                 const void *kpts, bool kpts_f64, int n, int h, int w, int chunk, double min_h,
+                                 double max_h, double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
                                  cudaStream_t st) {
     const size_t plane = (size_t)h * w;
     const int vec_ok = (plane % 16 == 0) && ((uintptr_t)chunk_frames % 16 == 0) && ((uintptr_t)mask % 16 == 0);   // NULL mask is "aligned"
@@ -378,8 +337,14 @@ int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mas
     mm.fh = 424 / (2 * ((60.0 / 2) * kPiOver180));
     mm.depth = true_depth;
     TimedLaunch timed(K_SCALARS_KPTS, st);
-    scalars_keypoints_kernel<<<(n + 127) / 128, 128, 0, st>>>(cleaned, centroid, angle_deg, axis, kpts, sums_scratch, n,
-                                                            h, w, chunk, mm, scalars, kcols);
+    if (kpts_f64)
+        scalars_keypoints_kernel<double><<<(n + 127) / 128, 128, 0, st>>>(cleaned, centroid, angle_deg, axis,
+                                                                         static_cast<const double *>(kpts), sums_scratch, n, h,
+                                                                         w, chunk, mm, scalars, kcols);
+    else
+        scalars_keypoints_kernel<float><<<(n + 127) / 128, 128, 0, st>>>(cleaned, centroid, angle_deg, axis,
+                                                                        static_cast<const float *>(kpts), sums_scratch, n, h,
+                                                                        w, chunk, mm, scalars, kcols);
     MSQ_LAUNCH_OK("scalars_and_keypoints");
     return MSQ_OK;
 }
@@ -399,15 +364,26 @@ extern "C" int msq_angles_and_flips(const double *orientation, const double *axi
                                    (cudaStream_t)stream);
 }
 
-extern "C" int msq_flips_from_keypoints(const float *kpts, const double *centroid, const double *angles,
-                                        const double *lengths, int n, uint8_t *flips, double *conf, void *stream) {
+static int flips_from_keypoints_any(const void *kpts, bool f64, const double *centroid, const double *angles,
+                                   const double *lengths, int n, uint8_t *flips, double *conf, void *stream) {
     MSQ_REQUIRE(kpts && centroid && angles && lengths && flips, MSQ_EINVAL, "msq_flips_from_keypoints: null pointer");
     MSQ_REQUIRE(n >= 0, MSQ_EINVAL, "msq_flips_from_keypoints: bad n=%d", n);
     if (n == 0) return MSQ_OK;
     TimedLaunch timed(K_ANGLES, (cudaStream_t)stream);
-    flips_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kpts, centroid, angles, lengths, n, flips, conf);
+    if (f64)
+        flips_kernel<double><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(static_cast<const double *>(kpts), centroid, angles, lengths, n, flips, conf);
+    else
+        flips_kernel<float><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(static_cast<const float *>(kpts), centroid, angles, lengths, n, flips, conf);
     MSQ_LAUNCH_OK("flips_from_keypoints");
     return MSQ_OK;
+}
+extern "C" int msq_flips_from_keypoints(const float *kpts, const double *centroid, const double *angles,
+                                        const double *lengths, int n, uint8_t *flips, double *conf, void *stream) {
+    return flips_from_keypoints_any(kpts, false, centroid, angles, lengths, n, flips, conf, stream);
+}
+extern "C" int msq_flips_from_keypoints_f64(const double *kpts, const double *centroid, const double *angles,
+                                            const double *lengths, int n, uint8_t *flips, double *conf, void *stream) {
+    return flips_from_keypoints_any(kpts, true, centroid, angles, lengths, n, flips, conf, stream);
 }
 
 extern "C" int msq_iterative_filter_angles(const double *angles, int n, int chunk, int window, double tolerance,
@@ -429,11 +405,11 @@ extern "C" int msq_iterative_filter_angles(const double *angles, int n, int chun
 
 extern "C" size_t msq_scalars_scratch_bytes(int n) { return (size_t)(n > 0 ? n : 0) * sizeof(int2); }
 
-extern "C" int msq_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
-                                         const double *centroid, const double *angle_deg, const double *axis,
-                                         const float *kpts, int n, int h, int w, int chunk, double min_h,
-                                         double max_h, double true_depth, double *scalars, double *kcols,
-                                         void *scratch, size_t scratch_bytes, void *stream) {
+static int scalars_and_keypoints_any(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
+                                    const double *centroid, const double *angle_deg, const double *axis, const void *kpts,
+                                    bool kpts_f64, int n, int h, int w, int chunk, double min_h, double max_h,
+                                    double true_depth, double *scalars, double *kcols, void *scratch, size_t scratch_bytes,
+                                    void *stream) {
     MSQ_REQUIRE(chunk_frames && cleaned && centroid && angle_deg && axis && kpts, MSQ_EINVAL,
                 "msq_scalars_and_keypoints: null input pointer");        // mask may be NULL (= all ones)
     MSQ_REQUIRE(scalars || kcols, MSQ_EINVAL, "msq_scalars_and_keypoints: both outputs are null");
@@ -441,9 +417,25 @@ extern "C" int msq_scalars_and_keypoints(const uint8_t *chunk_frames, const uint
     if (n == 0) return MSQ_OK;
     MSQ_REQUIRE(scratch && scratch_bytes >= msq_scalars_scratch_bytes(n) && (uintptr_t)scratch % 8 == 0, MSQ_ENOMEM,
                 "msq_scalars_and_keypoints: scratch must be 8-byte aligned and >= %zu bytes", msq_scalars_scratch_bytes(n));
-    return launch_scalars_and_keypoints(chunk_frames, mask, cleaned, centroid, angle_deg, axis, kpts, n, h, w, chunk,
+    return launch_scalars_and_keypoints(chunk_frames, mask, cleaned, centroid, angle_deg, axis, kpts, kpts_f64, n, h, w, chunk,
                                         min_h, max_h, true_depth, scalars, kcols, reinterpret_cast<int2 *>(scratch),
                                         (cudaStream_t)stream);
+}
+extern "C" int msq_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
+                                         const double *centroid, const double *angle_deg, const double *axis,
+                                         const float *kpts, int n, int h, int w, int chunk, double min_h,
+                                         double max_h, double true_depth, double *scalars, double *kcols,
+                                         void *scratch, size_t scratch_bytes, void *stream) {
+    return scalars_and_keypoints_any(chunk_frames, mask, cleaned, centroid, angle_deg, axis, kpts, false, n, h, w, chunk, min_h,
+                                     max_h, true_depth, scalars, kcols, scratch, scratch_bytes, stream);
+}
+extern "C" int msq_scalars_and_keypoints_f64(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
+                                             const double *centroid, const double *angle_deg, const double *axis,
+                                             const double *kpts, int n, int h, int w, int chunk, double min_h,
+                                             double max_h, double true_depth, double *scalars, double *kcols,
+                                             void *scratch, size_t scratch_bytes, void *stream) {
+    return scalars_and_keypoints_any(chunk_frames, mask, cleaned, centroid, angle_deg, axis, kpts, true, n, h, w, chunk, min_h,
+                                     max_h, true_depth, scalars, kcols, scratch, scratch_bytes, stream);
 }
 
 extern "C" const char *msq_scalar_name(int i) {

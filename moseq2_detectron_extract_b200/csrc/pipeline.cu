@@ -39,7 +39,7 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
     if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
                                       out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
     if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,
-                                           out->axis_length, kpts_dev, n, h, w, chunk, min_height, max_height,
+                                           out->axis_length, kpts_dev, false, n, h, w, chunk, min_height, max_height,
                                            true_depth, out->scalars, out->kpt_cols, sums, st)) != MSQ_OK) return rc;
     return launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
                               out->depth_crops, out->mask_crops, crop_scratch, st);

@@ -79,6 +79,18 @@ class ChunkEngine:
             'filter_passes': b['filter_passes'][:n_chunks],
         }
 
+    # ---- a6 + a7 only (the tracking branch post-processes the raw moment features itself) ----------
+    def clean_and_features(self, chunk: torch.Tensor, masks: torch.Tensor) -> Dict[str, torch.Tensor]:
+        n, h, w = (int(v) for v in chunk.shape)
+        e = _dev.empty
+        cleaned = torch.empty_like(chunk)
+        centroid, orientation, axis = e((n, 2), torch.float64), e((n,), torch.float64), e((n, 2), torch.float64)
+        st = _dev.stream()
+        _lib.call('msq_clean_frames', _dev.ptr(chunk), _dev.ptr(cleaned), n, h, w, st)
+        _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(centroid),
+                  _dev.ptr(orientation), _dev.ptr(axis), ctypes.c_void_p(0), ctypes.c_void_p(0), 0, st)
+        return {'cleaned': cleaned, 'centroid': centroid, 'orientation_rad': orientation, 'axis_length': axis}
+
     # ---- instances_to_features only --------------------------------------------------------------
     def features_only(self, chunk: torch.Tensor, masks: torch.Tensor, keypoints: torch.Tensor,
                       chunk_size: Optional[int] = None) -> Dict[str, torch.Tensor]:

@@ -10,7 +10,9 @@ from ..engine import ChunkEngine
 from ..model.instances import Instances
 from ..model.util import create_empty_instances
 from ..proc.keypoints import keypoints_from_table
-from ..proc.proc import _gather_instances
+from .. import _lib
+from ..proc.kalman import KalmanTracker, KalmanTrackerAngle, KalmanTrackerNPoints2D, KalmanTrackerPoint2D
+from ..proc.proc import _gather_instances, _tracked_angles_and_flips, crop_and_rotate_frames_batch
 from ..proc.scalars import scalars_from_table
 from .pipeline_step import ProcessPipelineStep
 
@@ -19,8 +21,13 @@ class ProcessFeaturesStep(ProcessPipelineStep):
     def initialize(self):
         self.crop = self.config['crop_size']
         if self.config.get('use_tracking', False):
-            raise NotImplementedError('ProcessFeaturesStep: use_tracking=True (Kalman branch, ref proc/kalman.py) is out of '
-                                      'scope of this build (SURVEY.md section 8f row f1); run with use_tracking=False')
+            # ref: process_features_step.py:41-50 -- centroid + 8 keypoints, and the angle, at order 3
+            self.point_tracker = KalmanTracker([KalmanTrackerPoint2D(order=3, delta_t=1.0),
+                                                KalmanTrackerNPoints2D(8, order=3, delta_t=1.0)])
+            self.angle_tracker = KalmanTracker([KalmanTrackerAngle(order=3, delta_t=1.0, degrees=True)])
+        else:
+            self.point_tracker = None
+            self.angle_tracker = None
         self.engine = ChunkEngine()
         self.to_host = bool(self.config.get('results_to_host', True))
 
@@ -63,6 +70,24 @@ class ProcessFeaturesStep(ProcessPipelineStep):
             frame['instances'] = inst
         return data
 
+    # ---- use_tracking=True: the same outputs through the Kalman branch (ref: proc/proc.py:730-826) ---------------
+    def _tracked(self, chunk, masks, kpts):
+        n, h, w = (int(v) for v in chunk.shape)
+        res = self.engine.clean_and_features(chunk, masks)
+        centroid, kp64, angles, flips = _tracked_angles_and_flips(res['centroid'], res['orientation_rad'], res['axis_length'],
+                                                                  kpts, self.point_tracker, self.angle_tracker)
+        e = _dev.empty
+        scalars, kcols = e((_lib.NUM_SCALARS, n), torch.float64), e((_lib.NUM_KPT_COLS, n), torch.float64)
+        scratch = e((int(_lib.load().msq_scalars_scratch_bytes(n)) + 8,), torch.uint8)
+        _lib.call('msq_scalars_and_keypoints_f64', _dev.ptr(chunk), _dev.ptr(masks), _dev.ptr(res['cleaned']), _dev.ptr(centroid),
+                  _dev.ptr(angles), _dev.ptr(res['axis_length']), _dev.ptr(kp64), n, h, w, max(n, 1),
+                  float(self.config['min_height']), float(self.config['max_height']), float(self.config['true_depth']),
+                  _dev.ptr(scalars), _dev.ptr(kcols), _dev.ptr(scratch), scratch.numel(), _dev.stream())
+        depth, mask_crops = crop_and_rotate_frames_batch(chunk, centroid, angles, self.crop, frames2=masks)
+        out = {'cleaned': res['cleaned'], 'centroid': centroid, 'angle_deg': angles, 'axis_length': res['axis_length'],
+               'flips': flips, 'scalars': scalars, 'kpt_cols': kcols, 'depth_crops': depth, 'mask_crops': mask_crops}
+        return out, kp64
+
     # ---- ref: process_features_step.py:163-199 ----------------------------------------------------------
     def _features_and_crops(self, data: dict) -> dict:
         chunk = _dev.as_device(data['chunk'], torch.uint8)
@@ -71,9 +96,12 @@ class ProcessFeaturesStep(ProcessPipelineStep):
         else:
             masks, kpts, ninst = _gather_instances(data['inference'])
         n = int(chunk.shape[0])
-        res = self.engine.extract(chunk, masks, kpts, chunk_size=max(n, 1), min_height=self.config['min_height'],
-                                  max_height=self.config['max_height'], true_depth=self.config['true_depth'],
-                                  crop_size=self.crop)
+        if self.point_tracker is not None:
+            res, kpts = self._tracked(chunk, masks, kpts)
+        else:
+            res = self.engine.extract(chunk, masks, kpts, chunk_size=max(n, 1), min_height=self.config['min_height'],
+                                      max_height=self.config['max_height'], true_depth=self.config['true_depth'],
+                                      crop_size=self.crop)
         for i in np.flatnonzero(np.asarray(ninst) <= 0):
             self.write_message(f"WARN: No instances found for frame {data['frame_idxs'][i]}")
         conv = (lambda t: t.cpu().numpy()) if self.to_host else (lambda t: t.clone())

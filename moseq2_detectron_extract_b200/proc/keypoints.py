@@ -60,7 +60,9 @@ def keypoints_from_table(table, like=None) -> Dict[str, np.ndarray]:
 def keypoints_to_dict(keypoints, frames, centers, angles, true_depth: float = 673.1,
                       keypoint_names: Optional[List[str]] = None) -> Dict[str, np.ndarray]:
     """Reference / rotated keypoints in px and mm plus the z lookup (ref: proc/keypoints.py:93-165)."""
-    kp = _dev.as_device(keypoints, torch.float32)
+    f64 = (isinstance(keypoints, torch.Tensor) and keypoints.dtype == torch.float64) or \
+          (isinstance(keypoints, np.ndarray) and keypoints.dtype == np.float64)
+    kp = _dev.as_device(keypoints, torch.float64 if f64 else torch.float32)
     fr = _dev.as_device(frames, torch.uint8)
     n, h, w = (int(v) for v in fr.shape)
     if tuple(kp.shape) != (n, 8, 3):
@@ -70,7 +72,7 @@ def keypoints_to_dict(keypoints, frames, centers, angles, true_depth: float = 67
     axis = torch.zeros((n, 2), dtype=torch.float64, device='cuda')
     table = _dev.empty((_lib.NUM_KPT_COLS, n), torch.float64)
     scratch = _dev.empty((int(_lib.load().msq_scalars_scratch_bytes(n)) + 8,), torch.uint8)
-    _lib.call('msq_scalars_and_keypoints', _dev.ptr(fr), None, _dev.ptr(fr), _dev.ptr(cen), _dev.ptr(ang), _dev.ptr(axis),
-              _dev.ptr(kp), n, h, w, max(n, 1), 0.0, 0.0, float(true_depth), None, _dev.ptr(table), _dev.ptr(scratch),
-              scratch.numel(), _dev.stream())
+    _lib.call('msq_scalars_and_keypoints_f64' if f64 else 'msq_scalars_and_keypoints', _dev.ptr(fr), None, _dev.ptr(fr),
+              _dev.ptr(cen), _dev.ptr(ang), _dev.ptr(axis), _dev.ptr(kp), n, h, w, max(n, 1), 0.0, 0.0, float(true_depth), None,
+              _dev.ptr(table), _dev.ptr(scratch), scratch.numel(), _dev.stream())
     return keypoints_from_table(table, like=keypoints)

@@ -297,8 +297,10 @@ def clamp_angles_deg(angles: np.ndarray) -> np.ndarray:
 
 
 def flips_from_keypoints(keypoints, centroids, angles, length=80):
-    """Estimate flips from keypoint votes (ref: proc/proc.py:851-889).  Returns (flips bool, confidence)."""
-    kp = _dev.as_device(keypoints, torch.float32)
+    """Estimate flips from keypoint votes (ref: proc/proc.py:851-889).  Returns (flips bool, confidence).
+    float64 keypoints (the smoothed ones of the tracking branch) are voted on in float64."""
+    f64 = _is_f64(keypoints)
+    kp = _dev.as_device(keypoints, torch.float64 if f64 else torch.float32)
     n = int(kp.shape[0])
     cen = _dev.as_device(centroids, torch.float64)
     ang = _dev.as_device(angles, torch.float64)
@@ -307,8 +309,8 @@ def flips_from_keypoints(keypoints, centroids, angles, length=80):
     lens = _dev.as_device(length, torch.float64)
     flips = _dev.empty((n,), torch.uint8)
     conf = _dev.empty((n,), torch.float64)
-    _lib.call('msq_flips_from_keypoints', _dev.ptr(kp), _dev.ptr(cen), _dev.ptr(ang), _dev.ptr(lens), n,
-              _dev.ptr(flips), _dev.ptr(conf), _dev.stream())
+    _lib.call('msq_flips_from_keypoints_f64' if f64 else 'msq_flips_from_keypoints', _dev.ptr(kp), _dev.ptr(cen),
+              _dev.ptr(ang), _dev.ptr(lens), n, _dev.ptr(flips), _dev.ptr(conf), _dev.stream())
     return _dev.give_back(flips.to(torch.bool), keypoints), _dev.give_back(conf, keypoints)
 
 
@@ -363,19 +365,71 @@ def _gather_instances(model_outputs: List[dict]):
     return torch.stack(mask_rows).contiguous(), torch.stack(kp_rows).contiguous(), ninst
 
 
+def _is_f64(x) -> bool:
+    return (isinstance(x, torch.Tensor) and x.dtype == torch.float64) or (isinstance(x, np.ndarray) and x.dtype == np.float64)
+
+
+def _tracked_angles_and_flips(centroid, orientation_rad, axis, kpts32, point_tracker, angle_tracker):
+    """The tracking strategy of the reference (proc/proc.py:730-826) on device tensors:
+    1) Kalman-smooth centroids and keypoints (tail tip keeps its raw position, :752);
+    2) flips from the smoothed keypoints, angles[flips] = clamp(angles + 180);
+    3) per frame: read the tracked angle, defer to it when the keypoints are badly aligned (score < 0.4), flip by 180
+       when it disagrees by more than 140 degrees, then update the angle filter with the result.
+    `KalmanTracker.sample(1)` is the last filtered state itself (the draw it makes only perturbs a discarded
+    observation), so the branch is deterministic; estimate_keypoint_rotation (:765) only feeds the debug TSV."""
+    from .kalman import KalmanTracker, KalmanTrackerAngle
+    if not isinstance(point_tracker, KalmanTracker) or not isinstance(angle_tracker, KalmanTracker):
+        raise TypeError('instances_to_features: point_tracker / angle_tracker must be moseq2_detectron_extract_b200.proc.kalman.KalmanTracker')
+    if len(angle_tracker.items) != 1 or not isinstance(angle_tracker.items[0], KalmanTrackerAngle) or not angle_tracker.items[0].degrees:
+        raise ValueError('instances_to_features: angle_tracker must track exactly one KalmanTrackerAngle in degrees')
+    n = int(centroid.shape[0])
+    kp64 = kpts32.to(torch.float64).contiguous()
+    xy = kp64[:, :, :2].contiguous()
+    if not point_tracker.is_initialized:
+        point_tracker.initialize([centroid, xy])
+    s_centroid, s_xy = point_tracker.smooth_update([centroid, xy])
+    centroid = s_centroid.contiguous()
+    kp64[:, :7, :2] = s_xy[:, :7, :]
+    e = _dev.empty
+    angles, flips, conf, scores = e((n,), torch.float64), e((n,), torch.uint8), e((n,), torch.float64), e((n,), torch.float64)
+    st = _dev.stream()
+    _lib.call('msq_tracking_prepare', _dev.ptr(orientation_rad), _dev.ptr(axis), _dev.ptr(centroid), _dev.ptr(kp64), n,
+              _dev.ptr(angles), _dev.ptr(flips), _dev.ptr(conf), _dev.ptr(scores), st)
+    if not angle_tracker.is_initialized:
+        angle_tracker.initialize([angles])
+    m = angle_tracker.device_model()
+    mean, cov = angle_tracker.last_mean.clone(), angle_tracker.last_covar.clone()
+    _lib.call('msq_track_angles', _dev.ptr(m['A']), _dev.ptr(m['H']), _dev.ptr(m['Q']), _dev.ptr(m['R']), _dev.ptr(mean),
+              _dev.ptr(cov), angle_tracker.n_state, _dev.ptr(angles), _dev.ptr(flips), _dev.ptr(scores), n, st)
+    angle_tracker.last_mean, angle_tracker.last_covar = mean, cov
+    return centroid, kp64, angles, flips
+
+
 def instances_to_features(model_outputs: List[dict], raw_frames, point_tracker=None, angle_tracker=None,
                           debug: bool = True) -> dict:
-    """Clean frames, moment features, flips and angle filtering for one chunk (ref: proc/proc.py:700-848,
-    non-tracking branch :827-839).  The Kalman tracking branch (:730-826) is not part of this build."""
-    if point_tracker is not None or angle_tracker is not None:
-        raise NotImplementedError('instances_to_features: the Kalman tracking branch (use_tracking=True) is out of '
-                                  'scope of this build; run with use_tracking=False')
+    """Clean frames, moment features, flips and angle post-processing for one chunk (ref: proc/proc.py:700-848).
+    Without trackers: keypoint flips + the iterative 180-degree filter (:827-839).  With a point and an angle
+    `KalmanTracker` (proc/kalman.py of this package): the Kalman tracking branch (:730-826); `debug` only controlled
+    the reference's flip_info.tsv dump and is ignored."""
     from ..engine import ChunkEngine
     masks, kpts, ninst = _gather_instances(model_outputs)
     chunk = _dev.as_device(raw_frames, torch.uint8)
-    res = ChunkEngine.shared().features_only(chunk, masks, kpts)
     on_dev = _dev.is_device_tensor(raw_frames)
     conv = (lambda t: t) if on_dev else (lambda t: t.cpu().numpy())
+    if point_tracker is not None and angle_tracker is not None:
+        res = ChunkEngine.shared().clean_and_features(chunk, masks)
+        centroid, kp64, angles, flips = _tracked_angles_and_flips(res['centroid'], res['orientation_rad'], res['axis_length'],
+                                                                  kpts, point_tracker, angle_tracker)
+        return {
+            'cleaned_frames': conv(res['cleaned']),
+            'masks': conv(masks),
+            'features': {'centroid': conv(centroid), 'orientation': conv(angles),
+                         'axis_length': conv(res['axis_length']), 'contour': []},
+            'flips': conv(flips.to(torch.bool)),
+            'keypoints': conv(kp64),
+            'num_instances': ninst,
+        }
+    res = ChunkEngine.shared().features_only(chunk, masks, kpts)
     return {
         'cleaned_frames': conv(res['cleaned']),
         'masks': conv(masks),

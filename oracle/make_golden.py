@@ -98,6 +98,56 @@ def run_reference(name):
     return out
 
 
+TRACKING_CASE = dict(n_frames=180, seed=11, t0=20, missing_every=23, chunks=(100, 80))
+
+
+def run_reference_tracking():
+    """The Kalman tracking branch (ref proc/proc.py:730-826) over two consecutive chunks with fresh trackers built like
+    pipeline/process_features_step.py:41-50.  pykalman is absent here: the reference runs on oracle/pykalman_standin.py."""
+    ref = ref_import.load()
+    K = ref.kalman
+    geom = synthetic.SessionGeometry.kinect_v2()
+    kw = {k: v for k, v in TRACKING_CASE.items() if k != 'chunks'}
+    chunk = synthetic.generate_chunk(geom=geom, **kw)
+    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+    cfg = synthetic.default_config(geom)
+    prepped = ref.proc.prep_raw_frames(chunk.frames.copy(), bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'])
+    pt = K.KalmanTracker([K.KalmanTrackerPoint2D(order=3, delta_t=1.0), K.KalmanTrackerNPoints2D(8, order=3, delta_t=1.0)])
+    at = K.KalmanTracker([K.KalmanTrackerAngle(order=3, delta_t=1.0, degrees=True)])
+    outputs = [{'instances': FakeInstances(chunk.masks[i], chunk.keypoints[i], chunk.num_instances[i] > 0)}
+               for i in range(prepped.shape[0])]
+    out, start = {}, 0
+    for c, n in enumerate(TRACKING_CASE['chunks']):
+        sl = slice(start, start + n)
+        feats = ref.proc.instances_to_features(outputs[sl], prepped[sl], pt, at, debug=False)
+        out[f'c{c}/centroid'] = feats['features']['centroid']
+        out[f'c{c}/orientation'] = feats['features']['orientation']
+        out[f'c{c}/flips'] = feats['flips']
+        out[f'c{c}/keypoints'] = feats['keypoints']
+        out[f'c{c}/point_last_mean'] = np.array(pt.last_mean)
+        out[f'c{c}/angle_last_mean'] = np.array(at.last_mean)
+        scal = ref.scalars.compute_scalars(prepped[sl] * feats['masks'], feats['features'], min_height=cfg['min_height'],
+                                           max_height=cfg['max_height'], true_depth=cfg['true_depth'])
+        for k, v in scal.items():
+            out[f'c{c}/scalars/' + k] = np.asarray(v)
+        kd = ref.keypoints.keypoints_to_dict(feats['keypoints'], feats['cleaned_frames'], feats['features']['centroid'],
+                                             feats['features']['orientation'], true_depth=cfg['true_depth'])
+        for k, v in kd.items():
+            out[f'c{c}/keypoints/' + k] = np.asarray(v)
+        crop = cfg['crop_size']
+        dc = np.zeros((n, crop[0], crop[1]), dtype='uint8')
+        for i in range(n):
+            dc[i] = ref.proc.crop_and_rotate_frame(prepped[sl][i], feats['features']['centroid'][i],
+                                                   feats['features']['orientation'][i], crop)
+        out[f'c{c}/depth_frames'] = dc
+        start += n
+    for name in ('transition_covariance', 'observation_covariance', 'initial_state_covariance'):
+        out['point_' + name] = np.array(getattr(pt.kalman_filter, name))
+    out['angle_transition_covariance'] = np.array(at.kalman_filter.transition_covariance)
+    out['angle_observation_covariance'] = np.array(at.kalman_filter.observation_covariance)
+    return out
+
+
 def main():
     import cv2
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
@@ -107,6 +157,11 @@ def main():
         path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
         np.savez_compressed(path, **out)
         print(name, '->', path, f'{os.path.getsize(path) / 1e6:.2f} MB')
+    out = run_reference_tracking()
+    out['_versions'] = np.array([f'cv2={cv2.__version__}', f'numpy={np.__version__}', 'pykalman=stand-in (oracle/pykalman_standin.py)'])
+    path = os.path.join(ROOT, 'tests', 'golden', 'kinect_tracking.npz')
+    np.savez_compressed(path, **out)
+    print('kinect_tracking ->', path, f'{os.path.getsize(path) / 1e6:.2f} MB')
 
 
 if __name__ == '__main__':

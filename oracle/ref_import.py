@@ -6,7 +6,8 @@ Used (a) by oracle/make_golden.py to generate the committed fixtures under tests
 
 The reference drags in third-party modules that are absent here and never executed on the
 extract hot path.  They are replaced by inert stubs *before* import.
-`bottleneck.move_median` IS executed (reference proc/proc.py:618) so it gets a functional
+`pykalman.KalmanFilter` IS executed on the tracking branch (reference proc/kalman.py) and gets the restated
+stand-in of oracle/pykalman_standin.py.  `bottleneck.move_median` IS executed (reference proc/proc.py:618) so it gets a functional
 stand-in built on pandas' trailing rolling median, which has the same semantics
 (trailing window, NaN-skipping, min_count == min_periods).
 """
@@ -24,7 +25,7 @@ _STUBS = [
     "skimage.morphology", "skimage.filters",
     "pycocotools", "pycocotools.mask", "detectron2", "detectron2.data", "detectron2.structures",
     "detectron2.utils", "detectron2.utils.visualizer", "detectron2.utils.colormap", "detectron2.data.catalog",
-    "pykalman", "norfair", "click", "statsmodels", "statsmodels.api",
+    "norfair", "click", "statsmodels", "statsmodels.api",
 ]
 
 
@@ -70,6 +71,14 @@ def load():
             bn = types.ModuleType("bottleneck")
             bn.move_median = _move_median
             sys.modules["bottleneck"] = bn
+    if "pykalman" not in sys.modules:
+        try:
+            importlib.import_module("pykalman")
+        except Exception:       # absent -> restated stand-in (oracle/pykalman_standin.py, "parity unpinned")
+            import pykalman_standin
+            pk = types.ModuleType("pykalman")
+            pk.KalmanFilter = pykalman_standin.KalmanFilter
+            sys.modules["pykalman"] = pk
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     ns = types.SimpleNamespace()
@@ -78,4 +87,5 @@ def load():
     ns.scalars = importlib.import_module("moseq2_detectron_extract.proc.scalars")
     ns.keypoints = importlib.import_module("moseq2_detectron_extract.proc.keypoints")
     ns.util = importlib.import_module("moseq2_detectron_extract.proc.util")
+    ns.kalman = importlib.import_module("moseq2_detectron_extract.proc.kalman")
     return ns

@@ -240,3 +240,27 @@ def test_read_frames_raw_matches_reference_semantics(tmp_path):
     assert [c[0][0] for c in chunks] == [0, 7, 14] and np.array_equal(np.concatenate([c[1] for c in chunks]), frames)
     with pytest.raises(EOFError):
         read_frames_raw(str(path), range(10, 30), frame_dims=(W, H))
+
+
+def test_kalman_items_build_the_reference_model_blocks():
+    """Model blocks of the tracker items (host side, no GPU): constant-jerk transition per coordinate, position-only
+    observation, same layout as reference proc/kalman.py:146-278 (restated in oracle/tracking_oracle.py)."""
+    import tracking_oracle as TO
+    from moseq2_detectron_extract_b200.proc import kalman as K
+    for item, n_coords in ((K.KalmanTrackerPoint1D(3, 1.0), 1), (K.KalmanTrackerPoint2D(3, 1.0), 2),
+                           (K.KalmanTrackerAngle(3, 1.0), 2), (K.KalmanTrackerNPoints2D(8, 3, 1.0), 16),
+                           (K.KalmanTrackerPoint2D(4, 0.5), 2)):
+        ref = TO.Tracker(n_coords, item.order)
+        if item.delta_t == 1.0:
+            assert np.array_equal(item.build_trans_mat(), ref.A)
+        assert np.array_equal(item.build_observ_mat(), ref.H)
+        assert item.state_size == n_coords * item.order and item.obs_size == n_coords
+    blk = K.KalmanTrackerPoint1D(4, 0.5).build_trans_mat()
+    assert np.allclose(blk, [[1, .5, .125, .125 / 6], [0, 1, .5, .125], [0, 0, 1, .5], [0, 0, 0, 1]])
+    with pytest.raises(ValueError):
+        K.KalmanTracker([])
+    with pytest.raises(ValueError):
+        K.KalmanTracker([K.KalmanTrackerPoint2D(3, 1.0), K.KalmanTrackerPoint2D(3, 2.0)])
+    tr = K.KalmanTracker([K.KalmanTrackerPoint2D(3, 1.0), K.KalmanTrackerNPoints2D(8, 3, 1.0)])
+    assert (tr.n_state, tr.n_obs, tr.is_initialized) == (54, 18, False)
+    assert np.allclose(K.angle_difference(np.array([350.0, 10.0, 0.0]), np.array([10.0, 350.0, 180.0])), [20.0, -20.0, 180.0])

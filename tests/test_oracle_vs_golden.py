@@ -1,5 +1,7 @@
 """CPU: pin oracle/extract_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz,
 made by oracle/make_golden.py) and its numpy restatements against OpenCV itself."""
+import os
+
 import numpy as np
 import pytest
 
@@ -171,3 +173,49 @@ def test_inpaint_restatement_equals_opencv():
             m[0, :] = 1
             m[:, 0] = 1
         assert np.array_equal(inpaint_ns(img, m, 3), cv2.inpaint(img, m, 3, cv2.INPAINT_NS)), t
+
+
+# ----------------------------------------------------------------------------- a14 tracking branch
+def test_tracking_oracle_matches_reference_golden():
+    """oracle/tracking_oracle.py (restated KalmanTracker + tracking strategy over the restated pykalman filter) against
+    the outputs of the UNMODIFIED reference proc/proc.py:730-826 + proc/kalman.py run on the same stand-in."""
+    import make_golden
+    import tracking_oracle as TO
+    from moseq2_detectron_extract_b200 import synthetic
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kinect_tracking.npz'))
+    geom = synthetic.SessionGeometry.kinect_v2()
+    kw = {k: v for k, v in make_golden.TRACKING_CASE.items() if k != 'chunks'}
+    chunk = synthetic.generate_chunk(geom=geom, **kw)
+    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+    prep = O.prep_frames(chunk.frames, bg, roi, 0, 100)
+    pt, at = TO.Tracker(18), TO.Tracker(2)
+    start = 0
+    for c, n in enumerate(make_golden.TRACKING_CASE['chunks']):
+        sl = slice(start, start + n)
+        feats = O.frame_features_cv2(O.clean_frames_cv2(prep[sl]), chunk.masks[sl])
+        cen, kp, ang, fl = TO.track_chunk(feats['centroid'], feats['orientation'], feats['axis_length'], chunk.keypoints[sl], pt, at)
+        np.testing.assert_allclose(cen, g[f'c{c}/centroid'], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(kp, g[f'c{c}/keypoints'], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(ang, g[f'c{c}/orientation'], rtol=0, atol=1e-9)
+        assert np.array_equal(fl, g[f'c{c}/flips'])
+        assert not np.isnan(ang).any() and np.isnan(g[f'c{c}/keypoints']).any()     # missing frames get the tracked angle
+        start += n
+    np.testing.assert_allclose(pt.kf.transition_covariance, g['point_transition_covariance'], rtol=1e-10, atol=1e-12)
+
+
+def test_restated_pykalman_conventions():
+    """The documented pykalman behaviours the tracking branch leans on (oracle/pykalman_standin.py)."""
+    from numpy import ma
+    from pykalman_standin import KalmanFilter
+    import tracking_oracle as TO
+    tr = TO.Tracker(2)
+    kf = KalmanFilter(transition_matrices=tr.A, observation_matrices=tr.H, initial_state_mean=np.arange(6.0))
+    # sample(1, x) returns x itself: `KalmanTracker.sample(1)` is deterministic (reference proc/kalman.py:370-377)
+    states, _ = kf.sample(1, np.arange(6.0) + 1)
+    assert np.array_equal(states[0], np.arange(6.0) + 1)
+    # the first predicted state is the prior itself; a partly masked observation is skipped entirely
+    z = ma.masked_invalid(np.array([[1.0, np.nan], [2.0, 3.0]]))
+    means, covs = kf.filter(z)
+    assert np.array_equal(means[0], np.arange(6.0)) and np.array_equal(covs[0], np.eye(6))
+    m1, c1 = kf.filter_update(np.arange(6.0), np.eye(6), z[0])
+    assert np.allclose(m1, tr.A @ np.arange(6.0)) and np.allclose(c1, tr.A @ tr.A.T + np.eye(6))
