@@ -8,6 +8,7 @@
 // numpy restatement of the same arithmetic is pinned against cv2).  Here that is a gather straight
 // from the un-padded frame: one CTA per frame warps both planes, one thread per output pixel.
 #include "common.cuh"
+#include <limits.h>
 #include <math.h>
 
 namespace msq {
@@ -131,14 +132,161 @@ crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path: one CTA per frame, the source footprint of the crop staged in shared memory.
+// The rotated crop reads a box of at most ~hypot(cw, ch) + 2 pixels a side around the centroid (26 KB for two planes of
+// an 80x80 crop).  Loading that box with coalesced 32-bit words and gathering the four taps from shared memory replaces
+// eight scattered one-byte global loads per output pixel (the old kernel was L1-tag bound), and zero-filling everything
+// the reference cannot read (outside the frame, outside the [int(c-crop/2), int(c+crop/2)) slice) while staging removes
+// every bounds test from the gather: an unreadable tap is a zero pixel instead of a zero weight -- the same product.
+// Coefficients and OpenCV's fixed-point tables are computed by the CTA itself (no scratch traffic, one launch).
+// ---------------------------------------------------------------------------------------------------------------
+struct StagedGeom {
+    int pitch_max, rows_max;      // staging capacity per plane (bytes per row, rows)
+};
+
+__global__ void __launch_bounds__(kCropThreads)
+crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int H, int W,
+                          const double *__restrict__ centroid, const double *__restrict__ angle_deg, int cw, int ch,
+                          StagedGeom G, uint8_t *__restrict__ out0, uint8_t *__restrict__ out1) {
+    extern __shared__ __align__(16) unsigned char crop_smem[];
+    __shared__ WarpCoeffs k;
+    __shared__ int box[4];                                       // gx_lo (4-aligned), gy_lo, pitch, rows; pitch 0 = global path
+    int *adelta = reinterpret_cast<int *>(crop_smem), *bdelta = adelta + cw, *X0 = bdelta + cw, *Y0 = X0 + ch;
+    uint8_t *plane0 = reinterpret_cast<uint8_t *>(Y0 + ch);
+    uint8_t *plane1 = plane0 + (size_t)G.pitch_max * G.rows_max;
+    const int f = blockIdx.x;
+    const size_t crop_base = (size_t)f * cw * ch;
+    if (threadIdx.x == 0) make_coeffs(centroid[2 * f], centroid[2 * f + 1], angle_deg[f], cw, ch, W, H, k);
+    __syncthreads();
+    if (k.sw == 0) {                                             // NaN / negative centre / empty slice: a zero crop
+        for (int i = threadIdx.x; i < (cw * ch) / 4; i += kCropThreads) {
+            reinterpret_cast<uint32_t *>(out0 + crop_base)[i] = 0u;
+            if (out1) reinterpret_cast<uint32_t *>(out1 + crop_base)[i] = 0u;
+        }
+        return;
+    }
+    for (int x = threadIdx.x; x < cw; x += kCropThreads) {
+        adelta[x] = __double2int_rn(k.i00 * (double)x * 1024.0);
+        bdelta[x] = __double2int_rn(k.i10 * (double)x * 1024.0);
+    }
+    for (int y = threadIdx.x; y < ch; y += kCropThreads) {
+        X0[y] = __double2int_rn((k.i01 * (double)y + k.b1) * 1024.0) + 16;
+        Y0[y] = __double2int_rn((k.i11 * (double)y + k.b2) * 1024.0) + 16;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // adelta/bdelta are monotone in x and X0/Y0 in y (rounded linear maps): the extreme taps are at the corners
+        int x_lo = INT_MAX, x_hi = INT_MIN, y_lo = INT_MAX, y_hi = INT_MIN;
+        for (int c = 0; c < 4; ++c) {
+            const int x = (c & 1) ? cw - 1 : 0, y = (c & 2) ? ch - 1 : 0;
+            const int sx = (X0[y] + adelta[x]) >> 10, sy = (Y0[y] + bdelta[x]) >> 10;
+            x_lo = min(x_lo, sx); x_hi = max(x_hi, sx + 1);
+            y_lo = min(y_lo, sy); y_hi = max(y_hi, sy + 1);
+        }
+        const int gx_lo = (x_lo + k.ox) & ~3, gx_hi = x_hi + k.ox;   // frame coordinates, left edge on a 32-bit word
+        const int pitch = ((gx_hi - gx_lo + 1) + 3) & ~3, rows = y_hi - y_lo + 1;
+        const bool fits = pitch <= G.pitch_max && rows <= G.rows_max && x_lo > -32000 && x_hi < 32000 && y_lo > -32000 && y_hi < 32000;
+        box[0] = gx_lo; box[1] = y_lo + k.oy; box[2] = fits ? pitch : 0; box[3] = rows;
+    }
+    __syncthreads();
+    const int gx_lo = box[0], gy_lo = box[1], pitch = box[2], rows = box[3];
+    if (pitch == 0) {
+        // not expected for a rotation about the crop centre; kept for exactness: gather from global memory per tap
+        const int lo_x = max(0, -k.ox), hi_x = min(k.sw, W - k.ox), lo_y = max(0, -k.oy), hi_y = min(k.sh, H - k.oy);
+        for (int i = threadIdx.x; i < cw * ch; i += kCropThreads) {
+            const int y = i / cw, x = i - y * cw;
+            const int X = (X0[y] + adelta[x]) >> 5, Y = (Y0[y] + bdelta[x]) >> 5;
+            const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5), fx = X & 31, fy = Y & 31;
+            int acc0 = 0, acc1 = 0;
+            for (int t = 0; t < 4; ++t) {
+                const int px = sx + (t & 1), py = sy + (t >> 1);
+                if (px < lo_x || px >= hi_x || py < lo_y || py >= hi_y) continue;
+                const int wgt = ((t & 1) ? fx : 32 - fx) * ((t >> 1) ? fy : 32 - fy);
+                const size_t o = (size_t)f * H * W + (size_t)(py + k.oy) * W + px + k.ox;
+                acc0 += (int)__ldg(src0 + o) * wgt;
+                if (src1) acc1 += (int)__ldg(src1 + o) * wgt;
+            }
+            out0[crop_base + i] = (uint8_t)((acc0 + 512) >> 10);
+            if (out1) out1[crop_base + i] = (uint8_t)((acc1 + 512) >> 10);
+        }
+        return;
+    }
+    // ---- stage: frame pixels readable by the reference (inside the frame AND inside its slice), zero elsewhere ----
+    const int rx0 = max(0, k.ox), rx1 = min(k.ox + k.sw, W), ry0 = max(0, k.oy), ry1 = min(k.oy + k.sh, H);
+    const int words = pitch >> 2;
+    const uint8_t *f0 = src0 + (size_t)f * H * W;
+    const uint8_t *f1 = src1 ? src1 + (size_t)f * H * W : nullptr;
+    for (int i = threadIdx.x; i < rows * words; i += kCropThreads) {
+        const int r = i / words, c = i - r * words;
+        const int gy = gy_lo + r, gx = gx_lo + 4 * c;
+        uint32_t v0 = 0u, v1 = 0u;
+        if (gy >= ry0 && gy < ry1 && gx + 3 >= rx0 && gx < rx1) {
+            uint32_t keep = 0xffffffffu;                         // bytes gx..gx+3, little endian
+            if (gx < rx0) keep &= 0xffffffffu << (8 * (rx0 - gx));
+            if (gx + 4 > rx1) keep &= 0xffffffffu >> (8 * (gx + 4 - rx1));
+            const size_t o = (size_t)gy * W + gx;
+            v0 = __ldg(reinterpret_cast<const uint32_t *>(f0 + o)) & keep;
+            if (f1) v1 = __ldg(reinterpret_cast<const uint32_t *>(f1 + o)) & keep;
+        }
+        reinterpret_cast<uint32_t *>(plane0)[r * words + c] = v0;
+        if (f1) reinterpret_cast<uint32_t *>(plane1)[r * words + c] = v1;
+    }
+    __syncthreads();
+    // ---- gather: a thread produces 4 neighbouring output pixels of a row, one 32-bit store per plane ---------------
+    const int groups = cw >> 2;
+    const int sh_x = k.ox - gx_lo, sh_y = k.oy - gy_lo;
+    for (int i = threadIdx.x; i < ch * groups; i += kCropThreads) {
+        const int y = i / groups, xg = (i - y * groups) << 2;
+        const int x0v = X0[y], y0v = Y0[y];
+        uint32_t o0 = 0u, o1 = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int X = (x0v + adelta[xg + q]) >> 5, Y = (y0v + bdelta[xg + q]) >> 5;
+            const int fx = X & 31, fy = Y & 31;
+            const int idx = ((Y >> 5) + sh_y) * pitch + (X >> 5) + sh_x;
+            {
+                const int top = (int)plane0[idx] * (32 - fx) + (int)plane0[idx + 1] * fx;
+                const int bot = (int)plane0[idx + pitch] * (32 - fx) + (int)plane0[idx + pitch + 1] * fx;
+                o0 |= (uint32_t)((top * (32 - fy) + bot * fy + 512) >> 10) << (8 * q);
+            }
+            if (f1) {
+                const int top = (int)plane1[idx] * (32 - fx) + (int)plane1[idx + 1] * fx;
+                const int bot = (int)plane1[idx + pitch] * (32 - fx) + (int)plane1[idx + pitch + 1] * fx;
+                o1 |= (uint32_t)((top * (32 - fy) + bot * fy + 512) >> 10) << (8 * q);
+            }
+        }
+        reinterpret_cast<uint32_t *>(out0 + crop_base)[i] = o0;
+        if (out1) reinterpret_cast<uint32_t *>(out1 + crop_base)[i] = o1;
+    }
+}
+
 }  // namespace
 
 int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
                        const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch,
                        cudaStream_t st) {
+    const bool two = src2 && out2;
+    // fast path: 32-bit staging loads and stores need 4-byte friendly shapes and bases
+    const int side = (int)ceil(hypot((double)cw, (double)ch)) + 4;
+    StagedGeom G;
+    G.pitch_max = (side + 4 + 3) & ~3;
+    G.rows_max = side;
+    const size_t smem = (size_t)2 * (cw + ch) * sizeof(int) + (size_t)(two ? 2 : 1) * G.pitch_max * G.rows_max;
+    const bool aligned = (w % 4 == 0) && (cw % 4 == 0) && ((uintptr_t)src % 4 == 0) && ((uintptr_t)out % 4 == 0) &&
+                         (!two || (((uintptr_t)src2 % 4 == 0) && ((uintptr_t)out2 % 4 == 0))) && (((size_t)h * w) % 4 == 0);
+    if (aligned && smem <= 160 * 1024) {
+        if (smem > 48 * 1024)
+            MSQ_CUDA_OK(cudaFuncSetAttribute(crop_rotate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TimedLaunch timed(K_CROP, st);
+        crop_rotate_staged_kernel<<<n, kCropThreads, smem, st>>>(src, two ? src2 : nullptr, h, w, centroid, angle_deg, cw, ch, G,
+                                                                 out, two ? out2 : nullptr);
+        MSQ_LAUNCH_OK("crop_rotate (staged)");
+        return MSQ_OK;
+    }
     WarpCoeffs *coeffs = reinterpret_cast<WarpCoeffs *>(scratch);
     int *tables = reinterpret_cast<int *>(reinterpret_cast<char *>(scratch) + (size_t)n * sizeof(WarpCoeffs));
-    const bool two = src2 && out2;
     TimedLaunch timed(K_CROP, st);          // the coefficient kernel is part of the crop step
     crop_coeffs_kernel<<<n, 128, 0, st>>>(centroid, angle_deg, n, cw, ch, w, h, coeffs, tables);
     MSQ_LAUNCH_OK("crop_coeffs");

@@ -66,14 +66,14 @@ def test_steps_match_oracle_chunk_by_chunk():
         assert np.array_equal(r['mask_frames'], ref['mask_frames'])
 
 
-def test_tracking_fails_loudly_and_invalid_pixels_are_inpainted():
+def test_tracking_step_builds_trackers_and_invalid_pixels_are_inpainted():
     from moseq2_detectron_extract_b200 import synthetic
     from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
     cfg = synthetic.default_config()
     cfg['use_tracking'] = True
     step = ProcessFeaturesStep(cfg, 'features')
-    with pytest.raises(NotImplementedError):
-        step.initialize()
+    step.initialize()             # ref process_features_step.py:41-50: centroid + 8 keypoints, and the angle, at order 3
+    assert step.point_tracker.n_state == 54 and step.angle_tracker.n_state == 6 and not step.point_tracker.is_initialized
     sess, cfg, results = _run_pipeline(20, 10, invalid_rate=0.002)     # Kinect-like invalid pixels inside the ROI
     for r in results:
         idxs = r['frame_idxs']
