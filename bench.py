@@ -465,6 +465,31 @@ def secondary_figures(args, geom, cfg, roi, bg):
     out['prep_with_invalid_pixels'] = {'frames': int(fr.shape[0]), 'invalid_rate': 0.002, 'ms_prep_only': ms_raw,
                                        'ms_prep_plus_inpaint': ms_fix, 'frames_per_s': fr.shape[0] / (ms_fix * 1e-3)}
     del fr
+    # (3) use_tracking=True: the Kalman branch (a14) -- EM initialisation once, then 1000-frame chunks of one session in
+    # sequence (the running state makes chunks of a session sequential; other sessions would run beside them)
+    try:
+        from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
+        tcfg = dict(cfg, use_tracking=True, results_to_host=False, expected_instances=1)
+        step = ProcessFeaturesStep(tcfg, 'features-tracking')
+        step.initialize()
+        tch = synthetic.generate_chunk(1000, seed=13, geom=geom, missing_every=97)
+        tprep = prep_raw_frames(torch.from_numpy(tch.frames).cuda(), bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'])
+        tmask, tkp = _dev.as_device(tch.masks), _dev.as_device(tch.keypoints, torch.float32)
+
+        def tracked_chunk():
+            step.process({'batch': 0, 'chunk': tprep, 'frame_idxs': list(range(1000)), 'offset': 0,
+                          '_dense_instances': (tmask, tkp, tch.num_instances)})
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); tracked_chunk(); b.record(); torch.cuda.synchronize()      # first chunk: 2 x EM(10 iterations)
+        ms_first = a.elapsed_time(b)
+        ms_next = timed(tracked_chunk, iters=3)
+        out['tracking_branch'] = {'workload': 'ProcessFeaturesStep(use_tracking=True), one session, 1000-frame chunks in sequence: '
+                                              'clean + features + Kalman smoother (54 states) + angle filter + scalars + crops',
+                                  'ms_first_chunk_with_em_init': ms_first, 'ms_per_chunk': ms_next,
+                                  'frames_per_s': 1000 / (ms_next * 1e-3)}
+    except Exception as exc:      # secondary figure only
+        out['tracking_branch'] = {'error': repr(exc)}
     if args.rcnn_frames > 0:
         from moseq2_detectron_extract_b200.pipeline import InferenceStep, ProcessFeaturesStep
         n = args.rcnn_frames

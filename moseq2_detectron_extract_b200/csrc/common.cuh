@@ -99,6 +99,31 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     return v;
 }
 
+// ---- SWAR byte tests (shared by features.cu and epilogue.cu) ------------------------------------
+// SWAR byte tests on 4 packed pixels, result in bit 7 of every byte, no cross-byte carries:
+//   c >= g  (1 <= g <= 255):  low 7 bits compared by adding (128 - (g & 127)); the top bit decides the rest
+//   m != 0
+struct ByteTest {
+    uint32_t k;        // (0x80 - (g & 0x7f)) replicated
+    uint32_t hi_or;    // g < 128: a set top bit alone passes;  g >= 128: the top bit is required
+    int mode;          // 0: everything passes (g <= 0), 1: g in 1..127, 2: g in 128..255, 3: nothing passes
+};
+__device__ __forceinline__ ByteTest make_byte_test(int ge) {
+    ByteTest t;
+    t.mode = ge <= 0 ? 0 : (ge > 255 ? 3 : (ge < 128 ? 1 : 2));
+    t.k = (uint32_t)(0x80 - (ge & 0x7f)) * 0x01010101u;
+    t.hi_or = 0u;
+    return t;
+}
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t c, const ByteTest &t) {
+    const uint32_t low = ((c & 0x7f7f7f7fu) + t.k);
+    if (t.mode == 1) return (low | c) & 0x80808080u;
+    if (t.mode == 2) return (low & c) & 0x80808080u;
+    return t.mode == 0 ? 0x80808080u : 0u;
+}
+__device__ __forceinline__ uint32_t bytes_nonzero(uint32_t m) {
+    return (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u;
+}
 #endif  // __CUDACC__
 }  // namespace msq
 

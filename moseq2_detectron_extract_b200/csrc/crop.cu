@@ -218,47 +218,50 @@ crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__res
     const int words = pitch >> 2;
     const uint8_t *f0 = src0 + (size_t)f * H * W;
     const uint8_t *f1 = src1 ? src1 + (size_t)f * H * W : nullptr;
-    for (int i = threadIdx.x; i < rows * words; i += kCropThreads) {
-        const int r = i / words, c = i - r * words;
-        const int gy = gy_lo + r, gx = gx_lo + 4 * c;
-        uint32_t v0 = 0u, v1 = 0u;
-        if (gy >= ry0 && gy < ry1 && gx + 3 >= rx0 && gx < rx1) {
-            uint32_t keep = 0xffffffffu;                         // bytes gx..gx+3, little endian
-            if (gx < rx0) keep &= 0xffffffffu << (8 * (rx0 - gx));
-            if (gx + 4 > rx1) keep &= 0xffffffffu >> (8 * (gx + 4 - rx1));
-            const size_t o = (size_t)gy * W + gx;
-            v0 = __ldg(reinterpret_cast<const uint32_t *>(f0 + o)) & keep;
-            if (f1) v1 = __ldg(reinterpret_cast<const uint32_t *>(f1 + o)) & keep;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = kCropThreads / 32;
+    // a warp stages whole rows (lane = 32-bit word), so there is no per-element index arithmetic
+    for (int r = warp; r < rows; r += kWarps) {
+        const int gy = gy_lo + r;
+        const bool row_ok = gy >= ry0 && gy < ry1;
+        const size_t row_off = (size_t)gy * W;
+        for (int c = lane; c < words; c += 32) {
+            const int gx = gx_lo + 4 * c;
+            uint32_t v0 = 0u, v1 = 0u;
+            if (row_ok && gx + 3 >= rx0 && gx < rx1) {
+                uint32_t keep = 0xffffffffu;                     // bytes gx..gx+3, little endian
+                if (gx < rx0) keep &= 0xffffffffu << (8 * (rx0 - gx));
+                if (gx + 4 > rx1) keep &= 0xffffffffu >> (8 * (gx + 4 - rx1));
+                v0 = __ldg(reinterpret_cast<const uint32_t *>(f0 + row_off + gx)) & keep;
+                if (f1) v1 = __ldg(reinterpret_cast<const uint32_t *>(f1 + row_off + gx)) & keep;
+            }
+            reinterpret_cast<uint32_t *>(plane0)[r * words + c] = v0;
+            if (f1) reinterpret_cast<uint32_t *>(plane1)[r * words + c] = v1;
         }
-        reinterpret_cast<uint32_t *>(plane0)[r * words + c] = v0;
-        if (f1) reinterpret_cast<uint32_t *>(plane1)[r * words + c] = v1;
     }
     __syncthreads();
-    // ---- gather: a thread produces 4 neighbouring output pixels of a row, one 32-bit store per plane ---------------
-    const int groups = cw >> 2;
+    // ---- gather: a warp walks output rows, neighbouring lanes take neighbouring output pixels.  (4 pixels per lane
+    // with one 32-bit store was measured first: lanes 4 px apart step through the staged box in multiples of 4 words
+    // along a rotated line, which folds the 32 lanes onto 8 banks -- 60 % of the shared-memory wavefronts conflicted.)
     const int sh_x = k.ox - gx_lo, sh_y = k.oy - gy_lo;
-    for (int i = threadIdx.x; i < ch * groups; i += kCropThreads) {
-        const int y = i / groups, xg = (i - y * groups) << 2;
-        const int x0v = X0[y], y0v = Y0[y];
-        uint32_t o0 = 0u, o1 = 0u;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int X = (x0v + adelta[xg + q]) >> 5, Y = (y0v + bdelta[xg + q]) >> 5;
+    for (int x = lane; x < cw; x += 32) {
+        const int ad = adelta[x], bd = bdelta[x];
+        for (int y = warp; y < ch; y += kWarps) {
+            const int X = (X0[y] + ad) >> 5, Y = (Y0[y] + bd) >> 5;
             const int fx = X & 31, fy = Y & 31;
             const int idx = ((Y >> 5) + sh_y) * pitch + (X >> 5) + sh_x;
+            const size_t o = crop_base + (size_t)y * cw + x;
             {
                 const int top = (int)plane0[idx] * (32 - fx) + (int)plane0[idx + 1] * fx;
                 const int bot = (int)plane0[idx + pitch] * (32 - fx) + (int)plane0[idx + pitch + 1] * fx;
-                o0 |= (uint32_t)((top * (32 - fy) + bot * fy + 512) >> 10) << (8 * q);
+                out0[o] = (uint8_t)((top * (32 - fy) + bot * fy + 512) >> 10);
             }
             if (f1) {
                 const int top = (int)plane1[idx] * (32 - fx) + (int)plane1[idx + 1] * fx;
                 const int bot = (int)plane1[idx + pitch] * (32 - fx) + (int)plane1[idx + pitch + 1] * fx;
-                o1 |= (uint32_t)((top * (32 - fy) + bot * fy + 512) >> 10) << (8 * q);
+                out1[o] = (uint8_t)((top * (32 - fy) + bot * fy + 512) >> 10);
             }
         }
-        reinterpret_cast<uint32_t *>(out0 + crop_base)[i] = o0;
-        if (out1) reinterpret_cast<uint32_t *>(out1 + crop_base)[i] = o1;
     }
 }
 

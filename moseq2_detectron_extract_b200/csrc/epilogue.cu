@@ -155,25 +155,34 @@ masked_sums_kernel(const uint8_t *__restrict__ chunk, const uint8_t *__restrict_
     __shared__ int s_cnt[kSumThreads / 32], s_sum[kSumThreads / 32];
     // value passes if min_h < v < max_h; on integers: v in [lo, hi]
     const int lo = (int)floor(min_h) + 1, hi = (int)ceil(max_h) - 1;
+    const ByteTest t_lo = make_byte_test(lo), t_hi1 = make_byte_test(hi + 1);      // value >= lo, value >= hi + 1
     for (int f = blockIdx.x; f < n; f += gridDim.x) {
         const uint8_t *c = chunk + (size_t)f * plane, *m = mask ? mask + (size_t)f * plane : nullptr;
         int cnt = 0, sum = 0;
         size_t done = 0;
         if (vec_ok) {
             const size_t nvec = plane / 16;
+            // SWAR over 4 pixels per word: value = chunk * mask (mod 256), in range iff lo <= value <= hi, count by popcount,
+            // sum by a 4-way byte dot product.  (ncu on the per-pixel form: ALU pipe 80 % busy, DRAM 54 %.)
             for (size_t i = threadIdx.x; i < nvec; i += kSumThreads) {
                 const uint4 cv = ldg_stream_u4(c + i * 16);
                 const uint4 mv = m ? ldg_stream_u4(m + i * 16) : make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
                 const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t v;
+                    if ((mw[q] & 0xfefefefeu) == 0u) {
+                        v = cw[q] & (mw[q] * 0xffu);                     // mask bytes 0/1 -> 0x00/0xff, no carries
+                    } else {                                              // arbitrary uint8 masks multiply and wrap
+                        v = 0u;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int v = (int)(((cw[q] >> (8 * b)) & 0xff) * ((mw[q] >> (8 * b)) & 0xff)) & 0xff;
-                        const bool in = (v >= lo) && (v <= hi);
-                        cnt += in;
-                        sum += in ? v : 0;
+                        for (int b = 0; b < 4; ++b)
+                            v |= ((((cw[q] >> (8 * b)) & 0xffu) * ((mw[q] >> (8 * b)) & 0xffu)) & 0xffu) << (8 * b);
                     }
+                    const uint32_t in = bytes_ge(v, t_lo) & ~bytes_ge(v, t_hi1);
+                    cnt += __popc(in);
+                    sum = __dp4a(v & ((in >> 7) * 0xffu), 0x01010101u, (unsigned)sum);
+                }
             }
             done = nvec * 16;
         }

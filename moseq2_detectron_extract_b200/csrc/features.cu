@@ -122,30 +122,6 @@ __device__ void moment_epilogue(const long long s[6], double *centroid, double *
     axis[1] = __dmul_rn(two_root2, __dsqrt_rn(__ddiv_rn(__dsub_rn(tr, common), m00)));
 }
 
-// SWAR byte tests on 4 packed pixels, result in bit 7 of every byte, no cross-byte carries:
-//   c >= g  (1 <= g <= 255):  low 7 bits compared by adding (128 - (g & 127)); the top bit decides the rest
-//   m != 0
-struct ByteTest {
-    uint32_t k;        // (0x80 - (g & 0x7f)) replicated
-    uint32_t hi_or;    // g < 128: a set top bit alone passes;  g >= 128: the top bit is required
-    int mode;          // 0: everything passes (g <= 0), 1: g in 1..127, 2: g in 128..255, 3: nothing passes
-};
-__device__ __forceinline__ ByteTest make_byte_test(int ge) {
-    ByteTest t;
-    t.mode = ge <= 0 ? 0 : (ge > 255 ? 3 : (ge < 128 ? 1 : 2));
-    t.k = (uint32_t)(0x80 - (ge & 0x7f)) * 0x01010101u;
-    t.hi_or = 0u;
-    return t;
-}
-__device__ __forceinline__ uint32_t bytes_ge(uint32_t c, const ByteTest &t) {
-    const uint32_t low = ((c & 0x7f7f7f7fu) + t.k);
-    if (t.mode == 1) return (low | c) & 0x80808080u;
-    if (t.mode == 2) return (low & c) & 0x80808080u;
-    return t.mode == 0 ? 0x80808080u : 0u;
-}
-__device__ __forceinline__ uint32_t bytes_nonzero(uint32_t m) {
-    return (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u;
-}
 // bits 7,15,23,31 -> bits 0..3
 __device__ __forceinline__ uint32_t gather_nibble(uint32_t on) {
     return (((on >> 7) * 0x01020408u) >> 24) & 0xfu;
@@ -268,9 +244,9 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                 if (!__any_sync(0xffffffffu, changed) && sweep > 0) break;
                 down = !down;
             }
-            // F = everything not reached (foreground + enclosed holes); becomes the "remaining" set
-            for (int r = r_lo; r <= r_hi; ++r)
-                if (act) Q[r * LPR + lane] = ~Q[r * LPR + lane] & lane_mask_row;
+            // F = everything not reached (foreground + enclosed holes) is the "remaining" set of phase 2.  It is never
+            // materialised: Q keeps meaning "reached by the background flood OR already peeled", and phase 2 reads
+            // ~Q & lane_mask_row (a separate complement pass over the rows was 14 % of the kernel's instructions).
             __syncwarp();
 
             // ---------------- phase 2: peel blobs in raster order ----------------
@@ -279,7 +255,7 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                 // raster-first remaining pixel
                 int r0 = -1; uint32_t seed = 0u;
                 for (int r = scan; r <= r_hi; ++r) {
-                    const uint32_t v = act ? Q[r * LPR + lane] : 0u;
+                    const uint32_t v = act ? (~Q[r * LPR + lane] & lane_mask_row) : 0u;
                     const uint32_t b = __ballot_sync(0xffffffffu, v != 0u);
                     if (b) {
                         const int kw = __ffs(b) - 1;
@@ -295,7 +271,7 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                 // 8-connected flood of the blob inside the remaining set; blob rows are [r0, rmax]
                 int rmax = r0;
                 {
-                    const uint32_t rem0 = act ? Q[r0 * LPR + lane] : 0u;
+                    const uint32_t rem0 = act ? (~Q[r0 * LPR + lane] & lane_mask_row) : 0u;
                     uint32_t prev = fill_row(seed, rem0, lane);
                     if (act) P[r0 * LPR + lane] = prev;
                     bool go_down = true;
@@ -304,7 +280,7 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                         if (go_down) {
                             prev = act ? P[r0 * LPR + lane] : 0u;
                             for (int r = r0 + 1; r <= r_hi; ++r) {
-                                const uint32_t rem = act ? Q[r * LPR + lane] : 0u;
+                                const uint32_t rem = act ? (~Q[r * LPR + lane] & lane_mask_row) : 0u;
                                 const uint32_t old = (act && r <= rmax) ? P[r * LPR + lane] : 0u;
                                 const uint32_t now = fill_row((spread3(prev, lane) | old) & rem, rem, lane);
                                 const bool any_now = __any_sync(0xffffffffu, now != 0u);
@@ -317,7 +293,7 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                         } else {
                             prev = act ? P[rmax * LPR + lane] : 0u;
                             for (int r = rmax - 1; r >= r0; --r) {
-                                const uint32_t rem = act ? Q[r * LPR + lane] : 0u;
+                                const uint32_t rem = act ? (~Q[r * LPR + lane] & lane_mask_row) : 0u;
                                 const uint32_t old = act ? P[r * LPR + lane] : 0u;
                                 const uint32_t now = fill_row((spread3(prev, lane) | old) & rem, rem, lane);
                                 if (act) P[r * LPR + lane] = now;
@@ -385,7 +361,7 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                 }
                 // remove the blob from the remaining set
                 for (int r = r0 + sub; r <= rmax; r += RPW)
-                    if (k < wpr) Q[r * LPR + k] &= ~P[r * LPR + k];
+                    if (k < wpr) Q[r * LPR + k] |= P[r * LPR + k];
                 __syncwarp();
             }
         }
