@@ -225,6 +225,16 @@ MSQ_API int msq_track_angles(const double *A_dev, const double *H_dev, const dou
                      double *mean_dev, double *cov_dev, int S, double *angles_deg_dev, uint8_t *flips_dev,
                      const double *scores_dev, int n, void *stream);
 
+/* ---- f4  get_bground_im (session setup; ref: proc/roi.py:293-307, io/session.py:217-218) --------------
+ * frames_dev (n,H,W) 16-bit (int16 as read by read_frames_raw, or uint16 with is_unsigned != 0): every frame is
+ * median-blurred with a med_scale x med_scale window (3 or 5, replicated border = cv2.medianBlur) into scratch --
+ * the input is NOT modified, unlike the reference -- and out_dev (H,W) float64 receives the per-pixel median over
+ * the n blurred frames (np.median: mean of the two middle values for even n).  Bit-exact.
+ * scratch_dev: msq_bground_scratch_bytes(n,H,W) bytes.  n <= 3200. */
+MSQ_API size_t msq_bground_scratch_bytes(int n, int H, int W);
+MSQ_API int msq_get_bground_im(const void *frames_dev, int n, int H, int W, int med_scale, int is_unsigned,
+                       double *out_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
+
 /* ---- whole-chunk pipeline: everything ProcessFeaturesStep.process does (ref:
  *      pipeline/process_features_step.py:56-60,163-199 with use_tracking=False), device buffers ------- */
 typedef struct msq_chunk_outputs {

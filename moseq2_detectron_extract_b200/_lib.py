@@ -77,6 +77,8 @@ SIGNATURES = {
                                               c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_track_angles': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_void_p, c_int, c_void_p]),
+    'msq_bground_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'msq_get_bground_im': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),

@@ -32,3 +32,27 @@ def apply_roi(frames, roi):
     if box is not None:
         dev = dev[:, int(box[0, 0]):int(box[1, 0]), int(box[0, 1]):int(box[1, 1])]
     return _dev.give_back(dev.contiguous(), frames)
+
+
+def get_bground_im(frames, med_scale: int = 5):
+    """Background image: per-frame `med_scale` x `med_scale` median blur, then the per-pixel median over frames
+    (ref: proc/roi.py:293-307; io/session.py:217-218 passes every 500th frame of the session).
+
+    `frames`: (n, H, W) int16 / uint16, numpy or CUDA tensor.  Returns (H, W) float64, bit-identical to
+    cv2.medianBlur + np.median.  Unlike the reference the input frames are not overwritten with their blurred
+    versions.  16-bit frames allow med_scale 3 or 5 only (the same restriction cv2.medianBlur has)."""
+    from .. import _lib
+    unsigned = isinstance(frames, np.ndarray) and frames.dtype == np.uint16
+    if isinstance(frames, np.ndarray) and frames.dtype not in (np.int16, np.uint16):
+        raise TypeError(f'get_bground_im: frames must be int16 or uint16, got {frames.dtype}')
+    if isinstance(frames, torch.Tensor) and frames.dtype != torch.int16:
+        raise TypeError(f'get_bground_im: tensor frames must be int16, got {frames.dtype}')
+    dev = _dev.as_device(frames, torch.int16)
+    if dev.dim() != 3:
+        raise ValueError(f'get_bground_im: frames must be (nframes, rows, cols), got {tuple(dev.shape)}')
+    n, h, w = (int(v) for v in dev.shape)
+    out = _dev.empty((h, w), torch.float64)
+    scratch = _dev.empty((int(_lib.load().msq_bground_scratch_bytes(n, h, w)) + 16,), torch.uint8)
+    _lib.call('msq_get_bground_im', _dev.ptr(dev), n, h, w, int(med_scale), int(unsigned), _dev.ptr(out), _dev.ptr(scratch),
+              scratch.numel(), _dev.stream())
+    return _dev.give_back(out, frames)

@@ -597,6 +597,23 @@ def paste_masks_np(soft: np.ndarray, boxes: np.ndarray, height: int, width: int,
 # instances_to_features (non-tracking) + ProcessFeaturesStep glue
 #                     ref: proc/proc.py:700-848 and pipeline/process_features_step.py:163-199
 # ------------------------------------------------------------------------------------------
+def bground_im(frames: np.ndarray, med_scale: int = 5) -> np.ndarray:
+    """ref: proc/roi.py:293-307 -- cv2.medianBlur per frame (on a copy: the reference overwrites its input), then
+    np.median over the frame axis."""
+    blurred = np.stack([cv2.medianBlur(np.ascontiguousarray(f), med_scale) for f in frames])
+    return np.median(blurred, axis=0)
+
+
+def bground_im_np(frames: np.ndarray, med_scale: int = 5) -> np.ndarray:
+    """The same without OpenCV: replicate border, middle of the sorted window (pins what medianBlur computes)."""
+    r = med_scale // 2
+    n, h, w = frames.shape
+    p = np.pad(frames, ((0, 0), (r, r), (r, r)), mode='edge')
+    win = np.stack([p[:, i:i + h, j:j + w] for i in range(med_scale) for j in range(med_scale)], axis=0)
+    blurred = np.sort(win, axis=0)[(med_scale * med_scale) // 2]
+    return np.median(blurred, axis=0)
+
+
 def extract_chunk(chunk_u8: np.ndarray, masks: np.ndarray, keypoints: np.ndarray, num_instances: np.ndarray,
                   min_height: float = 0, max_height: float = 100, true_depth: float = 673.0,
                   crop: Tuple[int, int] = (80, 80), use_cv2: bool = True) -> dict:

@@ -399,3 +399,42 @@ def test_full_size_chunk_properties(P):
     assert_close(part['angle_deg'].cpu().numpy(), ref['features']['orientation'], 0, 1e-9, what='angles')
     assert np.array_equal(part['depth_crops'].cpu().numpy(), ref['depth_frames'])
     assert np.array_equal(part['mask_crops'].cpu().numpy(), ref['mask_frames'])
+
+
+# ----------------------------------------------------------------------------- f4 get_bground_im (session setup)
+@pytest.mark.parametrize('n,shape,scale,dtype', [(9, (48, 64), 5, np.int16), (10, (37, 53), 5, np.int16), (4, (16, 24), 3, np.uint16),
+                                                   (1, (20, 20), 5, np.int16), (216, (424, 512), 5, np.int16)])
+def test_bground_im_matches_opencv_and_numpy(P, n, shape, scale, dtype):
+    """ref proc/roi.py:293-307: cv2.medianBlur(frame, med_scale) per frame then np.median over frames -- bit-exact, odd and
+    even frame counts, signed (negative values included) and unsigned 16-bit, the full-size case io/session.py:217 produces."""
+    rng = np.random.default_rng(n * 7 + scale)
+    if n == 216:
+        from moseq2_detectron_extract_b200 import synthetic
+        geom = synthetic.SessionGeometry()
+        base = synthetic.generate_chunk(8, seed=3, geom=geom, t0=0, invalid_rate=0.002).frames
+        frames = base[rng.integers(0, 8, size=n)].astype(dtype)
+        frames = (frames + rng.integers(-2, 3, size=frames.shape)).astype(dtype)
+    elif dtype == np.uint16:
+        frames = rng.integers(0, 65536, size=(n,) + shape).astype(np.uint16)
+    else:
+        frames = rng.integers(-300, 3000, size=(n,) + shape).astype(np.int16)
+        frames[rng.random(frames.shape) < 0.05] = 0
+    keep = frames.copy()
+    got = P.get_bground_im(frames, med_scale=scale)
+    assert got.dtype == np.float64 and got.shape == shape
+    assert np.array_equal(frames, keep)                                  # the input is left alone (the reference blurs in place)
+    assert np.array_equal(got, O.bground_im(keep, scale))
+    dev = P.get_bground_im(torch.from_numpy(keep.view(np.int16)).cuda(), med_scale=scale) if dtype == np.int16 else None
+    if dev is not None:
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), got)
+
+
+def test_bground_im_rejects_unsupported(P):
+    from moseq2_detectron_extract_b200 import _lib
+    frames = np.zeros((3, 8, 8), dtype=np.int16)
+    with pytest.raises(_lib.MoseqB200Error, match='med_scale'):
+        P.get_bground_im(frames, med_scale=7)                            # cv2.medianBlur: 16-bit only for ksize 3 and 5
+    with pytest.raises(TypeError):
+        P.get_bground_im(frames.astype(np.float32))
+    with pytest.raises(ValueError):
+        P.get_bground_im(frames[0])

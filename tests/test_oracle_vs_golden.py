@@ -219,3 +219,16 @@ def test_restated_pykalman_conventions():
     assert np.array_equal(means[0], np.arange(6.0)) and np.array_equal(covs[0], np.eye(6))
     m1, c1 = kf.filter_update(np.arange(6.0), np.eye(6), z[0])
     assert np.allclose(m1, tr.A @ np.arange(6.0)) and np.allclose(c1, tr.A @ tr.A.T + np.eye(6))
+
+
+def test_bground_oracle_twins_agree():
+    """cv2.medianBlur(16-bit, 5) == middle of the replicate-padded sorted window; np.median averages the two middle frames."""
+    rng = np.random.default_rng(4)
+    for n, dtype in ((6, np.int16), (7, np.uint16)):
+        frames = rng.integers(0, 4000, size=(n, 30, 41)).astype(dtype)
+        if dtype == np.int16:
+            frames -= 500
+        for scale in (3, 5):
+            a, b = O.bground_im(frames, scale), O.bground_im_np(frames, scale)
+            assert a.dtype == np.float64 and np.array_equal(a, b)
+    assert (O.bground_im(np.stack([np.full((8, 8), v, np.int16) for v in (1, 2, 4, 9)]), 5) == 3.0).all()
