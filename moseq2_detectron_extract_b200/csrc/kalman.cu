@@ -568,16 +568,24 @@ struct AngleArgs {
     int n, S, order;
 };
 
+// S is a template parameter so that every small matrix lives in registers (with a run-time S the arrays went to local
+// memory: 22 ms per 1000 frames)
+template <int S>
 __global__ void track_angles_kernel(AngleArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int S = a.S, O = kAngO;
-    double A[kAngS][kAngS], Q[kAngS][kAngS], P[kAngS][kAngS], H[kAngO][kAngS], R[kAngO][kAngO], m[kAngS];
+    constexpr int O = kAngO;
+    double A[S][S], Q[S][S], P[S][S], H[O][S], R[O][O], m[S];
+#pragma unroll
     for (int i = 0; i < S; ++i) {
         m[i] = a.mean[i];
+#pragma unroll
         for (int j = 0; j < S; ++j) { A[i][j] = a.A[i * S + j]; Q[i][j] = a.Q[i * S + j]; P[i][j] = a.cov[i * S + j]; }
     }
+#pragma unroll
     for (int i = 0; i < O; ++i) {
+#pragma unroll
         for (int j = 0; j < S; ++j) H[i][j] = a.H[i * S + j];
+#pragma unroll
         for (int j = 0; j < O; ++j) R[i][j] = a.R[i * O + j];
     }
     for (int f = 0; f < a.n; ++f) {
@@ -595,21 +603,28 @@ __global__ void track_angles_kernel(AngleArgs a) {
         }
         a.angles[f] = ang;
         // filter_update: predict, then correct with (sin, cos) unless the angle is not finite
-        double m2[kAngS], T1[kAngS][kAngS];
+        double m2[S], T1[S][S];
+#pragma unroll
         for (int i = 0; i < S; ++i) {
             double acc = 0.0;
+#pragma unroll
             for (int k = 0; k < S; ++k) acc += A[i][k] * m[k];
             m2[i] = acc;
+#pragma unroll
             for (int j = 0; j < S; ++j) {
                 double t = 0.0;
+#pragma unroll
                 for (int k = 0; k < S; ++k) t += A[i][k] * P[k][j];
                 T1[i][j] = t;
             }
         }
+#pragma unroll
         for (int i = 0; i < S; ++i) {
             m[i] = m2[i];
+#pragma unroll
             for (int j = 0; j < S; ++j) {
                 double t = 0.0;
+#pragma unroll
                 for (int k = 0; k < S; ++k) t += T1[i][k] * A[j][k];
                 P[i][j] = t + Q[i][j];
             }
@@ -617,44 +632,63 @@ __global__ void track_angles_kernel(AngleArgs a) {
         const double rad = ang * 0.017453292519943295;
         const double z[2] = {sin(rad), cos(rad)};
         if (finite_f64(z[0]) && finite_f64(z[1])) {
-            double PHt[kAngS][kAngO], Sm[kAngO][kAngO], y[kAngO];
+            double PHt[S][O], Sm[O][O], y[O];
+#pragma unroll
             for (int i = 0; i < S; ++i)
+#pragma unroll
                 for (int o = 0; o < O; ++o) {
                     double t = 0.0;
+#pragma unroll
                     for (int k = 0; k < S; ++k) t += P[i][k] * H[o][k];
                     PHt[i][o] = t;
                 }
+#pragma unroll
             for (int o = 0; o < O; ++o) {
                 double hm = 0.0;
+#pragma unroll
                 for (int k = 0; k < S; ++k) hm += H[o][k] * m[k];
                 y[o] = z[o] - hm;
+#pragma unroll
                 for (int q = 0; q < O; ++q) {
                     double t = 0.0;
+#pragma unroll
                     for (int k = 0; k < S; ++k) t += H[o][k] * PHt[k][q];
                     Sm[o][q] = t + R[o][q];
                 }
             }
             const double det = Sm[0][0] * Sm[1][1] - Sm[0][1] * Sm[1][0];
             const double Si[2][2] = {{Sm[1][1] / det, -Sm[0][1] / det}, {-Sm[1][0] / det, Sm[0][0] / det}};
-            double K[kAngS][kAngO];
+            double K[S][O];
+#pragma unroll
             for (int i = 0; i < S; ++i)
+#pragma unroll
                 for (int o = 0; o < O; ++o) K[i][o] = PHt[i][0] * Si[0][o] + PHt[i][1] * Si[1][o];
+#pragma unroll
             for (int i = 0; i < S; ++i) m[i] += K[i][0] * y[0] + K[i][1] * y[1];
-            double HP[kAngO][kAngS];                                  // H P (see kalman_filter_kernel: not (P H^T)^T)
+            double HP[O][S];                                  // H P (see kalman_filter_kernel: not (P H^T)^T)
+#pragma unroll
             for (int o = 0; o < O; ++o)
+#pragma unroll
                 for (int j = 0; j < S; ++j) {
                     double t = 0.0;
+#pragma unroll
                     for (int k = 0; k < S; ++k) t += H[o][k] * P[k][j];
                     HP[o][j] = t;
                 }
+#pragma unroll
             for (int i = 0; i < S; ++i)
+#pragma unroll
                 for (int j = 0; j < S; ++j) T1[i][j] = P[i][j] - (K[i][0] * HP[0][j] + K[i][1] * HP[1][j]);
+#pragma unroll
             for (int i = 0; i < S; ++i)
+#pragma unroll
                 for (int j = 0; j < S; ++j) P[i][j] = T1[i][j];
         }
     }
+#pragma unroll
     for (int i = 0; i < S; ++i) {
         a.mean[i] = m[i];
+#pragma unroll
         for (int j = 0; j < S; ++j) a.cov[i * S + j] = P[i][j];
     }
 }
@@ -829,7 +863,12 @@ extern "C" int msq_track_angles(const double *A, const double *H, const double *
     MSQ_REQUIRE(A && H && Q && R && mean && cov && angles && flips && scores, MSQ_EINVAL, "msq_track_angles: null pointer");
     AngleArgs aa{A, H, Q, R, mean, cov, angles, flips, scores, n, S, S / 2};
     TimedLaunch timed(K_KALMAN, (cudaStream_t)stream);
-    track_angles_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(aa);
+    switch (S) {
+        case 2: track_angles_kernel<2><<<1, 32, 0, (cudaStream_t)stream>>>(aa); break;
+        case 4: track_angles_kernel<4><<<1, 32, 0, (cudaStream_t)stream>>>(aa); break;
+        case 6: track_angles_kernel<6><<<1, 32, 0, (cudaStream_t)stream>>>(aa); break;
+        default: track_angles_kernel<8><<<1, 32, 0, (cudaStream_t)stream>>>(aa); break;
+    }
     MSQ_LAUNCH_OK("track_angles");
     return MSQ_OK;
 }
