@@ -238,3 +238,39 @@ def test_tracking_step_matches_reference():
         diff = np.abs(out['depth_frames'].astype(int) - g[f'c{c}/depth_frames'].astype(int))
         assert diff.max() <= 1 and np.count_nonzero(diff) <= 1e-3 * diff.size, (diff.max(), np.count_nonzero(diff))
         start += n
+
+
+def test_tracking_edge_chunks_match_oracle():
+    """Chunk shapes the reference handles specially: a single-frame chunk (smooth_update -> filter_update, proc/kalman.py:392-395),
+    a chunk in which every frame lacks an instance (prediction only; the tracked angle replaces the NaN one), then normal
+    frames again -- trackers carry their state across all of them.  Checked against oracle/tracking_oracle.py."""
+    import extract_oracle as O
+    import moseq2_detectron_extract_b200.proc as P
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.proc.kalman import (KalmanTracker, KalmanTrackerAngle, KalmanTrackerNPoints2D,
+                                                           KalmanTrackerPoint2D)
+    geom = synthetic.SessionGeometry.kinect_v2()
+    chunk = synthetic.generate_chunk(n_frames=111, seed=21, geom=geom, t0=5)
+    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+    prep = O.prep_frames(chunk.frames, bg, roi, 0, 100)
+    masks, kpts, present = chunk.masks.copy(), chunk.keypoints.copy(), (chunk.num_instances > 0).copy()
+    gone = slice(81, 91)
+    masks[gone] = 0
+    kpts[gone] = np.nan
+    present[gone] = False
+    pt = KalmanTracker([KalmanTrackerPoint2D(order=3, delta_t=1.0), KalmanTrackerNPoints2D(8, order=3, delta_t=1.0)])
+    at = KalmanTracker([KalmanTrackerAngle(order=3, delta_t=1.0, degrees=True)])
+    pt_ref, at_ref = TO.Tracker(18), TO.Tracker(2)
+    for sl in (slice(0, 80), slice(80, 81), gone, slice(91, 111)):
+        outs = [{'instances': make_golden.FakeInstances(masks[i], kpts[i], bool(present[i]))} for i in range(sl.start, sl.stop)]
+        feats = P.instances_to_features(outs, prep[sl], pt, at, debug=False)
+        f = O.frame_features_cv2(O.clean_frames_cv2(prep[sl]), masks[sl])
+        cen, kp, ang, fl = TO.track_chunk(f['centroid'], f['orientation'], f['axis_length'], kpts[sl], pt_ref, at_ref)
+        what = f'frames {sl.start}..{sl.stop}'
+        assert_close(feats['features']['centroid'], cen, 0, 1e-6, what=what + ' centroid')
+        assert_close(feats['keypoints'], kp, 0, 1e-6, what=what + ' keypoints')
+        assert_close(feats['features']['orientation'], ang, 0, 1e-5, what=what + ' angle')
+        assert np.array_equal(feats['flips'], fl), what
+        if sl == gone:
+            assert np.isfinite(feats['features']['centroid']).all() and np.isfinite(feats['features']['orientation']).all()
+            assert np.isnan(feats['keypoints'][:, 7, :2]).all()           # the tail tip keeps its raw (missing) position
