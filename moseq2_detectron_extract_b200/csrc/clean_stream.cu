@@ -5,11 +5,14 @@
 // an 8-pixel halo lane on either side) and walks down its rows.  Per input row, in registers:
 //   raw row  --3x3 median-->  M[m]  --row min 7/9-->  H7[m], H9[m]
 //   V7[m-1] = min(H7[m-1], H7[m])            T3[m-1] = min(H9[m-2], H9[m-1], H9[m])
-//   E[e]  = min(M[e-4], M[e+4], V7[e-3], V7[e+2], T3[e])        e = m-4     (the 9x9 ellipse is rows of width 1,7,7,9,9,9,7,7,1)
+//   A[a]  = min(M[a-4], V7[a-3], T3[a])                          a = m-1     (the upper rows of the ellipse, as soon as T3 exists)
+//   E[e]  = min(A[e], V7[e+2], M[e+4])                           e = m-4     (the 9x9 ellipse is rows of width 1,7,7,9,9,9,7,7,1)
 //   ... and the same chain with max on E for the dilation, d = e-4.
 // Horizontal neighbours come from warp shuffles (lane +-1); vertical history is a set of per-lane delay lines in
 // shared memory (each lane only ever touches its own 16-byte slots, so there is no synchronisation at all), and the
-// pair/triple pre-combination (V7, T3) means every delay line is written once and read at most twice per row.
+// pair/triple pre-combination (V7, T3, A) means every delay line is written once and read once per row; 12 rows of delay
+// per pass (6 + 3 + 3; an earlier version delayed M by 8, V7 by 6 and T3 by 3 = 17 rows) keep 12 KB per warp, so that
+// shared memory allows 16 warps per SM, and with 6-row trips every slot index is a literal.
 // ncu on the tiled kernel showed 52 M shared-memory wavefronts / 1000 frames (LSU pipe 68 % busy) next to a 53 %
 // busy ALU pipe; this formulation needs ~3x fewer wavefronts, no block barriers and no second pass over the raw tile.
 #include "common.cuh"
@@ -21,9 +24,9 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kOutCols = 240;              // output columns per warp-row (lanes 1..30)
-constexpr int kDelay = 8;                  // rows in the M delay line   (M[m-8] is read, then M[m] overwrites it)
-constexpr int kDelayV = 6;                 // rows in the V7 delay line  (V7[m-7] is read, then V7[m-1] overwrites it)
-constexpr int kDelayT = 3;                 // rows in the T3 delay line  (T3[m-4] is read, then T3[m-1] overwrites it)
+constexpr int kDelayM = 6;                 // rows in the M delay line   (M[m-5] is read from the slot after the one M[m] is written to)
+constexpr int kDelayV = 3;                 // rows in the V7 delay line  (V7[m-4] is read, then V7[m-1] overwrites it)
+constexpr int kDelayA = 3;                 // rows in the A delay line   (A[m-4] is read, then A[m-1] overwrites it)
 constexpr int kPrefetch = 3;               // raw rows requested ahead of use (divides kUnroll: the queue rotates by renaming)
 constexpr int kUnroll = 6;                 // lcm of the delay-line / history periods (6, 3, 2): no register moves, static slots
 constexpr int kWarpsPerCta = 1;
@@ -88,24 +91,30 @@ template <class OP> __device__ __forceinline__ uint4 op3_4(const uint4 &a, const
 }
 
 struct StreamGeom {
-    int h, w, tiles_x, strips, strip_rows;
+    int h, w, tiles_x, rows_per_cta;
     uint32_t one, neg1;        // 1 and -1, opaque to the compiler (see med3_of_sorted)
 };
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 16)
 clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, StreamGeom G) {
     // per-lane delay lines: [row slot][lane] uint4
-    __shared__ uint4 ring_m[kDelay][32], ring_v[kDelayV][32], ring_t[kDelayT][32];
-    __shared__ uint4 ring_e[kDelay][32], ring_w[kDelayV][32], ring_u[kDelayT][32];
+    __shared__ uint4 ring_m[kDelayM][32], ring_v[kDelayV][32], ring_a[kDelayA][32];
+    __shared__ uint4 ring_e[kDelayM][32], ring_w[kDelayV][32], ring_b[kDelayA][32];
     const int lane = threadIdx.x & 31;
     const int h = G.h, w = G.w;
-    const long long tasks = (long long)n * G.tiles_x * G.strips;
+    // Work is cut by ROWS, not by frames: the launch is one tall stack of n * tiles_x columns of h rows each, and CTA c owns
+    // rows [c * rows_per_cta, (c + 1) * rows_per_cta) of it, processed as one strip per column it touches (each strip pays
+    // its 20-row lead-in).  Every CTA gets the same number of rows, so there is no tail: with whole-frame / half-frame
+    // tasks dealt round-robin the slowest CTA did 6 tasks where the average was 5.07 (16 % of the kernel's time).
+    const long long total_rows = (long long)n * G.tiles_x * h;
+    long long g0 = (long long)blockIdx.x * G.rows_per_cta;
+    const long long g1 = min(total_rows, g0 + G.rows_per_cta);
 
-    for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
-        const int f = (int)(task / (G.tiles_x * G.strips));
-        const int rem = (int)(task - (long long)f * G.tiles_x * G.strips);
-        const int tx = rem / G.strips, sy = rem - tx * G.strips;
-        const int y_out0 = sy * G.strip_rows, y_out1 = min(h, y_out0 + G.strip_rows);
+    while (g0 < g1) {
+        const long long col = g0 / h;                                  // (frame, tile) column of the stack
+        const int f = (int)(col / G.tiles_x), tx = (int)(col - (long long)f * G.tiles_x);
+        const int y_out0 = (int)(g0 - col * h), y_out1 = (int)min((long long)h, y_out0 + (g1 - g0));
+        g0 += y_out1 - y_out0;
         const int x_lane = tx * kOutCols - 8 + (lane << 3);            // image column of this lane's first pixel
         const bool col_in = (unsigned)x_lane < (unsigned)w;            // groups are 8-aligned: all in or all out
         const bool writes = lane >= 1 && lane <= 30 && col_in;
@@ -161,7 +170,7 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const int s = s0 + u;
-                const int slot6 = u % kDelayV, slot3 = u % kDelayT;
+                const int slot_w = u % kDelayM, slot_r = (u + 1) % kDelayM, slot3 = u % kDelayV;
                 // ================= stage 3: dilation row d = e-4 from E_cur = E[e], e = s-7 =================
                 {
                     const int e = s - 7;
@@ -169,13 +178,14 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
                     row_extrema<MaxOp>(E_cur, g7, g9);
                     const uint4 w7 = op2_4<MaxOp>(g7_prev, g7);                 // W7[e-1]
                     const uint4 u3 = op3_4<MaxOp>(g9_prev2, g9_prev, g9);       // U3[e-1]
-                    const uint4 e_old = ring_e[e & (kDelay - 1)][lane];         // E[e-8]: read before the slot is overwritten
-                    ring_e[e & (kDelay - 1)][lane] = E_cur;
-                    const uint4 w_old = ring_w[slot6][lane];                    // W7[e-7], then W7[e-1] takes its slot
-                    ring_w[slot6][lane] = w7;
-                    const uint4 u_old = ring_u[slot3][lane];                    // U3[e-4], then U3[e-1] takes its slot
-                    ring_u[slot3][lane] = u3;
-                    const uint4 D = op3_4<MaxOp>(op3_4<MaxOp>(e_old, E_cur, w_old), w7_prev, u_old);    // w7_prev = W7[e-2]
+                    const uint4 e_old = ring_e[slot_r][lane];                   // E[e-5]
+                    ring_e[slot_w][lane] = E_cur;
+                    const uint4 w_old = ring_w[slot3][lane];                    // W7[e-4], then W7[e-1] takes its slot
+                    ring_w[slot3][lane] = w7;
+                    const uint4 b_new = op3_4<MaxOp>(e_old, w_old, u3);         // B[e-1] = max(E[e-5], W7[e-4], U3[e-1])
+                    const uint4 b_old = ring_b[slot3][lane];                    // B[e-4], then B[e-1] takes its slot
+                    ring_b[slot3][lane] = b_new;
+                    const uint4 D = op3_4<MaxOp>(b_old, w7_prev, E_cur);        // D[e-4] = max(B[e-4], W7[e-2], E[e])
                     g7_prev = g7; g9_prev2 = g9_prev; g9_prev = g9; w7_prev = w7;
                     const int yd = y_first + e - 4;
                     if (writes && yd >= y_out0 && yd < y_out1) {
@@ -191,13 +201,14 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
                     row_extrema<MinOp>(M_cur, h7, h9);
                     const uint4 v7 = op2_4<MinOp>(h7_prev, h7);                 // V7[m-1]
                     const uint4 t3 = op3_4<MinOp>(h9_prev2, h9_prev, h9);       // T3[m-1]
-                    const uint4 m_old = ring_m[m & (kDelay - 1)][lane];         // M[m-8]
-                    ring_m[m & (kDelay - 1)][lane] = M_cur;
-                    const uint4 v_old = ring_v[slot6][lane];                    // V7[m-7], then V7[m-1] takes its slot
-                    ring_v[slot6][lane] = v7;
-                    const uint4 t_old = ring_t[slot3][lane];                    // T3[m-4], then T3[m-1] takes its slot
-                    ring_t[slot3][lane] = t3;
-                    E_next = op3_4<MinOp>(op3_4<MinOp>(m_old, M_cur, v_old), v7_prev, t_old);      // v7_prev = V7[m-2]
+                    const uint4 m_old = ring_m[slot_r][lane];                   // M[m-5]
+                    ring_m[slot_w][lane] = M_cur;
+                    const uint4 v_old = ring_v[slot3][lane];                    // V7[m-4], then V7[m-1] takes its slot
+                    ring_v[slot3][lane] = v7;
+                    const uint4 a_new = op3_4<MinOp>(m_old, v_old, t3);         // A[m-1] = min(M[m-5], V7[m-4], T3[m-1])
+                    const uint4 a_old = ring_a[slot3][lane];                    // A[m-4], then A[m-1] takes its slot
+                    ring_a[slot3][lane] = a_new;
+                    E_next = op3_4<MinOp>(a_old, v7_prev, M_cur);               // E[m-4] = min(A[m-4], V7[m-2], M[m])
                     h7_prev = h7; h9_prev2 = h9_prev; h9_prev = h9; v7_prev = v7;
                     const int ye = y_first + m - 4;
                     if (!(col_in && (unsigned)ye < (unsigned)h)) E_next = splat(0u);               // dilation identity outside the image
@@ -249,21 +260,19 @@ int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cu
     StreamGeom G;
     G.h = h; G.w = w; G.one = 1u; G.neg1 = 0xffffffffu;
     G.tiles_x = (w + kOutCols - 1) / kOutCols;
-    // strips: enough warp tasks for ~3 waves of 11 warps/SM, but at least ~40 rows per strip (18 rows of halo each)
     static thread_local int resident = 0;          // co-resident CTAs per SM (shared-memory limited, ~10)
     if (resident == 0) {
         int r = 0;
         MSQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, clean_stream_kernel, 32 * kWarpsPerCta, 0));
         resident = std::max(1, r);
     }
-    const long long want = (long long)sm_count() * resident * 3;
-    int strips = (int)std::min<long long>(std::max<long long>(1, (want + (long long)n * G.tiles_x - 1) / ((long long)n * G.tiles_x)),
-                                          std::max(1, h / 40));
-    if (const char *e = getenv("MSQ_CLEAN_STRIPS")) { int v = atoi(e); if (v >= 1 && v <= h) strips = v; }
-    G.strip_rows = (h + strips - 1) / strips;
-    G.strips = (h + G.strip_rows - 1) / G.strip_rows;
-    const long long tasks = (long long)n * G.tiles_x * G.strips;
-    const int grid = (int)std::min<long long>(tasks, (long long)sm_count() * resident);   // persistent: every CTA is resident
+    // persistent grid: every CTA is resident and gets the same number of rows; at least ~120 rows each so that the
+    // 20-row lead-in of a strip stays a small part of it
+    const long long total_rows = (long long)n * G.tiles_x * h;
+    long long ctas = std::min<long long>((long long)sm_count() * resident, std::max<long long>(1, total_rows / 120));
+    if (const char *e = getenv("MSQ_CLEAN_CTAS")) { long long v = atoll(e); if (v >= 1) ctas = v; }
+    G.rows_per_cta = (int)((total_rows + ctas - 1) / ctas);
+    const int grid = (int)((total_rows + G.rows_per_cta - 1) / G.rows_per_cta);
     TimedLaunch timed(K_CLEAN, st);
     clean_stream_kernel<<<grid, 32 * kWarpsPerCta, 0, st>>>(in, out, n, G);
     MSQ_LAUNCH_OK("clean_frames (streaming)");
