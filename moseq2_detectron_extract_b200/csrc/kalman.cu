@@ -24,97 +24,139 @@
 namespace msq {
 namespace {
 
-constexpr int kKalThreads = 256;
+constexpr int kKalThreads = 512;      // one CTA is alone on its SM in the sequential kernels: more warps hide the latencies
 constexpr int kMaxS = 64, kMaxO = 32;
 
 __device__ __forceinline__ bool finite_f64(double v) { return fabs(v) <= 1.79769313486231570e308; }   // false for NaN/Inf
 
-// ---- per-row non-zero lists of a small dense matrix (rows x cols, row-major) ---------------------------------------
+// ---- per-row non-zero lists of a small dense matrix (rows x cols, row-major), ELL layout: every row holds `width`
+// (= the largest non-zero count of any row) entries, short rows padded with (col 0, val 0.0) -------------------------
 struct SparseRows {
-    int *nnz;        // [rows]
-    int *col;        // [rows * cols]
-    double *val;     // [rows * cols]
+    int *width;      // [1]
+    int *col;        // [rows * cols] capacity, rows * width used
+    double *val;     // [rows * cols] capacity
     int cols;
 };
 __device__ void build_sparse(const double *__restrict__ M, int rows, int cols, SparseRows sp) {
+    if (threadIdx.x == 0) *sp.width = 1;
+    __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        int c = 0;
+        for (int k = 0; k < cols; ++k) c += M[r * cols + k] != 0.0;
+        atomicMax(sp.width, c);
+    }
+    __syncthreads();
+    const int wd = *sp.width;
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         int c = 0;
         for (int k = 0; k < cols; ++k) {
             const double v = M[r * cols + k];
-            if (v != 0.0) { sp.col[r * cols + c] = k; sp.val[r * cols + c] = v; ++c; }
+            if (v != 0.0) { sp.col[r * wd + c] = k; sp.val[r * wd + c] = v; ++c; }
         }
-        sp.nnz[r] = c;
+        for (; c < wd; ++c) { sp.col[r * wd + c] = 0; sp.val[r * wd + c] = 0.0; }
     }
+    __syncthreads();
 }
 __host__ __device__ constexpr size_t up16(size_t v) { return (v + 15) / 16 * 16; }
 __device__ SparseRows carve_sparse(unsigned char *&p, int rows, int cols) {
     SparseRows sp;
     sp.val = reinterpret_cast<double *>(p); p += (size_t)rows * cols * sizeof(double);
     sp.col = reinterpret_cast<int *>(p); p += up16((size_t)rows * cols * sizeof(int));
-    sp.nnz = reinterpret_cast<int *>(p); p += up16((size_t)rows * sizeof(int));
+    sp.width = reinterpret_cast<int *>(p); p += up16((size_t)rows * sizeof(int));
     sp.cols = cols;
     return sp;
 }
 
+// Loop over the elements e = threadIdx.x, +blockDim.x, ... of an (n_rows x n_cols) matrix with (i, j) kept incrementally
+// (ncu on the first version of these kernels: a quarter of all instructions were the e / n_cols divisions).
+#define MSQ_FOR_ELEMENTS(e, i, j, n_rows, n_cols)                                                              \
+    for (int e = threadIdx.x, i = e / (n_cols), j = e - i * (n_cols), _di = (int)blockDim.x / (n_cols),           \
+             _dj = (int)blockDim.x - _di * (n_cols);                                                              \
+         e < (n_rows) * (n_cols); e += blockDim.x, i += _di, j += _dj, i += (j >= (n_cols)), j -= (j >= (n_cols)) ? (n_cols) : 0)
+
 // C[n x m] = Asp[n x k] * B[k x m]   (B, C dense in shared memory, ld = m)
-__device__ void spmm_left(double *C, const SparseRows A, const double *B, int n, int m) {
-    for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
-        const int i = e / m, j = e - i * m;
+template <int W>
+__device__ __forceinline__ void spmm_left_w(double *__restrict__ C, const SparseRows A, const double *__restrict__ B, int n, int m,
+                                            const double *__restrict__ add) {
+    const int wd = W > 0 ? W : *A.width;
+    MSQ_FOR_ELEMENTS(e, i, j, n, m) {
         double acc = 0.0;
-        const int c = A.nnz[i];
-        for (int q = 0; q < c; ++q) acc += A.val[i * A.cols + q] * B[A.col[i * A.cols + q] * m + j];
-        C[e] = acc;
+#pragma unroll
+        for (int q = 0; q < wd; ++q) acc = fma(A.val[i * wd + q], B[A.col[i * wd + q] * m + j], acc);
+        C[e] = add ? acc + add[e] : acc;
+    }
+}
+__device__ void spmm_left(double *C, const SparseRows A, const double *B, int n, int m, const double *add = nullptr) {
+    switch (*A.width) {
+        case 1: spmm_left_w<1>(C, A, B, n, m, add); break;
+        case 2: spmm_left_w<2>(C, A, B, n, m, add); break;
+        case 3: spmm_left_w<3>(C, A, B, n, m, add); break;
+        case 4: spmm_left_w<4>(C, A, B, n, m, add); break;
+        default: spmm_left_w<0>(C, A, B, n, m, add); break;
     }
 }
 // C[n x r] = B[n x k] * Asp^T  (Asp is r x k)  + (add ? add[n x r] : 0)
-__device__ void spmm_right_t(double *C, const double *B, const SparseRows A, int n, int r, const double *add) {
+template <int W>
+__device__ __forceinline__ void spmm_right_t_w(double *__restrict__ C, const double *__restrict__ B, const SparseRows A, int n, int r,
+                                               const double *__restrict__ add) {
     const int k = A.cols;
-    for (int e = threadIdx.x; e < n * r; e += blockDim.x) {
-        const int i = e / r, j = e - i * r;
+    const int wd = W > 0 ? W : *A.width;
+    MSQ_FOR_ELEMENTS(e, i, j, n, r) {
         double acc = 0.0;
-        const int c = A.nnz[j];
-        for (int q = 0; q < c; ++q) acc += B[i * k + A.col[j * k + q]] * A.val[j * k + q];
+#pragma unroll
+        for (int q = 0; q < wd; ++q) acc = fma(B[i * k + A.col[j * wd + q]], A.val[j * wd + q], acc);
         C[e] = add ? acc + add[e] : acc;
+    }
+}
+__device__ void spmm_right_t(double *C, const double *B, const SparseRows A, int n, int r, const double *add) {
+    switch (*A.width) {
+        case 1: spmm_right_t_w<1>(C, B, A, n, r, add); break;
+        case 2: spmm_right_t_w<2>(C, B, A, n, r, add); break;
+        case 3: spmm_right_t_w<3>(C, B, A, n, r, add); break;
+        case 4: spmm_right_t_w<4>(C, B, A, n, r, add); break;
+        default: spmm_right_t_w<0>(C, B, A, n, r, add); break;
     }
 }
 // y[n] = Asp x
 __device__ void spmv(double *y, const SparseRows A, const double *x, int n) {
+    const int wd = *A.width;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double acc = 0.0;
-        const int c = A.nnz[i];
-        for (int q = 0; q < c; ++q) acc += A.val[i * A.cols + q] * x[A.col[i * A.cols + q]];
+        for (int q = 0; q < wd; ++q) acc = fma(A.val[i * wd + q], x[A.col[i * wd + q]], acc);
         y[i] = acc;
     }
 }
 
-// Dense C[n x m] (op)= A[n x k] * B   with B given as [k x m] (transB = false) or [m x k] (transB = true); 3x4 register
-// tiles so that a step of the k loop costs 7 shared-memory loads for 12 FMAs.  op: 0 store, +1 add to C, -1 subtract from C.
+// Dense C[n x m] (op)= A[n x k] * B   with B given as [k x m] (transB = false) or [m x k] (transB = true); 2x3 register
+// tiles (486 tiles for 54 x 54: every thread of the CTA has one).  op: 0 store, +1 add to C, -1 subtract from C.
+// fma() explicitly: the library is built with --fmad=false for the bit-exact float64 epilogues elsewhere.
 __device__ void mm_dense(double *C, const double *A, const double *B, int n, int k, int m, bool transB, int op) {
-    const int ti_n = (n + 2) / 3, tj_n = (m + 3) / 4;
+    constexpr int TI = 2, TJ = 3;
+    const int ti_n = (n + TI - 1) / TI, tj_n = (m + TJ - 1) / TJ;
     for (int tile = threadIdx.x; tile < ti_n * tj_n; tile += blockDim.x) {
         const int ti = tile / tj_n, tj = tile - ti * tj_n;
-        const int i0 = ti * 3, j0 = tj * 4;
-        double acc[3][4] = {};
-        int ia[3], jb[4];
+        const int i0 = ti * TI, j0 = tj * TJ;
+        double acc[TI][TJ] = {};
+        int ia[TI], jb[TJ];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) ia[a] = min(i0 + a, n - 1);
+        for (int a = 0; a < TI; ++a) ia[a] = min(i0 + a, n - 1) * k;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) jb[b] = min(j0 + b, m - 1);
+        for (int b = 0; b < TJ; ++b) jb[b] = transB ? min(j0 + b, m - 1) * k : min(j0 + b, m - 1);
         for (int kk = 0; kk < k; ++kk) {
-            double av[3], bv[4];
+            double av[TI], bv[TJ];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) av[a] = A[ia[a] * k + kk];
+            for (int a = 0; a < TI; ++a) av[a] = A[ia[a] + kk];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bv[b] = transB ? B[jb[b] * k + kk] : B[kk * m + jb[b]];
+            for (int b = 0; b < TJ; ++b) bv[b] = transB ? B[jb[b] + kk] : B[kk * m + jb[b]];
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+            for (int a = 0; a < TI; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+                for (int b = 0; b < TJ; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
         }
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < TI; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < TJ; ++b)
                 if (i0 + a < n && j0 + b < m) {
                     double *c = C + (i0 + a) * m + j0 + b;
                     *c = op == 0 ? acc[a][b] : (op > 0 ? *c + acc[a][b] : *c - acc[a][b]);
@@ -122,27 +164,60 @@ __device__ void mm_dense(double *C, const double *A, const double *B, int n, int
     }
 }
 
-// In-place Gauss-Jordan inverse of the symmetric positive-definite n x n matrix in the left half of aug[n x 2n]
-// (right half must hold I); on return the right half holds the inverse.  colk/rowk: n and 2n doubles of scratch.
-__device__ void gauss_jordan(double *aug, int n, double *colk, double *rowk) {
-    const int w = 2 * n;
+// In-place Gauss-Jordan inverse of the symmetric positive-definite n x n matrix M (no pivoting).  Step k divides row k by
+// the pivot (its own column becoming 1 / pivot) and eliminates column k from every other row (leaving -f / pivot there):
+// the columns of the inverse grow in the place of the eliminated ones.  colk / rowk: n doubles of scratch each.
+__device__ void gauss_jordan_inplace(double *M, int n, double *colk, double *rowk) {
+    // (i, j) of this thread's first element and the step to its next one, computed once for all n elimination steps
+    const int i0 = threadIdx.x / n, j0 = threadIdx.x - i0 * n, di = (int)blockDim.x / n, dj = (int)blockDim.x - di * n;
     for (int k = 0; k < n; ++k) {
-        const double pivot = aug[k * w + k];
-        for (int j = threadIdx.x; j < w; j += blockDim.x) rowk[j] = aug[k * w + j] / pivot;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) colk[i] = aug[i * w + k];
+        const double pivot = M[k * n + k];
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            rowk[j] = (j == k ? 1.0 : M[k * n + j]) / pivot;
+            colk[j] = (j == k) ? 0.0 : M[j * n + k];
+        }
         __syncthreads();
-        for (int e = threadIdx.x; e < n * w; e += blockDim.x) {
-            const int i = e / w, j = e - i * w;
-            aug[e] = (i == k) ? rowk[j] : aug[e] - colk[i] * rowk[j];
+        for (int e = threadIdx.x, i = i0, j = j0; e < n * n; e += blockDim.x) {
+            M[e] = (i == k) ? rowk[j] : fma(-colk[i], rowk[j], j == k ? 0.0 : M[e]);
+            i += di; j += dj;
+            if (j >= n) { j -= n; ++i; }
         }
         __syncthreads();
     }
 }
-__device__ void load_aug(double *aug, const double *M, int n) {       // [M | I]
-    const int w = 2 * n;
-    for (int e = threadIdx.x; e < n * w; e += blockDim.x) {
-        const int i = e / w, j = e - i * w;
-        aug[e] = j < n ? M[i * n + j] : (j - n == i ? 1.0 : 0.0);
+
+// The same elimination for small fixed sizes inside ONE warp: lane r keeps row r in registers, the scaled pivot row is
+// broadcast by shuffles -- no shared-memory traffic and no block barriers (the block version above needs 2 n of them, which
+// was two thirds of a filter step for the 18 x 18 innovation covariance).  All 32 lanes of the calling warp must take part.
+template <int N>
+__device__ void gauss_jordan_warp(double *M) {
+    const int lane = threadIdx.x & 31;
+    double row[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) row[j] = lane < N ? M[lane * N + j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double inv = 1.0 / __shfl_sync(0xffffffffu, row[k], k);
+        const double f = (lane == k) ? 0.0 : row[k];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double rkj = __shfl_sync(0xffffffffu, (j == k ? 1.0 : row[j]) * inv, k);     // scaled pivot row
+            row[j] = (lane == k) ? rkj : fma(-f, rkj, j == k ? 0.0 : row[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        if (lane < N) M[lane * N + j] = row[j];
+}
+// inverse of the O x O innovation covariance: warp version for the sizes the reference's trackers have, block version otherwise
+__device__ void invert_innovation(double *Sm, int O, double *colk, double *rowk) {
+    if (O == 18 || O == 2) {
+        if (threadIdx.x < 32) {
+            if (O == 18) gauss_jordan_warp<18>(Sm); else gauss_jordan_warp<2>(Sm);
+        }
+        __syncthreads();
+    } else {
+        gauss_jordan_inplace(Sm, O, colk, rowk);
     }
 }
 
@@ -166,7 +241,7 @@ kalman_filter_kernel(FilterArgs a) {
     double *Q = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
     double *PHt = reinterpret_cast<double *>(p); p += (size_t)S * O * 8;
     double *K = reinterpret_cast<double *>(p); p += (size_t)S * O * 8;
-    double *aug = reinterpret_cast<double *>(p); p += (size_t)O * 2 * O * 8;
+    double *Sm = reinterpret_cast<double *>(p); p += (size_t)O * 2 * O * 8;
     double *R = reinterpret_cast<double *>(p); p += (size_t)O * O * 8;
     double *m = reinterpret_cast<double *>(p); p += (size_t)S * 8;
     double *m2 = reinterpret_cast<double *>(p); p += (size_t)S * 8;
@@ -183,59 +258,43 @@ kalman_filter_kernel(FilterArgs a) {
     for (int e = threadIdx.x; e < S; e += blockDim.x) m[e] = a.m0[e];
     __syncthreads();
 
+    // thread e < O keeps component e of the observation in a register; the next step's value is requested right after the
+    // vote so that its global-memory latency is off the critical path of the (sequential) step
+    double z_cur = (threadIdx.x < O) ? a.obs[threadIdx.x] : 0.0;
     for (int t = 0; t < T; ++t) {
+        // pykalman: any masked component -> the whole observation is skipped
+        const int ok = finite_f64(z_cur) ? 1 : 0;
+        const double z_now = z_cur;
         if (t > 0 || a.predict_first) {
             spmv(m2, As, m, S);
             spmm_left(tmp, As, P, S, S);                 // A P
             __syncthreads();
             spmm_right_t(P, tmp, As, S, S, Q);           // (A P) A^T + Q
             for (int e = threadIdx.x; e < S; e += blockDim.x) m[e] = m2[e];
-            __syncthreads();
         }
+        const int valid = __syncthreads_and(ok);         // also the barrier that publishes the predicted state
+        if (threadIdx.x < O && t + 1 < T) z_cur = a.obs[(size_t)(t + 1) * O + threadIdx.x];
         for (int e = threadIdx.x; e < S * S; e += blockDim.x) a.Pp[(size_t)t * S * S + e] = P[e];
         for (int e = threadIdx.x; e < S; e += blockDim.x) a.mp[(size_t)t * S + e] = m[e];
-        // pykalman: any masked component -> the whole observation is skipped
-        const double *z = a.obs + (size_t)t * O;
-        int ok = 1;
-        for (int e = threadIdx.x; e < O; e += blockDim.x) ok &= finite_f64(z[e]) ? 1 : 0;
-        const int valid = __syncthreads_and(ok);
         if (threadIdx.x == 0) a.valid[t] = (unsigned char)valid;
         if (valid) {
             spmm_right_t(PHt, P, Hs, S, O, nullptr);     // P H^T
+            spmm_left(tmp, Hs, P, O, S);                 // H P   (O x S, in the scratch matrix)
             spmv(m2, Hs, m, O);                           // H m
             __syncthreads();
-            for (int e = threadIdx.x; e < O; e += blockDim.x) y[e] = z[e] - m2[e];
-            // [H P H^T + R | I]
-            for (int e = threadIdx.x; e < O * 2 * O; e += blockDim.x) {
-                const int i = e / (2 * O), j = e - i * 2 * O;
-                if (j < O) {
-                    double acc = 0.0;
-                    const int c = Hs.nnz[i];
-                    for (int q = 0; q < c; ++q) acc += Hs.val[i * S + q] * PHt[Hs.col[i * S + q] * O + j];
-                    aug[e] = acc + R[i * O + j];
-                } else {
-                    aug[e] = (j - O == i) ? 1.0 : 0.0;
-                }
-            }
+            if (threadIdx.x < O) y[threadIdx.x] = z_now - m2[threadIdx.x];
+            spmm_left(Sm, Hs, PHt, O, O, R);             // H P H^T + R
             __syncthreads();
-            gauss_jordan(aug, O, colk, rowk);
-            // K = P H^T S^-1
-            for (int e = threadIdx.x; e < S * O; e += blockDim.x) {
-                const int i = e / O, j = e - i * O;
-                double acc = 0.0;
-                for (int q = 0; q < O; ++q) acc += PHt[i * O + q] * aug[q * 2 * O + O + j];
-                K[e] = acc;
-            }
+            invert_innovation(Sm, O, colk, rowk);
+            mm_dense(K, PHt, Sm, S, O, O, false, 0);     // K = P H^T S^-1
             __syncthreads();
             for (int i = threadIdx.x; i < S; i += blockDim.x) {
                 double acc = 0.0;
-                for (int q = 0; q < O; ++q) acc += K[i * O + q] * y[q];
+                for (int q = 0; q < O; ++q) acc = fma(K[i * O + q], y[q], acc);
                 m[i] += acc;
             }
             // P -= K (H P).  NOT K (P H^T)^T: rounding leaves P slightly asymmetric, and with the transposed form the
             // antisymmetric part is multiplied by (I + K H) every step instead of (I - K H) -- it grows until overflow.
-            spmm_left(tmp, Hs, P, O, S);                 // H P   (O x S, in the scratch matrix)
-            __syncthreads();
             mm_dense(P, K, tmp, S, O, S, false, -1);
             __syncthreads();
         }
@@ -252,22 +311,21 @@ kalman_gain_kernel(const double *__restrict__ A, const double *__restrict__ Pf, 
                    double *__restrict__ J) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *p = smem_raw;
-    double *aug = reinterpret_cast<double *>(p); p += (size_t)S * 2 * S * 8;
+    double *inv = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
     double *F = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
     double *FA = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
-    double *inv = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
     double *colk = reinterpret_cast<double *>(p); p += (size_t)S * 8;
-    double *rowk = reinterpret_cast<double *>(p); p += (size_t)2 * S * 8;
+    double *rowk = reinterpret_cast<double *>(p); p += (size_t)S * 8;
     SparseRows As = carve_sparse(p, S, S);
     const int t = blockIdx.x;
     build_sparse(A, S, S, As);
-    load_aug(aug, Pp + (size_t)(t + 1) * S * S, S);
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) F[e] = Pf[(size_t)t * S * S + e];
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+        inv[e] = Pp[(size_t)(t + 1) * S * S + e];
+        F[e] = Pf[(size_t)t * S * S + e];
+    }
     __syncthreads();
     spmm_right_t(FA, F, As, S, S, nullptr);               // Pf A^T
-    gauss_jordan(aug, S, colk, rowk);
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) { const int i = e / S, j = e - i * S; inv[e] = aug[i * 2 * S + S + j]; }
-    __syncthreads();
+    gauss_jordan_inplace(inv, S, colk, rowk);
     mm_dense(F, FA, inv, S, S, S, false, 0);
     __syncthreads();
     for (int e = threadIdx.x; e < S * S; e += blockDim.x) J[(size_t)t * S * S + e] = F[e];
@@ -292,6 +350,7 @@ kalman_backward_kernel(BackwardArgs a) {
     double *d = reinterpret_cast<double *>(p); p += (size_t)S * 8;
     double *msn = reinterpret_cast<double *>(p); p += (size_t)S * 8;
     double *msn2 = reinterpret_cast<double *>(p); p += (size_t)S * 8;
+    double *mfs = reinterpret_cast<double *>(p); p += (size_t)S * 8;
     double *Psn = nullptr, *D = nullptr, *JD = nullptr;
     if (a.want_cov) {
         Psn = reinterpret_cast<double *>(p); p += (size_t)SS * 8;
@@ -308,37 +367,50 @@ kalman_backward_kernel(BackwardArgs a) {
             a.pair[e] = 0.0;                                         // pair[0] is never defined
         }
     }
-    // the gain of the first step, in registers; the next one is requested before the current one is consumed
+    // Everything step t reads from global memory (J[t], mp[t+1], mf[t], and for EM Pp[t+1], Pf[t]) is requested one step
+    // ahead into registers: the recursion is sequential, so a global-memory latency on its critical path costs every step.
     constexpr int kPer = (kMaxS * kMaxS + kKalThreads - 1) / kKalThreads;
-    double jreg[kPer];
+    double jreg[kPer], ppreg[kPer], pfreg[kPer], mp_r = 0.0, mf_r = 0.0;
     auto fetch = [&](int t) {
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
             const int e = threadIdx.x + q * kKalThreads;
-            jreg[q] = (t >= 0 && e < SS) ? a.J[(size_t)t * SS + e] : 0.0;
+            const bool on = t >= 0 && e < SS;
+            jreg[q] = on ? a.J[(size_t)t * SS + e] : 0.0;
+            if (a.want_cov) {
+                ppreg[q] = on ? a.Pp[(size_t)(t + 1) * SS + e] : 0.0;
+                pfreg[q] = on ? a.Pf[(size_t)t * SS + e] : 0.0;
+            }
+        }
+        if (t >= 0 && threadIdx.x < S) {
+            mp_r = a.mp[(size_t)(t + 1) * S + threadIdx.x];
+            mf_r = a.mf[(size_t)t * S + threadIdx.x];
         }
     };
     fetch(T - 2);
     __syncthreads();
     for (int t = T - 2; t >= 0; --t) {
+        double pf_now[kPer];
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
             const int e = threadIdx.x + q * kKalThreads;
-            if (e < SS) Jt[e] = jreg[q];
+            if (e < SS) {
+                Jt[e] = jreg[q];
+                if (a.want_cov) D[e] = Psn[e] - ppreg[q];
+            }
+            pf_now[q] = pfreg[q];
         }
+        if (threadIdx.x < S) { d[threadIdx.x] = msn[threadIdx.x] - mp_r; mfs[threadIdx.x] = mf_r; }
         fetch(t - 1);
-        for (int e = threadIdx.x; e < S; e += blockDim.x) d[e] = msn[e] - a.mp[(size_t)(t + 1) * S + e];
-        if (a.want_cov)
-            for (int e = threadIdx.x; e < SS; e += blockDim.x) D[e] = Psn[e] - a.Pp[(size_t)(t + 1) * SS + e];
         __syncthreads();
         // ms[t] = mf[t] + J d : one warp per row, lanes stride the row
         for (int r = warp; r < S; r += warps) {
             double acc = 0.0;
-            for (int c = lane; c < S; c += 32) acc += Jt[r * S + c] * d[c];
+            for (int c = lane; c < S; c += 32) acc = fma(Jt[r * S + c], d[c], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) {
-                const double v = a.mf[(size_t)t * S + r] + acc;
+                const double v = mfs[r] + acc;
                 a.ms[(size_t)t * S + r] = v;
                 msn2[r] = v;
             }
@@ -352,8 +424,11 @@ kalman_backward_kernel(BackwardArgs a) {
             for (int e = threadIdx.x; e < SS; e += blockDim.x) a.pair[(size_t)(t + 1) * SS + e] = JD[e];
             __syncthreads();
             mm_dense(JD, Jt, D, S, S, S, false, 0);                   // J (Ps[t+1] - Pp[t+1])
-            __syncthreads();
-            for (int e = threadIdx.x; e < SS; e += blockDim.x) Psn[e] = a.Pf[(size_t)t * SS + e];
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                const int e = threadIdx.x + q * kKalThreads;
+                if (e < SS) Psn[e] = pf_now[q];                       // (Psn was last read by the first product)
+            }
             __syncthreads();
             mm_dense(Psn, JD, Jt, S, S, S, true, +1);                 // Ps[t] = Pf[t] + (J D) J^T
             __syncthreads();
@@ -471,8 +546,8 @@ kalman_em_finish_kernel(EmArgs a) {
         if (e < O * O) {
             const int i = e / O, j = e - i * O;
             double acc = 0.0;
-            const int c = Hs.nnz[i];
-            for (int k = 0; k < c; ++k) acc += Hs.val[i * S + k] * Y[Hs.col[i * S + k] * O + j];
+            const int c = *Hs.width;
+            for (int k = 0; k < c; ++k) acc += Hs.val[i * c + k] * Y[Hs.col[i * c + k] * O + j];
             const double tot = accZ[q] + acc;
             a.R[e] = n_obs > 0 ? tot / (double)n_obs : tot;
         }
@@ -700,8 +775,8 @@ size_t sparse_bytes_host(int rows, int cols) {
 size_t filter_smem(int S, int O) {
     return (size_t)8 * (3 * S * S + 2 * S * O + 2 * O * O + O * O + 2 * S + 4 * O) + sparse_bytes_host(S, S) + sparse_bytes_host(O, S) + 64;
 }
-size_t gain_smem(int S) { return (size_t)8 * (2 * S * S + 3 * S * S + 3 * S) + sparse_bytes_host(S, S) + 64; }
-size_t backward_smem(int S, bool cov) { return (size_t)8 * (S * S + 3 * S + (cov ? 3 * S * S : 0)) + 64; }
+size_t gain_smem(int S) { return (size_t)8 * (3 * S * S + 2 * S) + sparse_bytes_host(S, S) + 64; }
+size_t backward_smem(int S, bool cov) { return (size_t)8 * (S * S + 4 * S + (cov ? 3 * S * S : 0)) + 64; }
 size_t em_smem(int S, int O) { return (size_t)8 * (3 * S * S + 3 * S + O) + sparse_bytes_host(S, S) + sparse_bytes_host(O, S) + 64; }
 
 struct Workspace {
