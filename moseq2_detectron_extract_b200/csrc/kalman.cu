@@ -239,6 +239,7 @@ kalman_filter_kernel(FilterArgs a) {
     double *P = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
     double *tmp = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
     double *Q = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;
+    double *Pps = reinterpret_cast<double *>(p); p += (size_t)S * S * 8;      // the last predicted covariance
     double *PHt = reinterpret_cast<double *>(p); p += (size_t)S * O * 8;
     double *K = reinterpret_cast<double *>(p); p += (size_t)S * O * 8;
     double *Sm = reinterpret_cast<double *>(p); p += (size_t)O * 2 * O * 8;
@@ -261,27 +262,71 @@ kalman_filter_kernel(FilterArgs a) {
     // thread e < O keeps component e of the observation in a register; the next step's value is requested right after the
     // vote so that its global-memory latency is off the critical path of the (sequential) step
     double z_cur = (threadIdx.x < O) ? a.obs[threadIdx.x] : 0.0;
+    // The covariances do not depend on the observed values, only on which steps have an observation, and the Riccati
+    // recursion converges geometrically (for the reference's trackers: to rounding level within ~30 observed steps).  Once
+    // the predicted covariance repeats to 1e-13 of its scale over two observed steps, further observed steps reuse P_pred,
+    // K and P_filt and only move the mean -- until an observation is missing, which restarts the full recursion.
+    bool steady = false, prev_valid = false;
     for (int t = 0; t < T; ++t) {
         // pykalman: any masked component -> the whole observation is skipped
         const int ok = finite_f64(z_cur) ? 1 : 0;
         const double z_now = z_cur;
-        if (t > 0 || a.predict_first) {
+        const int valid = __syncthreads_and(ok);         // also separates this step from the previous one
+        if (threadIdx.x < O && t + 1 < T) z_cur = a.obs[(size_t)(t + 1) * O + threadIdx.x];
+        if (threadIdx.x == 0) a.valid[t] = (unsigned char)valid;
+        const bool predict = t > 0 || a.predict_first;
+        if (steady && valid && predict) {
+            spmv(m2, As, m, S);                           // predicted mean
+            __syncthreads();
+            if (threadIdx.x < O) {                        // innovation z - H m_pred
+                const int wd = *Hs.width;
+                double hm = 0.0;
+                for (int q = 0; q < wd; ++q) hm = fma(Hs.val[threadIdx.x * wd + q], m2[Hs.col[threadIdx.x * wd + q]], hm);
+                y[threadIdx.x] = z_now - hm;
+            }
+            for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+                a.Pp[(size_t)t * S * S + e] = Pps[e];
+                a.Pf[(size_t)t * S * S + e] = P[e];
+            }
+            for (int e = threadIdx.x; e < S; e += blockDim.x) a.mp[(size_t)t * S + e] = m2[e];
+            __syncthreads();
+            for (int i = threadIdx.x; i < S; i += blockDim.x) {
+                double acc = 0.0;
+                for (int q = 0; q < O; ++q) acc = fma(K[i * O + q], y[q], acc);
+                const double v = m2[i] + acc;
+                m[i] = v;
+                a.mf[(size_t)t * S + i] = v;
+            }
+            prev_valid = true;
+            continue;
+        }
+        int moved = 1;
+        if (predict) {
             spmv(m2, As, m, S);
             spmm_left(tmp, As, P, S, S);                 // A P
             __syncthreads();
             spmm_right_t(P, tmp, As, S, S, Q);           // (A P) A^T + Q
             for (int e = threadIdx.x; e < S; e += blockDim.x) m[e] = m2[e];
+            __syncthreads();
+            // has the predicted covariance stopped moving?  (element scale: sqrt(P_ii P_jj) bounds |P_ij|)
+            moved = 0;
+            MSQ_FOR_ELEMENTS(e, i, j, S, S) {
+                const double pe = P[e];
+                moved |= fabs(pe - Pps[e]) > 1e-13 * sqrt(fabs(P[i * S + i] * P[j * S + j]));
+                Pps[e] = pe;
+            }
+        } else {
+            for (int e = threadIdx.x; e < S * S; e += blockDim.x) Pps[e] = P[e];
         }
-        const int valid = __syncthreads_and(ok);         // also the barrier that publishes the predicted state
-        if (threadIdx.x < O && t + 1 < T) z_cur = a.obs[(size_t)(t + 1) * O + threadIdx.x];
         for (int e = threadIdx.x; e < S * S; e += blockDim.x) a.Pp[(size_t)t * S * S + e] = P[e];
         for (int e = threadIdx.x; e < S; e += blockDim.x) a.mp[(size_t)t * S + e] = m[e];
-        if (threadIdx.x == 0) a.valid[t] = (unsigned char)valid;
+        steady = false;
         if (valid) {
             spmm_right_t(PHt, P, Hs, S, O, nullptr);     // P H^T
             spmm_left(tmp, Hs, P, O, S);                 // H P   (O x S, in the scratch matrix)
             spmv(m2, Hs, m, O);                           // H m
-            __syncthreads();
+            const int moved_any = __syncthreads_or(moved);
+            steady = predict && prev_valid && !moved_any;
             if (threadIdx.x < O) y[threadIdx.x] = z_now - m2[threadIdx.x];
             spmm_left(Sm, Hs, PHt, O, O, R);             // H P H^T + R
             __syncthreads();
@@ -298,6 +343,7 @@ kalman_filter_kernel(FilterArgs a) {
             mm_dense(P, K, tmp, S, O, S, false, -1);
             __syncthreads();
         }
+        prev_valid = valid != 0;
         for (int e = threadIdx.x; e < S * S; e += blockDim.x) a.Pf[(size_t)t * S * S + e] = P[e];
         for (int e = threadIdx.x; e < S; e += blockDim.x) a.mf[(size_t)t * S + e] = m[e];
     }
@@ -643,18 +689,23 @@ struct AngleArgs {
     int n, S, order;
 };
 
-// S is a template parameter so that every small matrix lives in registers (with a run-time S the arrays went to local
-// memory: 22 ms per 1000 frames)
+// S is a template parameter so that the state lives in registers (with a run-time S the arrays went to local memory:
+// 22 ms per 1000 frames); the constant model matrices and the last predicted covariance sit in shared memory.  The same
+// steady-state shortcut as in kalman_filter_kernel: once the predicted covariance repeats over two observed frames, observed
+// frames only move the mean (K, P_filt reused) until an angle is missing.
 template <int S>
 __global__ void track_angles_kernel(AngleArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     constexpr int O = kAngO;
-    double A[S][S], Q[S][S], P[S][S], H[O][S], R[O][O], m[S];
+    __shared__ double A[S][S], Q[S][S], H[O][S], R[O][O], Ppp[S][S];
+    double P[S][S], K[S][O], m[S];
 #pragma unroll
     for (int i = 0; i < S; ++i) {
         m[i] = a.mean[i];
 #pragma unroll
-        for (int j = 0; j < S; ++j) { A[i][j] = a.A[i * S + j]; Q[i][j] = a.Q[i * S + j]; P[i][j] = a.cov[i * S + j]; }
+        for (int j = 0; j < S; ++j) { A[i][j] = a.A[i * S + j]; Q[i][j] = a.Q[i * S + j]; P[i][j] = a.cov[i * S + j]; Ppp[i][j] = 0.0; }
+#pragma unroll
+        for (int o = 0; o < O; ++o) K[i][o] = 0.0;
     }
 #pragma unroll
     for (int i = 0; i < O; ++i) {
@@ -663,6 +714,7 @@ __global__ void track_angles_kernel(AngleArgs a) {
 #pragma unroll
         for (int j = 0; j < O; ++j) R[i][j] = a.R[i * O + j];
     }
+    bool steady = false, prev_valid = false;
     for (int f = 0; f < a.n; ++f) {
         // KalmanTracker.sample(1): the last filtered state itself, read back as an angle (kalman.py:376, :236-242)
         double pred = atan2(m[0], m[a.order]);
@@ -678,87 +730,97 @@ __global__ void track_angles_kernel(AngleArgs a) {
         }
         a.angles[f] = ang;
         // filter_update: predict, then correct with (sin, cos) unless the angle is not finite
-        double m2[S], T1[S][S];
+        const double rad = ang * 0.017453292519943295;
+        const double z[2] = {sin(rad), cos(rad)};
+        const bool valid = finite_f64(z[0]) && finite_f64(z[1]);
+        double m2[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < S; ++k) acc += A[i][k] * m[k];
+            for (int k = 0; k < S; ++k) acc = fma(A[i][k], m[k], acc);
             m2[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < S; ++i) m[i] = m2[i];
+        double y[O];
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            double hm = 0.0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) hm = fma(H[o][k], m[k], hm);
+            y[o] = z[o] - hm;
+        }
+        if (steady && valid) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) m[i] += K[i][0] * y[0] + K[i][1] * y[1];
+            continue;
+        }
+        // ---- full covariance step ----
+        double T1[S][S];
+#pragma unroll
+        for (int i = 0; i < S; ++i)
 #pragma unroll
             for (int j = 0; j < S; ++j) {
                 double t = 0.0;
 #pragma unroll
-                for (int k = 0; k < S; ++k) t += A[i][k] * P[k][j];
+                for (int k = 0; k < S; ++k) t = fma(A[i][k], P[k][j], t);
                 T1[i][j] = t;
             }
-        }
 #pragma unroll
-        for (int i = 0; i < S; ++i) {
-            m[i] = m2[i];
+        for (int i = 0; i < S; ++i)
 #pragma unroll
             for (int j = 0; j < S; ++j) {
                 double t = 0.0;
 #pragma unroll
-                for (int k = 0; k < S; ++k) t += T1[i][k] * A[j][k];
+                for (int k = 0; k < S; ++k) t = fma(T1[i][k], A[j][k], t);
                 P[i][j] = t + Q[i][j];
             }
-        }
-        const double rad = ang * 0.017453292519943295;
-        const double z[2] = {sin(rad), cos(rad)};
-        if (finite_f64(z[0]) && finite_f64(z[1])) {
-            double PHt[S][O], Sm[O][O], y[O];
+        bool moved = false;
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                moved |= fabs(P[i][j] - Ppp[i][j]) > 1e-13 * sqrt(fabs(P[i][i] * P[j][j]));
+                Ppp[i][j] = P[i][j];
+            }
+        steady = false;
+        if (valid) {
+            steady = prev_valid && !moved;
+            double PHt[S][O], HP[O][S], Sm[O][O];
 #pragma unroll
             for (int i = 0; i < S; ++i)
 #pragma unroll
                 for (int o = 0; o < O; ++o) {
-                    double t = 0.0;
+                    double t = 0.0, u = 0.0;
 #pragma unroll
-                    for (int k = 0; k < S; ++k) t += P[i][k] * H[o][k];
+                    for (int k = 0; k < S; ++k) { t = fma(P[i][k], H[o][k], t); u = fma(H[o][k], P[k][i], u); }
                     PHt[i][o] = t;
+                    HP[o][i] = u;                              // H P (see kalman_filter_kernel: not (P H^T)^T)
                 }
 #pragma unroll
-            for (int o = 0; o < O; ++o) {
-                double hm = 0.0;
-#pragma unroll
-                for (int k = 0; k < S; ++k) hm += H[o][k] * m[k];
-                y[o] = z[o] - hm;
+            for (int o = 0; o < O; ++o)
 #pragma unroll
                 for (int q = 0; q < O; ++q) {
                     double t = 0.0;
 #pragma unroll
-                    for (int k = 0; k < S; ++k) t += H[o][k] * PHt[k][q];
+                    for (int k = 0; k < S; ++k) t = fma(H[o][k], PHt[k][q], t);
                     Sm[o][q] = t + R[o][q];
                 }
-            }
             const double det = Sm[0][0] * Sm[1][1] - Sm[0][1] * Sm[1][0];
             const double Si[2][2] = {{Sm[1][1] / det, -Sm[0][1] / det}, {-Sm[1][0] / det, Sm[0][0] / det}};
-            double K[S][O];
 #pragma unroll
             for (int i = 0; i < S; ++i)
 #pragma unroll
                 for (int o = 0; o < O; ++o) K[i][o] = PHt[i][0] * Si[0][o] + PHt[i][1] * Si[1][o];
 #pragma unroll
             for (int i = 0; i < S; ++i) m[i] += K[i][0] * y[0] + K[i][1] * y[1];
-            double HP[O][S];                                  // H P (see kalman_filter_kernel: not (P H^T)^T)
-#pragma unroll
-            for (int o = 0; o < O; ++o)
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int k = 0; k < S; ++k) t += H[o][k] * P[k][j];
-                    HP[o][j] = t;
-                }
 #pragma unroll
             for (int i = 0; i < S; ++i)
 #pragma unroll
-                for (int j = 0; j < S; ++j) T1[i][j] = P[i][j] - (K[i][0] * HP[0][j] + K[i][1] * HP[1][j]);
-#pragma unroll
-            for (int i = 0; i < S; ++i)
-#pragma unroll
-                for (int j = 0; j < S; ++j) P[i][j] = T1[i][j];
+                for (int j = 0; j < S; ++j) P[i][j] -= K[i][0] * HP[0][j] + K[i][1] * HP[1][j];
         }
+        prev_valid = valid;
     }
 #pragma unroll
     for (int i = 0; i < S; ++i) {
@@ -773,7 +835,7 @@ size_t sparse_bytes_host(int rows, int cols) {
     return up16((size_t)rows * sizeof(int)) + up16((size_t)rows * cols * sizeof(int)) + (size_t)rows * cols * sizeof(double);
 }
 size_t filter_smem(int S, int O) {
-    return (size_t)8 * (3 * S * S + 2 * S * O + 2 * O * O + O * O + 2 * S + 4 * O) + sparse_bytes_host(S, S) + sparse_bytes_host(O, S) + 64;
+    return (size_t)8 * (4 * S * S + 2 * S * O + 2 * O * O + O * O + 2 * S + 4 * O) + sparse_bytes_host(S, S) + sparse_bytes_host(O, S) + 64;
 }
 size_t gain_smem(int S) { return (size_t)8 * (3 * S * S + 2 * S) + sparse_bytes_host(S, S) + 64; }
 size_t backward_smem(int S, bool cov) { return (size_t)8 * (S * S + 4 * S + (cov ? 3 * S * S : 0)) + 64; }
