@@ -223,7 +223,84 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
         long long best[6] = {0, 0, 0, 0, 0, 0};
         bool have = false;
 
-        if (r_hi >= 0) {
+        // exact cell sums of the blob held in P (rows r0..rmax), lanes = (row-in-step, word)
+        auto blob_sums = [&](int r0, int rmax, long long (&s)[6]) {
+        CellAcc acc[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[c] = {0, 0, 0, 0, 0, 0};
+        for (int r = r0 + sub; r < rmax; r += RPW) {
+            if (k >= wpr) continue;
+            const uint32_t a = P[r * LPR + k], b = P[(r + 1) * LPR + k];
+            const uint32_t an = (k + 1 < wpr) ? P[r * LPR + k + 1] : 0u;
+            const uint32_t bn = (k + 1 < wpr) ? P[(r + 1) * LPR + k + 1] : 0u;
+            if ((a | b) == 0u) continue;
+            const uint32_t a1 = (a >> 1) | (an << 31), b1 = (b >> 1) | (bn << 31);
+            const uint32_t cls[5] = {a & a1 & b & b1, ~a & a1 & b & b1, a & ~a1 & b & b1,
+                                     a & a1 & ~b & b1, a & a1 & b & ~b1};
+            const long long x0 = (long long)k << 5, y = r;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                if (cls[c] == 0u) continue;
+                int cnt, s1, s2;
+                bit_moments(cls[c], cnt, s1, s2);
+                const long long si = x0 * cnt + s1;
+                const long long sii = x0 * x0 * cnt + 2 * x0 * s1 + s2;
+                acc[c].n += cnt;
+                acc[c].i += si;
+                acc[c].j += y * cnt;
+                acc[c].ii += sii;
+                acc[c].ij += y * si;
+                acc[c].jj += y * y * cnt;
+            }
+        }
+        for (int q = 0; q < 6; ++q) s[q] = 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const long long A = kCell24[c][0], U = kCell24[c][1], V = kCell24[c][2], UU = kCell24[c][3],
+                            UV = kCell24[c][4], VV = kCell24[c][5];
+            s[0] += A * acc[c].n;
+            s[1] += A * acc[c].i + U * acc[c].n;
+            s[2] += A * acc[c].j + V * acc[c].n;
+            s[3] += A * acc[c].ii + 2 * U * acc[c].i + UU * acc[c].n;
+            s[4] += A * acc[c].ij + V * acc[c].i + U * acc[c].j + UV * acc[c].n;
+            s[5] += A * acc[c].jj + 2 * V * acc[c].j + VV * acc[c].n;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s[q] = warp_sum_ll(s[q]);
+        };
+
+        // ---------------- fast path: a row-convex blob ----------------
+        // If every row of [r_lo, r_hi] holds exactly one run and consecutive runs touch (8-connected), the foreground is one
+        // component, every background pixel reaches the left or right image edge along its own row (no holes), and the
+        // general machinery below -- background flood, peeling, 3 + 3 sequential sweeps over the rows -- would return the
+        // foreground itself.  The test is one parallel pass; mouse-shaped masks pass it almost always.
+        bool simple = r_hi >= 0;
+        if (simple) {
+            for (int base = r_lo; base <= r_hi; base += RPW) {
+                const int r = base + sub;
+                const bool in = r <= r_hi && k < wpr;
+                const uint32_t v = in ? P[r * LPR + k] : 0u;
+                const uint32_t nxt = (in && r < r_hi) ? P[(r + 1) * LPR + k] : 0u;
+                uint32_t lo_nb = __shfl_up_sync(0xffffffffu, v, 1), hi_nb = __shfl_down_sync(0xffffffffu, v, 1);
+                if (k == 0) lo_nb = 0u;
+                if (k == LPR - 1) hi_nb = 0u;
+                int starts = __popc(v & ~((v << 1) | (lo_nb >> 31)));                       // run starts in this word
+                int touch = ((v | (v << 1) | (v >> 1) | (lo_nb >> 31) | (hi_nb << 31)) & nxt) != 0u;
+#pragma unroll
+                for (int o = LPR >> 1; o > 0; o >>= 1) {
+                    starts += __shfl_xor_sync(0xffffffffu, starts, o);
+                    touch |= __shfl_xor_sync(0xffffffffu, touch, o);
+                }
+                const bool row_ok = r > r_hi || (starts == 1 && (r == r_hi || touch));
+                simple = __all_sync(0xffffffffu, row_ok) && simple;
+            }
+        }
+
+
+        if (simple) {
+            blob_sums(r_lo, r_hi, best);
+            have = true;
+        } else if (r_hi >= 0) {
             // ---------------- phase 1: flood the background from outside (4-connected) ----------------
             const uint32_t edge = (lane == 0 ? 1u : 0u) | (lane == ((w - 1) >> 5) ? (1u << ((w - 1) & 31)) : 0u);
             const bool act = lane < LPR;
@@ -309,49 +386,8 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                 }
                 __syncwarp();
 
-                // exact cell sums of the blob (rows r0..rmax), lanes = (row-in-step, word)
-                CellAcc acc[5];
-#pragma unroll
-                for (int c = 0; c < 5; ++c) acc[c] = {0, 0, 0, 0, 0, 0};
-                for (int r = r0 + sub; r < rmax; r += RPW) {
-                    if (k >= wpr) continue;
-                    const uint32_t a = P[r * LPR + k], b = P[(r + 1) * LPR + k];
-                    const uint32_t an = (k + 1 < wpr) ? P[r * LPR + k + 1] : 0u;
-                    const uint32_t bn = (k + 1 < wpr) ? P[(r + 1) * LPR + k + 1] : 0u;
-                    if ((a | b) == 0u) continue;
-                    const uint32_t a1 = (a >> 1) | (an << 31), b1 = (b >> 1) | (bn << 31);
-                    const uint32_t cls[5] = {a & a1 & b & b1, ~a & a1 & b & b1, a & ~a1 & b & b1,
-                                             a & a1 & ~b & b1, a & a1 & b & ~b1};
-                    const long long x0 = (long long)k << 5, y = r;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        if (cls[c] == 0u) continue;
-                        int cnt, s1, s2;
-                        bit_moments(cls[c], cnt, s1, s2);
-                        const long long si = x0 * cnt + s1;
-                        const long long sii = x0 * x0 * cnt + 2 * x0 * s1 + s2;
-                        acc[c].n += cnt;
-                        acc[c].i += si;
-                        acc[c].j += y * cnt;
-                        acc[c].ii += sii;
-                        acc[c].ij += y * si;
-                        acc[c].jj += y * y * cnt;
-                    }
-                }
-                long long s[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const long long A = kCell24[c][0], U = kCell24[c][1], V = kCell24[c][2], UU = kCell24[c][3],
-                                    UV = kCell24[c][4], VV = kCell24[c][5];
-                    s[0] += A * acc[c].n;
-                    s[1] += A * acc[c].i + U * acc[c].n;
-                    s[2] += A * acc[c].j + V * acc[c].n;
-                    s[3] += A * acc[c].ii + 2 * U * acc[c].i + UU * acc[c].n;
-                    s[4] += A * acc[c].ij + V * acc[c].i + U * acc[c].j + UV * acc[c].n;
-                    s[5] += A * acc[c].jj + 2 * V * acc[c].j + VV * acc[c].n;
-                }
-#pragma unroll
-                for (int q = 0; q < 6; ++q) s[q] = warp_sum_ll(s[q]);
+                long long s[6];
+                blob_sums(r0, rmax, s);
                 // OpenCV lists sibling contours in reverse raster order and np.argmax keeps the first
                 // maximum, so a later blob with an equal area replaces the current best
                 if (!have || s[0] >= best[0]) {

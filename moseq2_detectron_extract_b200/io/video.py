@@ -106,6 +106,15 @@ class RawDepthSession:
     def iterate(self, chunk_size: int = 1000, chunk_overlap: int = 0):
         return _RawIterator(self, chunk_size, chunk_overlap)
 
+    def compute_bground(self, frame_stride: int = 500, med_scale: int = 5) -> np.ndarray:
+        """Background image from every `frame_stride`-th frame (ref: io/session.py:217-218 -> proc/roi.py:293-307), on
+        the GPU (`proc.get_bground_im`); stores it as `.bground_im` and returns it (float64, (height, width))."""
+        from ..proc.roi import get_bground_im
+        idxs = list(range(0, self.nframes, max(1, int(frame_stride))))
+        frames = read_frames_raw(self.depth_file, idxs, frame_dims=self.frame_dims)
+        self.bground_im = get_bground_im(frames, med_scale=med_scale)
+        return self.bground_im
+
 
 class _RawIterator:
     def __init__(self, session: RawDepthSession, chunk_size: int, chunk_overlap: int):

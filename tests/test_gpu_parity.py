@@ -220,6 +220,36 @@ def test_features_without_mask_and_thresholds(P):
         assert_close(feats['centroid'], ref['centroid'], 1e-12, what=f'centroid thr={thr}')
 
 
+def test_features_row_convex_fast_path_agrees_with_general_path(P):
+    """features_kernel skips the flood / peel machinery when every row of the foreground is a single run and consecutive
+    runs touch.  The same blobs with one far-away speck (second component -> general path) must give the same features,
+    and both must match OpenCV; shapes that narrowly fail the test (a row with two runs, a diagonal-only contact, a
+    one-pixel gap between rows) go through the general path."""
+    h, w = 96, 240
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = []
+    for cx, cy, a, b, t in ((60, 40, 30, 12, 0.3), (200, 50, 22, 20, 1.2), (120, 48, 45, 9, -0.6), (31, 30, 28, 14, 0.0)):
+        u = (xx - cx) * np.cos(t) + (yy - cy) * np.sin(t)
+        v = -(xx - cx) * np.sin(t) + (yy - cy) * np.cos(t)
+        frames.append(((u / a) ** 2 + (v / b) ** 2 <= 1).astype(np.uint8) * 50)
+    stair = np.zeros((h, w), np.uint8)                       # runs that only touch diagonally: still one 8-connected blob
+    for i in range(20):
+        stair[20 + i, 40 + 3 * i:43 + 3 * i] = 50
+    two_runs = frames[0].copy(); two_runs[40, 55:62] = 0     # a notch splits one row into two runs (no hole: open to the top? no -> a hole-free dent)
+    two_runs[30:41, 58] = 0
+    gap = frames[1].copy(); gap[50, :] = 0                   # an empty row: two components
+    clean = np.stack(frames + [stair, two_runs, gap])
+    speck = clean.copy()
+    speck[:, 90, 5] = 50                                     # a second, 1-pixel component far from the blob
+    ones = np.ones_like(clean)
+    f_fast, _ = P.get_frame_features(clean, frame_threshold=3, mask=ones)
+    f_gen, _ = P.get_frame_features(speck, frame_threshold=3, mask=ones)
+    ref = O.frame_features_cv2(clean, ones, 3)
+    for key in ('centroid', 'orientation', 'axis_length'):
+        assert np.array_equal(f_fast[key], f_gen[key], equal_nan=True), key  # the speck has zero contour area: it never wins
+        assert_close(f_fast[key], ref[key], 1e-10, 1e-12, what=key)
+
+
 # ----------------------------------------------------------------------------- a8-a10 angles / flips / filter
 @pytest.mark.parametrize('name', ['kinect_clean', 'kinect_missing_holes', 'azure_clean'])
 def test_instances_to_features_matches_reference(P, name):

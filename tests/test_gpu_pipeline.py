@@ -141,3 +141,19 @@ def test_raw_file_session_zero_copy_prep(tmp_path):
     pipe.link(a, b)
     pipe.run()
     assert np.array_equal(np.concatenate(got), ref)
+
+
+def test_raw_session_background_from_file(tmp_path):
+    """RawDepthSession.compute_bground: every k-th frame of a raw .dat file -> GPU median blur + temporal median, equal to
+    the reference's get_bground_im on the same frames (ref io/session.py:217-218, proc/roi.py:293-307)."""
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.io.video import RawDepthSession
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(23, seed=8, geom=geom, invalid_rate=0.002)
+    path = tmp_path / 'depth.dat'
+    ch.frames.astype('<i2').tofile(path)
+    sess = RawDepthSession(str(path), bground_im=None, roi=synthetic.make_roi(geom), true_depth=673.0, pinned=False)
+    assert sess.nframes == 23
+    bg = sess.compute_bground(frame_stride=3)
+    assert bg.dtype == np.float64 and bg.shape == (geom.height, geom.width)
+    assert np.array_equal(bg, O.bground_im(ch.frames[::3].copy(), 5)) and sess.bground_im is bg
