@@ -178,7 +178,7 @@ MSQ_API int msq_scalars_and_keypoints_f64(const uint8_t *chunk_dev, const uint8_
  * angle_deg[i] into out[i] (crop_h,crop_w) u8; NaN / negative centre -> zeros.  src2/out2 optional
  * second plane (the mask) warped with the same transform.  scratch_dev: msq_crop_scratch_bytes(n) bytes,
  * 16-byte aligned (per-frame float64 rotation coefficients + OpenCV's fixed-point row/column tables).
- * n <= 65535 per call, crops up to 512x512. */
+ * Crops up to 512x512; n <= 65535 per call only when the 4-byte-aligned fast path does not apply (w, crop_w % 4, bases). */
 MSQ_API size_t msq_crop_scratch_bytes(int n);
 MSQ_API int msq_crop_rotate(const uint8_t *src_dev, const uint8_t *src2_dev, int n, int h, int w,
                     const double *centroid_dev, const double *angle_deg_dev, int crop_w, int crop_h,

@@ -288,6 +288,7 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
         MSQ_LAUNCH_OK("crop_rotate (staged)");
         return MSQ_OK;
     }
+    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_crop_rotate: at most 65535 frames per call for unaligned shapes (got %d)", n);
     WarpCoeffs *coeffs = reinterpret_cast<WarpCoeffs *>(scratch);
     int *tables = reinterpret_cast<int *>(reinterpret_cast<char *>(scratch) + (size_t)n * sizeof(WarpCoeffs));
     TimedLaunch timed(K_CROP, st);          // the coefficient kernel is part of the crop step
@@ -312,7 +313,6 @@ extern "C" int msq_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, i
     MSQ_REQUIRE((src2 == nullptr) == (out2 == nullptr), MSQ_EINVAL, "msq_crop_rotate: src2/out2 must both be set or both be null");
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && cw > 0 && ch > 0, MSQ_EINVAL, "msq_crop_rotate: bad sizes");
     if (n == 0) return MSQ_OK;
-    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_crop_rotate: at most 65535 frames per call (got %d)", n);
     MSQ_REQUIRE(cw <= 512 && ch <= 512, MSQ_EUNSUPPORTED, "msq_crop_rotate: crop %dx%d exceeds 512x512", cw, ch);
     MSQ_REQUIRE(scratch && (uintptr_t)scratch % 16 == 0 && scratch_bytes >= msq_crop_scratch_bytes(n), MSQ_ENOMEM,
                 "msq_crop_rotate: scratch must be 16-byte aligned and >= %zu bytes", msq_crop_scratch_bytes(n));

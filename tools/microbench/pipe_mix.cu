@@ -10,7 +10,7 @@ __device__ __forceinline__ uint32_t hmin2u(uint32_t a, uint32_t b) {
     x = __hmin2(x, y); return *reinterpret_cast<uint32_t *>(&x);
 }
 template <int MODE>
-__global__ void bench(uint32_t *out, uint32_t seed, uint32_t one, uint32_t neg1) {
+__global__ void bench(uint32_t *out, uint32_t seed, uint32_t one, uint32_t neg1, uint32_t k16) {
     uint32_t a[ILP], b[ILP], c[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; ++i) { a[i] = seed * (threadIdx.x + 1 + i); b[i] = seed ^ (0x9e3779b9u * (i + 1 + threadIdx.x)); c[i] = a[i] ^ b[i]; }
@@ -41,6 +41,10 @@ __global__ void bench(uint32_t *out, uint32_t seed, uint32_t one, uint32_t neg1)
                               uint32_t s = a[i] * one + b[i]; s = c[i] * one + s; s = lo * neg1 + s; a[i] = hi * neg1 + s; }  // 2 x VIMNMX3 + 4 x IMAD
             if (MODE == 19) { a[i] = a[i] * one + b[i]; }                                                      // IMAD alone
             if (MODE == 20) { a[i] = a[i] * one + b[i]; c[i] = __vminu2(c[i], b[i]); }
+            if (MODE == 21) { a[i] = __umulhi(a[i], k16) + b[i]; }                                                // IMAD.HI alone
+            if (MODE == 22) { c[i] = b[i] * k16 + __umulhi(c[i], k16); a[i] = __vimin3_u16x2(a[i], b[i], b[i] + 1); }   // funnel shift on the FMA pipe + VIMNMX3
+            if (MODE == 23) { c[i] = __funnelshift_r(c[i], b[i], 16); a[i] = __vimin3_u16x2(a[i], b[i], b[i] + 1); }       // SHF + VIMNMX3
+            if (MODE == 24) { c[i] = b[i] * k16 + __umulhi(c[i], k16); }                                              // IMAD.HI + IMAD
             asm volatile("" : "+r"(a[i]), "+r"(c[i]));
         }
     }
@@ -54,11 +58,11 @@ void run(const char *name, int instr_per_op) {
     uint32_t *out;
     const int threads = 1024, blocks = 148 * 2;
     cudaMalloc(&out, blocks * threads * 4);
-    bench<MODE><<<blocks, threads>>>(out, 12345u, 1u, 0xffffffffu);
+    bench<MODE><<<blocks, threads>>>(out, 12345u, 1u, 0xffffffffu, 65536u);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    bench<MODE><<<blocks, threads>>>(out, 12345u, 1u, 0xffffffffu);
+    bench<MODE><<<blocks, threads>>>(out, 12345u, 1u, 0xffffffffu, 65536u);
     cudaEventRecord(e1); cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     int clk_khz; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
@@ -89,5 +93,9 @@ int main() {
     run<18>("med3 = 2 x VIMNMX3 + 4 x IMAD (per med3)", 1);
     run<19>("IMAD", 1);
     run<20>("IMAD + VIMNMX2", 2);
+    run<21>("IMAD.HI (+IADD)", 1);
+    run<24>("funnel shift as IMAD.HI + IMAD (per shift)", 1);
+    run<23>("SHF + VIMNMX3 (per pair)", 1);
+    run<22>("IMAD.HI + IMAD + VIMNMX3 (per pair)", 1);
     return 0;
 }
