@@ -69,6 +69,32 @@ def test_kalman_smooth_matches_restated_pykalman(n_coords, T):
     assert_close(lc, ref_fc[-1], 1e-9, 1e-10, what='last covariance (smoother)')
 
 
+def test_kalman_full_chunk_steady_state_and_linearity():
+    """BASELINE-size chunk (1000 steps, 54 states).  The filter kernel stops updating covariances once they repeat and restarts
+    when an observation is missing: bursts of missing rows at several places exercise entering and leaving that mode, and
+    the result must still match the restated pykalman filter / smoother.  Size-independent property: with the covariances
+    fixed, filtered and smoothed means are linear in (observations, prior mean)."""
+    rng = np.random.default_rng(2024)
+    A, H, Q, R, m0, P0 = _random_model(rng, 18)
+    T = 1000
+    missing = [1, 2, 40, 41, 42, 300, 555, 556, 998, 999]
+    obs = _obs(rng, T, H, missing)
+    kf = KalmanFilter(transition_matrices=A, observation_matrices=H, transition_covariance=Q, observation_covariance=R,
+                      initial_state_mean=m0, initial_state_covariance=P0)
+    ref_f, ref_fc = kf.filter(ma.masked_invalid(obs))
+    ref_s, _ = kf.smooth(ma.masked_invalid(obs))
+    got_f, lm, lc = _device_smooth(A, H, Q, R, m0, P0, obs, smooth=False)
+    got_s, _, _ = _device_smooth(A, H, Q, R, m0, P0, obs, smooth=True)
+    assert_close(got_f, ref_f, 1e-9, 1e-9, what='filtered means, 1000 steps')
+    assert_close(got_s, ref_s, 1e-8, 1e-8, what='smoothed means, 1000 steps')
+    assert_close(lc, ref_fc[-1], 1e-9, 1e-11, what='last covariance, 1000 steps')
+    obs2 = _obs(rng, T, H, missing)                              # same missing pattern, other values
+    m02 = rng.normal(size=m0.shape)
+    s2, _, _ = _device_smooth(A, H, Q, R, m02, P0, obs2, smooth=True)
+    mix, _, _ = _device_smooth(A, H, Q, R, 0.25 * m0 - 3.0 * m02, P0, 0.25 * obs - 3.0 * obs2, smooth=True)
+    assert_close(mix, 0.25 * got_s - 3.0 * s2, 1e-9, 1e-8, what='linearity of the smoother')
+
+
 def test_kalman_filter_update_and_all_missing():
     rng = np.random.default_rng(5)
     A, H, Q, R, m0, P0 = _random_model(rng, 4)
