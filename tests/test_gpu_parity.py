@@ -330,9 +330,10 @@ def test_crops_match_reference_bit_exact(P, name):
     assert np.array_equal(one, g['depth_frames'][3])
 
 
-def test_crops_match_opencv_on_random_transforms(P):
+@pytest.mark.parametrize('w', [150, 152])       # 150: per-tap global gather (unaligned rows); 152: the staged shared-memory kernel
+def test_crops_match_opencv_on_random_transforms(P, w):
     rng = np.random.default_rng(21)
-    n, h, w = 300, 120, 150
+    n, h = 300, 120
     fr = rng.integers(0, 101, size=(n, h, w)).astype(np.uint8)
     cen = np.stack([rng.uniform(-2, w + 1, n), rng.uniform(-2, h + 1, n)], axis=1)
     cen[::7] = np.stack([rng.uniform(0, 45, n), rng.uniform(0, 45, n)], axis=1)[::7]
@@ -341,7 +342,7 @@ def test_crops_match_opencv_on_random_transforms(P):
     ang[::13] = np.floor(ang[::13] / 45) * 45
     ang[5] = np.nan
     cen[6, 0] = np.nan
-    for crop in [(80, 80), (128, 128), (31, 31)]:
+    for crop in [(80, 80), (128, 128), (31, 31), (32, 32)]:
         got = P.crop_and_rotate_frames_batch(fr, cen, ang, crop)
         bad = 0
         for i in range(n):
