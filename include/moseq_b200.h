@@ -111,7 +111,8 @@ MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int
  * fm = (cleaned > frame_threshold) & (mask != 0); polygon moments of the largest outer contour.
  * centroid_dev (n,2) f64 [x,y]; orientation_dev (n) f64 radians; axis_length_dev (n,2) f64;
  * sums24_dev (n,6) int64 or NULL: exact 24x polygon integrals (1,x,y,xx,xy,yy) of the winning blob.
- * scratch_dev: msq_frame_features_scratch_bytes(n,h,w) bytes. */
+ * scratch_dev: msq_frame_features_scratch_bytes(n,h,w) bytes, 4-byte aligned (the list of frames the streaming
+ * row-convex fast path passes on to the general flood/peel kernel); NULL or too small: every frame takes the general kernel. */
 MSQ_API size_t msq_frame_features_scratch_bytes(int n, int h, int w);
 MSQ_API int msq_frame_features(const uint8_t *cleaned_dev, const uint8_t *mask_dev, int n, int h, int w,
                        double frame_threshold, double *centroid_dev, double *orientation_dev,

@@ -132,7 +132,8 @@ namespace msq {
 int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);
 int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);   // -100: shape not served
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
-                          double *centroid, double *orientation, double *axis, int64_t *sums24, cudaStream_t st);
+                          double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
+                          cudaStream_t st);
 int launch_angles_and_flips(const double *orientation, const double *axis, const double *centroid, const float *kpts,
                             int n, int chunk, double *angle_out, uint8_t *flips, double *conf, int32_t *passes,
                             cudaStream_t st);

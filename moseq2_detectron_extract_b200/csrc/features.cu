@@ -165,7 +165,7 @@ template <int LPR>      // lanes per row: power of two >= words per row
 __global__ void __launch_bounds__(kFeatWarps * 32)
 features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__ mask, int n, int h, int w,
                 int ge, double *__restrict__ centroid, double *__restrict__ orientation,
-                double *__restrict__ axis_length, long long *__restrict__ sums24) {
+                double *__restrict__ axis_length, long long *__restrict__ sums24, const int *__restrict__ list) {
     extern __shared__ __align__(16) uint32_t smem_bits[];
     constexpr int RPW = 32 / LPR;                       // rows handled per warp step in the parallel phases
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,15 +177,65 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
     const uint32_t lane_mask_row =                      // valid pixel bits of word `lane` (sequential phases)
         lane < wpr - 1 ? 0xffffffffu : (lane == wpr - 1 ? ((w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu) : 0u);
 
-    for (int f = blockIdx.x * kFeatWarps + warp; f < n; f += gridDim.x * kFeatWarps) {
+    // with a list (written by features_stream_kernel: [0] = count, [1..] = frame indices) only those frames are processed
+    const int todo = list ? list[0] : n;
+    for (int item = blockIdx.x * kFeatWarps + warp; item < todo; item += gridDim.x * kFeatWarps) {
+        const int f = list ? list[1 + item] : item;
         const uint8_t *cf = cleaned + (size_t)f * h * w;
         const uint8_t *mf = mask + (size_t)f * h * w;
 
         // ---------------- phase 0: bit rows ----------------
-        // The row loop is software-pipelined: the 4 x 128-bit loads of the NEXT row step are in flight while
-        // the current one is thresholded (ncu: the un-pipelined loop spent its time in long_scoreboard).
+        // A row step is 2 KB per warp (every lane: 32 B of the frame + 32 B of the mask).  kStages steps are kept in flight
+        // with cp.async into the (still unused) Q plane -- no registers are tied up, so three steps ride the HBM latency
+        // instead of one (ncu on the register-prefetch version: 53 % of the stall samples sat on this loop, DRAM 36 % busy).
         int r_lo = h, r_hi = -1;
-        if (vec_ok) {
+        constexpr int kStages = 3;
+        const bool staged = vec_ok && (size_t)h * LPR * sizeof(uint32_t) >= (size_t)kStages * 2048;
+        if (staged) {
+            const ByteTest bt = make_byte_test(ge);
+            const bool lane_on = k < wpr;
+            const int x = k << 5;
+            const bool second = x + 16 < w;
+            unsigned char *ring = reinterpret_cast<unsigned char *>(Q);      // [stage][part 0..3][lane] x 16 B
+            const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+            auto issue = [&](int r, int stage) {
+                if (lane_on && r < h) {
+                    const uint8_t *c = cf + (size_t)r * w + x, *m = mf + (size_t)r * w + x;
+                    const uint32_t dst = ring_sa + stage * 2048;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(c) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 1024), "l"(m) : "memory");
+                    if (second) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 512), "l"(c + 16) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 1536), "l"(m + 16) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+#pragma unroll
+            for (int sgl = 0; sgl < kStages; ++sgl) issue(sub + sgl * RPW, sgl);
+            int stage = 0;
+#pragma unroll 3
+            for (int r = sub; r < h; r += RPW) {
+                asm volatile("cp.async.wait_group %0;" :: "n"(kStages - 1) : "memory");
+                uint32_t bits = 0u;
+                if (lane_on) {
+                    const uint4 *slot = reinterpret_cast<const uint4 *>(ring + stage * 2048) + lane;
+                    RowWordRaw cur;
+                    cur.c0 = slot[0];
+                    cur.m0 = slot[64];
+                    if (second) { cur.c1 = slot[32]; cur.m1 = slot[96]; }
+                    else cur.c1 = cur.m1 = make_uint4(0u, 0u, 0u, 0u);
+                    bits = threshold_raw(cur, bt);
+                    if (x + 32 > w) bits &= (w - x >= 32) ? 0xffffffffu : ((1u << (w - x)) - 1u);   // drop pixels beyond the row end
+                }
+                P[r * LPR + k] = bits;
+                if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
+                issue(r + kStages * RPW, stage);                            // refill the slot that was just consumed
+                stage = (stage + 1 == kStages) ? 0 : stage + 1;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if (vec_ok) {
+            // small frames (the Q plane cannot hold the ring): one step of register prefetch
             const ByteTest bt = make_byte_test(ge);
             const bool lane_on = k < wpr;
             RowWordRaw cur, nxt;
@@ -200,7 +250,6 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                     if (x0 + 32 > w) bits &= (w - x0 >= 32) ? 0xffffffffu : ((1u << (w - x0)) - 1u);
                 }
                 P[r * LPR + k] = bits;
-                Q[r * LPR + k] = 0u;
                 if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
                 cur = nxt;
             }
@@ -209,7 +258,6 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
                 uint32_t bits = 0u;
                 if (k < wpr) bits = threshold_word_scalar(cf + (size_t)r * w, mf + (size_t)r * w, k, w, ge);
                 P[r * LPR + k] = bits;
-                Q[r * LPR + k] = 0u;
                 if (bits) { r_lo = min(r_lo, r); r_hi = max(r_hi, r); }
             }
         }
@@ -301,6 +349,9 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
             blob_sums(r_lo, r_hi, best);
             have = true;
         } else if (r_hi >= 0) {
+            // the general path needs the Q plane (phase 0 may have used it as its load ring): nothing reached yet
+            for (int r = sub; r < h; r += RPW) Q[r * LPR + k] = 0u;
+            __syncwarp();
             // ---------------- phase 1: flood the background from outside (4-connected) ----------------
             const uint32_t edge = (lane == 0 ? 1u : 0u) | (lane == ((w - 1) >> 5) ? (1u << ((w - 1) & 31)) : 0u);
             const bool act = lane < LPR;
@@ -418,9 +469,212 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming fast path.  For a row-convex foreground (every row one run, consecutive runs touching) the answer is the cell
+// sums of the foreground itself, and both the test and the sums only ever look at a row and the row above it.  So the frame
+// is consumed in ONE pass straight from global memory: lane (sub, k) thresholds word k of row base + sub, the row above
+// comes from the neighbouring lane group (or, for the first row of a step, from the previous step's registers), run counts
+// and contacts are popcounts + shuffles, and nothing touches shared memory.  ~100 registers and no shared memory give
+// 16+ warps per SM instead of the 12 the general kernel gets.  Frames that fail the test are appended to `fallback`
+// ([0] = count, [1..] = frame indices) and redone by features_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStreamWarps = 4;
+constexpr int kChunkSteps = 3;         // row steps per bulk copy: 12 rows x 240 B = 2.9 KB contiguous per array (2 and 4 measured: no better)
+constexpr int kStreamStages = 2;       // bulk copies in flight per warp
+
+// ---- mbarrier / bulk-copy (TMA, 1-D) primitives ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+                    "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kStreamWarps * 32, 4)
+features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__ mask, int n, int h, int w, int ge,
+                       double *__restrict__ centroid, double *__restrict__ orientation, double *__restrict__ axis_length,
+                       long long *__restrict__ sums24, int *__restrict__ fallback) {
+    constexpr int RPW = 32 / LPR;
+    constexpr int kChunkRows = kChunkSteps * RPW;
+    constexpr unsigned kAll = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char stream_smem[];
+    __shared__ uint64_t bars[kStreamWarps][kStreamStages];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpr = (w + 31) >> 5;
+    const int sub = lane / LPR, k = lane % LPR;
+    const bool lane_on = k < wpr;
+    const int x = k << 5;
+    const bool second = x + 16 < w;
+    const uint32_t tail = (x + 32 > w) ? ((w - x >= 32) ? 0xffffffffu : ((w - x) > 0 ? ((1u << (w - x)) - 1u) : 0u)) : 0xffffffffu;
+    const ByteTest bt = make_byte_test(ge);
+    // per warp: kStreamStages slots of [kChunkRows rows of the frame | kChunkRows rows of the mask], filled by 1-D bulk copies
+    const size_t slot_bytes = (size_t)2 * kChunkRows * w;
+    unsigned char *slots = stream_smem + (size_t)warp * kStreamStages * slot_bytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStreamStages; ++st) mbar_init(&bars[warp][st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int first = blockIdx.x * kStreamWarps + warp, stride = gridDim.x * kStreamWarps;
+    const int n_chunks = (h + kChunkRows - 1) / kChunkRows;
+    const int my_frames = first < n ? (n - first + stride - 1) / stride : 0;
+    const long long items = (long long)my_frames * n_chunks;            // (frame, chunk) pairs of this warp, in order
+    auto issue = [&](long long item) {                                   // lane 0 only
+        const int fi = (int)(item / n_chunks), c = (int)(item - (long long)fi * n_chunks);
+        const int f = first + fi * stride, st = (int)(item % kStreamStages);
+        const int rows = min(kChunkRows, h - c * kChunkRows);
+        const uint32_t bytes = (uint32_t)rows * w;
+        const size_t off = (size_t)f * h * w + (size_t)c * kChunkRows * w;
+        unsigned char *slot = slots + (size_t)st * slot_bytes;
+        mbar_expect_tx(&bars[warp][st], 2 * bytes);
+        bulk_g2s(slot, cleaned + off, bytes, &bars[warp][st]);
+        bulk_g2s(slot + (size_t)kChunkRows * w, mask + off, bytes, &bars[warp][st]);
+    };
+    if (lane == 0)
+        for (int i = 0; i < kStreamStages && i < items; ++i) issue(i);
+    uint32_t parity = 0u;                                                // bit st: phase of stage st
+
+    long long item = 0;
+    for (int fi = 0; fi < my_frames; ++fi) {
+        const int f = first + fi * stride;
+        CellAcc acc[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[c] = {0, 0, 0, 0, 0, 0};
+        bool simple = true, started = false, ended = false, prev_ne = false;      // warp-uniform
+        int my_starts = 0, ne_rows = 0;                                            // run starts seen by this lane; non-empty rows
+        uint32_t prev_bits = 0u;
+        for (int c = 0; c < n_chunks; ++c, ++item) {
+            const int st = (int)(item % kStreamStages);
+            mbar_wait(&bars[warp][st], (parity >> st) & 1u);
+            parity ^= 1u << st;
+            const unsigned char *slot = slots + (size_t)st * slot_bytes;
+            if (simple) {
+#pragma unroll
+                for (int j = 0; j < kChunkSteps; ++j) {
+                    const int rr = j * RPW + sub;                        // row inside the chunk
+                    const int r = c * kChunkRows + rr;
+                    uint32_t b = 0u;
+                    if (lane_on && r < h) {
+                        RowWordRaw cur;
+                        const unsigned char *crow = slot + (size_t)rr * w + x, *mrow = crow + (size_t)kChunkRows * w;
+                        cur.c0 = *reinterpret_cast<const uint4 *>(crow);
+                        cur.m0 = *reinterpret_cast<const uint4 *>(mrow);
+                        if (second) {
+                            cur.c1 = *reinterpret_cast<const uint4 *>(crow + 16);
+                            cur.m1 = *reinterpret_cast<const uint4 *>(mrow + 16);
+                        } else {
+                            cur.c1 = cur.m1 = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        b = threshold_raw(cur, bt) & tail;
+                    }
+                    // word k of the row above: the lane group below this one, or the last row of the previous step
+                    const uint32_t up = __shfl_up_sync(kAll, b, LPR & 31);
+                    const uint32_t carry = __shfl_sync(kAll, prev_bits, (RPW - 1) * LPR + k);
+                    const uint32_t a = (sub == 0) ? carry : up;
+                    uint32_t a_lo = __shfl_up_sync(kAll, a, 1), a_hi = __shfl_down_sync(kAll, a, 1);
+                    uint32_t b_lo = __shfl_up_sync(kAll, b, 1), b_hi = __shfl_down_sync(kAll, b, 1);
+                    if (k == 0) { a_lo = 0u; b_lo = 0u; }
+                    if (k == LPR - 1) { a_hi = 0u; b_hi = 0u; }
+                    // ---- row-convexity: runs in this row, contact with the row above.  Two ballots give, for all RPW rows
+                    // of the step at once, which rows are non-empty and which touch the row above; run starts are only
+                    // counted per lane and compared with the number of non-empty rows once per frame (every non-empty row
+                    // has >= 1 start, so the totals agree iff every such row is a single run). ----
+                    my_starts += __popc(b & ~((b << 1) | (b_lo >> 31)));
+                    const unsigned nz = __ballot_sync(kAll, b != 0u);
+                    const unsigned tz = __ballot_sync(kAll, ((a | (a << 1) | (a >> 1) | (a_lo >> 31) | (a_hi << 31)) & b) != 0u);
+                    constexpr unsigned kGroup = (LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u);
+#pragma unroll
+                    for (int q = 0; q < RPW; ++q) {
+                        const bool ne = ((nz >> (q * LPR)) & kGroup) != 0u;     // rows >= h hold no bits
+                        if (ne) {
+                            if (ended || (prev_ne && ((tz >> (q * LPR)) & kGroup) == 0u)) simple = false;
+                            started = true;
+                            ++ne_rows;
+                        } else if (started) {
+                            ended = true;
+                        }
+                        prev_ne = ne;
+                    }
+                    // ---- exact cell sums of the row pair (r - 1, r), as in features_kernel ----
+                    if ((a | b) != 0u) {
+                        const uint32_t a1 = (a >> 1) | (a_hi << 31), b1 = (b >> 1) | (b_hi << 31);
+                        const uint32_t cls[5] = {a & a1 & b & b1, ~a & a1 & b & b1, a & ~a1 & b & b1, a & a1 & ~b & b1,
+                                                 a & a1 & b & ~b1};
+                        const long long x0 = (long long)x, y = r - 1;
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            if (cls[q] == 0u) continue;
+                            int cnt, s1, s2;
+                            bit_moments(cls[q], cnt, s1, s2);
+                            const long long si = x0 * cnt + s1;
+                            const long long sii = x0 * x0 * cnt + 2 * x0 * s1 + s2;
+                            acc[q].n += cnt;
+                            acc[q].i += si;
+                            acc[q].j += y * cnt;
+                            acc[q].ii += sii;
+                            acc[q].ij += y * si;
+                            acc[q].jj += y * y * cnt;
+                        }
+                    }
+                    prev_bits = b;
+                }
+            }
+            __syncwarp();                                                // every lane is done with the slot
+            if (lane == 0 && item + kStreamStages < items) issue(item + kStreamStages);
+        }
+        if (simple) simple = warp_sum(my_starts) == ne_rows;
+        if (!simple) {
+            if (lane == 0) fallback[1 + atomicAdd(fallback, 1)] = f;
+            continue;
+        }
+        long long s[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const long long A = kCell24[c][0], U = kCell24[c][1], V = kCell24[c][2], UU = kCell24[c][3],
+                            UV = kCell24[c][4], VV = kCell24[c][5];
+            s[0] += A * acc[c].n;
+            s[1] += A * acc[c].i + U * acc[c].n;
+            s[2] += A * acc[c].j + V * acc[c].n;
+            s[3] += A * acc[c].ii + 2 * U * acc[c].i + UU * acc[c].n;
+            s[4] += A * acc[c].ij + V * acc[c].i + U * acc[c].j + UV * acc[c].n;
+            s[5] += A * acc[c].jj + 2 * V * acc[c].j + VV * acc[c].n;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s[q] = warp_sum_ll(s[q]);
+        if (lane == 0) {
+            double c[2], o, ax[2];
+            moment_epilogue(s, c, &o, ax);
+            centroid[2 * (size_t)f] = c[0];
+            centroid[2 * (size_t)f + 1] = c[1];
+            orientation[f] = o;
+            axis_length[2 * (size_t)f] = ax[0];
+            axis_length[2 * (size_t)f + 1] = ax[1];
+            if (sums24)
+                for (int q = 0; q < 6; ++q) sums24[6 * (size_t)f + q] = s[q];
+        }
+    }
+}
+
 template <int LPR>
 int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, int ge,
-                    double *centroid, double *orientation, double *axis, long long *sums24, cudaStream_t st) {
+                    double *centroid, double *orientation, double *axis, long long *sums24, int *fallback, cudaStream_t st) {
     const size_t smem = (size_t)kFeatWarps * 2 * h * LPR * sizeof(uint32_t);
     MSQ_REQUIRE(smem <= 227 * 1024, MSQ_EUNSUPPORTED,
                 "frame_features: %dx%d frames need %zu B of shared memory per CTA (max 232448)", h, w, smem);
@@ -428,9 +682,21 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
     const int per_sm = std::max(1, std::min(16, (int)((227 * 1024) / (smem + 1024))));
     const int ctas = (n + kFeatWarps - 1) / kFeatWarps;
     const int grid = std::min(ctas, sm_count() * per_sm);
+    // streaming fast path first (needs 16-byte aligned rows and a place for the list of frames it could not settle)
+    const bool stream_ok = fallback && (w % 16 == 0) && ((uintptr_t)cleaned % 16 == 0) && ((uintptr_t)mask % 16 == 0) &&
+                           (size_t)kStreamWarps * kStreamStages * 2 * (kChunkSteps * (32 / LPR)) * w <= 160 * 1024;
     TimedLaunch timed(K_FEATURES, st);
+    if (stream_ok) {
+        MSQ_CUDA_OK(cudaMemsetAsync(fallback, 0, sizeof(int), st));
+        const size_t ssmem = (size_t)kStreamWarps * kStreamStages * 2 * (kChunkSteps * (32 / LPR)) * w;
+        MSQ_CUDA_OK(cudaFuncSetAttribute(features_stream_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+        const int sgrid = std::min((n + kStreamWarps - 1) / kStreamWarps, sm_count() * 4);
+        features_stream_kernel<LPR><<<sgrid, kStreamWarps * 32, ssmem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
+                                                                            axis, sums24, fallback);
+        MSQ_LAUNCH_OK("frame_features (streaming)");
+    }
     features_kernel<LPR><<<grid, kFeatWarps * 32, smem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
-                                                            axis, sums24);
+                                                            axis, sums24, stream_ok ? fallback : nullptr);
     MSQ_LAUNCH_OK("frame_features");
     return MSQ_OK;
 }
@@ -438,7 +704,8 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
 }  // namespace
 
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
-                          double *centroid, double *orientation, double *axis, int64_t *sums24, cudaStream_t st) {
+                          double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
+                          cudaStream_t st) {
     MSQ_REQUIRE(w <= 1024, MSQ_EUNSUPPORTED, "frame_features: width %d > 1024 is not supported", w);
     // pixel > thr on integers  <=>  pixel >= floor(thr) + 1; clamp to [0, 256] (0: all pass, 256: none)
     int ge;
@@ -447,24 +714,28 @@ int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, in
     else ge = (int)floor(frame_threshold) + 1;
     const int wpr = (w + 31) / 32;
     long long *s24 = reinterpret_cast<long long *>(sums24);
-    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
-    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
-    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
-    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
-    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
-    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, st);
+    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
+    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
+    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
+    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
+    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
+    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
 }
 
 }  // namespace msq
 
-extern "C" size_t msq_frame_features_scratch_bytes(int, int, int) { return 0; }
+// scratch = the list of frames the streaming fast path hands to the general kernel: a count + up to n frame indices
+extern "C" size_t msq_frame_features_scratch_bytes(int n, int, int) { return n > 0 ? ((size_t)n + 1) * sizeof(int) : 0; }
 
 extern "C" int msq_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w,
                                   double frame_threshold, double *centroid, double *orientation, double *axis,
-                                  int64_t *sums24, void * /*scratch*/, size_t /*scratch_bytes*/, void *stream) {
+                                  int64_t *sums24, void *scratch, size_t scratch_bytes, void *stream) {
     MSQ_REQUIRE(cleaned && mask && centroid && orientation && axis, MSQ_EINVAL, "msq_frame_features: null pointer");
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0, MSQ_EINVAL, "msq_frame_features: bad sizes n=%d h=%d w=%d", n, h, w);
     if (n == 0) return MSQ_OK;
-    return msq::launch_frame_features(cleaned, mask, n, h, w, frame_threshold, centroid, orientation, axis, sums24,
+    // without (enough, 4-byte aligned) scratch every frame goes through the general kernel
+    int *fallback = (scratch && scratch_bytes >= msq_frame_features_scratch_bytes(n, h, w) && (uintptr_t)scratch % 4 == 0)
+                        ? static_cast<int *>(scratch) : nullptr;
+    return msq::launch_frame_features(cleaned, mask, n, h, w, frame_threshold, centroid, orientation, axis, sums24, fallback,
                                       (cudaStream_t)stream);
 }

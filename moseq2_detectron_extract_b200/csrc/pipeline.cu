@@ -8,7 +8,8 @@ using namespace msq;
 
 extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
     const size_t nn = (size_t)(n > 0 ? n : 0);
-    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256) + align_up(msq_crop_scratch_bytes((int)nn), 256);
+    return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256) + align_up(msq_crop_scratch_bytes((int)nn), 256) +
+           align_up((nn + 1) * sizeof(int), 256);
 }
 
 extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,
@@ -30,12 +31,13 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
     char *base = reinterpret_cast<char *>(scratch);
     int2 *sums = reinterpret_cast<int2 *>(base + align_up((size_t)n * sizeof(double), 256));
     void *crop_scratch = base + align_up((size_t)n * sizeof(double), 256) + align_up((size_t)n * sizeof(int2), 256);
+    int *feature_list = reinterpret_cast<int *>(reinterpret_cast<char *>(crop_scratch) + align_up(msq_crop_scratch_bytes(n), 256));
 
     int rc;
     if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st)) != MSQ_OK) return rc;
     // frame_threshold = 3 (ref proc/proc.py:716)
     if ((rc = launch_frame_features(out->cleaned, mask_dev, n, h, w, 3.0, out->centroid, orientation, out->axis_length,
-                                    nullptr, st)) != MSQ_OK) return rc;
+                                    nullptr, feature_list, st)) != MSQ_OK) return rc;
     if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
                                       out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
     if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,

@@ -180,8 +180,9 @@ def _features_device(cleaned: torch.Tensor, mask: torch.Tensor, frame_threshold:
     orientation = _dev.empty((n,), torch.float64)
     axis = _dev.empty((n, 2), torch.float64)
     sums = _dev.empty((n, 6), torch.int64) if want_sums else None
+    flist = _dev.empty((max(n, 1) + 1,), torch.int32)     # scratch: frames the streaming fast path leaves to the general kernel
     _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(mask), n, h, w, float(frame_threshold),
-              _dev.ptr(centroid), _dev.ptr(orientation), _dev.ptr(axis), _dev.ptr(sums), ctypes.c_void_p(0), 0,
+              _dev.ptr(centroid), _dev.ptr(orientation), _dev.ptr(axis), _dev.ptr(sums), _dev.ptr(flist), flist.numel() * 4,
               _dev.stream())
     return centroid, orientation, axis, sums
 

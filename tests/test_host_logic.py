@@ -44,7 +44,7 @@ def test_library_metadata_without_gpu(lib):
     from moseq2_detectron_extract_b200.proc.scalars import scalar_attributes
     assert set(cols) == set(keypoint_attributes()) and set(names) == set(scalar_attributes())
     assert lib.kernel_names()[0] == 'prep_frames'
-    assert l.msq_frame_features_scratch_bytes(10, 240, 240) == 0
+    assert l.msq_frame_features_scratch_bytes(10, 240, 240) == 44          # count + one index per frame
     assert l.msq_extract_scratch_bytes(1000, 240, 240) >= 1000 * (8 + 8 + 64)
 
 

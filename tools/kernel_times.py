@@ -39,10 +39,11 @@ cleaned = torch.empty_like(prep); cen = _dev.empty((n, 2), torch.float64); ori =
 ang = _dev.empty((n,), torch.float64); fl = _dev.empty((n,), torch.uint8); ps = _dev.empty((64,), torch.int32)
 sc = _dev.empty((17, n), torch.float64); kc = _dev.empty((96, n), torch.float64); scr = _dev.empty((16 * n + 512,), torch.uint8)
 cscr = _dev.empty((int(_lib.load().msq_crop_scratch_bytes(n)) + 16,), torch.uint8); dc = _dev.empty((n, 80, 80), torch.uint8); mc = _dev.empty((n, 80, 80), torch.uint8)
+flist = _dev.empty((n + 1,), torch.int32)
 out = {}
 out['prep'] = timeit(lambda: _lib.call('msq_prep_frames', _dev.ptr(frames), n, geom.height, geom.width, _dev.ptr(bgd), 1, _dev.ptr(roid), y0, x0, h, w, 0.0, 100.0, 3, _dev.ptr(prep), _dev.ptr(inv), None, st))
 out['clean'] = timeit(lambda: _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, st))
-out['features'] = timeit(lambda: _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(cen), _dev.ptr(ori), _dev.ptr(ax), None, None, 0, st))
+out['features'] = timeit(lambda: _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(cen), _dev.ptr(ori), _dev.ptr(ax), None, _dev.ptr(flist), flist.numel() * 4, st))
 out['angles'] = timeit(lambda: _lib.call('msq_angles_and_flips', _dev.ptr(ori), _dev.ptr(ax), _dev.ptr(cen), _dev.ptr(kpts), n, 1000, _dev.ptr(ang), _dev.ptr(fl), None, _dev.ptr(ps), st))
 out['scalars_kpts'] = timeit(lambda: _lib.call('msq_scalars_and_keypoints', _dev.ptr(prep), _dev.ptr(masks), _dev.ptr(cleaned), _dev.ptr(cen), _dev.ptr(ang), _dev.ptr(ax), _dev.ptr(kpts), n, h, w, 1000, 0.0, 100.0, 673.0, _dev.ptr(sc), _dev.ptr(kc), _dev.ptr(scr), scr.numel(), st))
 out['crop'] = timeit(lambda: _lib.call('msq_crop_rotate', _dev.ptr(prep), _dev.ptr(masks), n, h, w, _dev.ptr(cen), _dev.ptr(ang), 80, 80, _dev.ptr(dc), _dev.ptr(mc), _dev.ptr(cscr), cscr.numel(), st))
