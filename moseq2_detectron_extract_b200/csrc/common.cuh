@@ -133,7 +133,9 @@ int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStrea
 int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);   // -100: shape not served
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
                           double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
-                          cudaStream_t st);
+                          cudaStream_t st, cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join);
+int launch_masked_sums(const uint8_t *chunk_frames, const uint8_t *mask, int n, int h, int w, double min_h, double max_h,
+                       int2 *sums_scratch, cudaStream_t st);
 int launch_angles_and_flips(const double *orientation, const double *axis, const double *centroid, const float *kpts,
                             int n, int chunk, double *angle_out, uint8_t *flips, double *conf, int32_t *passes,
                             cudaStream_t st);
@@ -141,7 +143,7 @@ int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mas
                                  const double *centroid, const double *angle_deg, const double *axis,
                                  const void *kpts, bool kpts_f64, int n, int h, int w, int chunk, double min_h,
                                  double max_h, double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
-                                 cudaStream_t st);
+                                 cudaStream_t st, bool sums_done = false);
 int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, int w, const double *centroid,
                        const double *angle_deg, int cw, int ch, uint8_t *out, uint8_t *out2, void *scratch, cudaStream_t st);
 }  // namespace msq

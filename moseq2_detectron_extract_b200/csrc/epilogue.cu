@@ -327,19 +327,26 @@ int launch_angles_and_flips(const double *orientation, const double *axis, const
     return MSQ_OK;
 }
 
+int launch_masked_sums(const uint8_t *chunk_frames, const uint8_t *mask, int n, int h, int w, double min_h, double max_h,
+                       int2 *sums_scratch, cudaStream_t st) {
+    const size_t plane = (size_t)h * w;
+    const int vec_ok = (plane % 16 == 0) && ((uintptr_t)chunk_frames % 16 == 0) && ((uintptr_t)mask % 16 == 0);   // NULL mask is "aligned"
+    TimedLaunch timed(K_MASKED_SUMS, st);
+    masked_sums_kernel<<<std::min(n, sm_count() * 8), kSumThreads, 0, st>>>(chunk_frames, mask, n, plane, min_h, max_h,
+                                                                          vec_ok, sums_scratch);
+    MSQ_LAUNCH_OK("masked_sums");
+    return MSQ_OK;
+}
+
 int launch_scalars_and_keypoints(const uint8_t *chunk_frames, const uint8_t *mask, const uint8_t *cleaned,
                                  const double *centroid, const double *angle_deg, const double *axis,
                                  const void *kpts, bool kpts_f64, int n, int h, int w, int chunk, double min_h,
                                  double max_h, double true_depth, double *scalars, double *kcols, int2 *sums_scratch,
-                                 cudaStream_t st) {
-    const size_t plane = (size_t)h * w;
-    const int vec_ok = (plane % 16 == 0) && ((uintptr_t)chunk_frames % 16 == 0) && ((uintptr_t)mask % 16 == 0);   // NULL mask is "aligned"
-    {
-        TimedLaunch timed(K_MASKED_SUMS, st);
-        masked_sums_kernel<<<std::min(n, sm_count() * 8), kSumThreads, 0, st>>>(chunk_frames, mask, n, plane, min_h, max_h,
-                                                                              vec_ok, sums_scratch);
+                                 cudaStream_t st, bool sums_done) {
+    if (!sums_done) {
+        const int rc = launch_masked_sums(chunk_frames, mask, n, h, w, min_h, max_h, sums_scratch, st);
+        if (rc != MSQ_OK) return rc;
     }
-    MSQ_LAUNCH_OK("masked_sums");
     MmScale mm;
     // ref proc/util.py:53-54: f = resolution / (2 * deg2rad(fov / 2)), same float64 operation order
     mm.fw = 512 / (2 * ((70.6 / 2) * kPiOver180));

@@ -674,7 +674,8 @@ features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__res
 
 template <int LPR>
 int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, int ge,
-                    double *centroid, double *orientation, double *axis, long long *sums24, int *fallback, cudaStream_t st) {
+                    double *centroid, double *orientation, double *axis, long long *sums24, int *fallback, cudaStream_t st,
+                    cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join) {
     const size_t smem = (size_t)kFeatWarps * 2 * h * LPR * sizeof(uint32_t);
     MSQ_REQUIRE(smem <= 227 * 1024, MSQ_EUNSUPPORTED,
                 "frame_features: %dx%d frames need %zu B of shared memory per CTA (max 232448)", h, w, smem);
@@ -695,9 +696,25 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
                                                                             axis, sums24, fallback);
         MSQ_LAUNCH_OK("frame_features (streaming)");
     }
-    features_kernel<LPR><<<grid, kFeatWarps * 32, smem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
+    // The general kernel only has the few frames of the list to do, each a long sequential chain in one warp.  A caller
+    // with independent work (the whole-chunk pipeline: the masked sums) passes a side stream + fork/join events, so that
+    // this latency is hidden; `join` is recorded on the side stream and must be waited for before the features are read.
+    cudaStream_t sg = st;
+    if (stream_ok && st_general != st) {
+        MSQ_CUDA_OK(cudaEventRecord(fork, st));
+        MSQ_CUDA_OK(cudaStreamWaitEvent(st_general, fork, 0));
+        sg = st_general;
+    }
+    features_kernel<LPR><<<grid, kFeatWarps * 32, smem, sg>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
                                                             axis, sums24, stream_ok ? fallback : nullptr);
     MSQ_LAUNCH_OK("frame_features");
+    if (st_general != st) {
+        if (sg == st) {                     // nothing was forked: make the caller's later wait on `join` a no-op
+            MSQ_CUDA_OK(cudaEventRecord(join, st));
+        } else {
+            MSQ_CUDA_OK(cudaEventRecord(join, sg));
+        }
+    }
     return MSQ_OK;
 }
 
@@ -705,7 +722,7 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
 
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
                           double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
-                          cudaStream_t st) {
+                          cudaStream_t st, cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join) {
     MSQ_REQUIRE(w <= 1024, MSQ_EUNSUPPORTED, "frame_features: width %d > 1024 is not supported", w);
     // pixel > thr on integers  <=>  pixel >= floor(thr) + 1; clamp to [0, 256] (0: all pass, 256: none)
     int ge;
@@ -714,12 +731,12 @@ int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, in
     else ge = (int)floor(frame_threshold) + 1;
     const int wpr = (w + 31) / 32;
     long long *s24 = reinterpret_cast<long long *>(sums24);
-    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
-    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
-    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
-    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
-    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
-    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st);
+    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
+    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
+    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
+    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
+    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
+    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
 }
 
 }  // namespace msq
@@ -737,5 +754,5 @@ extern "C" int msq_frame_features(const uint8_t *cleaned, const uint8_t *mask, i
     int *fallback = (scratch && scratch_bytes >= msq_frame_features_scratch_bytes(n, h, w) && (uintptr_t)scratch % 4 == 0)
                         ? static_cast<int *>(scratch) : nullptr;
     return msq::launch_frame_features(cleaned, mask, n, h, w, frame_threshold, centroid, orientation, axis, sums24, fallback,
-                                      (cudaStream_t)stream);
+                                      (cudaStream_t)stream, (cudaStream_t)stream, nullptr, nullptr);
 }

@@ -1,7 +1,8 @@
 // Whole-chunk pipeline: what ProcessFeaturesStep.process does per chunk with use_tracking=False and
 // <=1 instance per frame (ref pipeline/process_features_step.py:56-60, 163-199; proc/proc.py:700-848):
 //   clean -> moment features -> degrees/flips/angle filter -> scalars + keypoint table -> crops.
-// Pure sequencing on one stream; no allocation, no synchronisation.
+// Pure sequencing: the caller's stream plus one internal side stream forked and joined with events (no host
+// synchronisation, no device allocation).
 #include "common.cuh"
 
 using namespace msq;
@@ -33,16 +34,27 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
     void *crop_scratch = base + align_up((size_t)n * sizeof(double), 256) + align_up((size_t)n * sizeof(int2), 256);
     int *feature_list = reinterpret_cast<int *>(reinterpret_cast<char *>(crop_scratch) + align_up(msq_crop_scratch_bytes(n), 256));
 
+    // a side stream for the few frames the streaming feature kernel leaves to the general one: their long sequential
+    // chains run beside the masked sums (which do not depend on the features).  Created once per host thread.
+    static thread_local cudaStream_t side = nullptr;
+    static thread_local cudaEvent_t fork = nullptr, join = nullptr;
+    if (!side) {
+        MSQ_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        MSQ_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        MSQ_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    }
     int rc;
     if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st)) != MSQ_OK) return rc;
     // frame_threshold = 3 (ref proc/proc.py:716)
     if ((rc = launch_frame_features(out->cleaned, mask_dev, n, h, w, 3.0, out->centroid, orientation, out->axis_length,
-                                    nullptr, feature_list, st)) != MSQ_OK) return rc;
+                                    nullptr, feature_list, st, side, fork, join)) != MSQ_OK) return rc;
+    if ((rc = launch_masked_sums(chunk_dev, mask_dev, n, h, w, min_height, max_height, sums, st)) != MSQ_OK) return rc;
+    MSQ_CUDA_OK(cudaStreamWaitEvent(st, join, 0));
     if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
                                       out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
     if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,
                                            out->axis_length, kpts_dev, false, n, h, w, chunk, min_height, max_height,
-                                           true_depth, out->scalars, out->kpt_cols, sums, st)) != MSQ_OK) return rc;
+                                           true_depth, out->scalars, out->kpt_cols, sums, st, true)) != MSQ_OK) return rc;
     return launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
                               out->depth_crops, out->mask_crops, crop_scratch, st);
 }
