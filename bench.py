@@ -180,6 +180,8 @@ def run_ours(args):
 
     torch.cuda.set_device(local_rank)
     _dev.require_cuda()
+    from moseq2_detectron_extract_b200.shard import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: host buffers land on the GPU's NUMA node
     if world > 1:
         # NCCL carries only the barrier and the max-over-ranks of two timing scalars (no data-path collective);
         # keep its banner off stdout so that the single JSON line is the only output
@@ -416,6 +418,7 @@ def run_ours(args):
 
     cfg_out = workload_config(args, geom, world)
     cfg_out['roi_box'] = [y0, x0, y1, x1]
+    cfg_out['host_numa_binding'] = numa if numa else 'unavailable'      # rank 0's; every rank binds to its own GPU's node
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

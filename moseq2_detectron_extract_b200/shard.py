@@ -14,6 +14,42 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of /sys/.../local_cpulist)."""
+    cpus: List[int] = []
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[Dict[str, object]]:
+    """Pin this process to the CPUs local to GPU `device_index` (one process per GPU): page-locked buffers allocated
+    afterwards are first-touched on that NUMA node, so every rank streams its frames over its own PCIe root instead of
+    across the socket interconnect.  Best effort: returns {'bus_id', 'numa_node', 'cpus'} or None when the topology cannot
+    be read (no NVML, no sysfs entry, single-node machine reporting -1)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = int(visible.split(',')[device_index]) if visible and visible.split(',')[device_index].isdigit() else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        sysfs = '/sys/bus/pci/devices/' + bus.lower()[-12:]
+        node = int(open(sysfs + '/numa_node').read())
+        cpus = parse_cpulist(open(sysfs + '/local_cpulist').read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if node < 0 or not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {'bus_id': bus, 'numa_node': node, 'cpus': len(allowed)}
+    except Exception:       # pylint: disable=broad-except
+        return None
+
+
 def chunk_ranges(nframes: int, chunk_size: int, chunk_overlap: int = 0) -> List[range]:
     """Frame ranges of the chunks of a session (ref: io/util.py:24-35 gen_batch_sequence)."""
     out = []

@@ -264,3 +264,12 @@ def test_kalman_items_build_the_reference_model_blocks():
     tr = K.KalmanTracker([K.KalmanTrackerPoint2D(3, 1.0), K.KalmanTrackerNPoints2D(8, 3, 1.0)])
     assert (tr.n_state, tr.n_obs, tr.is_initialized) == (54, 18, False)
     assert np.allclose(K.angle_difference(np.array([350.0, 10.0, 0.0]), np.array([10.0, 350.0, 180.0])), [20.0, -20.0, 180.0])
+
+
+def test_numa_binding_helpers():
+    from moseq2_detectron_extract_b200.shard import bind_to_gpu_numa_node, parse_cpulist
+    assert parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11] and parse_cpulist('') == [] and parse_cpulist('5') == [5]
+    before = os.sched_getaffinity(0)
+    out = bind_to_gpu_numa_node(0)                 # no GPU / no NVML here: must degrade to None and leave the affinity alone
+    assert out is None or set(os.sched_getaffinity(0)) <= set(before)
+    os.sched_setaffinity(0, before)
