@@ -686,9 +686,9 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
     // streaming fast path first (needs 16-byte aligned rows and a place for the list of frames it could not settle)
     const bool stream_ok = fallback && (w % 16 == 0) && ((uintptr_t)cleaned % 16 == 0) && ((uintptr_t)mask % 16 == 0) &&
                            (size_t)kStreamWarps * kStreamStages * 2 * (kChunkSteps * (32 / LPR)) * w <= 160 * 1024;
-    TimedLaunch timed(K_FEATURES, st);
     if (stream_ok) {
         MSQ_CUDA_OK(cudaMemsetAsync(fallback, 0, sizeof(int), st));
+        TimedLaunch timed(K_FEATURES, st);
         const size_t ssmem = (size_t)kStreamWarps * kStreamStages * 2 * (kChunkSteps * (32 / LPR)) * w;
         MSQ_CUDA_OK(cudaFuncSetAttribute(features_stream_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
         const int sgrid = std::min((n + kStreamWarps - 1) / kStreamWarps, sm_count() * 4);
@@ -705,9 +705,12 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
         MSQ_CUDA_OK(cudaStreamWaitEvent(st_general, fork, 0));
         sg = st_general;
     }
-    features_kernel<LPR><<<grid, kFeatWarps * 32, smem, sg>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
-                                                            axis, sums24, stream_ok ? fallback : nullptr);
-    MSQ_LAUNCH_OK("frame_features");
+    {
+        TimedLaunch timed(K_FEATURES, sg);          // a launch of its own in the counters (and timed on its own stream)
+        features_kernel<LPR><<<grid, kFeatWarps * 32, smem, sg>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
+                                                                axis, sums24, stream_ok ? fallback : nullptr);
+        MSQ_LAUNCH_OK("frame_features");
+    }
     if (st_general != st) {
         if (sg == st) {                     // nothing was forked: make the caller's later wait on `join` a no-op
             MSQ_CUDA_OK(cudaEventRecord(join, st));
