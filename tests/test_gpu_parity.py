@@ -182,7 +182,7 @@ def test_features_match_reference(P, name):
     assert mask is d2_masks                      # the reference returns the given mask untouched
 
 
-@pytest.mark.parametrize('w', [5, 20, 33, 64, 100, 240, 300, 520])
+@pytest.mark.parametrize('w', [5, 20, 33, 64, 100, 128, 240, 300, 400, 512, 520, 544, 1024])
 def test_feature_sums_are_bit_exact_on_random_masks(P, w):
     import cv2
     from moseq2_detectron_extract_b200 import _dev
@@ -199,6 +199,11 @@ def test_feature_sums_are_bit_exact_on_random_masks(P, w):
             masks[i] = s > np.quantile(s, rng.uniform(0.2, 0.8))
     masks[1] = 0
     masks[2] = 1
+    yy, xx = np.mgrid[0:h, 0:w]                         # row-convex shapes: the streaming fast path at every lanes-per-row layout
+    masks[5] = ((xx - w * 0.6) / max(w * 0.3, 1)) ** 2 + ((yy - h * 0.5) / max(h * 0.4, 1)) ** 2 <= 1
+    masks[7] = (np.abs(xx - w // 2) + 2 * np.abs(yy - h // 2)) <= min(w, 2 * h) // 3
+    masks[8] = 0
+    masks[8, h // 3:h // 3 + 2, :] = 1                  # two full rows: runs crossing every 32-pixel word boundary
     cleaned = (masks * 7).astype(np.uint8)
     cleaned[4] = 200                                # threshold passes everywhere: mask alone decides
     ref = O.frame_features_np(cleaned, masks, 3, return_sums=True)
