@@ -11,7 +11,8 @@
  *   - plain pointers + sizes, no torch / C++ types; every image is dense row-major
  *   - "dev" pointers are CUDA device pointers on the current device; "host" pointers are host memory
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
- *   - device entry points never allocate, never synchronise and are re-entrant per stream;
+ *   - device entry points never allocate device memory, never synchronise with the host and are re-entrant per
+ *     stream (msq_extract_chunk lazily creates one side stream + two events per host thread);
  *     scratch memory is passed in by the caller (sizes from the *_scratch_bytes helpers)
  *   - return 0 on success, a negative MSQ_E* code otherwise; msq_last_error() gives the message of
  *     the last failure on the calling thread (Python raises from it)
@@ -237,7 +238,10 @@ MSQ_API int msq_get_bground_im(const void *frames_dev, int n, int H, int W, int 
                        double *out_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
 
 /* ---- whole-chunk pipeline: everything ProcessFeaturesStep.process does (ref:
- *      pipeline/process_features_step.py:56-60,163-199 with use_tracking=False), device buffers ------- */
+ *      pipeline/process_features_step.py:56-60,163-199 with use_tracking=False), device buffers -------
+ * Everything is ordered on `stream`; internally the few frames the streaming feature kernel hands to the general one run
+ * on a library-owned side stream that is forked from and joined back into `stream` with events (no host
+ * synchronisation, capturable in a CUDA graph).  scratch_dev: msq_extract_scratch_bytes(n,h,w) bytes, 256-byte aligned. */
 typedef struct msq_chunk_outputs {
     uint8_t *cleaned;        /* (n,h,w)  */
     double  *centroid;       /* (n,2)    */
