@@ -27,6 +27,16 @@ class InferenceStep(ProcessPipelineStep):
         raw = _dev.as_device(data['chunk'], torch.uint8)
         n = int(raw.shape[0])
         batch_size = min(self.config['batch_size'], n)
+        if self.config.get('dense_inference', False) and self.config.get('expected_instances', 1) == 1:
+            # batched hand-over of the first instance of every frame (what ProcessFeaturesStep consumes); the reference's
+            # data['inference'] list of Instances is not built
+            parts = []
+            for i in range(0, n, batch_size):
+                parts.append(self.predictor.predict_dense(raw[i:i + batch_size], self.config['min_height'], self.config['max_height']))
+                self.update_progress(min(batch_size, n - i))
+            data['_dense_instances'] = tuple(torch.cat([p[j] for p in parts]) for j in range(3))
+            data['inference'] = None
+            return data
         outputs = []
         for i in range(0, n, batch_size):
             pred = self.predictor.predict_prepared(raw[i:i + batch_size], self.config['min_height'], self.config['max_height'])

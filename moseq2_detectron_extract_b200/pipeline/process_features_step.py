@@ -95,6 +95,8 @@ class ProcessFeaturesStep(ProcessPipelineStep):
             masks, kpts, ninst = data.pop('_dense_instances')
         else:
             masks, kpts, ninst = _gather_instances(data['inference'])
+        if isinstance(ninst, torch.Tensor):
+            ninst = ninst.cpu().numpy()
         n = int(chunk.shape[0])
         if self.point_tracker is not None:
             res, kpts = self._tracked(chunk, masks, kpts)

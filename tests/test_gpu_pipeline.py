@@ -157,3 +157,24 @@ def test_raw_session_background_from_file(tmp_path):
     bg = sess.compute_bground(frame_stride=3)
     assert bg.dtype == np.float64 and bg.shape == (geom.height, geom.width)
     assert np.array_equal(bg, O.bground_im(ch.frames[::3].copy(), 5)) and sess.bground_im is bg
+
+
+def test_dense_inference_matches_per_image_instances():
+    """Predictor.predict_dense (batched detector_postprocess + first-instance gather, one paste launch) against the
+    reference-shaped path: predict_prepared -> outputs_to_instances -> mask_and_keypoints_from_model_output."""
+    pytest.importorskip('torchvision')
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.model.predict import Predictor
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    from moseq2_detectron_extract_b200.proc.proc import _gather_instances
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(6, seed=10, geom=geom)
+    prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom),
+                           roi=synthetic.make_roi(geom), vmin=0, vmax=100)
+    pred = Predictor.from_random_init(detections_per_img=1)
+    ref_masks, ref_kpts, ref_n = _gather_instances(pred.predict_prepared(prep, 0, 100))
+    masks, kpts, ninst = pred.predict_dense(prep, 0, 100)
+    assert masks.shape == ref_masks.shape and masks.dtype == torch.uint8
+    assert np.array_equal(ninst.cpu().numpy(), ref_n)
+    assert torch.equal(masks, ref_masks)
+    assert torch.allclose(kpts, ref_kpts, rtol=0, atol=0, equal_nan=True)
