@@ -63,7 +63,7 @@ class PipelineStep(threading.Thread):
             self.shutdown_event.set()
 
     def shutdown(self) -> None:
-        pass
+        """Called once when the step's loop ends (normally or not)."""
 
     @property
     def total_items(self) -> int:
@@ -101,6 +101,10 @@ class PipelineStep(threading.Thread):
             self.signal_shutdown()
         finally:
             self.flush_progress()
+            try:
+                self.shutdown()          # end-of-stream hook (the reference leaves it commented out, pipeline_step.py:157):
+            except Exception:            # writers close their files here; pylint: disable=broad-except
+                self.error = (self.error or '') + traceback.format_exc()
             self.is_complete.set()
 
     def initialize(self) -> None:

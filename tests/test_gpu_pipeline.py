@@ -178,3 +178,40 @@ def test_dense_inference_matches_per_image_instances():
     assert np.array_equal(ninst.cpu().numpy(), ref_n)
     assert torch.equal(masks, ref_masks)
     assert torch.allclose(kpts, ref_kpts, rtol=0, atol=0, equal_nan=True)
+
+
+def test_pipeline_with_result_writer(tmp_path):
+    """Produce -> (synthetic) inference -> features -> ResultWriterStep over chunks with overlap: the stored crops, masks,
+    scalars and flips are the oracle's, every frame exactly once (ref pipeline/write_results_step.py, io/result.py:105-130)."""
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.pipeline import (Pipeline, ProcessFeaturesStep, ProduceFramesStep, ResultWriterStep,
+                                                        SyntheticInferenceStep)
+    nframes, chunk_size = 70, 30
+    sess = synthetic.SyntheticSession(nframes, seed=6)
+    cfg = synthetic.default_config(sess.geom)
+    cfg.update(chunk_size=chunk_size, nframes=nframes, output_dir=str(tmp_path), bg_roi_index=0, roi=sess.roi,
+               bground_im=sess.bground_im, timestamps=np.arange(nframes) / 30.0)
+    pipe = Pipeline()
+    steps = [pipe.add_step(ProduceFramesStep(sess, cfg, 'produce')), pipe.add_step(SyntheticInferenceStep(cfg, 'infer')),
+             pipe.add_step(ProcessFeaturesStep(cfg, 'features')), pipe.add_step(ResultWriterStep(cfg, 'writer'))]
+    for a, b in zip(steps[:-1], steps[1:]):
+        pipe.link(a, b)
+    pipe.run()
+    store = steps[-1].store
+    assert store.closed
+    if not store.path.endswith('.npz'):
+        pytest.skip('h5py present: layout checked by the CPU test')
+    out = np.load(store.path)
+    roi, bg = sess.roi, sess.bground_im
+    for start in range(0, nframes, chunk_size):
+        idxs = list(range(start, min(start + chunk_size, nframes)))
+        ch = synthetic.generate_chunk(len(idxs), seed=6, geom=sess.geom, t0=idxs[0])
+        prep = O.prep_frames(ch.frames, bg, roi, cfg['min_height'], cfg['max_height'])
+        ref = O.extract_chunk(prep, ch.masks, ch.keypoints, ch.num_instances, cfg['min_height'], cfg['max_height'],
+                              cfg['true_depth'], cfg['crop_size'])
+        assert np.array_equal(out['frames'][idxs], ref['depth_frames'])
+        assert np.array_equal(out['frames_mask'][idxs], ref['mask_frames'] != 0)
+        assert np.array_equal(out['metadata/extraction/flips'][idxs], ref['flips'])
+        assert np.allclose(out['scalars/centroid_x_px'][idxs], ref['scalars']['centroid_x_px'].astype(np.float32), equal_nan=True)
+    tsv = open(steps[-1].keypoint_data_dest).read().strip().split('\n')
+    assert len(tsv) == 1 + nframes and tsv[-1].split('\t')[0] == str(nframes - 1)

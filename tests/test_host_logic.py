@@ -273,3 +273,48 @@ def test_numa_binding_helpers():
     out = bind_to_gpu_numa_node(0)                 # no GPU / no NVML here: must degrade to None and leave the affinity alone
     assert out is None or set(os.sched_getaffinity(0)) <= set(before)
     os.sched_setaffinity(0, before)
+
+
+def test_result_writer_step_layout_and_offsets(tmp_path):
+    """ResultWriterStep (ref pipeline/write_results_step.py:14-73, io/result.py:14-130): dataset paths, dtypes, chunk offsets
+    (overlap frames dropped) and the keypoint TSV columns, through the pipeline's queue / sentinel machinery.  No GPU."""
+    import queue as _queue
+    import threading
+    from moseq2_detectron_extract_b200.pipeline.write_results_step import ResultWriterStep
+    from moseq2_detectron_extract_b200.proc.keypoints import keypoint_attributes
+    from moseq2_detectron_extract_b200.proc.scalars import scalar_attributes
+    n, crop = 7, (8, 8)
+    cfg = {'nframes': n, 'crop_size': crop, 'output_dir': str(tmp_path), 'bg_roi_index': 0, 'true_depth': 673.0,
+           'roi': np.ones((4, 4), bool), 'bground_im': np.full((4, 4), 673.0), 'timestamps': np.arange(n) * 33.3}
+
+    def chunk(idxs, offset):
+        m = len(idxs)
+        return {'batch': 0, 'chunk': np.zeros((m, 4, 4), np.uint8), 'frame_idxs': idxs, 'offset': offset,
+                'scalars': {k: np.array(idxs, dtype=float) + 0.5 for k in scalar_attributes()},
+                'keypoints': {k: np.array(idxs, dtype=float) * 2 for k in keypoint_attributes()},
+                'features': {'flips': np.array([i % 2 == 0 for i in idxs]),
+                             'features': {'centroid': np.stack([np.array(idxs, float), np.array(idxs, float) + 1], 1),
+                                          'orientation': np.array(idxs, float) * 10}},
+                'depth_frames': np.stack([np.full(crop, i, np.uint8) for i in idxs]),
+                'mask_frames': np.stack([np.full(crop, i % 2, np.uint8) for i in idxs])}
+
+    step = ResultWriterStep(cfg, 'writer')
+    step.shutdown_event = threading.Event()
+    step.in_queue = _queue.Queue()
+    step.in_queue.put(chunk([0, 1, 2, 3], 0))
+    step.in_queue.put(chunk([3, 4, 5, 6], 1))          # one frame of overlap with the previous chunk
+    step.in_queue.put(None)
+    step.run()
+    assert step.error is None and step.is_complete.is_set()
+    out = np.load(step.store.path) if step.store.path.endswith('.npz') else None
+    if out is not None:
+        assert out['frames'].shape == (n, 8, 8) and out['frames'].dtype == np.uint8 and out['frames_mask'].dtype == bool
+        assert [int(f[0, 0]) for f in out['frames']] == list(range(n))
+        assert np.array_equal(out['scalars/centroid_x_px'], np.arange(n, dtype=np.float32) + 0.5)
+        assert out['scalars/area_px'].dtype == np.float32 and len([k for k in out.files if k.startswith('keypoints/')]) == 96
+        assert np.array_equal(out['metadata/extraction/flips'], np.arange(n) % 2 == 0)
+        assert float(out['metadata/extraction/true_depth']) == 673.0 and out['metadata/extraction/background'].shape == (4, 4)
+    lines = open(step.keypoint_data_dest).read().strip().split('\n')
+    header = lines[0].split('\t')
+    assert header[:5] == ['Frame_Idx', 'Flip', 'Centroid_X', 'Centroid_Y', 'Angle'] and len(header) == 5 + 96
+    assert len(lines) == 1 + 8 and lines[1].split('\t')[:3] == ['0', 'True', '0.0']
