@@ -104,6 +104,14 @@ MSQ_API int msq_scale_frames(const uint8_t *in_dev, uint8_t *out_dev, size_t cou
 MSQ_API int msq_scale_frames_chw3_f32(const uint8_t *in_dev, float *out_dev, int n, int h, int w,
                               double vmin, double vmax, int vmin_is_int, void *stream);
 
+/* Segmented greedy NMS for the RPN proposal filtering of a whole batch (replaces the per-image box_ops.batched_nms calls of
+ * torchvision's RegionProposalNetwork.filter_proposals behind Predictor; the reference's detectron2 RPN does the same
+ * per-image loop).  boxes_dev (n,K,4) float32, per image sorted by descending score and already shifted per pyramid level
+ * (the "coordinate trick"); valid_dev (n,K) u8; keep_dev (n,max_keep) int32 receives the indices of the first max_keep
+ * survivors (-1 padded), count_dev (n) their number.  boxes_dev 16-byte aligned. */
+MSQ_API int msq_nms_sorted(const float *boxes_dev, const uint8_t *valid_dev, int n, int K, float iou_threshold, int max_keep,
+                   int32_t *keep_dev, int32_t *count_dev, void *stream);
+
 /* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
 MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);

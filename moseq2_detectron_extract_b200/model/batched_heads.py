@@ -1,0 +1,130 @@
+"""Batched replacements for the per-image loops of torchvision's detection post-processing (a4 glue).
+
+`RegionProposalNetwork.filter_proposals` and `RoIHeads.postprocess_detections` loop over the images of a batch in Python;
+every iteration is a dozen tiny kernels plus an NMS that synchronises with the host (tools/rcnn_profile.py: 0.6 and 0.45 ms
+per frame, more than the backbone).  When all images of the batch have the same size -- always the case on the extract
+path -- the same arithmetic runs on (n, K, ...) tensors with ONE segmented NMS launch (`msq_nms_sorted`, csrc/nms.cu).
+`enable_batched_heads(model)` patches a torchvision GeneralizedRCNN in place; outputs are identical to the per-image code
+(tests/test_gpu_pipeline.py), and any batch the fast path cannot serve (mixed image sizes, fewer survivors than
+`post_nms_top_n`, several detections per image) falls back to torchvision's own method.
+"""
+from __future__ import annotations
+
+import types
+from typing import List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .. import _dev, _lib
+
+
+def _same_shapes(image_shapes) -> bool:
+    return len(image_shapes) > 0 and all(tuple(s) == tuple(image_shapes[0]) for s in image_shapes)
+
+
+def _filter_proposals(self, proposals, objectness, image_shapes, num_anchors_per_level):
+    """RegionProposalNetwork.filter_proposals for a batch of equally sized images."""
+    if not (proposals.is_cuda and _same_shapes(image_shapes)):
+        return self._msq_filter_proposals(proposals, objectness, image_shapes, num_anchors_per_level)
+    n = proposals.shape[0]
+    device = proposals.device
+    objectness = objectness.detach().reshape(n, -1)
+    levels = torch.cat([torch.full((c,), idx, dtype=torch.int64, device=device) for idx, c in enumerate(num_anchors_per_level)], 0)
+    levels = levels.reshape(1, -1).expand_as(objectness)
+    top_n_idx = self._get_top_n_idx(objectness, num_anchors_per_level)
+    batch_idx = torch.arange(n, device=device)[:, None]
+    objectness = objectness[batch_idx, top_n_idx]
+    levels = levels[batch_idx, top_n_idx]
+    boxes = proposals[batch_idx, top_n_idx].float()
+    prob = torch.sigmoid(objectness).float()
+    # ---- per-image loop of torchvision, on (n, K) tensors ----
+    height, width = image_shapes[0]
+    boxes = torch.stack([boxes[..., 0].clamp(0, width), boxes[..., 1].clamp(0, height),
+                         boxes[..., 2].clamp(0, width), boxes[..., 3].clamp(0, height)], dim=-1)
+    ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+    valid = (ws >= self.min_size) & (hs >= self.min_size) & (prob >= self.score_thresh)
+    order = torch.sort(torch.where(valid, prob, prob.new_full((), -1.0)), dim=1, descending=True, stable=True).indices
+    boxes = torch.gather(boxes, 1, order[..., None].expand(-1, -1, 4))
+    prob = torch.gather(prob, 1, order)
+    levels = torch.gather(levels, 1, order)
+    valid = torch.gather(valid, 1, order)
+    # batched_nms' coordinate trick: shift every level by (largest coordinate of the image's boxes + 1)
+    max_coord = torch.where(valid[..., None], boxes, boxes.new_full((), float('-inf'))).amax(dim=(1, 2))
+    shifted = (boxes + (levels.to(boxes) * (max_coord[:, None] + 1))[..., None]).contiguous()
+    K, top_n = int(boxes.shape[1]), int(self.post_nms_top_n())
+    keep = torch.empty((n, top_n), dtype=torch.int32, device=device)
+    count = torch.empty((n,), dtype=torch.int32, device=device)
+    valid_u8 = valid.to(torch.uint8).contiguous()
+    _lib.call('msq_nms_sorted', _dev.ptr(shifted), _dev.ptr(valid_u8), n, K, float(self.nms_thresh), top_n, _dev.ptr(keep),
+              _dev.ptr(count), _dev.stream())
+    if int(count.min()) < top_n:            # an image with fewer survivors than requested: ragged per-image lists
+        return _ragged(boxes, prob, keep, count)
+    keep = keep.long()
+    final_boxes = torch.gather(boxes, 1, keep[..., None].expand(-1, -1, 4))
+    final_scores = torch.gather(prob, 1, keep)
+    return list(final_boxes.unbind(0)), list(final_scores.unbind(0))
+
+
+def _ragged(boxes, prob, keep, count):
+    """Per-image lists when some image kept fewer than `post_nms_top_n` boxes."""
+    counts = count.tolist()
+    out_b, out_s = [], []
+    for i, c in enumerate(counts):
+        idx = keep[i, :c].long()
+        out_b.append(boxes[i, idx])
+        out_s.append(prob[i, idx])
+    return out_b, out_s
+
+
+def _postprocess_detections(self, class_logits, box_regression, proposals, image_shapes):
+    """RoIHeads.postprocess_detections when one detection per image is kept: after score / size filtering the best box
+    always survives its class's NMS, so the result is a (stable) arg-max -- no NMS at all."""
+    per_image = [int(p.shape[0]) for p in proposals]
+    num_classes = int(class_logits.shape[-1])
+    if not (class_logits.is_cuda and self.detections_per_img == 1 and num_classes == 2 and _same_shapes(image_shapes)
+            and len(set(per_image)) == 1 and per_image[0] > 0):
+        return self._msq_postprocess_detections(class_logits, box_regression, proposals, image_shapes)
+    n, k = len(proposals), per_image[0]
+    pred_boxes = self.box_coder.decode(box_regression, proposals)              # (n*k, classes, 4)
+    pred_scores = F.softmax(class_logits, -1)
+    height, width = image_shapes[0]
+    boxes = pred_boxes.reshape(n, k, num_classes, 4)[:, :, 1:].reshape(n, -1, 4)
+    scores = pred_scores.reshape(n, k, num_classes)[:, :, 1:].reshape(n, -1)
+    boxes = torch.stack([boxes[..., 0].clamp(0, width), boxes[..., 1].clamp(0, height),
+                         boxes[..., 2].clamp(0, width), boxes[..., 3].clamp(0, height)], dim=-1)
+    ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+    valid = (scores > self.score_thresh) & (ws >= 1e-2) & (hs >= 1e-2)
+    best = torch.sort(torch.where(valid, scores, scores.new_full((), -1.0)), dim=1, descending=True, stable=True).indices[:, :1]
+    top_boxes = torch.gather(boxes, 1, best[..., None].expand(-1, -1, 4))      # (n, 1, 4)
+    top_scores = torch.gather(scores, 1, best)
+    has = torch.gather(valid, 1, best)[:, 0].tolist()                          # one small read-back per batch
+    labels = torch.ones((1,), dtype=torch.int64, device=class_logits.device)
+    all_boxes, all_scores, all_labels = [], [], []
+    for i in range(n):
+        c = 1 if has[i] else 0
+        all_boxes.append(top_boxes[i, :c])
+        all_scores.append(top_scores[i, :c])
+        all_labels.append(labels[:c])
+    return all_boxes, all_scores, all_labels
+
+
+def enable_batched_heads(model) -> None:
+    """Patch a torchvision detection model (RPN + RoIHeads) in place; idempotent."""
+    rpn, heads = model.rpn, model.roi_heads
+    if not hasattr(rpn, '_msq_filter_proposals'):
+        rpn._msq_filter_proposals = rpn.filter_proposals
+        rpn.filter_proposals = types.MethodType(_filter_proposals, rpn)
+    if not hasattr(heads, '_msq_postprocess_detections'):
+        heads._msq_postprocess_detections = heads.postprocess_detections
+        heads.postprocess_detections = types.MethodType(_postprocess_detections, heads)
+
+
+def disable_batched_heads(model) -> None:
+    rpn, heads = model.rpn, model.roi_heads
+    if hasattr(rpn, '_msq_filter_proposals'):
+        rpn.filter_proposals = rpn._msq_filter_proposals
+        del rpn._msq_filter_proposals
+    if hasattr(heads, '_msq_postprocess_detections'):
+        heads.postprocess_detections = heads._msq_postprocess_detections
+        del heads._msq_postprocess_detections

@@ -92,10 +92,13 @@ class Predictor:
         return cls(model, is_torchscript=True)
 
     @classmethod
-    def from_random_init(cls, device: str = 'cuda', seed: int = 0, amp: bool = False, **kwargs):
+    def from_random_init(cls, device: str = 'cuda', seed: int = 0, amp: bool = False, batched_heads: bool = True, **kwargs):
         _dev.require_cuda()
         torch.manual_seed(seed)
         model = _TorchvisionAdapter(build_random_keypoint_mask_rcnn(**kwargs)).to(device).eval()
+        if batched_heads:               # one segmented NMS launch per batch instead of torchvision's per-image loops
+            from .batched_heads import enable_batched_heads
+            enable_batched_heads(model.model)
         if amp:
             model = model.to(memory_format=torch.channels_last)
         return cls(model, is_torchscript=True, amp=amp)

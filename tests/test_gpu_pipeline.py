@@ -215,3 +215,44 @@ def test_pipeline_with_result_writer(tmp_path):
         assert np.allclose(out['scalars/centroid_x_px'][idxs], ref['scalars']['centroid_x_px'].astype(np.float32), equal_nan=True)
     tsv = open(steps[-1].keypoint_data_dest).read().strip().split('\n')
     assert len(tsv) == 1 + nframes and tsv[-1].split('\t')[0] == str(nframes - 1)
+
+
+def test_batched_rcnn_heads_match_torchvision():
+    """model/batched_heads.py (batched proposal filtering with ONE segmented NMS launch, arg-max detections) against
+    torchvision's own per-image RegionProposalNetwork.filter_proposals / RoIHeads.postprocess_detections: same outputs."""
+    pytest.importorskip('torchvision')
+    from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+    from moseq2_detectron_extract_b200.model.batched_heads import disable_batched_heads, enable_batched_heads
+    from moseq2_detectron_extract_b200.model.predict import Predictor
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(5, seed=12, geom=geom)
+    prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom),
+                           roi=synthetic.make_roi(geom), vmin=0, vmax=100)
+    pred = Predictor.from_random_init(detections_per_img=1)
+    net = pred.model.model
+    assert hasattr(net.rpn, '_msq_filter_proposals')
+    fast = pred.predict_dense(prep, 0, 100)
+    disable_batched_heads(net)
+    slow = pred.predict_dense(prep, 0, 100)
+    enable_batched_heads(net)
+    assert torch.equal(fast[0], slow[0]) and torch.equal(fast[2], slow[2])
+    assert torch.allclose(fast[1], slow[1], rtol=0, atol=0, equal_nan=True)
+    # the NMS entry point on its own: random boxes in score order vs torchvision.ops.nms
+    import torchvision
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    n, K = 3, 400
+    xy = torch.rand((n, K, 2), device='cuda', generator=gen) * 200
+    wh = torch.rand((n, K, 2), device='cuda', generator=gen) * 60 + 1
+    boxes = torch.cat([xy, xy + wh], dim=-1).contiguous()
+    valid = (torch.rand((n, K), device='cuda', generator=gen) > 0.1)
+    keep = torch.empty((n, 50), dtype=torch.int32, device='cuda')
+    count = torch.empty((n,), dtype=torch.int32, device='cuda')
+    v8 = valid.to(torch.uint8).contiguous()
+    _lib.call('msq_nms_sorted', _dev.ptr(boxes), _dev.ptr(v8), n, K, 0.5, 50, _dev.ptr(keep), _dev.ptr(count), _dev.stream())
+    scores = torch.arange(K, 0, -1, device='cuda', dtype=torch.float32)          # already in descending order
+    for i in range(n):
+        idx = torch.nonzero(valid[i])[:, 0]
+        ref = idx[torchvision.ops.nms(boxes[i, idx], scores[idx], 0.5)][:50]
+        c = int(count[i])
+        assert c == len(ref) and torch.equal(keep[i, :c].long(), ref)
