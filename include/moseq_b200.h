@@ -112,6 +112,14 @@ MSQ_API int msq_scale_frames_chw3_f32(const uint8_t *in_dev, float *out_dev, int
 MSQ_API int msq_nms_sorted(const float *boxes_dev, const uint8_t *valid_dev, int n, int K, float iou_threshold, int max_keep,
                    int32_t *keep_dev, int32_t *count_dev, void *stream);
 
+/* Keypoint decoding for a batch (replaces the per-RoI loop of torchvision's heatmaps_to_keypoints / detectron2's keypoint
+ * head inference): for every RoI and keypoint, the arg-max of the heatmap (maps_dev (R,K,Hm,Wm) float32) bicubically
+ * resized to the RoI's ceil(width) x ceil(height), mapped back to image coordinates.  rois_dev (R,4) float32 x1,y1,x2,y2;
+ * xyv_dev (R,K,3) float32 (x, y, 1); scores_dev (R,K) the heatmap value at the arg-max.  round_bf16 != 0: values are rounded
+ * to bfloat16 before the comparison (what the resize yields under bf16 autocast). */
+MSQ_API int msq_keypoints_from_heatmaps(const float *maps_dev, const float *rois_dev, int n_rois, int K, int Hm, int Wm,
+                                int round_bf16, float *xyv_dev, float *scores_dev, void *stream);
+
 /* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
 MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);

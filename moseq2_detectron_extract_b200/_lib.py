@@ -50,6 +50,7 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_paste_masks': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     'msq_nms_sorted': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    'msq_keypoints_from_heatmaps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'msq_angles_and_flips': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     'msq_flips_from_keypoints': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -7,6 +7,8 @@
 // Boxes arrive sorted by score and already shifted per pyramid level (torchvision's "coordinate trick", so that levels
 // never suppress each other and the float32 arithmetic is the one torchvision does); IoU as in torchvision's devIoU.
 #include "common.cuh"
+#include <limits.h>
+#include <math.h>
 
 namespace msq {
 namespace {
@@ -67,5 +69,108 @@ extern "C" int msq_nms_sorted(const float *boxes, const uint8_t *valid, int n, i
     nms_sorted_kernel<<<(n + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(boxes), valid, n, K, iou_threshold, max_keep, keep, count);
     MSQ_LAUNCH_OK("nms_sorted");
+    return MSQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Keypoint decoding for a whole batch: torchvision's heatmaps_to_keypoints (the reference's detectron2 keypoint head does
+// the same) resizes every RoI's K heatmaps to the RoI's size with bicubic interpolation and takes the arg-max -- one
+// F.interpolate + arg-max + two host synchronisations per RoI.  Here one CTA per (RoI, keypoint) holds the heatmap in
+// shared memory, evaluates PyTorch's bicubic kernel (A = -0.75, align_corners = False, taps clamped to the map) at every
+// pixel of the virtual resized map and reduces to the first maximum.  With `round_bf16` the values are rounded to bfloat16
+// before they are compared, which is what the resize returns under autocast.
+// ---------------------------------------------------------------------------------------------------------------
+namespace msq {
+namespace {
+
+__device__ __forceinline__ float cubic1(float x) { return ((-0.75f + 2.f) * x - (-0.75f + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x) { return ((-0.75f * x - 5.f * -0.75f) * x + 8.f * -0.75f) * x - 4.f * -0.75f; }
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
+    c[0] = cubic2(t + 1.f);
+    c[1] = cubic1(t);
+    const float u = 1.f - t;
+    c[2] = cubic1(u);
+    c[3] = cubic2(u + 1.f);
+}
+__device__ __forceinline__ float round_to_bf16(float v) {
+    uint32_t u = __float_as_uint(v);
+    if ((u & 0x7f800000u) == 0x7f800000u) return v;                    // inf / nan unchanged
+    u += 0x7fffu + ((u >> 16) & 1u);                                    // round to nearest even
+    return __uint_as_float(u & 0xffff0000u);
+}
+
+constexpr int kKpThreads = 256;
+
+__global__ void __launch_bounds__(kKpThreads)
+keypoint_decode_kernel(const float *__restrict__ maps, const float *__restrict__ rois, int K, int Hm, int Wm, int round_bf16,
+                       float *__restrict__ xyv, float *__restrict__ scores) {
+    extern __shared__ float heat[];
+    __shared__ float best_v[kKpThreads / 32];
+    __shared__ int best_i[kKpThreads / 32];
+    const int roi = blockIdx.x / K, kp = blockIdx.x - roi * K;
+    const float *m = maps + ((size_t)roi * K + kp) * Hm * Wm;
+    for (int i = threadIdx.x; i < Hm * Wm; i += kKpThreads) heat[i] = m[i];
+    const float x1 = rois[4 * roi], y1 = rois[4 * roi + 1], x2 = rois[4 * roi + 2], y2 = rois[4 * roi + 3];
+    const float width = fmaxf(x2 - x1, 1.f), height = fmaxf(y2 - y1, 1.f);
+    const int ow = (int)ceilf(width), oh = (int)ceilf(height);
+    const float sx = (float)Wm / (float)ow, sy = (float)Hm / (float)oh;
+    __syncthreads();
+    float bv = -INFINITY;
+    int bi = INT_MAX;
+    for (int p = threadIdx.x; p < ow * oh; p += kKpThreads) {
+        const int oy = p / ow, ox = p - oy * ow;
+        const float rx = sx * ((float)ox + 0.5f) - 0.5f, ry = sy * ((float)oy + 0.5f) - 0.5f;
+        const float fx = floorf(rx), fy = floorf(ry);
+        const int ix = (int)fx, iy = (int)fy;
+        float cx[4], cy[4];
+        cubic_coeffs(rx - fx, cx);
+        cubic_coeffs(ry - fy, cy);
+        float row[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float *r = heat + min(max(iy - 1 + a, 0), Hm - 1) * Wm;
+            row[a] = r[min(max(ix - 1, 0), Wm - 1)] * cx[0] + r[min(max(ix, 0), Wm - 1)] * cx[1] +
+                     r[min(max(ix + 1, 0), Wm - 1)] * cx[2] + r[min(max(ix + 2, 0), Wm - 1)] * cx[3];
+        }
+        float v = row[0] * cy[0] + row[1] * cy[1] + row[2] * cy[2] + row[3] * cy[3];
+        if (round_bf16) v = round_to_bf16(v);
+        if (v > bv) { bv = v; bi = p; }                                 // p ascends per thread: the first maximum stays
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { best_v[threadIdx.x >> 5] = bv; best_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wv = 1; wv < kKpThreads / 32; ++wv)
+            if (best_v[wv] > bv || (best_v[wv] == bv && best_i[wv] < bi)) { bv = best_v[wv]; bi = best_i[wv]; }
+        if (bi == INT_MAX) bi = 0;                                      // all NaN: torch returns index 0 as well
+        const int yi = bi / ow, xi = bi - yi * ow;
+        float *o = xyv + ((size_t)roi * K + kp) * 3;
+        o[0] = ((float)xi + 0.5f) * (width / (float)ow) + x1;
+        o[1] = ((float)yi + 0.5f) * (height / (float)oh) + y1;
+        o[2] = 1.f;
+        scores[(size_t)roi * K + kp] = bv;
+    }
+}
+
+}  // namespace
+}  // namespace msq
+
+extern "C" int msq_keypoints_from_heatmaps(const float *maps, const float *rois, int n_rois, int K, int Hm, int Wm, int round_bf16,
+                                           float *xyv, float *scores, void *stream) {
+    MSQ_REQUIRE(n_rois >= 0 && K > 0 && Hm > 0 && Wm > 0, MSQ_EINVAL, "msq_keypoints_from_heatmaps: bad sizes");
+    if (n_rois == 0) return MSQ_OK;
+    MSQ_REQUIRE(maps && rois && xyv && scores, MSQ_EINVAL, "msq_keypoints_from_heatmaps: null pointer");
+    const size_t smem = (size_t)Hm * Wm * sizeof(float);
+    MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "msq_keypoints_from_heatmaps: %dx%d heatmaps are too large", Hm, Wm);
+    if (smem > 48 * 1024)
+        MSQ_CUDA_OK(cudaFuncSetAttribute(msq::keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msq::TimedLaunch timed(msq::K_PASTE, (cudaStream_t)stream);
+    msq::keypoint_decode_kernel<<<n_rois * K, msq::kKpThreads, smem, (cudaStream_t)stream>>>(maps, rois, K, Hm, Wm, round_bf16, xyv, scores);
+    MSQ_LAUNCH_OK("keypoint_decode");
     return MSQ_OK;
 }

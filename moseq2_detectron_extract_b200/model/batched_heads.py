@@ -109,6 +109,30 @@ def _postprocess_detections(self, class_logits, box_regression, proposals, image
     return all_boxes, all_scores, all_labels
 
 
+def keypoints_from_heatmaps(maps: torch.Tensor, rois: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """torchvision's heatmaps_to_keypoints for all RoIs at once (`msq_keypoints_from_heatmaps`, csrc/nms.cu):
+    maps (R, K, Hm, Wm), rois (R, 4) -> xy_preds (R, K, 3) float32, scores (R, K) float32."""
+    r, k, hm, wm = (int(v) for v in maps.shape)
+    xyv = torch.empty((r, k, 3), dtype=torch.float32, device=maps.device)
+    scores = torch.empty((r, k), dtype=torch.float32, device=maps.device)
+    if r == 0:
+        return xyv, scores
+    m32 = maps.float().contiguous()
+    b32 = rois.float().contiguous()
+    _lib.call('msq_keypoints_from_heatmaps', _dev.ptr(m32), _dev.ptr(b32), r, k, hm, wm, int(maps.dtype == torch.bfloat16),
+              _dev.ptr(xyv), _dev.ptr(scores), _dev.stream())
+    return xyv, scores
+
+
+def _keypointrcnn_inference(x, boxes):
+    """torchvision.models.detection.roi_heads.keypointrcnn_inference without the per-RoI Python loop."""
+    if not x.is_cuda:
+        return _keypointrcnn_inference.original(x, boxes)
+    per_image = [int(b.shape[0]) for b in boxes]
+    xyv, scores = keypoints_from_heatmaps(x, torch.cat(boxes, dim=0))
+    return list(xyv.split(per_image, 0)), list(scores.split(per_image, 0))
+
+
 def enable_batched_heads(model) -> None:
     """Patch a torchvision detection model (RPN + RoIHeads) in place; idempotent."""
     rpn, heads = model.rpn, model.roi_heads
@@ -118,6 +142,10 @@ def enable_batched_heads(model) -> None:
     if not hasattr(heads, '_msq_postprocess_detections'):
         heads._msq_postprocess_detections = heads.postprocess_detections
         heads.postprocess_detections = types.MethodType(_postprocess_detections, heads)
+    from torchvision.models.detection import roi_heads as tv_heads
+    if tv_heads.keypointrcnn_inference is not _keypointrcnn_inference:      # module-level function: patched process-wide
+        _keypointrcnn_inference.original = tv_heads.keypointrcnn_inference
+        tv_heads.keypointrcnn_inference = _keypointrcnn_inference
 
 
 def disable_batched_heads(model) -> None:
@@ -128,3 +156,6 @@ def disable_batched_heads(model) -> None:
     if hasattr(heads, '_msq_postprocess_detections'):
         heads.postprocess_detections = heads._msq_postprocess_detections
         del heads._msq_postprocess_detections
+    from torchvision.models.detection import roi_heads as tv_heads
+    if tv_heads.keypointrcnn_inference is _keypointrcnn_inference:
+        tv_heads.keypointrcnn_inference = _keypointrcnn_inference.original
