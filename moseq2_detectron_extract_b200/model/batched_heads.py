@@ -133,6 +133,31 @@ def _keypointrcnn_inference(x, boxes):
     return list(xyv.split(per_image, 0)), list(scores.split(per_image, 0))
 
 
+def _transform_forward(self, images, targets=None):
+    """GeneralizedRCNNTransform.forward for a batch of equally sized CUDA images in eval mode: normalise, resize and pad
+    once on the stacked batch (per-sample arithmetic identical to the per-image loop)."""
+    from torchvision.models.detection.image_list import ImageList
+    same = (targets is None and not self.training and len(images) > 0 and self.fixed_size is None
+            and all(i.is_cuda and i.dim() == 3 and i.shape == images[0].shape and i.dtype == images[0].dtype for i in images))
+    if not same:
+        return self._msq_forward(images, targets)
+    x = torch.stack(list(images))
+    if not x.is_floating_point():
+        raise TypeError(f'Expected input images to be of floating type (in range [0, 1]), but found type {x.dtype} instead')
+    mean = torch.as_tensor(self.image_mean, dtype=x.dtype, device=x.device)
+    std = torch.as_tensor(self.image_std, dtype=x.dtype, device=x.device)
+    x = (x - mean[None, :, None, None]) / std[None, :, None, None]
+    h, w = int(x.shape[-2]), int(x.shape[-1])
+    scale_factor = min(self.min_size[-1] / min(h, w), self.max_size / max(h, w))
+    x = F.interpolate(x, size=None, scale_factor=scale_factor, mode='bilinear', recompute_scale_factor=True, align_corners=False)
+    oh, ow = int(x.shape[-2]), int(x.shape[-1])
+    div = int(self.size_divisible)
+    ph, pw = -(-oh // div) * div, -(-ow // div) * div
+    if (ph, pw) != (oh, ow):
+        x = F.pad(x, (0, pw - ow, 0, ph - oh))
+    return ImageList(x, [(oh, ow)] * len(images)), targets
+
+
 def enable_batched_heads(model) -> None:
     """Patch a torchvision detection model (RPN + RoIHeads) in place; idempotent."""
     rpn, heads = model.rpn, model.roi_heads
@@ -142,6 +167,10 @@ def enable_batched_heads(model) -> None:
     if not hasattr(heads, '_msq_postprocess_detections'):
         heads._msq_postprocess_detections = heads.postprocess_detections
         heads.postprocess_detections = types.MethodType(_postprocess_detections, heads)
+    tr = model.transform
+    if not hasattr(tr, '_msq_forward'):
+        tr._msq_forward = tr.forward
+        tr.forward = types.MethodType(_transform_forward, tr)
     from torchvision.models.detection import roi_heads as tv_heads
     if tv_heads.keypointrcnn_inference is not _keypointrcnn_inference:      # module-level function: patched process-wide
         _keypointrcnn_inference.original = tv_heads.keypointrcnn_inference
@@ -156,6 +185,10 @@ def disable_batched_heads(model) -> None:
     if hasattr(heads, '_msq_postprocess_detections'):
         heads.postprocess_detections = heads._msq_postprocess_detections
         del heads._msq_postprocess_detections
+    tr = model.transform
+    if hasattr(tr, '_msq_forward'):
+        tr.forward = tr._msq_forward
+        del tr._msq_forward
     from torchvision.models.detection import roi_heads as tv_heads
     if tv_heads.keypointrcnn_inference is _keypointrcnn_inference:
         tv_heads.keypointrcnn_inference = _keypointrcnn_inference.original
