@@ -158,6 +158,20 @@ def _transform_forward(self, images, targets=None):
     return ImageList(x, [(oh, ow)] * len(images)), targets
 
 
+def _convert_to_roi_format(boxes):
+    """torchvision.ops.poolers._convert_to_roi_format without one tiny kernel per image: (image index, x1, y1, x2, y2)."""
+    counts = [int(b.shape[0]) for b in boxes]
+    concat = torch.cat(boxes, dim=0)
+    if len(boxes) == 0 or not concat.is_cuda:
+        return _convert_to_roi_format.original(boxes)
+    if len(set(counts)) == 1:
+        ids = torch.arange(len(boxes), device=concat.device, dtype=concat.dtype).repeat_interleave(counts[0])
+    else:
+        ids = torch.repeat_interleave(torch.arange(len(boxes), device=concat.device, dtype=concat.dtype),
+                                      torch.tensor(counts, device=concat.device))
+    return torch.cat([ids[:, None], concat], dim=1)
+
+
 def enable_batched_heads(model) -> None:
     """Patch a torchvision detection model (RPN + RoIHeads) in place; idempotent."""
     rpn, heads = model.rpn, model.roi_heads
@@ -171,6 +185,10 @@ def enable_batched_heads(model) -> None:
     if not hasattr(tr, '_msq_forward'):
         tr._msq_forward = tr.forward
         tr.forward = types.MethodType(_transform_forward, tr)
+    from torchvision.ops import poolers as tv_poolers
+    if tv_poolers._convert_to_roi_format is not _convert_to_roi_format:
+        _convert_to_roi_format.original = tv_poolers._convert_to_roi_format
+        tv_poolers._convert_to_roi_format = _convert_to_roi_format
     from torchvision.models.detection import roi_heads as tv_heads
     if tv_heads.keypointrcnn_inference is not _keypointrcnn_inference:      # module-level function: patched process-wide
         _keypointrcnn_inference.original = tv_heads.keypointrcnn_inference
@@ -189,6 +207,9 @@ def disable_batched_heads(model) -> None:
     if hasattr(tr, '_msq_forward'):
         tr.forward = tr._msq_forward
         del tr._msq_forward
+    from torchvision.ops import poolers as tv_poolers
+    if tv_poolers._convert_to_roi_format is _convert_to_roi_format:
+        tv_poolers._convert_to_roi_format = _convert_to_roi_format.original
     from torchvision.models.detection import roi_heads as tv_heads
     if tv_heads.keypointrcnn_inference is _keypointrcnn_inference:
         tv_heads.keypointrcnn_inference = _keypointrcnn_inference.original
