@@ -172,6 +172,14 @@ def _convert_to_roi_format(boxes):
     return torch.cat([ids[:, None], concat], dim=1)
 
 
+def _roi_heads_forward(self, features, proposals, image_shapes, targets=None):
+    """RoIHeads.forward with the pyramid features converted to float32 ONCE: under autocast every roi_align call casts its
+    whole input feature map to float32 (three poolers x four levels per batch); the pooled values are the same."""
+    if not self.training and any(v.dtype != torch.float32 for v in features.values()):
+        features = type(features)((k, v.float()) for k, v in features.items())
+    return self._msq_forward(features, proposals, image_shapes, targets)
+
+
 def enable_batched_heads(model) -> None:
     """Patch a torchvision detection model (RPN + RoIHeads) in place; idempotent."""
     rpn, heads = model.rpn, model.roi_heads
@@ -185,6 +193,9 @@ def enable_batched_heads(model) -> None:
     if not hasattr(tr, '_msq_forward'):
         tr._msq_forward = tr.forward
         tr.forward = types.MethodType(_transform_forward, tr)
+    if not hasattr(heads, '_msq_forward'):
+        heads._msq_forward = heads.forward
+        heads.forward = types.MethodType(_roi_heads_forward, heads)
     from torchvision.ops import poolers as tv_poolers
     if tv_poolers._convert_to_roi_format is not _convert_to_roi_format:
         _convert_to_roi_format.original = tv_poolers._convert_to_roi_format
@@ -207,6 +218,9 @@ def disable_batched_heads(model) -> None:
     if hasattr(tr, '_msq_forward'):
         tr.forward = tr._msq_forward
         del tr._msq_forward
+    if hasattr(heads, '_msq_forward'):
+        heads.forward = heads._msq_forward
+        del heads._msq_forward
     from torchvision.ops import poolers as tv_poolers
     if tv_poolers._convert_to_roi_format is _convert_to_roi_format:
         tv_poolers._convert_to_roi_format = _convert_to_roi_format.original

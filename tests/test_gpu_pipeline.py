@@ -229,7 +229,7 @@ def test_batched_rcnn_heads_match_torchvision():
     ch = synthetic.generate_chunk(5, seed=12, geom=geom)
     prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom),
                            roi=synthetic.make_roi(geom), vmin=0, vmax=100)
-    pred = Predictor.from_random_init(detections_per_img=1)
+    pred = Predictor.from_random_init(detections_per_img=1, amp=True)          # bf16 autocast, like the bench
     net = pred.model.model
     assert hasattr(net.rpn, '_msq_filter_proposals')
     fast = pred.predict_dense(prep, 0, 100)

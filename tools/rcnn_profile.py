@@ -8,13 +8,14 @@ from moseq2_detectron_extract_b200.model.predict import Predictor
 from moseq2_detectron_extract_b200.proc import prep_raw_frames
 
 geom = synthetic.SessionGeometry()
-ch = synthetic.generate_chunk(50, seed=9, geom=geom)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+ch = synthetic.generate_chunk(B, seed=9, geom=geom)
 prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom), roi=synthetic.make_roi(geom), vmin=0, vmax=100)
 pred = Predictor.from_random_init(detections_per_img=1, amp=True)
 for _ in range(2):
-    pred.predict_prepared(prep, 0, 100)
+    pred.predict_dense(prep, 0, 100)
 torch.cuda.synchronize()
-t = time.time(); pred.predict_prepared(prep, 0, 100); torch.cuda.synchronize(); print('batch of 50:', (time.time() - t) * 1e3, 'ms')
+t = time.time(); pred.predict_dense(prep, 0, 100); torch.cuda.synchronize(); print(f'batch of {B}:', (time.time() - t) * 1e3, 'ms')
 model = pred.model.model
 import torchvision
 from torchvision.models.detection import roi_heads as RH, rpn as RPN
@@ -42,6 +43,6 @@ wrap(model.roi_heads, 'keypoint_head', '  roi.keypoint_head')
 wrap(RH, 'keypointrcnn_inference', '  roi.keypointrcnn_inference')
 wrap(RH, 'maskrcnn_inference', '  roi.maskrcnn_inference')
 orig_post = model.transform.postprocess
-torch.cuda.synchronize(); t = time.time(); pred.predict_prepared(prep, 0, 100); torch.cuda.synchronize(); print('instrumented batch:', (time.time() - t) * 1e3, 'ms')
+torch.cuda.synchronize(); t = time.time(); pred.predict_dense(prep, 0, 100); torch.cuda.synchronize(); print('instrumented batch:', (time.time() - t) * 1e3, 'ms')
 for k, v in timers.items():
     print(f'{k:40s} {v:8.1f} ms')
