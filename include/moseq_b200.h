@@ -253,6 +253,37 @@ MSQ_API size_t msq_bground_scratch_bytes(int n, int H, int W);
 MSQ_API int msq_get_bground_im(const void *frames_dev, int n, int H, int W, int med_scale, int is_unsigned,
                        double *out_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
 
+/* ---- f4  get_roi (session setup; ref: proc/roi.py:14-103 get_roi, :106-130 plane_fit3, :133-212 plane_ransac) ------
+ * The host side draws the RANSAC triples (np.random, the reference's order) and ranks the regions; these entry points do
+ * the per-pixel work.  depth_dev is the (H,W) background image as float64.
+ *
+ * msq_plane_ransac_score: idx_dev (npts) int32 = raster indices of the usable pixels (depth_range / gradient mask);
+ *   sel_dev (iters,3) int64 indexes idx_dev.  Per candidate: planes_dev (iters,4) = unit normal and offset of the plane
+ *   through its 3 points (NaN when they are collinear), ninliers_dev = #{|ax+by+cz+d| < tol}, sumdist_dev = sum of the
+ *   distances over the usable pixels (the reference's np.mean(dist) times npts; summation order differs).
+ * msq_plane_distance: dist_dev (H*W) float64 and/or on_plane_dev (H*W) u8 = dist < tol (and valid_dev != 0 when given);
+ *   plane_host = 4 doubles in HOST memory.
+ * msq_label_regions: 8-connected labels of on-plane pixels, 0 = background, regions numbered 1.. in raster order of
+ *   their first pixel (skimage.measure.label); n_regions_dev receives the count.  Bit-exact.
+ * msq_region_props: per region r (label r+1): area, bbox (ymin, xmin, ymax, xmax inclusive) and maxd4 = max over its
+ *   pixels of (2y-H)^2 + (2x-W)^2, i.e. 4x the squared distance to the image centre the reference ranks by.
+ * msq_region_rois: for the regions listed in order_dev (0-based region ids): cv2.dilate by se_dilate (dh x dw u8,
+ *   anchored at its centre; NULL = skip), cv2.erode by se_erode (NULL = skip), scipy binary_fill_holes when
+ *   fill_holes != 0; rois_dev (n_out,H,W) u8 0/1, bboxes_dev (n_out,4) = get_bbox of each mask (-1 when empty).
+ *   W <= 1024, H * ceil(W/32) * 8 bytes of shared memory <= 220 KB.  Bit-exact. */
+MSQ_API int msq_plane_ransac_score(const int *idx_dev, int npts, const double *depth_dev, int H, int W, const long long *sel_dev,
+                           int iters, double tol, double *planes_dev, int *ninliers_dev, double *sumdist_dev, void *stream);
+MSQ_API int msq_plane_distance(const double *depth_dev, int H, int W, const double *plane_host, double tol,
+                       const uint8_t *valid_dev, double *dist_dev, uint8_t *on_plane_dev, void *stream);
+MSQ_API size_t msq_label_scratch_bytes(int H, int W);
+MSQ_API int msq_label_regions(const uint8_t *bin_dev, int H, int W, int *labels_dev, int *n_regions_dev, void *scratch_dev,
+                      size_t scratch_bytes, void *stream);
+MSQ_API int msq_region_props(const int *labels_dev, int H, int W, int n_regions, int *area_dev, int *bbox_dev,
+                     unsigned *maxd4_dev, void *stream);
+MSQ_API int msq_region_rois(const int *labels_dev, int H, int W, const int *order_dev, int n_out, const uint8_t *se_dilate_dev,
+                    int dh, int dw, const uint8_t *se_erode_dev, int eh, int ew, int fill_holes, uint8_t *rois_dev,
+                    int *bboxes_dev, void *stream);
+
 /* ---- whole-chunk pipeline: everything ProcessFeaturesStep.process does (ref:
  *      pipeline/process_features_step.py:56-60,163-199 with use_tracking=False), device buffers -------
  * Everything is ordered on `stream`; internally the few frames the streaming feature kernel hands to the general one run

@@ -81,6 +81,12 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p]),
     'msq_bground_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_get_bground_im': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_plane_ransac_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'msq_plane_distance': (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_double), c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'msq_label_scratch_bytes': (c_size_t, [c_int, c_int]),
+    'msq_label_regions': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_region_props': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'msq_region_rois': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),

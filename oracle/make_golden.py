@@ -148,6 +148,37 @@ def run_reference_tracking():
     return out
 
 
+ROI_CASES = {
+    # name: (synthetic_bground kwargs, np.random seed, get_roi kwargs as a function of cv2)
+    'default': (dict(seed=0), 3, lambda cv2: dict()),
+    'ellipse_erode_nofill': (dict(seed=1, h=300, w=250), 5,
+                             lambda cv2: dict(strel_dilate=cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (9, 7)),
+                                              strel_erode=cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5)), fill_holes=False,
+                                              weights=(1, .5, .2), noise_tolerance=20, iters=300)),
+}
+ROI_KEEP = 4            # ranked masks stored per case (all bounding boxes are)
+
+
+def run_reference_roi():
+    """Session ROI detection (ref proc/roi.py:14-212) on oracle/roi_oracle.synthetic_bground images.  scikit-image is
+    absent here: the reference runs on oracle/skimage_standin.py."""
+    import cv2
+    import roi_oracle
+    ref = ref_import.load()
+    out = {}
+    for name, (bg_kw, seed, kw) in ROI_CASES.items():
+        bg = roi_oracle.synthetic_bground(**bg_kw)
+        np.random.seed(seed)
+        rois, plane, bboxes, label_im, ranks, shape_index = ref.roi.get_roi(bg, progress_bar=False, **kw(cv2))
+        out[name + '/plane'] = plane
+        out[name + '/label_im'] = label_im.astype(np.int32)
+        out[name + '/ranks'] = ranks
+        out[name + '/shape_index'] = shape_index
+        out[name + '/bboxes'] = np.stack(bboxes)
+        out[name + '/rois'] = np.packbits(np.stack([np.asarray(r) > 0 for r in rois[:ROI_KEEP]]), axis=-1)
+    return out
+
+
 def main():
     import cv2
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
@@ -162,6 +193,14 @@ def main():
     path = os.path.join(ROOT, 'tests', 'golden', 'kinect_tracking.npz')
     np.savez_compressed(path, **out)
     print('kinect_tracking ->', path, f'{os.path.getsize(path) / 1e6:.2f} MB')
+
+    import scipy
+    out = run_reference_roi()
+    out['_versions'] = np.array([f'cv2={cv2.__version__}', f'numpy={np.__version__}', f'scipy={scipy.__version__}',
+                                 'skimage=stand-in (oracle/skimage_standin.py)'])
+    path = os.path.join(ROOT, 'tests', 'golden', 'session_roi.npz')
+    np.savez_compressed(path, **out)
+    print('session_roi ->', path, f'{os.path.getsize(path) / 1e6:.2f} MB')
 
 
 if __name__ == '__main__':

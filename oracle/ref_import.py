@@ -6,7 +6,8 @@ Used (a) by oracle/make_golden.py to generate the committed fixtures under tests
 
 The reference drags in third-party modules that are absent here and never executed on the
 extract hot path.  They are replaced by inert stubs *before* import.
-`pykalman.KalmanFilter` IS executed on the tracking branch (reference proc/kalman.py) and gets the restated
+`skimage.measure.label/regionprops` ARE executed by get_roi (session setup) and get the stand-in of
+oracle/skimage_standin.py.  `pykalman.KalmanFilter` IS executed on the tracking branch (reference proc/kalman.py) and gets the restated
 stand-in of oracle/pykalman_standin.py.  `bottleneck.move_median` IS executed (reference proc/proc.py:618) so it gets a functional
 stand-in built on pandas' trailing rolling median, which has the same semantics
 (trailing window, NaN-skipping, min_count == min_periods).
@@ -63,6 +64,11 @@ def load():
                 importlib.import_module(name)
             except Exception:  # absent -> stub
                 sys.modules[name] = _Anything(name)
+    if isinstance(sys.modules.get("skimage.measure"), _Anything):    # absent -> restated stand-in for get_roi
+        import skimage_standin
+        sys.modules["skimage.measure"].label = skimage_standin.label
+        sys.modules["skimage.measure"].regionprops = skimage_standin.regionprops
+        sys.modules["skimage"].measure = sys.modules["skimage.measure"]
     import pandas  # noqa: F401  (must be imported BEFORE the bottleneck stand-in exists: pandas probes it)
     if "bottleneck" not in sys.modules:
         try:

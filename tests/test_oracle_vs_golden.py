@@ -232,3 +232,28 @@ def test_bground_oracle_twins_agree():
             a, b = O.bground_im(frames, scale), O.bground_im_np(frames, scale)
             assert a.dtype == np.float64 and np.array_equal(a, b)
     assert (O.bground_im(np.stack([np.full((8, 8), v, np.int16) for v in (1, 2, 4, 9)]), 5) == 3.0).all()
+
+
+def test_roi_oracle_matches_reference_golden():
+    """oracle/roi_oracle.py against the reference's get_roi outputs (tests/golden/session_roi.npz)."""
+    import cv2
+    import make_golden
+    import roi_oracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'session_roi.npz'))
+    for name, (bg_kw, seed, kw) in make_golden.ROI_CASES.items():
+        bg = roi_oracle.synthetic_bground(**bg_kw)
+        np.random.seed(seed)
+        rois, plane, bboxes, label_im, ranks, shape_index = roi_oracle.get_roi(bg, **kw(cv2))
+        assert np.array_equal(plane, g[name + '/plane'])
+        assert np.array_equal(label_im, g[name + '/label_im'])
+        assert np.array_equal(ranks, g[name + '/ranks'])
+        assert np.array_equal(shape_index, g[name + '/shape_index'])
+        assert np.array_equal(np.stack(bboxes), g[name + '/bboxes'])
+        want = np.unpackbits(g[name + '/rois'], axis=-1)[..., :bg.shape[1]].astype(bool)
+        assert len(rois) == len(shape_index) > make_golden.ROI_KEEP
+        for i in range(make_golden.ROI_KEEP):
+            assert np.array_equal(rois[i], want[i])
+        # the first-ranked region of the default case is the bucket floor with its closed hole filled
+        if name == 'default':
+            cy, cx = bg.shape[0] // 2, bg.shape[1] // 2
+            assert rois[0][cy - 25, cx + 25] and not g[name + '/label_im'][cy - 25, cx + 25]
