@@ -94,11 +94,11 @@ def read_frames_raw(filename: Union[str, tarfile.TarInfo], frames: Optional[Unio
 
 class RawDepthSession:
     """The slice of `io.session.Session` that ProduceFramesStep uses (ref: io/session.py:24, :352-466), backed by a raw
-    `.dat` depth file: `.bground_im`, `.roi`, `.nframes`, `.iterate(chunk_size, chunk_overlap)`.  Background and ROI
-    are supplied by the caller (their estimation, ref proc/roi.py:14/:293, is per-session set-up, not the hot path)."""
+    `.dat` depth file: `.bground_im`, `.roi`, `.nframes`, `.iterate(chunk_size, chunk_overlap)`.  Background, ROI and
+    true depth are either supplied by the caller or estimated from the file by `find_roi()` (ref io/session.py:181-264)."""
 
-    def __init__(self, depth_file: str, bground_im: np.ndarray, roi: np.ndarray, true_depth: float,
-                 frame_dims: Tuple[int, int] = (512, 424), pinned: bool = True):
+    def __init__(self, depth_file: str, bground_im: Optional[np.ndarray] = None, roi: Optional[np.ndarray] = None,
+                 true_depth: float = float('nan'), frame_dims: Tuple[int, int] = (512, 424), pinned: bool = True):
         self.depth_file, self.frame_dims, self.pinned = depth_file, frame_dims, pinned
         self.bground_im, self.roi, self.true_depth = bground_im, roi, float(true_depth)
         self.nframes = get_raw_info(depth_file, frame_dims=frame_dims)['nframes']
@@ -114,6 +114,33 @@ class RawDepthSession:
         frames = read_frames_raw(self.depth_file, idxs, frame_dims=self.frame_dims)
         self.bground_im = get_bground_im(frames, med_scale=med_scale)
         return self.bground_im
+
+
+    def find_roi(self, bg_roi_dilate: Tuple[int, int] = (10, 10), bg_roi_shape: str = 'ellipse', bg_roi_index: int = 0,
+                 bg_roi_weights=(1, .1, 1), bg_roi_depth_range: Tuple[int, int] = (650, 750), bg_roi_gradient_filter: bool = False,
+                 bg_roi_gradient_threshold: int = 3000, bg_roi_gradient_kernel: int = 7, bg_roi_fill_holes: bool = True,
+                 use_plane_bground: bool = False, verbose: bool = False, frame_stride: int = 500):
+        """Per-session set-up (ref: io/session.py:181-264 without its tiff cache): first frame, background image
+        (unless one was given to the constructor), arena ROI = the `bg_roi_index`-th ranked region of `proc.get_roi`, and
+        `true_depth` = median background depth inside the ROI.  Stores `.bground_im`, `.roi`, `.true_depth` and returns
+        `(first_frame, bground_im, roi, true_depth)`.  Background and ROI are computed on the GPU."""
+        from ..proc.roi import get_roi
+        from ..proc.util import select_strel
+        first_frame = read_frames_raw(self.depth_file, [0], frame_dims=self.frame_dims)
+        if self.bground_im is None:
+            self.compute_bground(frame_stride=frame_stride)
+        bground_im = np.asarray(self.bground_im)
+        rois, plane, _, _, _, _ = get_roi(bground_im, strel_dilate=select_strel(bg_roi_shape, bg_roi_dilate), weights=bg_roi_weights,
+                                          depth_range=bg_roi_depth_range, gradient_filter=bg_roi_gradient_filter,
+                                          gradient_threshold=bg_roi_gradient_threshold, gradient_kernel=bg_roi_gradient_kernel,
+                                          fill_holes=bg_roi_fill_holes, progress_bar=verbose)
+        if use_plane_bground:                               # io/session.py:245-252: the fitted plane replaces the median image
+            yy, xx = np.mgrid[:bground_im.shape[0], :bground_im.shape[1]]
+            bground_im = ((xx * plane[0] + yy * plane[1]) + plane[3]) / -plane[2]
+        roi = rois[bg_roi_index]
+        self.bground_im, self.roi = bground_im, roi
+        self.true_depth = float(np.median(bground_im[roi > 0]))
+        return first_frame, bground_im, roi, self.true_depth
 
 
 class _RawIterator:

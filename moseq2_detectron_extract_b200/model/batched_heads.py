@@ -158,6 +158,35 @@ def _transform_forward(self, images, targets=None):
     return ImageList(x, [(oh, ow)] * len(images)), targets
 
 
+def _transform_postprocess(self, result, image_shapes, original_image_sizes):
+    """GeneralizedRCNNTransform.postprocess (boxes and keypoints back to the original image scale) as one multiply over
+    the concatenated detections instead of ~40 tiny ops and 8 host-to-device scalar copies per image.  The ratios are the
+    float32 quotients torchvision forms (resize_boxes / resize_keypoints).  Mask pasting is not done here: models whose
+    soft masks are pasted by torchvision go through the original loop."""
+    if self.training or len(result) == 0:
+        return result
+    if any('masks' in r for r in result) and not getattr(self, '_msq_keep_soft_masks', False):
+        return self._msq_postprocess(result, image_shapes, original_image_sizes)
+    import numpy as np
+    ratios = np.array([[np.float32(o[1]) / np.float32(s[1]), np.float32(o[0]) / np.float32(s[0])]
+                       for s, o in zip(image_shapes, original_image_sizes)], dtype=np.float32)            # (n, 2): width, height
+    counts = [int(r['boxes'].shape[0]) for r in result]
+    dev = result[0]['boxes'].device
+    if (ratios == ratios[0]).all():
+        per_row = torch.tensor(ratios[0], device=dev)[None, :]
+    else:
+        per_row = torch.tensor(np.repeat(ratios, counts, axis=0), device=dev)
+    boxes = torch.cat([r['boxes'] for r in result]) * torch.cat([per_row, per_row], dim=1)
+    for r, b in zip(result, boxes.split(counts)):
+        r['boxes'] = b
+    if all('keypoints' in r for r in result):
+        kp = torch.cat([r['keypoints'] for r in result]).clone()
+        kp[..., :2] *= per_row[:, None, :]
+        for r, k in zip(result, kp.split(counts)):
+            r['keypoints'] = k
+    return result
+
+
 def _convert_to_roi_format(boxes):
     """torchvision.ops.poolers._convert_to_roi_format without one tiny kernel per image: (image index, x1, y1, x2, y2)."""
     counts = [int(b.shape[0]) for b in boxes]
@@ -196,6 +225,9 @@ def enable_batched_heads(model) -> None:
     if not hasattr(heads, '_msq_forward'):
         heads._msq_forward = heads.forward
         heads.forward = types.MethodType(_roi_heads_forward, heads)
+    if not hasattr(tr, '_msq_postprocess'):
+        tr._msq_postprocess = tr.postprocess
+        tr.postprocess = types.MethodType(_transform_postprocess, tr)
     from torchvision.ops import poolers as tv_poolers
     if tv_poolers._convert_to_roi_format is not _convert_to_roi_format:
         _convert_to_roi_format.original = tv_poolers._convert_to_roi_format
@@ -221,6 +253,9 @@ def disable_batched_heads(model) -> None:
     if hasattr(heads, '_msq_forward'):
         heads.forward = heads._msq_forward
         del heads._msq_forward
+    if hasattr(tr, '_msq_postprocess'):
+        tr.postprocess = tr._msq_postprocess
+        del tr._msq_postprocess
     from torchvision.ops import poolers as tv_poolers
     if tv_poolers._convert_to_roi_format is _convert_to_roi_format:
         tv_poolers._convert_to_roi_format = _convert_to_roi_format.original

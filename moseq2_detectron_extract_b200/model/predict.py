@@ -50,6 +50,7 @@ def build_random_keypoint_mask_rcnn(num_keypoints: int = 8, image_size: int = 25
         return result
 
     transform.postprocess = postprocess_keep_soft_masks
+    transform._msq_keep_soft_masks = True                  # tells model/batched_heads.py its batched postprocess may skip pasting
     return model
 
 
@@ -145,9 +146,11 @@ class Predictor:
             ninst = torch.zeros((n,), dtype=torch.int64, device=chw.device)
             if have:
                 sel = torch.tensor(have, device=chw.device)
-                boxes = torch.stack([outputs[i]['pred_boxes'][0] for i in have]).float()
-                soft = torch.stack([outputs[i]['pred_masks'][0] for i in have]).float()
-                kp = torch.stack([outputs[i]['pred_keypoints'][0] for i in have]).float()
+                # first instance of every frame that has one: one concatenation per field, then one row gather
+                first = torch.tensor(np.cumsum([0] + counts[:-1])[have], device=chw.device)
+                boxes = torch.cat([o['pred_boxes'] for o in outputs])[first].float()
+                soft = torch.cat([o['pred_masks'] for o in outputs])[first].float()
+                kp = torch.cat([o['pred_keypoints'] for o in outputs])[first].float()
                 if soft.dim() == 4:
                     soft = soft[:, 0]
                 # detector_postprocess at scale 1: clip to the image, keep non-empty boxes, paste at 0.5

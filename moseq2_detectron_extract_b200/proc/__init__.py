@@ -5,4 +5,4 @@ from .proc import (clean_frames, crop_and_rotate_frame, crop_and_rotate_frames_b
 from .roi import apply_roi, get_bbox, get_bground_im, get_roi, plane_fit3, plane_ransac  # noqa: F401
 from .scalars import compute_scalars, scalar_attributes  # noqa: F401
 from .keypoints import keypoints_to_dict, keypoint_attributes, rotate_points, rotate_points_batch  # noqa: F401
-from .util import convert_pxs_to_mm  # noqa: F401
+from .util import convert_pxs_to_mm, select_strel  # noqa: F401

@@ -25,3 +25,24 @@ def slice_dict(data: dict, index) -> dict:
     for key, value in data.items():
         out[key] = slice_dict(value, index) if isinstance(value, dict) else value[index]
     return out
+
+
+def select_strel(shape: str = 'e', size: Tuple[int, int] = (10, 10)) -> np.ndarray:
+    """Structuring element as a uint8 array of `size` = (width, height): 'r...' = rectangle, anything else = ellipse
+    (ref: proc/util.py:9-26).  Equal to cv2.getStructuringElement(MORPH_RECT / MORPH_ELLIPSE, size): OpenCV's ellipse
+    fills, in row i, the columns within round-half-even(c * sqrt(1 - (i - r)^2 / r^2)) of the centre column c = width // 2,
+    r = height // 2."""
+    width, height = int(size[0]), int(size[1])
+    if width <= 0 or height <= 0:
+        raise ValueError(f'select_strel: size must be positive, got {size}')
+    if shape[0].lower() == 'r' or (width == 1 and height == 1):
+        return np.ones((height, width), np.uint8)
+    out = np.zeros((height, width), np.uint8)
+    r, c = height // 2, width // 2
+    inv_r2 = 1.0 / (float(r) * r) if r else 0.0
+    for i in range(height):
+        dy = i - r
+        if abs(dy) <= r:
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+            out[i, max(c - dx, 0):min(c + dx + 1, width)] = 1
+    return out

@@ -159,6 +159,37 @@ def test_raw_session_background_from_file(tmp_path):
     assert np.array_equal(bg, O.bground_im(ch.frames[::3].copy(), 5)) and sess.bground_im is bg
 
 
+def test_raw_session_find_roi_from_file(tmp_path):
+    """RawDepthSession.find_roi: background + RANSAC floor plane + ranked, dilated, hole-filled region -> roi and true
+    depth, equal to the oracle's get_roi on the oracle's background (ref io/session.py:181-264)."""
+    import cv2
+    import roi_oracle
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.io.video import RawDepthSession
+    from moseq2_detectron_extract_b200.proc.util import select_strel
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(21, seed=12, geom=geom)
+    path = tmp_path / 'depth.dat'
+    ch.frames.astype('<i2').tofile(path)
+    assert np.array_equal(select_strel('ellipse', (10, 10)), cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (10, 10)))
+    bg = O.bground_im(ch.frames[::2].copy(), 5)
+    np.random.seed(4)
+    rois, plane, _, _, _, _ = roi_oracle.get_roi(bg, strel_dilate=cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (10, 10)))
+    for plane_bg in (False, True):
+        sess = RawDepthSession(str(path), pinned=False)
+        np.random.seed(4)
+        first, bground, roi, true_depth = sess.find_roi(frame_stride=2, use_plane_bground=plane_bg)
+        assert np.array_equal(np.asarray(first)[0], ch.frames[0])
+        assert roi.dtype == bool and np.array_equal(roi, rois[0]) and sess.roi is roi
+        yy, xx = np.mgrid[:geom.height, :geom.width]
+        want_bg = (xx * plane[0] + yy * plane[1] + plane[3]) / -plane[2] if plane_bg else bg
+        np.testing.assert_allclose(bground, want_bg, rtol=1e-14)
+        assert true_depth == pytest.approx(float(np.median(want_bg[rois[0]])), rel=1e-14) and sess.true_depth == true_depth
+        assert abs(true_depth - 673.0) < 2.0
+        # the detected arena covers the synthetic bucket floor the generator masks with
+        assert (roi & synthetic.make_roi(geom)).sum() > 0.95 * synthetic.make_roi(geom).sum()
+
+
 def test_dense_inference_matches_per_image_instances():
     """Predictor.predict_dense (batched detector_postprocess + first-instance gather, one paste launch) against the
     reference-shaped path: predict_prepared -> outputs_to_instances -> mask_and_keypoints_from_model_output."""
