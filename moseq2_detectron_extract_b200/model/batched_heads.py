@@ -201,11 +201,24 @@ def _convert_to_roi_format(boxes):
     return torch.cat([ids[:, None], concat], dim=1)
 
 
+def _level_mapper_call(self, boxlists):
+    """torchvision.ops.poolers.LevelMapper.__call__ with the box areas taken on the concatenated boxes (the original
+    computes them image by image: three tiny kernels per image and pooler)."""
+    boxes = torch.cat(list(boxlists))
+    if boxes.dtype in (torch.float16, torch.bfloat16) or not boxes.is_floating_point():
+        return _level_mapper_call.original(self, boxlists)
+    s = torch.sqrt((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]))
+    target_lvls = torch.floor(self.lvl0 + torch.log2(s / self.s0) + torch.tensor(self.eps, dtype=s.dtype))
+    target_lvls = torch.clamp(target_lvls, min=self.k_min, max=self.k_max)
+    return (target_lvls.to(torch.int64) - self.k_min).to(torch.int64)
+
+
 def _roi_heads_forward(self, features, proposals, image_shapes, targets=None):
-    """RoIHeads.forward with the pyramid features converted to float32 ONCE: under autocast every roi_align call casts its
-    whole input feature map to float32 (three poolers x four levels per batch); the pooled values are the same."""
-    if not self.training and any(v.dtype != torch.float32 for v in features.values()):
-        features = type(features)((k, v.float()) for k, v in features.items())
+    """RoIHeads.forward with the pyramid features converted to contiguous float32 ONCE: roi_align wants NCHW float32 and
+    otherwise casts / re-lays-out its whole input feature map on every call (three poolers x four levels per batch, and
+    the backbone runs channels-last bf16 under autocast); the pooled values are the same."""
+    if not self.training and any(v.dtype != torch.float32 or not v.is_contiguous() for v in features.values()):
+        features = type(features)((k, v.to(torch.float32, memory_format=torch.contiguous_format)) for k, v in features.items())
     return self._msq_forward(features, proposals, image_shapes, targets)
 
 
@@ -232,6 +245,9 @@ def enable_batched_heads(model) -> None:
     if tv_poolers._convert_to_roi_format is not _convert_to_roi_format:
         _convert_to_roi_format.original = tv_poolers._convert_to_roi_format
         tv_poolers._convert_to_roi_format = _convert_to_roi_format
+    if tv_poolers.LevelMapper.__call__ is not _level_mapper_call:
+        _level_mapper_call.original = tv_poolers.LevelMapper.__call__
+        tv_poolers.LevelMapper.__call__ = _level_mapper_call
     from torchvision.models.detection import roi_heads as tv_heads
     if tv_heads.keypointrcnn_inference is not _keypointrcnn_inference:      # module-level function: patched process-wide
         _keypointrcnn_inference.original = tv_heads.keypointrcnn_inference
@@ -259,6 +275,8 @@ def disable_batched_heads(model) -> None:
     from torchvision.ops import poolers as tv_poolers
     if tv_poolers._convert_to_roi_format is _convert_to_roi_format:
         tv_poolers._convert_to_roi_format = _convert_to_roi_format.original
+    if tv_poolers.LevelMapper.__call__ is _level_mapper_call:
+        tv_poolers.LevelMapper.__call__ = _level_mapper_call.original
     from torchvision.models.detection import roi_heads as tv_heads
     if tv_heads.keypointrcnn_inference is _keypointrcnn_inference:
         tv_heads.keypointrcnn_inference = _keypointrcnn_inference.original

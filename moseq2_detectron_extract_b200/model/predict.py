@@ -135,9 +135,12 @@ class Predictor:
         _lib.call('msq_scale_frames_chw3_f32', _dev.ptr(chunk_u8), _dev.ptr(chw), n, h, w, float(vmin), float(vmax),
                   int(isinstance(vmin, (int, np.integer))), _dev.stream())
         with torch.no_grad():
-            inputs = [{'image': chw[i]} for i in range(n)]
             with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
-                outputs = self.model(inputs)
+                if isinstance(self.model, _TorchvisionAdapter):          # straight to the detector: no per-image dicts
+                    outputs = [{'scores': o['scores'], 'pred_boxes': o['boxes'], 'pred_masks': o['masks'], 'pred_keypoints': o['keypoints']}
+                               for o in self.model.model(list(chw.unbind(0)))]
+                else:
+                    outputs = self.model([{'image': chw[i]} for i in range(n)])
             counts = [int(o['scores'].shape[0]) for o in outputs]                  # host-known sizes: no synchronisation
             have = [i for i, c in enumerate(counts) if c > 0]
             k = int(outputs[have[0]]['pred_keypoints'].shape[1]) if have else _lib.NUM_KEYPOINTS

@@ -18,10 +18,14 @@ def main():
         pred.predict_dense(chunk, 0, 100)
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=len(sys.argv) > 2) as prof:
         pred.predict_dense(chunk, 0, 100)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=90))
+    if len(sys.argv) > 2:                                  # second argument: where the many-call ops come from
+        rows = [e for e in prof.key_averages(group_by_stack_n=8) if e.count >= n // 2 and e.key.startswith('aten::')]
+        for e in sorted(rows, key=lambda e: -e.count)[:25]:
+            print(e.count, e.key, ' <- '.join(str(f) for f in e.stack[:8] if 'site-packages/torch/' not in str(f))[:600])
 
 
 if __name__ == '__main__':
