@@ -257,6 +257,9 @@ MSQ_API int msq_get_bground_im(const void *frames_dev, int n, int H, int W, int 
  * The host side draws the RANSAC triples (np.random, the reference's order) and ranks the regions; these entry points do
  * the per-pixel work.  depth_dev is the (H,W) background image as float64.
  *
+ * msq_sobel_gradient_mask (gradient_filter, proc/roi.py:29-35): mask_dev (H*W) u8 = |cv2.Sobel(depth, CV_64F, 1, 0, k)| <
+ *   threshold and the same for (0, 1); deriv_host / smooth_host are cv2.getDerivKernels' taps in HOST memory (odd counts
+ *   <= 31), border = BORDER_REFLECT_101.  Exact for integer- or half-integer-valued images (all sums are exact in float64).
  * msq_plane_ransac_score: idx_dev (npts) int32 = raster indices of the usable pixels (depth_range / gradient mask);
  *   sel_dev (iters,3) int64 indexes idx_dev.  Per candidate: planes_dev (iters,4) = unit normal and offset of the plane
  *   through its 3 points (NaN when they are collinear), ninliers_dev = #{|ax+by+cz+d| < tol}, sumdist_dev = sum of the
@@ -271,6 +274,8 @@ MSQ_API int msq_get_bground_im(const void *frames_dev, int n, int H, int W, int 
  *   anchored at its centre; NULL = skip), cv2.erode by se_erode (NULL = skip), scipy binary_fill_holes when
  *   fill_holes != 0; rois_dev (n_out,H,W) u8 0/1, bboxes_dev (n_out,4) = get_bbox of each mask (-1 when empty).
  *   W <= 1024, H * ceil(W/32) * 8 bytes of shared memory <= 220 KB.  Bit-exact. */
+MSQ_API int msq_sobel_gradient_mask(const double *depth_dev, int H, int W, const double *deriv_host, int n_deriv,
+                            const double *smooth_host, int n_smooth, double threshold, uint8_t *mask_dev, void *stream);
 MSQ_API int msq_plane_ransac_score(const int *idx_dev, int npts, const double *depth_dev, int H, int W, const long long *sel_dev,
                            int iters, double tol, double *planes_dev, int *ninliers_dev, double *sumdist_dev, void *stream);
 MSQ_API int msq_plane_distance(const double *depth_dev, int H, int W, const double *plane_host, double tol,

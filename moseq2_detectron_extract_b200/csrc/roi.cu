@@ -102,6 +102,38 @@ plane_distance_kernel(const double *__restrict__ depth, int H, int W, PlaneArg p
     }
 }
 
+// ---- gradient pre-mask: |Sobel_x| < thr and |Sobel_y| < thr (get_roi's gradient_filter, proc/roi.py:29-35) ----------------
+struct SobelTaps { double deriv[31]; double smooth[31]; int n_deriv, n_smooth; };
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+// cv2.Sobel(src, CV_64F, 1, 0, ksize) and (0, 1): separable correlation, rows first, BORDER_REFLECT_101
+__device__ double separable_at(const double *__restrict__ src, int H, int W, int y, int x, const double *kx, int nx, const double *ky, int ny) {
+    double acc = 0.0;
+    for (int i = 0; i < ny; ++i) {
+        const double *row = src + (size_t)reflect101(y + i - ny / 2, H) * W;
+        double r = 0.0;
+        for (int j = 0; j < nx; ++j) r += kx[j] * row[reflect101(x + j - nx / 2, W)];
+        acc += ky[i] * r;
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256)
+sobel_mask_kernel(const double *__restrict__ depth, int H, int W, SobelTaps taps, double threshold, uint8_t *__restrict__ mask) {
+    const int total = H * W;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        const int y = p / W, x = p - y * W;
+        const double gx = fabs(separable_at(depth, H, W, y, x, taps.deriv, taps.n_deriv, taps.smooth, taps.n_smooth));
+        const double gy = fabs(separable_at(depth, H, W, y, x, taps.smooth, taps.n_smooth, taps.deriv, taps.n_deriv));
+        mask[p] = (uint8_t)(gx < threshold && gy < threshold);
+    }
+}
+
 // ---- 8-connected labelling -------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(const int *L, int a) {
     const volatile int *V = L;
@@ -375,6 +407,21 @@ extern "C" int msq_plane_distance(const double *depth_dev, int H, int W, const d
     TimedLaunch timed(K_ROI, (cudaStream_t)stream);
     plane_distance_kernel<<<grid_for(H * W), 256, 0, (cudaStream_t)stream>>>(depth_dev, H, W, pl, tol, valid_dev, dist_dev, on_plane_dev);
     MSQ_LAUNCH_OK("plane_distance");
+    return MSQ_OK;
+}
+
+extern "C" int msq_sobel_gradient_mask(const double *depth_dev, int H, int W, const double *deriv_host, int n_deriv,
+                                       const double *smooth_host, int n_smooth, double threshold, uint8_t *mask_dev, void *stream) {
+    MSQ_REQUIRE(H > 0 && W > 0 && (long long)H * W < INT_MAX, MSQ_EINVAL, "msq_sobel_gradient_mask: bad image size %dx%d", H, W);
+    MSQ_REQUIRE(depth_dev && deriv_host && smooth_host && mask_dev, MSQ_EINVAL, "msq_sobel_gradient_mask: null pointer");
+    MSQ_REQUIRE(n_deriv >= 1 && n_deriv <= 31 && n_smooth >= 1 && n_smooth <= 31 && (n_deriv & 1) && (n_smooth & 1), MSQ_EINVAL,
+                "msq_sobel_gradient_mask: kernels must have an odd number of taps <= 31 (got %d, %d)", n_deriv, n_smooth);
+    SobelTaps taps;
+    taps.n_deriv = n_deriv; taps.n_smooth = n_smooth;
+    for (int k = 0; k < 31; ++k) { taps.deriv[k] = k < n_deriv ? deriv_host[k] : 0.0; taps.smooth[k] = k < n_smooth ? smooth_host[k] : 0.0; }
+    TimedLaunch timed(K_ROI, (cudaStream_t)stream);
+    sobel_mask_kernel<<<grid_for(H * W), 256, 0, (cudaStream_t)stream>>>(depth_dev, H, W, taps, threshold, mask_dev);
+    MSQ_LAUNCH_OK("sobel_mask");
     return MSQ_OK;
 }
 

@@ -54,6 +54,34 @@ def build_random_keypoint_mask_rcnn(num_keypoints: int = 8, image_size: int = 25
     return model
 
 
+def fold_batchnorm_into_convs(module: torch.nn.Module) -> int:
+    """Inference-time folding of every (Conv2d, BatchNorm2d / FrozenBatchNorm2d) pair registered next to each other in a
+    module (ResNet stem, bottleneck conv1-3, downsample branches): w' = w * s, b' = (b - mean) * s + beta with
+    s = gamma / sqrt(var + eps).  The normalisation layer becomes an Identity, which removes one or two full-tensor
+    elementwise kernels per convolution (tools/rcnn_kernels.py: as much device time as the convolutions themselves).
+    Returns the number of pairs folded; only valid for eval-mode models."""
+    from torchvision.ops.misc import FrozenBatchNorm2d
+    folded = 0
+    for parent in module.modules():
+        names = list(parent._modules.keys())
+        for a, b in zip(names, names[1:]):
+            conv, bn = parent._modules[a], parent._modules[b]
+            if not isinstance(conv, torch.nn.Conv2d) or not isinstance(bn, (torch.nn.BatchNorm2d, FrozenBatchNorm2d)):
+                continue
+            if isinstance(bn, torch.nn.BatchNorm2d) and (bn.training or bn.running_var is None):
+                continue
+            with torch.no_grad():
+                gamma = bn.weight if bn.weight is not None else torch.ones_like(bn.running_var)
+                beta = bn.bias if bn.bias is not None else torch.zeros_like(bn.running_var)
+                scale = gamma * torch.rsqrt(bn.running_var + bn.eps)
+                bias = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+                conv.weight.mul_(scale.reshape(-1, 1, 1, 1))
+                conv.bias = torch.nn.Parameter((bias - bn.running_mean) * scale + beta, requires_grad=False)
+            parent._modules[b] = torch.nn.Identity()
+            folded += 1
+    return folded
+
+
 class _TorchvisionAdapter(torch.nn.Module):
     """Gives a torchvision detector the I/O contract of the reference's TorchScript export
     (ref: model/deploy.py:73-102): list of {'image': CHW} in, list of dicts with pred_* keys out."""
@@ -96,7 +124,10 @@ class Predictor:
     def from_random_init(cls, device: str = 'cuda', seed: int = 0, amp: bool = False, batched_heads: bool = True, **kwargs):
         _dev.require_cuda()
         torch.manual_seed(seed)
+        fold_bn = kwargs.pop('fold_batchnorm', True)
         model = _TorchvisionAdapter(build_random_keypoint_mask_rcnn(**kwargs)).to(device).eval()
+        if fold_bn:
+            fold_batchnorm_into_convs(model.model.backbone)
         if batched_heads:               # one segmented NMS launch per batch instead of torchvision's per-image loops
             from .batched_heads import enable_batched_heads
             enable_batched_heads(model.model)

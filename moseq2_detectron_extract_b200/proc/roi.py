@@ -139,6 +139,32 @@ def plane_ransac(depth_image, depth_range=(650, 750), iters=1000, noise_toleranc
     return plane, _dev.give_back(dist, depth_image)
 
 
+def sobel_kernels(ksize: int):
+    """(derivative, smoothing) taps of cv2.getDerivKernels(1, 0, ksize, normalize=False): binomial smoothing of ksize
+    taps, and the first difference of the (ksize - 1)-tap binomial; ksize 1 is OpenCV's [-1, 0, 1] x [1]."""
+    ksize = int(ksize)
+    if ksize < 1 or ksize > 31 or ksize % 2 == 0:
+        raise ValueError(f'Sobel kernel size must be odd and in 1..31, got {ksize}')
+    if ksize == 1:
+        return np.array([-1.0, 0.0, 1.0]), np.array([1.0])
+    smooth, deriv = np.ones(1), np.ones(1)
+    for _ in range(ksize - 1):
+        smooth = np.convolve(smooth, [1.0, 1.0])
+    for _ in range(ksize - 2):
+        deriv = np.convolve(deriv, [1.0, 1.0])
+    return np.convolve(deriv, [1.0, -1.0])[::-1].copy(), smooth
+
+
+def _gradient_mask(depth: torch.Tensor, ksize: int, threshold: float) -> torch.Tensor:
+    from .. import _lib
+    h, w = (int(v) for v in depth.shape)
+    deriv, smooth = sobel_kernels(ksize)
+    mask = _dev.empty((h, w), torch.uint8)
+    _lib.call('msq_sobel_gradient_mask', _dev.ptr(depth), h, w, (ctypes.c_double * len(deriv))(*deriv), len(deriv),
+              (ctypes.c_double * len(smooth))(*smooth), len(smooth), float(threshold), _dev.ptr(mask), _dev.stream())
+    return mask.view(torch.bool)
+
+
 def _rank_max(values: np.ndarray) -> np.ndarray:
     """scipy.stats.rankdata(values, method='max'): the number of elements <= each value."""
     return np.searchsorted(np.sort(values), values, side='right').astype(np.float64)
@@ -159,18 +185,19 @@ def get_roi(depth_image, strel_dilate=_DEFAULT_STREL_DILATE, strel_erode=None, n
     ranked order (best first), masks are bool whatever `fill_holes` is (the reference leaves 0/1 images of the depth dtype
     when `fill_holes=False`).  numpy in -> numpy out; CUDA tensor in -> `rois` and `label_im` stay on the device.
     Labels, region features, ranks and masks are bit-identical to skimage / OpenCV / SciPy for the same plane.
-    `gradient_filter=True` (Sobel pre-mask, off by default in the reference's CLI) is not implemented."""
+    `gradient_filter=True` masks out pixels whose |cv2.Sobel| response (kernel `gradient_kernel`) reaches
+    `gradient_threshold` in x or y before the fit, like the reference."""
     from .. import _lib
-    if gradient_filter:
-        raise NotImplementedError('get_roi: gradient_filter=True is not part of this build')
     kwargs.pop('progress_bar', None)
     depth = _depth_f64(depth_image)
     h, w = (int(v) for v in depth.shape)
+    # gradient_filter: pixels with a steep Sobel response (walls, rims) neither vote for the plane nor belong to it
+    valid = _gradient_mask(depth, gradient_kernel, gradient_threshold) if gradient_filter else None
     roi_plane = _plane_ransac_device(depth, kwargs.pop('depth_range', (650, 750)), kwargs.pop('iters', 1000), noise_tolerance,
-                                     kwargs.pop('in_ratio', 0.1), None)
+                                     kwargs.pop('in_ratio', 0.1), valid)
     if kwargs:
         raise TypeError(f'get_roi: unexpected arguments {sorted(kwargs)}')
-    _, on_plane = _plane_distance(depth, roi_plane, noise_tolerance, None, False, True)
+    _, on_plane = _plane_distance(depth, roi_plane, noise_tolerance, None if valid is None else valid.view(torch.uint8), False, True)
 
     labels = _dev.empty((h, w), torch.int32)
     count = _dev.empty((1,), torch.int32)

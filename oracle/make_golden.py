@@ -155,6 +155,8 @@ ROI_CASES = {
                              lambda cv2: dict(strel_dilate=cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (9, 7)),
                                               strel_erode=cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5)), fill_holes=False,
                                               weights=(1, .5, .2), noise_tolerance=20, iters=300)),
+    'gradient_filter': (dict(seed=2, h=200, w=260), 6, lambda cv2: dict(gradient_filter=True, gradient_kernel=5, gradient_threshold=400,
+                                                                         strel_dilate=cv2.getStructuringElement(cv2.MORPH_RECT, (7, 7)))),
 }
 ROI_KEEP = 4            # ranked masks stored per case (all bounding boxes are)
 

@@ -74,8 +74,6 @@ def test_get_roi_device_tensor_in_device_tensors_out():
     rois, plane, bboxes, label_im, ranks, shape_index = _proc().get_roi(torch.from_numpy(bg).cuda())
     assert rois[0].is_cuda and rois[0].dtype == torch.bool and label_im.is_cuda
     _same_result(([r.cpu().numpy() for r in rois], plane, bboxes, label_im.cpu().numpy(), ranks, shape_index), want)
-    with pytest.raises(NotImplementedError):
-        _proc().get_roi(bg, gradient_filter=True)
 
 
 def test_plane_ransac_matches_oracle_and_plane_fit3():
@@ -173,3 +171,19 @@ def test_region_masks_equal_opencv_and_scipy_for_random_elements(h, w):
             rows, cols = np.nonzero(roi)
             exp = [-1] * 4 if len(rows) == 0 else [rows.min(), cols.min(), rows.max(), cols.max()]
             assert boxes[i].tolist() == exp
+
+
+@pytest.mark.parametrize('ksize,threshold', [(7, 3000), (5, 400), (3, 60), (1, 8)])
+@pytest.mark.parametrize('dtype', ['float32', 'float64', 'uint16'])
+def test_gradient_mask_equals_opencv_sobel(ksize, threshold, dtype):
+    from moseq2_detectron_extract_b200.proc.roi import _depth_f64, _gradient_mask, sobel_kernels
+    deriv, smooth = sobel_kernels(ksize)
+    kx, ky = cv2.getDerivKernels(1, 0, ksize, normalize=False, ktype=cv2.CV_64F)
+    assert np.array_equal(deriv, kx.ravel()) and np.array_equal(smooth, ky.ravel())
+    for h, w in ((200, 260), (33, 17), (424, 512)):
+        bg = roi_oracle.synthetic_bground(h=h, w=w, seed=h).astype(dtype)
+        if dtype == 'float64':
+            bg[::3, ::2] += 0.5                                   # np.median of an even frame count gives half steps
+        got = _gradient_mask(_depth_f64(bg), ksize, threshold).cpu().numpy()
+        assert np.array_equal(got, roi_oracle.gradient_mask(bg, ksize, threshold))
+        assert 0 < got.sum() < got.size

@@ -318,3 +318,45 @@ def test_result_writer_step_layout_and_offsets(tmp_path):
     header = lines[0].split('\t')
     assert header[:5] == ['Frame_Idx', 'Flip', 'Centroid_X', 'Centroid_Y', 'Angle'] and len(header) == 5 + 96
     assert len(lines) == 1 + 8 and lines[1].split('\t')[:3] == ['0', 'True', '0.0']
+
+
+def test_select_strel_and_sobel_kernels_equal_opencv():
+    import cv2
+    from moseq2_detectron_extract_b200.proc.roi import plane_fit3, sobel_kernels
+    from moseq2_detectron_extract_b200.proc.util import select_strel
+    for w in range(1, 24):
+        for h in range(1, 24):
+            assert np.array_equal(select_strel('ellipse', (w, h)), cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (w, h))), (w, h)
+            assert np.array_equal(select_strel('rect', (w, h)), cv2.getStructuringElement(cv2.MORPH_RECT, (w, h)))
+    assert np.array_equal(select_strel('x', (10, 10)), select_strel('e', (10, 10)))      # unknown shapes mean ellipse
+    for k in (1, 3, 5, 7, 9, 31):
+        kx, ky = cv2.getDerivKernels(1, 0, k, normalize=False, ktype=cv2.CV_64F)
+        deriv, smooth = sobel_kernels(k)
+        assert np.array_equal(deriv, kx.ravel()) and np.array_equal(smooth, ky.ravel())
+    with pytest.raises(ValueError):
+        sobel_kernels(4)
+    plane = plane_fit3(np.array([[0., 0., 2.], [4., 0., 2.], [0., 3., 2.]]))
+    assert np.allclose(plane, [0, 0, 1, -2])
+    assert np.isnan(plane_fit3(np.zeros((3, 3)))).all()
+
+
+def test_batchnorm_folding_preserves_backbone_outputs():
+    pytest.importorskip('torchvision')
+    import torch
+    from moseq2_detectron_extract_b200.model.predict import build_random_keypoint_mask_rcnn, fold_batchnorm_into_convs
+    torch.manual_seed(0)
+    backbone = build_random_keypoint_mask_rcnn().eval().backbone
+    for mod in backbone.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):              # non-trivial statistics, as a trained model would have
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.1)
+    x = torch.rand(1, 3, 64, 64)
+    with torch.no_grad():
+        want = backbone(x)
+        assert fold_batchnorm_into_convs(backbone) == 53       # stem + 16 bottlenecks x 3 + 4 downsample branches
+        got = backbone(x)
+    assert not any(isinstance(mod, torch.nn.BatchNorm2d) for mod in backbone.modules())
+    for k in want:
+        assert float((want[k] - got[k]).abs().max()) <= 1e-5 * float(want[k].abs().max())
