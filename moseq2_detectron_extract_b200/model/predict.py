@@ -125,9 +125,13 @@ class Predictor:
         _dev.require_cuda()
         torch.manual_seed(seed)
         fold_bn = kwargs.pop('fold_batchnorm', True)
+        fused_convs = kwargs.pop('fused_convs', True)
         model = _TorchvisionAdapter(build_random_keypoint_mask_rcnn(**kwargs)).to(device).eval()
         if fold_bn:
             fold_batchnorm_into_convs(model.model.backbone)
+        if fused_convs:                 # conv + bias + ReLU (+ residual) as single cuDNN calls
+            from .fused_convs import enable_fused_convs
+            enable_fused_convs(model.model)
         if batched_heads:               # one segmented NMS launch per batch instead of torchvision's per-image loops
             from .batched_heads import enable_batched_heads
             enable_batched_heads(model.model)

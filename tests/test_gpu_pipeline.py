@@ -305,3 +305,31 @@ def test_batched_rcnn_heads_match_torchvision():
         ref = idx[torchvision.ops.nms(boxes[i, idx], scores[idx], 0.5)][:50]
         c = int(count[i])
         assert c == len(ref) and torch.equal(keep[i, :c].long(), ref)
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_fused_conv_epilogues_match_eager_backbone_and_heads(amp):
+    """model/fused_convs.py (cuDNN conv+bias+ReLU / conv+bias+residual+ReLU) against the eager modules it replaces, on the
+    FPN features and the keypoint / mask / RPN head outputs of the same random-init network."""
+    pytest.importorskip('torchvision')
+    from moseq2_detectron_extract_b200.model.predict import Predictor
+    plain = Predictor.from_random_init(amp=amp, fused_convs=False).model.model
+    fused = Predictor.from_random_init(amp=amp, fused_convs=True).model.model
+    assert any(type(m).__name__ == 'FusedConvReLU' for m in fused.modules())
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.rand((4, 3, 256, 256), device='cuda', generator=g)
+    if amp:
+        x = x.contiguous(memory_format=torch.channels_last)
+    tol = 3e-2 if amp else 5e-3                                   # bf16 rounding of different fusion orders / TF32
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+        want, got = plain.backbone(x), fused.backbone(x)
+        for k in want:
+            scale = float(want[k].float().abs().max())
+            assert float((want[k].float() - got[k].float()).abs().max()) <= tol * scale, k
+        feat = want['0'].float()
+        pooled = torch.rand((6, 256, 14, 14), device='cuda', generator=g)
+        for a, b, inp in ((plain.roi_heads.keypoint_head, fused.roi_heads.keypoint_head, pooled),
+                          (plain.roi_heads.mask_head, fused.roi_heads.mask_head, pooled),
+                          (plain.rpn.head.conv, fused.rpn.head.conv, feat)):
+            ya, yb = a(inp).float(), b(inp).float()
+            assert float((ya - yb).abs().max()) <= tol * float(ya.abs().max())
