@@ -30,7 +30,7 @@ UNIT = 'frames/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--frames', type=int, default=54000, help='frames per session (per GPU)')
@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.FIELDS}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -84,6 +84,11 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout_s):
+        t_end = time.time() + timeout_s
+        while self.proc is not None and not self.samples and time.time() < t_end:
+            time.sleep(0.01)
 
     def stop(self, t0, t1):
         if self.proc is None:
@@ -104,8 +109,8 @@ class ClockSampler:
                             reasons.add(name)
             except ValueError:
                 continue
-        if not sm:   # timed region shorter than the sampling period: fall back to every sample
-            for ts, line in self.samples:
+        if not sm:   # timed region shorter than the sampling period: fall back to the samples since the warm-up began
+            for ts, line in self.samples[1:] or self.samples:
                 parts = [p.strip() for p in line.split(',')]
                 try:
                     sm.append(float(parts[1]))
@@ -235,15 +240,18 @@ def run_ours(args):
             engine.extract(prep_buf[:n], masks[s:s + n], kpts[s:s + n], **kw)
 
     # ---- device-resident throughput ------------------------------------------------------------------
+    # the clock sampler is started BEFORE the warm-up and must have delivered a line before timing starts (nvidia-smi
+    # needs a few hundred ms to come up; the timed region can be shorter than that), so its samples see the GPU under load
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first(3.0)
+    barrier()
     for _ in range(args.warmup):
         resident_step()
     barrier()
     launches_before = sum(_lib.kernel_launches().values())
     _lib.kernel_timing(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
     barrier()
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
