@@ -120,6 +120,15 @@ MSQ_API int msq_nms_sorted(const float *boxes_dev, const uint8_t *valid_dev, int
 MSQ_API int msq_keypoints_from_heatmaps(const float *maps_dev, const float *rois_dev, int n_rois, int K, int Hm, int Wm,
                                 int round_bf16, float *xyv_dev, float *scores_dev, void *stream);
 
+/* Multi-level RoIAlign (torchvision.ops.MultiScaleRoIAlign / ops/poolers.py:_multiscale_roi_align, aligned = false) in one
+ * launch.  feat_dev[l]: HOST array of n_levels device pointers to CHANNELS-LAST feature maps (n, H_l, W_l, C) of bf16
+ * (is_bf16 != 0) or float32; heights / widths / scales: HOST arrays per level.  rois_dev (n_rois,5) float32 = (image
+ * index, x1, y1, x2, y2) in image coordinates; levels_dev (n_rois) int64 = pyramid level of every RoI (LevelMapper; may
+ * be NULL when n_levels == 1).  out_dev (n_rois, C, P, P) in the dtype of the features.  C % 8 == 0, sampling_ratio >= 1. */
+MSQ_API int msq_roi_align_levels(const void *const *feat_dev, const int *heights, const int *widths, const float *scales,
+                         int n_levels, int C, int is_bf16, const float *rois_dev, const long long *levels_dev, int n_rois,
+                         int P, int sampling_ratio, void *out_dev, void *stream);
+
 /* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
 MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);

@@ -1,0 +1,154 @@
+// a4 glue: multi-level RoIAlign for the R-CNN's RoI heads -- torchvision.ops.MultiScaleRoIAlign in ONE launch.
+//   torchvision (ops/poolers.py:_multiscale_roi_align) runs, per pyramid level, torch.where (a host sync), a gather of the
+//   RoIs, roi_align with one THREAD per output element on NCHW float32 features (16 scattered 4-byte loads each) and an
+//   index_put into the result: 31 ms for the 100 000 box RoIs of a 1000-frame batch, a quarter of the whole model.
+// Here one CTA owns one RoI: every warp takes pooled bins in turn, its lanes own 8 consecutive CHANNELS of the
+// channels-last feature map (the backbone's native layout under autocast), so each of the 4 x sampling_ratio^2 bilinear taps
+// of a bin is one coalesced 16-byte load per lane; the (C, P, P) block of the RoI is assembled in shared memory and
+// written out contiguously in the dtype of the features (bf16 under autocast: what the box head's first Linear reads).
+// Arithmetic = torchvision's roi_align_forward_kernel_impl<float> (aligned = false) in float32, without fused
+// multiply-adds (results agree to an ulp of float32 before the final rounding).
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace msq {
+namespace {
+
+constexpr int kAlignThreads = 256;
+constexpr int kMaxLevels = 8;
+
+struct PyramidArg {
+    const void *feat[kMaxLevels];      // (n, H_l, W_l, C) channels-last
+    int H[kMaxLevels], W[kMaxLevels];
+    float scale[kMaxLevels];
+    int n_levels;
+};
+
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(w[k] << 16); v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+    }
+    static __device__ __forceinline__ __nv_bfloat16 store(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[8]) {
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ float store(float v) { return v; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kAlignThreads)
+roi_align_levels_kernel(PyramidArg pyr, int C, const float *__restrict__ rois, const long long *__restrict__ levels, int P, int sampling,
+                        T *__restrict__ out) {
+    extern __shared__ unsigned char smem_raw[];
+    T *block = reinterpret_cast<T *>(smem_raw);                    // (C, P*P) of this RoI
+    const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *roi = rois + (size_t)r * 5;
+    const int lvl = pyr.n_levels > 1 ? (int)levels[r] : 0;
+    const int H = pyr.H[lvl], W = pyr.W[lvl];
+    const float scale = pyr.scale[lvl];
+    const T *feat = static_cast<const T *>(pyr.feat[lvl]) + (size_t)(int)roi[0] * H * W * C;
+    const float x0 = roi[1] * scale, y0 = roi[2] * scale, x1 = roi[3] * scale, y1 = roi[4] * scale;
+    const float roi_w = fmaxf(x1 - x0, 1.f), roi_h = fmaxf(y1 - y0, 1.f);
+    const float bin_h = roi_h / (float)P, bin_w = roi_w / (float)P;
+    const float count = (float)max(sampling * sampling, 1);
+    const int bins = P * P, groups = (C + 255) / 256;
+    for (int bin = warp; bin < bins; bin += kAlignThreads / 32) {
+        const int ph = bin / P, pw = bin - ph * P;
+        for (int g = 0; g < groups; ++g) {
+            const int c0 = (g * 32 + lane) * 8;
+            const bool act = c0 < C;
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            for (int iy = 0; iy < sampling; ++iy) {
+                float y = y0 + ph * bin_h + (iy + .5f) * bin_h / (float)sampling;
+                for (int ix = 0; ix < sampling; ++ix) {
+                    float x = x0 + pw * bin_w + (ix + .5f) * bin_w / (float)sampling;
+                    float yy = y;
+                    if (yy < -1.0f || yy > (float)H || x < -1.0f || x > (float)W) continue;       // sample outside: contributes 0
+                    if (yy <= 0.f) yy = 0.f;
+                    if (x <= 0.f) x = 0.f;
+                    int y_low = (int)yy, x_low = (int)x, y_high, x_high;
+                    if (y_low >= H - 1) { y_high = y_low = H - 1; yy = (float)y_low; } else y_high = y_low + 1;
+                    if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else x_high = x_low + 1;
+                    const float ly = yy - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+                    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                    if (act) {
+                        float v1[8], v2[8], v3[8], v4[8];
+                        Vec8<T>::load(feat + ((size_t)y_low * W + x_low) * C + c0, v1);
+                        Vec8<T>::load(feat + ((size_t)y_low * W + x_high) * C + c0, v2);
+                        Vec8<T>::load(feat + ((size_t)y_high * W + x_low) * C + c0, v3);
+                        Vec8<T>::load(feat + ((size_t)y_high * W + x_high) * C + c0, v4);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] += ((w1 * v1[k] + w2 * v2[k]) + w3 * v3[k]) + w4 * v4[k];
+                    }
+                }
+            }
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) block[(size_t)(c0 + k) * bins + bin] = Vec8<T>::store(acc[k] / count);
+            }
+        }
+    }
+    __syncthreads();
+    // contiguous (C * P * P) write-out; 16-byte vectors when the RoI's block is 16-byte aligned and sized
+    T *dst = out + (size_t)r * C * bins;
+    const size_t bytes = (size_t)C * bins * sizeof(T);
+    if (bytes % 16 == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(block);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int i = threadIdx.x; i < (int)(bytes / 16); i += kAlignThreads) d4[i] = s4[i];
+    } else {
+        for (int i = threadIdx.x; i < C * bins; i += kAlignThreads) dst[i] = block[i];
+    }
+}
+
+}  // namespace
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" int msq_roi_align_levels(const void *const *feat_dev, const int *heights, const int *widths, const float *scales, int n_levels,
+                                    int C, int is_bf16, const float *rois_dev, const long long *levels_dev, int n_rois, int P,
+                                    int sampling_ratio, void *out_dev, void *stream) {
+    MSQ_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, MSQ_EINVAL, "msq_roi_align_levels: 1..%d pyramid levels (got %d)", kMaxLevels, n_levels);
+    MSQ_REQUIRE(C > 0 && C % 8 == 0, MSQ_EUNSUPPORTED, "msq_roi_align_levels: channel count must be a multiple of 8 (got %d)", C);
+    MSQ_REQUIRE(P >= 1 && sampling_ratio >= 1, MSQ_EUNSUPPORTED, "msq_roi_align_levels: output size and sampling ratio must be positive (P=%d, sampling=%d)", P, sampling_ratio);
+    MSQ_REQUIRE(n_rois >= 0, MSQ_EINVAL, "msq_roi_align_levels: n_rois=%d", n_rois);
+    if (n_rois == 0) return MSQ_OK;
+    MSQ_REQUIRE(feat_dev && heights && widths && scales && rois_dev && out_dev && (n_levels == 1 || levels_dev), MSQ_EINVAL,
+                "msq_roi_align_levels: null pointer");
+    PyramidArg pyr;
+    pyr.n_levels = n_levels;
+    for (int l = 0; l < n_levels; ++l) {
+        MSQ_REQUIRE(feat_dev[l] && heights[l] > 0 && widths[l] > 0 && (uintptr_t)feat_dev[l] % 16 == 0, MSQ_EINVAL,
+                    "msq_roi_align_levels: level %d: bad feature map", l);
+        pyr.feat[l] = feat_dev[l]; pyr.H[l] = heights[l]; pyr.W[l] = widths[l]; pyr.scale[l] = scales[l];
+    }
+    const size_t smem = (size_t)C * P * P * (is_bf16 ? 2 : 4);
+    MSQ_REQUIRE(smem <= 220 * 1024, MSQ_EUNSUPPORTED, "msq_roi_align_levels: C*P*P = %d*%d*%d needs %zu bytes of shared memory (limit 220 KB)", C, P, P, smem);
+    MSQ_REQUIRE((uintptr_t)out_dev % 16 == 0, MSQ_EINVAL, "msq_roi_align_levels: output must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[is_bf16 ? 1 : 0]) {
+        if (is_bf16) MSQ_CUDA_OK(cudaFuncSetAttribute(roi_align_levels_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else MSQ_CUDA_OK(cudaFuncSetAttribute(roi_align_levels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[is_bf16 ? 1 : 0] = smem;
+    }
+    TimedLaunch timed(K_PASTE, st);
+    if (is_bf16)
+        roi_align_levels_kernel<__nv_bfloat16><<<n_rois, kAlignThreads, smem, st>>>(pyr, C, rois_dev, levels_dev, P, sampling_ratio,
+                                                                                    static_cast<__nv_bfloat16 *>(out_dev));
+    else
+        roi_align_levels_kernel<float><<<n_rois, kAlignThreads, smem, st>>>(pyr, C, rois_dev, levels_dev, P, sampling_ratio,
+                                                                            static_cast<float *>(out_dev));
+    MSQ_LAUNCH_OK("roi_align_levels");
+    return MSQ_OK;
+}

@@ -213,11 +213,41 @@ def _level_mapper_call(self, boxlists):
     return (target_lvls.to(torch.int64) - self.k_min).to(torch.int64)
 
 
+def _multiscale_roi_align(x_filtered, boxes, output_size, sampling_ratio, scales, mapper):
+    """torchvision.ops.poolers._multiscale_roi_align as ONE launch of `msq_roi_align_levels` (csrc/roi_align.cu) on the
+    channels-last feature maps: no per-level torch.where host syncs, gathers, float32 / NCHW conversions or index_put."""
+    import ctypes
+    feats = list(x_filtered)
+    ok = (len(feats) >= 1 and feats[0].is_cuda and scales is not None and (mapper is not None or len(feats) == 1)
+          and int(sampling_ratio) >= 1 and len(feats) <= 8 and output_size[0] == output_size[1]
+          and feats[0].dtype in (torch.bfloat16, torch.float32) and all(f.dtype == feats[0].dtype for f in feats)
+          and feats[0].shape[1] % 8 == 0 and not torch.is_grad_enabled())
+    if not ok:
+        return _multiscale_roi_align.original(x_filtered, boxes, output_size, sampling_ratio, scales, mapper)
+    rois = _convert_to_roi_format(boxes).float().contiguous()
+    levels = mapper(boxes).contiguous() if len(feats) > 1 else None
+    n_rois, channels, pooled = int(rois.shape[0]), int(feats[0].shape[1]), int(output_size[0])
+    # (n, C, H, W) in channels-last memory is (n, H, W, C) contiguous: free for the autocast backbone's outputs
+    nhwc = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    out = torch.empty((n_rois, channels, pooled, pooled), dtype=feats[0].dtype, device=feats[0].device)
+    k = len(nhwc)
+    _lib.call('msq_roi_align_levels', (ctypes.c_void_p * k)(*[f.data_ptr() for f in nhwc]), (ctypes.c_int * k)(*[int(f.shape[2]) for f in nhwc]),
+              (ctypes.c_int * k)(*[int(f.shape[3]) for f in nhwc]), (ctypes.c_float * k)(*[float(s) for s in scales]), k, channels,
+              int(feats[0].dtype == torch.bfloat16), _dev.ptr(rois), _dev.ptr(levels), n_rois, pooled, int(sampling_ratio), _dev.ptr(out),
+              _dev.stream())
+    return out
+
+
 def _roi_heads_forward(self, features, proposals, image_shapes, targets=None):
-    """RoIHeads.forward with the pyramid features converted to contiguous float32 ONCE: roi_align wants NCHW float32 and
-    otherwise casts / re-lays-out its whole input feature map on every call (three poolers x four levels per batch, and
-    the backbone runs channels-last bf16 under autocast); the pooled values are the same."""
-    if not self.training and any(v.dtype != torch.float32 or not v.is_contiguous() for v in features.values()):
+    """RoIHeads.forward with the pyramid features laid out ONCE for the three poolers: channels-last in their own dtype
+    for `_multiscale_roi_align` above; contiguous float32 when torchvision's roi_align is in use (it wants NCHW float32
+    and otherwise casts / re-lays-out its whole input on every call, three poolers x four levels per batch)."""
+    from torchvision.ops import poolers as tv_poolers
+    if tv_poolers._multiscale_roi_align is _multiscale_roi_align:
+        # our pooler reads channels-last maps of either dtype in place; make them channels-last once, not per pooler
+        if not self.training:
+            features = type(features)((k, v.contiguous(memory_format=torch.channels_last)) for k, v in features.items())
+    elif not self.training and any(v.dtype != torch.float32 or not v.is_contiguous() for v in features.values()):
         features = type(features)((k, v.to(torch.float32, memory_format=torch.contiguous_format)) for k, v in features.items())
     return self._msq_forward(features, proposals, image_shapes, targets)
 
@@ -245,6 +275,9 @@ def enable_batched_heads(model) -> None:
     if tv_poolers._convert_to_roi_format is not _convert_to_roi_format:
         _convert_to_roi_format.original = tv_poolers._convert_to_roi_format
         tv_poolers._convert_to_roi_format = _convert_to_roi_format
+    if tv_poolers._multiscale_roi_align is not _multiscale_roi_align:
+        _multiscale_roi_align.original = tv_poolers._multiscale_roi_align
+        tv_poolers._multiscale_roi_align = _multiscale_roi_align
     if tv_poolers.LevelMapper.__call__ is not _level_mapper_call:
         _level_mapper_call.original = tv_poolers.LevelMapper.__call__
         tv_poolers.LevelMapper.__call__ = _level_mapper_call
@@ -275,6 +308,8 @@ def disable_batched_heads(model) -> None:
     from torchvision.ops import poolers as tv_poolers
     if tv_poolers._convert_to_roi_format is _convert_to_roi_format:
         tv_poolers._convert_to_roi_format = _convert_to_roi_format.original
+    if tv_poolers._multiscale_roi_align is _multiscale_roi_align:
+        tv_poolers._multiscale_roi_align = _multiscale_roi_align.original
     if tv_poolers.LevelMapper.__call__ is _level_mapper_call:
         tv_poolers.LevelMapper.__call__ = _level_mapper_call.original
     from torchvision.models.detection import roi_heads as tv_heads

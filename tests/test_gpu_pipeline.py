@@ -333,3 +333,55 @@ def test_fused_conv_epilogues_match_eager_backbone_and_heads(amp):
                           (plain.rpn.head.conv, fused.rpn.head.conv, feat)):
             ya, yb = a(inp).float(), b(inp).float()
             assert float((ya - yb).abs().max()) <= tol * float(ya.abs().max())
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('pooled,sampling', [(7, 2), (14, 2), (5, 3)])
+def test_multilevel_roi_align_matches_torchvision(dtype, pooled, sampling):
+    """msq_roi_align_levels (one launch, channels-last features) against torchvision's per-level roi_align + index_put,
+    RoIs on every pyramid level, partly or wholly outside the image, degenerate and sub-pixel ones included."""
+    pytest.importorskip('torchvision')
+    from torchvision.ops import poolers as tv_poolers
+    from moseq2_detectron_extract_b200.model import batched_heads as bh
+    g = torch.Generator(device='cuda').manual_seed(pooled)
+    n_img, ch, size = 3, 64, 256
+    feats = [torch.randn((n_img, ch, size // s, size // s), device='cuda', generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+             for s in (4, 8, 16, 32)]
+    boxes = []
+    for i in range(n_img):
+        c = torch.rand((40, 2), device='cuda', generator=g) * size
+        wh = torch.exp(torch.rand((40, 2), device='cuda', generator=g) * 6.5 - 1.0)          # 0.4 .. 245 px: all four levels
+        b = torch.cat([c - wh / 2, c + wh / 2], dim=1)
+        b[0] = torch.tensor([-30., -20., 10., 15.])                                             # sticks out of the image
+        b[1] = torch.tensor([300., 300., 340., 330.])                                           # wholly outside
+        b[2] = torch.tensor([50., 60., 50., 60.])                                               # zero size
+        b[3] = torch.tensor([0., 0., float(size), float(size)])                                 # the whole image
+        b[4] = torch.tensor([-200., -200., 456., 456.])                                         # coarsest level, mostly outside
+        boxes.append(b)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    mapper = tv_poolers.LevelMapper(2, 5)
+    original = getattr(bh._multiscale_roi_align, 'original', None) or tv_poolers._multiscale_roi_align
+    if original is bh._multiscale_roi_align:
+        pytest.skip('torchvision pooler already replaced and the original is unknown')
+    bh._multiscale_roi_align.original = original
+    with torch.no_grad():
+        want = original([f.float() for f in feats], boxes, (pooled, pooled), sampling, scales, mapper)
+        got = bh._multiscale_roi_align(feats, boxes, (pooled, pooled), sampling, scales, mapper)
+        one = bh._multiscale_roi_align(feats[:1], boxes, (pooled, pooled), sampling, scales[:1], None)
+        want_one = original([feats[0].float()], boxes, (pooled, pooled), sampling, scales[:1], mapper)
+    assert got.dtype == dtype and got.shape == want.shape == (n_img * 40, ch, pooled, pooled)
+    assert len(set(mapper(boxes).tolist())) == 4
+    for a, b in ((got, want), (one, want_one)):
+        # torchvision's kernel is compiled with fused multiply-adds, ours without: sample positions differ by an ulp of
+        # float32 (~1e-5 px), which moves the bilinear weights of white-noise features by as much
+        scale = max(1.0, float(b.abs().max()))
+        if dtype == torch.float32:
+            diff = float((a - b).abs().max())
+            assert diff <= 2e-4 * scale, diff
+            assert float(((a - b).abs() <= 2e-6 * scale).float().mean()) > 0.99
+        else:                                                        # same float32 arithmetic, then one rounding to bf16
+            ref = b.to(torch.bfloat16)
+            same = float((a == ref).float().mean())
+            assert same > 0.99, same
+            diff = float((a.float() - ref.float()).abs().max())
+            assert diff <= 2 ** -7 * scale, diff
