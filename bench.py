@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--rcnn-frames', type=int, default=2000, help='frames for the secondary full-extract (R-CNN) figure; 0 = skip')
-    ap.add_argument('--rcnn-batch', type=int, default=200)
+    ap.add_argument('--rcnn-batch', type=int, default=500)
     return ap.parse_args()
 
 

@@ -11,6 +11,7 @@ geom = synthetic.SessionGeometry()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 ch = synthetic.generate_chunk(B, seed=9, geom=geom)
 prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom), roi=synthetic.make_roi(geom), vmin=0, vmax=100)
+torch.backends.cudnn.benchmark = bool(int(os.environ.get("CUDNN_BENCH", "0")))
 pred = Predictor.from_random_init(detections_per_img=1, amp=True)
 for _ in range(2):
     pred.predict_dense(prep, 0, 100)
