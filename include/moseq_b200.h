@@ -124,7 +124,7 @@ MSQ_API int msq_keypoints_from_heatmaps(const float *maps_dev, const float *rois
  * launch.  feat_dev[l]: HOST array of n_levels device pointers to CHANNELS-LAST feature maps (n, H_l, W_l, C) of bf16
  * (is_bf16 != 0) or float32; heights / widths / scales: HOST arrays per level.  rois_dev (n_rois,5) float32 = (image
  * index, x1, y1, x2, y2) in image coordinates; levels_dev (n_rois) int64 = pyramid level of every RoI (LevelMapper; may
- * be NULL when n_levels == 1).  out_dev (n_rois, C, P, P) in the dtype of the features.  C % 8 == 0, sampling_ratio >= 1. */
+ * be NULL when n_levels == 1).  out_dev (n_rois, C, P, P) in the dtype of the features.  C % 8 == 0, sampling_ratio 1..4. */
 MSQ_API int msq_roi_align_levels(const void *const *feat_dev, const int *heights, const int *widths, const float *scales,
                          int n_levels, int C, int is_bf16, const float *rois_dev, const long long *levels_dev, int n_rois,
                          int P, int sampling_ratio, void *out_dev, void *stream);

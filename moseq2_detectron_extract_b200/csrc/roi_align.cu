@@ -24,6 +24,12 @@ struct PyramidArg {
     int n_levels;
 };
 
+// acc / count, IEEE-exact: a power-of-two count (sampling 1, 2, 4, 8) multiplies by its exact reciprocal
+__device__ __forceinline__ float __fdividef_exact(float a, float count) {
+    const int c = (int)count;
+    return (c & (c - 1)) == 0 ? a * (1.0f / count) : a / count;
+}
+
 template <typename T> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
     static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
@@ -42,10 +48,13 @@ template <> struct Vec8<float> {
     static __device__ __forceinline__ float store(float v) { return v; }
 };
 
-template <typename T>
+constexpr int kMaxSampling = 4;
+
+template <typename T, int S>                                       // S = sampling ratio (compile time: the sample loops unroll)
 __global__ void __launch_bounds__(kAlignThreads)
-roi_align_levels_kernel(PyramidArg pyr, int C, const float *__restrict__ rois, const long long *__restrict__ levels, int P, int sampling,
+roi_align_levels_kernel(PyramidArg pyr, int C, const float *__restrict__ rois, const long long *__restrict__ levels, int P,
                         T *__restrict__ out) {
+    constexpr int sampling = S;
     extern __shared__ unsigned char smem_raw[];
     T *block = reinterpret_cast<T *>(smem_raw);                    // (C, P*P) of this RoI
     const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -58,42 +67,58 @@ roi_align_levels_kernel(PyramidArg pyr, int C, const float *__restrict__ rois, c
     const float roi_w = fmaxf(x1 - x0, 1.f), roi_h = fmaxf(y1 - y0, 1.f);
     const float bin_h = roi_h / (float)P, bin_w = roi_w / (float)P;
     const float count = (float)max(sampling * sampling, 1);
+    // the sample offsets inside a bin, (i + .5) * bin / sampling, are the same for every bin: divide once per RoI
+    float off_y[S], off_x[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        off_y[i] = (i + .5f) * bin_h / (float)sampling;
+        off_x[i] = (i + .5f) * bin_w / (float)sampling;
+    }
     const int bins = P * P, groups = (C + 255) / 256;
     for (int bin = warp; bin < bins; bin += kAlignThreads / 32) {
         const int ph = bin / P, pw = bin - ph * P;
+        const float by = y0 + ph * bin_h, bx = x0 + pw * bin_w;
         for (int g = 0; g < groups; ++g) {
             const int c0 = (g * 32 + lane) * 8;
             const bool act = c0 < C;
+            const T *base = feat + c0;
             float acc[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-            for (int iy = 0; iy < sampling; ++iy) {
-                float y = y0 + ph * bin_h + (iy + .5f) * bin_h / (float)sampling;
-                for (int ix = 0; ix < sampling; ++ix) {
-                    float x = x0 + pw * bin_w + (ix + .5f) * bin_w / (float)sampling;
-                    float yy = y;
-                    if (yy < -1.0f || yy > (float)H || x < -1.0f || x > (float)W) continue;       // sample outside: contributes 0
-                    if (yy <= 0.f) yy = 0.f;
+#pragma unroll
+            for (int iy = 0; iy < S; ++iy) {
+                float y = by + off_y[iy];
+                const bool y_out = y < -1.0f || y > (float)H;
+                if (y <= 0.f) y = 0.f;
+                int y_low = (int)y, y_high;
+                if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else y_high = y_low + 1;
+                const float ly = y - y_low, hy = 1.f - ly;
+                const int row_lo = y_low * W * C, row_hi = y_high * W * C;          // element offsets inside one image's map
+#pragma unroll
+                for (int ix = 0; ix < S; ++ix) {
+                    float x = bx + off_x[ix];
+                    if (y_out || x < -1.0f || x > (float)W) continue;               // sample outside: contributes 0
                     if (x <= 0.f) x = 0.f;
-                    int y_low = (int)yy, x_low = (int)x, y_high, x_high;
-                    if (y_low >= H - 1) { y_high = y_low = H - 1; yy = (float)y_low; } else y_high = y_low + 1;
+                    int x_low = (int)x, x_high;
                     if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else x_high = x_low + 1;
-                    const float ly = yy - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+                    const float lx = x - x_low, hx = 1.f - lx;
                     const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
                     if (act) {
                         float v1[8], v2[8], v3[8], v4[8];
-                        Vec8<T>::load(feat + ((size_t)y_low * W + x_low) * C + c0, v1);
-                        Vec8<T>::load(feat + ((size_t)y_low * W + x_high) * C + c0, v2);
-                        Vec8<T>::load(feat + ((size_t)y_high * W + x_low) * C + c0, v3);
-                        Vec8<T>::load(feat + ((size_t)y_high * W + x_high) * C + c0, v4);
+                        Vec8<T>::load(base + row_lo + x_low * C, v1);
+                        Vec8<T>::load(base + row_lo + x_high * C, v2);
+                        Vec8<T>::load(base + row_hi + x_low * C, v3);
+                        Vec8<T>::load(base + row_hi + x_high * C, v4);
+                        // w1*v1 + w2*v2 + w3*v3 + w4*v4 contracted the way nvcc contracts torchvision's expression
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] += ((w1 * v1[k] + w2 * v2[k]) + w3 * v3[k]) + w4 * v4[k];
+                        for (int k = 0; k < 8; ++k)
+                            acc[k] += __fmaf_rn(w4, v4[k], __fmaf_rn(w3, v3[k], __fmaf_rn(w2, v2[k], w1 * v1[k])));
                     }
                 }
             }
             if (act) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) block[(size_t)(c0 + k) * bins + bin] = Vec8<T>::store(acc[k] / count);
+                for (int k = 0; k < 8; ++k) block[(size_t)(c0 + k) * bins + bin] = Vec8<T>::store(__fdividef_exact(acc[k], count));
             }
         }
     }
@@ -120,7 +145,8 @@ extern "C" int msq_roi_align_levels(const void *const *feat_dev, const int *heig
                                     int sampling_ratio, void *out_dev, void *stream) {
     MSQ_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, MSQ_EINVAL, "msq_roi_align_levels: 1..%d pyramid levels (got %d)", kMaxLevels, n_levels);
     MSQ_REQUIRE(C > 0 && C % 8 == 0, MSQ_EUNSUPPORTED, "msq_roi_align_levels: channel count must be a multiple of 8 (got %d)", C);
-    MSQ_REQUIRE(P >= 1 && sampling_ratio >= 1, MSQ_EUNSUPPORTED, "msq_roi_align_levels: output size and sampling ratio must be positive (P=%d, sampling=%d)", P, sampling_ratio);
+    MSQ_REQUIRE(P >= 1 && sampling_ratio >= 1 && sampling_ratio <= kMaxSampling, MSQ_EUNSUPPORTED,
+                "msq_roi_align_levels: output size must be positive and the sampling ratio in 1..4 (P=%d, sampling=%d)", P, sampling_ratio);
     MSQ_REQUIRE(n_rois >= 0, MSQ_EINVAL, "msq_roi_align_levels: n_rois=%d", n_rois);
     if (n_rois == 0) return MSQ_OK;
     MSQ_REQUIRE(feat_dev && heights && widths && scales && rois_dev && out_dev && (n_levels == 1 || levels_dev), MSQ_EINVAL,
@@ -136,19 +162,24 @@ extern "C" int msq_roi_align_levels(const void *const *feat_dev, const int *heig
     MSQ_REQUIRE(smem <= 220 * 1024, MSQ_EUNSUPPORTED, "msq_roi_align_levels: C*P*P = %d*%d*%d needs %zu bytes of shared memory (limit 220 KB)", C, P, P, smem);
     MSQ_REQUIRE((uintptr_t)out_dev % 16 == 0, MSQ_EINVAL, "msq_roi_align_levels: output must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[is_bf16 ? 1 : 0]) {
-        if (is_bf16) MSQ_CUDA_OK(cudaFuncSetAttribute(roi_align_levels_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else MSQ_CUDA_OK(cudaFuncSetAttribute(roi_align_levels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[is_bf16 ? 1 : 0] = smem;
+    // one instantiation per (dtype, sampling ratio); launched through a type-erased trampoline
+    auto launch = [&](auto kernel, auto *typed_out) -> int {
+        if (smem > 48 * 1024) MSQ_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TimedLaunch timed(K_PASTE, st);
+        kernel<<<n_rois, kAlignThreads, smem, st>>>(pyr, C, rois_dev, levels_dev, P, typed_out);
+        return MSQ_OK;
+    };
+    int rc = MSQ_OK;
+#define MSQ_ALIGN_CASE(S_)                                                                                                    \
+    case S_:                                                                                                                  \
+        rc = is_bf16 ? launch(roi_align_levels_kernel<__nv_bfloat16, S_>, static_cast<__nv_bfloat16 *>(out_dev))              \
+                     : launch(roi_align_levels_kernel<float, S_>, static_cast<float *>(out_dev));                             \
+        break;
+    switch (sampling_ratio) {
+        MSQ_ALIGN_CASE(1) MSQ_ALIGN_CASE(2) MSQ_ALIGN_CASE(3) MSQ_ALIGN_CASE(4)
     }
-    TimedLaunch timed(K_PASTE, st);
-    if (is_bf16)
-        roi_align_levels_kernel<__nv_bfloat16><<<n_rois, kAlignThreads, smem, st>>>(pyr, C, rois_dev, levels_dev, P, sampling_ratio,
-                                                                                    static_cast<__nv_bfloat16 *>(out_dev));
-    else
-        roi_align_levels_kernel<float><<<n_rois, kAlignThreads, smem, st>>>(pyr, C, rois_dev, levels_dev, P, sampling_ratio,
-                                                                            static_cast<float *>(out_dev));
+#undef MSQ_ALIGN_CASE
+    if (rc != MSQ_OK) return rc;
     MSQ_LAUNCH_OK("roi_align_levels");
     return MSQ_OK;
 }

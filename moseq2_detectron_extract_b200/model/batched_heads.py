@@ -219,7 +219,7 @@ def _multiscale_roi_align(x_filtered, boxes, output_size, sampling_ratio, scales
     import ctypes
     feats = list(x_filtered)
     ok = (len(feats) >= 1 and feats[0].is_cuda and scales is not None and (mapper is not None or len(feats) == 1)
-          and int(sampling_ratio) >= 1 and len(feats) <= 8 and output_size[0] == output_size[1]
+          and 1 <= int(sampling_ratio) <= 4 and len(feats) <= 8 and output_size[0] == output_size[1]
           and feats[0].dtype in (torch.bfloat16, torch.float32) and all(f.dtype == feats[0].dtype for f in feats)
           and feats[0].shape[1] % 8 == 0 and not torch.is_grad_enabled())
     if not ok:
