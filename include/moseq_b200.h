@@ -104,6 +104,15 @@ MSQ_API int msq_scale_frames(const uint8_t *in_dev, uint8_t *out_dev, size_t cou
 MSQ_API int msq_scale_frames_chw3_f32(const uint8_t *in_dev, float *out_dev, int n, int h, int w,
                               double vmin, double vmax, int vmin_is_int, void *stream);
 
+/* a3 fused with the detector's image transform (ref: model/predict.py:77-98 staging + the GeneralizedRCNNTransform of the
+ * graph): out_dev (n, ph, pw, 3) CHANNELS-LAST bf16 (out_is_bf16 != 0) or float32 = zero-padded canvas whose top-left
+ * (oh, ow) block is bilinear_resize((scale(in) - mean[c]) / std[c]) -- scale() as msq_scale_frames, resize as
+ * torch.nn.functional.interpolate(mode="bilinear", align_corners=False) from (h, w) to (oh, ow); mean / std: 3 floats in
+ * HOST memory, in the 0..255 units of the scaled image. */
+MSQ_API int msq_detector_input(const uint8_t *in_dev, void *out_dev, int out_is_bf16, int n, int h, int w, int oh, int ow,
+                       int ph, int pw, const float *mean_host, const float *std_host, double vmin, double vmax,
+                       int vmin_is_int, void *stream);
+
 /* Segmented greedy NMS for the RPN proposal filtering of a whole batch (replaces the per-image box_ops.batched_nms calls of
  * torchvision's RegionProposalNetwork.filter_proposals behind Predictor; the reference's detectron2 RPN does the same
  * per-image loop).  boxes_dev (n,K,4) float32, per image sorted by descending score and already shifted per pyramid level

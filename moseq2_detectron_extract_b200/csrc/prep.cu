@@ -7,6 +7,7 @@
 // frames, so the background and ROI values live in registers for the whole walk and every raw
 // access is one 128-bit streaming load (8 x int16) / one 64-bit store.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <type_traits>
 #include <algorithm>
 
@@ -348,10 +349,77 @@ scale_chw3_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, int n
     }
 }
 
+// a3 + the detector's image transform in one pass: intensity scaling (LUT), 3-channel replication, per-channel
+// normalisation (x - mean) / std, bilinear resize (torch upsample_bilinear2d, align_corners = false, scale = in / out) and
+// zero padding to the stride-aligned canvas, written channels-last in the dtype the backbone's first convolution reads.
+// Replaces six full-tensor passes (scale -> stack -> subtract -> divide -> interpolate -> pad -> cast) by one.
+struct NormArg { float mean[3], std[3]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+detector_input_kernel(const uint8_t *__restrict__ in, T *__restrict__ out, int n, int h, int w, int oh, int ow, int ph, int pw,
+                      NormArg norm, double vmin, double vmax, int vmin_is_int) {
+    __shared__ uint8_t lut8[256];
+    __shared__ float lut[3][256];
+    build_scale_lut(lut8, vmin, vmax, vmin_is_int);
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        lut[c][v] = ((float)lut8[v] - norm.mean[c]) / norm.std[c];               // torchvision: (image - mean) / std
+    }
+    __syncthreads();
+    const float rh = (float)h / (float)oh, rw = (float)w / (float)ow;
+    const size_t total = (size_t)n * ph * pw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / ((size_t)ph * pw);
+        const int p = (int)(i - f * (size_t)ph * pw), y = p / pw, x = p - y * pw;
+        float o[3] = {0.f, 0.f, 0.f};
+        if (y < oh && x < ow) {
+            const float sy = fmaxf(rh * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(rw * ((float)x + 0.5f) - 0.5f, 0.f);
+            const int y1 = (int)sy, x1 = (int)sx;
+            const int yp = y1 < h - 1 ? 1 : 0, xp = x1 < w - 1 ? 1 : 0;
+            const float ly = sy - (float)y1, lx = sx - (float)x1, hy = 1.f - ly, hx = 1.f - lx;
+            const uint8_t *src = in + f * (size_t)h * w + (size_t)y1 * w + x1;
+            const int a = src[0], b = src[xp], c = src[(size_t)yp * w], d = src[(size_t)yp * w + xp];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                o[k] = hy * (hx * lut[k][a] + lx * lut[k][b]) + ly * (hx * lut[k][c] + lx * lut[k][d]);
+        }
+        T *dst = out + i * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dst[k] = (T)o[k];
+    }
+}
+
 }  // namespace
 }  // namespace msq
 
 using namespace msq;
+
+extern "C" int msq_detector_input(const uint8_t *in, void *out, int out_is_bf16, int n, int h, int w, int oh, int ow, int ph, int pw,
+                                  const float *mean_host, const float *std_host, double vmin, double vmax, int vmin_is_int,
+                                  void *stream) {
+    MSQ_REQUIRE(in && out && mean_host && std_host, MSQ_EINVAL, "msq_detector_input: null pointer");
+    MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && ph >= oh && pw >= ow, MSQ_EINVAL,
+                "msq_detector_input: bad sizes n=%d %dx%d -> %dx%d in %dx%d", n, h, w, oh, ow, ph, pw);
+    MSQ_REQUIRE(vmax != vmin, MSQ_EINVAL, "msq_detector_input: vmax == vmin");
+    if (n == 0) return MSQ_OK;
+    NormArg norm;
+    for (int c = 0; c < 3; ++c) {
+        MSQ_REQUIRE(std_host[c] != 0.f, MSQ_EINVAL, "msq_detector_input: std[%d] == 0", c);
+        norm.mean[c] = mean_host[c]; norm.std[c] = std_host[c];
+    }
+    const size_t work = (size_t)n * ph * pw;
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 16);
+    TimedLaunch timed(K_SCALE, (cudaStream_t)stream);
+    if (out_is_bf16)
+        detector_input_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16 *>(out), n, h, w, oh, ow,
+                                                                                       ph, pw, norm, vmin, vmax, vmin_is_int);
+    else
+        detector_input_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<float *>(out), n, h, w, oh, ow, ph, pw, norm,
+                                                                               vmin, vmax, vmin_is_int);
+    MSQ_LAUNCH_OK("detector_input");
+    return MSQ_OK;
+}
 
 extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const void *bground, int bg_dtype,
                                const uint8_t *roi, int y0, int x0, int h, int w, double vmin, double vmax,

@@ -152,8 +152,23 @@ class Predictor:
         return preds[0] if single else preds
 
     # ---- device fast path used by InferenceStep: scale + replicate + CHW in one kernel -----------------
+    def _fused_input_ok(self) -> bool:
+        """The one-kernel input path serves the torchvision detectors built here (a chunk's images all have one size)."""
+        if not isinstance(self.model, _TorchvisionAdapter):
+            return False
+        tr = self.model.model.transform
+        return bool(getattr(tr, '_msq_keep_soft_masks', False)) and tr.fixed_size is None
+
     def predict_prepared(self, chunk_u8: torch.Tensor, vmin, vmax) -> List[dict]:
         n, h, w = (int(v) for v in chunk_u8.shape)
+        if self._fused_input_ok():
+            with torch.no_grad():
+                with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
+                    dets = self._detect_from_chunk(chunk_u8, vmin, vmax)
+                outputs = [{'pred_boxes': o['boxes'].float(), 'scores': o['scores'].float(), 'pred_classes': o['labels'] - 1,
+                            'pred_masks': o['masks'].float(), 'pred_keypoints': o['keypoints'].float()} for o in dets]
+                size = {'height': h, 'width': w}
+                return outputs_to_instances([size] * n, outputs)
         chw = _dev.empty((n, 3, h, w), torch.float32)
         _lib.call('msq_scale_frames_chw3_f32', _dev.ptr(chunk_u8), _dev.ptr(chw), n, h, w, float(vmin), float(vmax),
                   int(isinstance(vmin, (int, np.integer))), _dev.stream())
@@ -166,12 +181,17 @@ class Predictor:
         f32 with NaN where a frame has no instance, num_instances (n,) int64 on the device).  One concatenation per field,
         one clip, ONE mask-paste launch for the whole batch -- the per-image form costs ~0.6 ms of launch latency a frame."""
         n, h, w = (int(v) for v in chunk_u8.shape)
-        chw = _dev.empty((n, 3, h, w), torch.float32)
-        _lib.call('msq_scale_frames_chw3_f32', _dev.ptr(chunk_u8), _dev.ptr(chw), n, h, w, float(vmin), float(vmax),
-                  int(isinstance(vmin, (int, np.integer))), _dev.stream())
+        fused_input = self._fused_input_ok()
+        if not fused_input:
+            chw = _dev.empty((n, 3, h, w), torch.float32)
+            _lib.call('msq_scale_frames_chw3_f32', _dev.ptr(chunk_u8), _dev.ptr(chw), n, h, w, float(vmin), float(vmax),
+                      int(isinstance(vmin, (int, np.integer))), _dev.stream())
         with torch.no_grad():
             with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
-                if isinstance(self.model, _TorchvisionAdapter):          # straight to the detector: no per-image dicts
+                if fused_input:                                          # scale + normalise + resize + pad in ONE kernel
+                    outputs = [{'scores': o['scores'], 'pred_boxes': o['boxes'], 'pred_masks': o['masks'], 'pred_keypoints': o['keypoints']}
+                               for o in self._detect_from_chunk(chunk_u8, vmin, vmax)]
+                elif isinstance(self.model, _TorchvisionAdapter):        # straight to the detector: no per-image dicts
                     outputs = [{'scores': o['scores'], 'pred_boxes': o['boxes'], 'pred_masks': o['masks'], 'pred_keypoints': o['keypoints']}
                                for o in self.model.model(list(chw.unbind(0)))]
                 else:
@@ -179,13 +199,14 @@ class Predictor:
             counts = [int(o['scores'].shape[0]) for o in outputs]                  # host-known sizes: no synchronisation
             have = [i for i, c in enumerate(counts) if c > 0]
             k = int(outputs[have[0]]['pred_keypoints'].shape[1]) if have else _lib.NUM_KEYPOINTS
-            masks = torch.zeros((n, h, w), dtype=torch.uint8, device=chw.device)
-            kpts = torch.full((n, k, 3), float('nan'), dtype=torch.float32, device=chw.device)
-            ninst = torch.zeros((n,), dtype=torch.int64, device=chw.device)
+            dev = chunk_u8.device
+            masks = torch.zeros((n, h, w), dtype=torch.uint8, device=dev)
+            kpts = torch.full((n, k, 3), float('nan'), dtype=torch.float32, device=dev)
+            ninst = torch.zeros((n,), dtype=torch.int64, device=dev)
             if have:
-                sel = torch.tensor(have, device=chw.device)
+                sel = torch.tensor(have, device=dev)
                 # first instance of every frame that has one: one concatenation per field, then one row gather
-                first = torch.tensor(np.cumsum([0] + counts[:-1])[have], device=chw.device)
+                first = torch.tensor(np.cumsum([0] + counts[:-1])[have], device=dev)
                 boxes = torch.cat([o['pred_boxes'] for o in outputs])[first].float()
                 soft = torch.cat([o['pred_masks'] for o in outputs])[first].float()
                 kp = torch.cat([o['pred_keypoints'] for o in outputs])[first].float()
@@ -203,9 +224,43 @@ class Predictor:
                 # detection per image (the extract configuration) they simply have no instance
                 masks[sel] = pasted * ok[:, None, None].to(torch.uint8)
                 kpts[sel] = torch.where(ok[:, None, None], kp, torch.full_like(kp, float('nan')))
-                totals = torch.tensor([counts[i] for i in have], device=chw.device)
+                totals = torch.tensor([counts[i] for i in have], device=dev)
                 ninst[sel] = torch.where(ok, totals, totals - 1)
         return masks, kpts, ninst
+
+    def detector_input(self, chunk_u8: torch.Tensor, vmin, vmax):
+        """What GeneralizedRCNNTransform.forward would hand the backbone for this chunk -- scaled, replicated to 3 channels,
+        normalised, resized, zero-padded to the stride -- from ONE kernel (`msq_detector_input`), channels-last, bf16 under
+        autocast.  Returns (tensor (n, 3, ph, pw), (oh, ow))."""
+        import ctypes
+        import math
+        tr = self.model.model.transform
+        n, h, w = (int(v) for v in chunk_u8.shape)
+        scale = min(tr.min_size[-1] / min(h, w), tr.max_size / max(h, w))
+        oh, ow = int(math.floor(h * scale)), int(math.floor(w * scale))       # interpolate(recompute_scale_factor=True)
+        div = int(tr.size_divisible)
+        ph, pw = -(-oh // div) * div, -(-ow // div) * div
+        dtype = torch.bfloat16 if self.amp else torch.float32
+        x = torch.empty((n, 3, ph, pw), dtype=dtype, device=chunk_u8.device, memory_format=torch.channels_last)
+        _lib.call('msq_detector_input', _dev.ptr(chunk_u8), _dev.ptr(x), int(self.amp), n, h, w, oh, ow, ph, pw,
+                  (ctypes.c_float * 3)(*[float(v) for v in tr.image_mean]), (ctypes.c_float * 3)(*[float(v) for v in tr.image_std]),
+                  float(vmin), float(vmax), int(isinstance(vmin, (int, np.integer))), _dev.stream())
+        return x, (oh, ow)
+
+    def _detect_from_chunk(self, chunk_u8: torch.Tensor, vmin, vmax):
+        """GeneralizedRCNN.forward (eval) with the transform replaced by `detector_input`."""
+        from collections import OrderedDict
+        from torchvision.models.detection.image_list import ImageList
+        net = self.model.model
+        n, h, w = (int(v) for v in chunk_u8.shape)
+        x, size = self.detector_input(chunk_u8.contiguous(), vmin, vmax)
+        images = ImageList(x, [size] * n)
+        features = net.backbone(x)
+        if isinstance(features, torch.Tensor):
+            features = OrderedDict([('0', features)])
+        proposals, _ = net.rpn(images, features, None)
+        detections, _ = net.roi_heads(features, proposals, images.image_sizes, None)
+        return net.transform.postprocess(detections, images.image_sizes, [(h, w)] * n)
 
     def _forward(self, chw: torch.Tensor) -> List[dict]:
         with torch.no_grad():

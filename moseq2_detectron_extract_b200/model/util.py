@@ -59,8 +59,8 @@ def outputs_to_instances(inputs: List[Dict[str, torch.Tensor]], outputs: List[Di
     """TorchScript model outputs (list of dicts of tensors) -> [{'instances': Instances}] (ref: model/util.py:45-62)."""
     instances = []
     for i, o in zip(inputs, outputs):
-        height = int(i.get('height', i['image'].shape[-2]))
-        width = int(i.get('width', i['image'].shape[-1]))
+        height = int(i['height']) if 'height' in i else int(i['image'].shape[-2])
+        width = int(i['width']) if 'width' in i else int(i['image'].shape[-1])
         o = dict(o)
         ins = Instances((height, width), pred_boxes=Boxes(o.pop('pred_boxes')), **o)
         instances.append({'instances': detector_postprocess(ins, height, width)})
