@@ -93,15 +93,78 @@ def read_frames_raw(filename: Union[str, tarfile.TarInfo], frames: Optional[Unio
 
 
 class RawDepthSession:
-    """The slice of `io.session.Session` that ProduceFramesStep uses (ref: io/session.py:24, :352-466), backed by a raw
-    `.dat` depth file: `.bground_im`, `.roi`, `.nframes`, `.iterate(chunk_size, chunk_overlap)`.  Background, ROI and
-    true depth are either supplied by the caller or estimated from the file by `find_roi()` (ref io/session.py:181-264)."""
+    """The slice of `io.session.Session` that the extract pipeline uses (ref: io/session.py:24-110, :112-178, :352-466),
+    backed by a raw `depth.dat` file or a `.tar.gz` / `.tgz` session archive holding one: `.bground_im`, `.roi`,
+    `.true_depth`, `.nframes`, `.iterate(chunk_size, chunk_overlap)`, `.load_metadata()`, `.load_timestamps()`.
+    Background, ROI and true depth are either supplied by the caller or estimated from the file by `find_roi()`
+    (ref io/session.py:181-264).  `frame_trim=(head, tail)` drops frames like the reference's `__trim_frames`;
+    `frame_dims=None` takes `DepthResolution` from the session's `metadata.json`."""
 
     def __init__(self, depth_file: str, bground_im: Optional[np.ndarray] = None, roi: Optional[np.ndarray] = None,
-                 true_depth: float = float('nan'), frame_dims: Tuple[int, int] = (512, 424), pinned: bool = True):
-        self.depth_file, self.frame_dims, self.pinned = depth_file, frame_dims, pinned
+                 true_depth: float = float('nan'), frame_dims: Optional[Tuple[int, int]] = (512, 424), pinned: bool = True,
+                 frame_trim: Tuple[int, int] = (0, 0)):
+        self.pinned = pinned
         self.bground_im, self.roi, self.true_depth = bground_im, roi, float(true_depth)
-        self.nframes = get_raw_info(depth_file, frame_dims=frame_dims)['nframes']
+        self.dirname = os.path.dirname(os.path.abspath(depth_file))
+        if depth_file.endswith('.tar.gz') or depth_file.endswith('.tgz'):         # ref io/session.py:53-70
+            self.tar: Optional[tarfile.TarFile] = tarfile.open(depth_file, mode='r:*')
+            self.tar_members = self.tar.getmembers()
+            self.tar_names = [m.name for m in self.tar_members]
+            if 'depth.dat' not in self.tar_names:
+                raise FileNotFoundError(f'{depth_file}: the archive holds no depth.dat')
+            self.depth_file: Union[str, tarfile.TarInfo] = self.tar_members[self.tar_names.index('depth.dat')]
+            self.session_id = os.path.basename(depth_file).split('.')[0]
+        else:
+            self.tar, self.tar_members, self.tar_names = None, None, []
+            self.depth_file = depth_file
+            self.session_id = os.path.basename(self.dirname)
+        if frame_dims is None:
+            frame_dims = tuple(int(v) for v in self.load_metadata()['DepthResolution'])
+        self.frame_dims = frame_dims
+        total = get_raw_info(self.depth_file, frame_dims=frame_dims)['nframes']
+        # ref io/session.py:85-99: a trim that would leave nothing is ignored
+        self.frame_trim = tuple(frame_trim)
+        self.first_frame_idx = frame_trim[0] if 0 < frame_trim[0] < total else 0
+        self.last_frame_idx = total - frame_trim[1] if total - frame_trim[1] > self.first_frame_idx else total
+        self.nframes = self.last_frame_idx - self.first_frame_idx
+
+    @property
+    def is_compressed(self) -> bool:
+        return self.tar is not None
+
+    def _open_member(self, name: str):
+        """File object of a sibling of the depth file (inside the archive, or next to depth.dat), or None."""
+        if self.tar is not None:
+            return self.tar.extractfile(self.tar_members[self.tar_names.index(name)]) if name in self.tar_names else None
+        path = os.path.join(self.dirname, name)
+        return open(path, 'rb') if os.path.exists(path) else None
+
+    def load_metadata(self) -> dict:
+        """The session's metadata.json (ref: io/session.py:112-128, io/util.py:66-81)."""
+        import json
+        handle = self._open_member('metadata.json')
+        if handle is None:
+            raise ValueError('Could not find metadata.json for this session')
+        with handle:
+            return json.load(handle)
+
+    def load_timestamps(self) -> np.ndarray:
+        """Depth timestamps (ref: io/session.py:131-178): first column of `depth_ts.txt`, else of `timestamps.csv` scaled by
+        1000, trimmed to `[first_frame_idx, last_frame_idx)`."""
+        for name, factor in (('depth_ts.txt', 1.0), ('timestamps.csv', 1000.0)):
+            handle = self._open_member(name)
+            if handle is None:
+                continue
+            with handle:
+                stamps = np.array([float(line.decode().split()[0]) for line in handle if line.strip()])
+            return stamps[self.first_frame_idx:self.last_frame_idx] * factor
+        raise ValueError('Could not locate timestamp file!')
+
+    def read_frames(self, frame_idxs, pinned: Optional[bool] = None, as_tensor: bool = False):
+        """Frames by session index (0 = first frame after the head trim)."""
+        idxs = [int(i) + self.first_frame_idx for i in frame_idxs]
+        pin = self.pinned if pinned is None else pinned
+        return read_frames_raw(self.depth_file, idxs, frame_dims=self.frame_dims, tar_object=self.tar, pinned=pin, as_tensor=as_tensor)
 
     def iterate(self, chunk_size: int = 1000, chunk_overlap: int = 0):
         return _RawIterator(self, chunk_size, chunk_overlap)
@@ -111,7 +174,7 @@ class RawDepthSession:
         the GPU (`proc.get_bground_im`); stores it as `.bground_im` and returns it (float64, (height, width))."""
         from ..proc.roi import get_bground_im
         idxs = list(range(0, self.nframes, max(1, int(frame_stride))))
-        frames = read_frames_raw(self.depth_file, idxs, frame_dims=self.frame_dims)
+        frames = self.read_frames(idxs, pinned=False)
         self.bground_im = get_bground_im(frames, med_scale=med_scale)
         return self.bground_im
 
@@ -126,7 +189,7 @@ class RawDepthSession:
         `(first_frame, bground_im, roi, true_depth)`.  Background and ROI are computed on the GPU."""
         from ..proc.roi import get_roi
         from ..proc.util import select_strel
-        first_frame = read_frames_raw(self.depth_file, [0], frame_dims=self.frame_dims)
+        first_frame = self.read_frames([0], pinned=False)
         if self.bground_im is None:
             self.compute_bground(frame_stride=frame_stride)
         bground_im = np.asarray(self.bground_im)
@@ -165,8 +228,7 @@ class _RawIterator:
             raise StopIteration
         idxs = self.batches[self._pos]
         self._pos += 1
-        frames = read_frames_raw(self.session.depth_file, idxs, frame_dims=self.session.frame_dims, pinned=self.session.pinned,
-                                 as_tensor=self.session.pinned)
+        frames = self.session.read_frames(idxs, as_tensor=self.session.pinned)
         for f in self.filters:
             frames = f(frames)
         return list(idxs), frames

@@ -51,11 +51,13 @@ def bind_to_gpu_numa_node(device_index: int) -> Optional[Dict[str, object]]:
 
 
 def chunk_ranges(nframes: int, chunk_size: int, chunk_overlap: int = 0) -> List[range]:
-    """Frame ranges of the chunks of a session (ref: io/util.py:24-35 gen_batch_sequence)."""
-    out = []
-    for start in range(0, nframes, chunk_size):
-        out.append(range(max(start - chunk_overlap, 0), min(start + chunk_size, nframes)))
-    return out
+    """Frame ranges of the chunks of a session, exactly the reference's gen_batch_sequence (io/util.py:24-35, offset 0):
+    chunks of `chunk_size` frames starting every `chunk_size - chunk_overlap` frames -- the first `chunk_overlap` frames of
+    every later chunk repeat the end of the previous one and are dropped by the writer (`data['offset']`)."""
+    if chunk_size <= chunk_overlap:
+        raise ValueError(f'chunk_size ({chunk_size}) must exceed chunk_overlap ({chunk_overlap})')
+    seq = range(nframes)
+    return [seq[i:i + chunk_size] for i in range(0, nframes - chunk_overlap, chunk_size - chunk_overlap)]
 
 
 def shard_chunks(n_chunks: int, rank: int, world: int) -> range:

@@ -210,11 +210,8 @@ class _SyntheticIterator:
     def __init__(self, session: SyntheticSession, chunk_size: int, chunk_overlap: int):
         self.session = session
         self.filters = []
-        starts = list(range(0, session.nframes, chunk_size))
-        self.batches: List[range] = []
-        for s in starts:   # reference io/util.py:24-35 (gen_batch_sequence): overlap prepends frames
-            lo = max(s - chunk_overlap, 0)
-            self.batches.append(range(lo, min(s + chunk_size, session.nframes)))
+        from .shard import chunk_ranges
+        self.batches: List[range] = chunk_ranges(session.nframes, chunk_size, chunk_overlap)   # reference io/util.py:24-35
         self._pos = 0
         self.instances = []   # ground-truth instances per yielded chunk (tests / bench use them)
 

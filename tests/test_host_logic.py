@@ -193,7 +193,9 @@ def test_synthetic_session_iterator_and_chunking():
     b = synthetic.generate_chunk(6, seed=1, t0=100)
     assert np.array_equal(a.frames, b.frames) and np.array_equal(a.keypoints, b.keypoints, equal_nan=True)
     assert [list(r) for r in shard.chunk_ranges(25, 10)] == [list(range(0, 10)), list(range(10, 20)), list(range(20, 25))]
-    assert shard.chunk_ranges(25, 10, 3)[1] == range(7, 20)
+    # overlap: the reference's gen_batch_sequence strides by chunk_size - overlap (io/util.py:33-35)
+    assert shard.chunk_ranges(25, 10, 3) == [range(0, 10), range(7, 17), range(14, 24), range(21, 25)]
+    assert shard.chunk_ranges(20, 10, 0) == [range(0, 10), range(10, 20)] and shard.chunk_ranges(0, 10) == []
     roi = synthetic.make_roi(synthetic.SessionGeometry())
     y0, x0, y1, x1 = synthetic.roi_bbox(roi)
     assert (y1 - y0, x1 - x0) == (240, 240) and x0 % 8 == 0
@@ -360,3 +362,48 @@ def test_batchnorm_folding_preserves_backbone_outputs():
     assert not any(isinstance(mod, torch.nn.BatchNorm2d) for mod in backbone.modules())
     for k in want:
         assert float((want[k] - got[k]).abs().max()) <= 1e-5 * float(want[k].abs().max())
+
+
+def test_raw_session_archive_metadata_timestamps_and_trim(tmp_path):
+    """RawDepthSession over a .tar.gz session archive (ref io/session.py:50-178): depth.dat member, DepthResolution from
+    metadata.json, depth_ts.txt / timestamps.csv, frame_trim like __trim_frames."""
+    import json
+    import tarfile
+    from moseq2_detectron_extract_b200.io import RawDepthSession
+    rng = np.random.default_rng(1)
+    W, H, N = 24, 18, 23
+    frames = rng.integers(0, 3000, size=(N, H, W)).astype('<i2')
+    (tmp_path / 'plain').mkdir()
+    frames.tofile(tmp_path / 'plain' / 'depth.dat')
+    (tmp_path / 'plain' / 'metadata.json').write_text(json.dumps({'DepthResolution': [W, H], 'SubjectName': 'm1'}))
+    stamps = np.arange(N) * 33.3 + 1000.0
+    (tmp_path / 'plain' / 'depth_ts.txt').write_text(''.join(f'{t:.3f} {i}\n' for i, t in enumerate(stamps)))
+    with tarfile.open(tmp_path / 'session_20260101.tar.gz', 'w:gz') as tar:
+        for name in ('depth.dat', 'metadata.json', 'depth_ts.txt'):
+            tar.add(tmp_path / 'plain' / name, arcname=name)
+
+    for path, compressed in ((str(tmp_path / 'plain' / 'depth.dat'), False), (str(tmp_path / 'session_20260101.tar.gz'), True)):
+        sess = RawDepthSession(path, frame_dims=None, pinned=False)
+        assert sess.is_compressed == compressed and sess.frame_dims == (W, H) and sess.nframes == N
+        assert sess.load_metadata()['SubjectName'] == 'm1'
+        np.testing.assert_allclose(sess.load_timestamps(), np.round(stamps, 3))
+        chunks = list(sess.iterate(10, 0))
+        assert [list(c[0]) for c in chunks] == [list(range(0, 10)), list(range(10, 20)), list(range(20, 23))]
+        assert np.array_equal(np.concatenate([c[1] for c in chunks]), frames)
+        assert np.array_equal(sess.read_frames([22, 3]), frames[[22, 3]])
+        # trimming: 4 frames off the head, 5 off the tail; session indices restart at 0
+        trimmed = RawDepthSession(path, frame_dims=(W, H), pinned=False, frame_trim=(4, 5))
+        assert (trimmed.first_frame_idx, trimmed.last_frame_idx, trimmed.nframes) == (4, N - 5, N - 9)
+        assert np.array_equal(np.concatenate([c[1] for c in trimmed.iterate(6, 0)]), frames[4:N - 5])
+        np.testing.assert_allclose(trimmed.load_timestamps(), np.round(stamps, 3)[4:N - 5])
+        # a trim that would leave nothing is ignored, like the reference
+        assert RawDepthSession(path, frame_dims=(W, H), pinned=False, frame_trim=(40, 0)).nframes == N
+    assert RawDepthSession(str(tmp_path / 'session_20260101.tar.gz'), frame_dims=(W, H), pinned=False).session_id == 'session_20260101'
+    # timestamps.csv fallback is in seconds -> milliseconds
+    (tmp_path / 'plain' / 'depth_ts.txt').unlink()
+    (tmp_path / 'plain' / 'timestamps.csv').write_text(''.join(f'{t / 1000.0:.6f}\n' for t in stamps))
+    np.testing.assert_allclose(RawDepthSession(str(tmp_path / 'plain' / 'depth.dat'), frame_dims=(W, H), pinned=False).load_timestamps(),
+                               stamps, rtol=1e-9)
+    (tmp_path / 'plain' / 'timestamps.csv').unlink()
+    with pytest.raises(ValueError):
+        RawDepthSession(str(tmp_path / 'plain' / 'depth.dat'), frame_dims=(W, H), pinned=False).load_timestamps()
