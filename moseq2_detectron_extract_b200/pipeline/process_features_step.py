@@ -38,25 +38,26 @@ class ProcessFeaturesStep(ProcessPipelineStep):
     # ---- ref: process_features_step.py:63-113 (mask-IoU NMS); norfair tracking (:140) needs >1 instance --------
     @staticmethod
     def _nms_mask_instances(instances: Instances, iou_threshold: float = 0.5) -> Instances:
+        """Mask-IoU suppression exactly as the reference runs it (process_features_step.py:63-113), which is NOT the textbook
+        greedy NMS: every round keeps the best remaining instance and then drops EVERY remaining instance that overlaps a
+        better-scored remaining one (not only those overlapping the one just kept).  The IoU matrix comes from one matmul on
+        the device; the rounds run on its few-by-few host copy."""
         if len(instances) <= 1:
             return instances
-        keep_nonempty = instances.pred_masks.flatten(1).any(dim=1)
-        instances = instances[keep_nonempty]
-        order = torch.argsort(instances.scores, descending=True).tolist()
+        instances = instances[instances.pred_masks.flatten(1).any(dim=1)]
+        if len(instances) == 0:
+            return instances
         flat = instances.pred_masks.flatten(1).float()
         inter = flat @ flat.T
         area = flat.sum(dim=1)
-        iou = inter / (area[:, None] + area[None, :] - inter)
+        iou = (inter / (area[:, None] + area[None, :] - inter)).cpu().numpy()
+        idxs = np.argsort(instances.scores.detach().cpu().numpy())           # ascending: the best instance is last
         picked: List[int] = []
-        alive = set(order)
-        for i in order:
-            if i not in alive:
-                continue
-            picked.append(i)
-            for j in list(alive):
-                if j != i and float(iou[i, j]) > iou_threshold:
-                    alive.discard(j)
-            alive.discard(i)
+        while len(idxs) > 0:
+            last = len(idxs) - 1
+            picked.append(int(idxs[last]))
+            rows = np.where(np.triu(iou[np.ix_(idxs, idxs)], k=1) > iou_threshold)[0]   # the lower-scored member of each pair
+            idxs = np.delete(idxs, np.unique(np.concatenate(([last], rows))))
         return instances[picked]
 
     def _select_instances(self, data: dict) -> dict:

@@ -647,3 +647,28 @@ def extract_chunk(chunk_u8: np.ndarray, masks: np.ndarray, keypoints: np.ndarray
         'num_instances': num_instances, 'scalars': scalars, 'keypoint_table': kp_table,
         'depth_frames': depth_crops, 'mask_frames': mask_crops, 'filter_passes': n_pass,
     }
+
+
+def nms_mask_instances(masks, scores, iou_threshold=0.5):
+    """reference pipeline/process_features_step.py:63-113 (__nms_mask_instances), restated on numpy arrays: returns the
+    indices (into `masks`) of the kept instances, best first.  Instances with empty masks are dropped first; then, round by
+    round, the best remaining instance is kept and every remaining instance that is the lower-scored member of ANY pair with
+    IoU above the threshold is removed together with it."""
+    masks = np.asarray(masks).astype(bool)
+    scores = np.asarray(scores)
+    if len(masks) <= 1:
+        return list(range(len(masks)))
+    alive = np.flatnonzero(masks.reshape(len(masks), -1).any(axis=1))
+    flat = masks[alive].reshape(len(alive), -1).astype(np.int64)
+    idxs = np.argsort(scores[alive])
+    pick = []
+    while len(idxs) > 0:
+        last = len(idxs) - 1
+        pick.append(int(alive[idxs[last]]))
+        m = flat[idxs]
+        inter = m @ m.T
+        areas = np.broadcast_to(m.sum(axis=1), inter.shape)
+        ious = np.triu((inter / (areas + areas.T - inter)).astype(np.float32), k=1)
+        drop = np.unique(np.concatenate(([last], np.where(ious > iou_threshold)[0])))
+        idxs = np.delete(idxs, drop)
+    return pick

@@ -423,3 +423,43 @@ def test_fused_detector_input_matches_torch_transform(amp, h, w, vmax):
         assert float(diff.max()) <= 2e-4 * float(want.abs().max()), float(diff.max())
         assert float(diff.mean()) <= 2e-6 * float(want.abs().max()), float(diff.mean())
     assert float(got[:, :, size[0]:, :].abs().max() if got.shape[2] > size[0] else 0.0) == 0.0      # padding is zero
+
+
+def test_mask_iou_suppression_matches_reference_semantics():
+    """ProcessFeaturesStep._nms_mask_instances against the oracle restatement of the reference's method (pinned against the
+    reference source in tests/test_oracle_vs_golden.py): random overlapping instances, empty masks, and the chain case in
+    which the reference keeps fewer instances than textbook greedy NMS."""
+    from moseq2_detectron_extract_b200.model.instances import Boxes, Instances
+    from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
+
+    def run(masks, scores):
+        n, h, w = masks.shape
+        inst = Instances((h, w), pred_boxes=Boxes(torch.zeros((n, 4), device='cuda')), scores=torch.from_numpy(scores).cuda(),
+                         pred_classes=torch.zeros((n,), dtype=torch.int64, device='cuda'), pred_masks=torch.from_numpy(masks).cuda(),
+                         pred_keypoints=torch.arange(n, device='cuda', dtype=torch.float32)[:, None, None].expand(n, 8, 3).contiguous())
+        out = ProcessFeaturesStep._nms_mask_instances(inst)
+        want = O.nms_mask_instances(masks, scores)
+        if n <= 1:
+            assert len(out) == n
+            return len(out)
+        assert len(out) == len(want)
+        assert np.array_equal(out.pred_masks.cpu().numpy(), masks[want])
+        assert out.pred_keypoints[:, 0, 0].cpu().numpy().astype(int).tolist() == want           # every field follows the pick
+        return len(out)
+
+    def box(x0, x1):
+        m = np.zeros((40, 40), bool)
+        m[10:30, x0:x1] = True
+        return m
+    assert run(np.stack([box(0, 20), box(5, 25), box(10, 30)]), np.array([.9, .8, .7], np.float32)) == 1
+    assert run(np.stack([box(0, 20)]), np.array([.5], np.float32)) == 1
+    rng = np.random.default_rng(3)
+    for trial in range(60):
+        n = int(rng.integers(2, 9))
+        masks = np.zeros((n, 48, 40), bool)
+        for i in range(n):
+            x0, y0 = int(rng.integers(0, 18)), int(rng.integers(0, 22))
+            masks[i, y0:y0 + int(rng.integers(6, 22)), x0:x0 + int(rng.integers(6, 20))] = True
+        if trial % 4 == 0:
+            masks[int(rng.integers(0, n))] = False
+        run(masks, rng.random(n).astype(np.float32))

@@ -257,3 +257,66 @@ def test_roi_oracle_matches_reference_golden():
         if name == 'default':
             cy, cx = bg.shape[0] // 2, bg.shape[1] // 2
             assert rois[0][cy - 25, cx + 25] and not g[name + '/label_im'][cy - 25, cx + 25]
+
+
+def _reference_function(relpath, name):
+    """Compile ONE function of the reference straight from its source file (this container only; the package around it
+    needs detectron2 / norfair to import)."""
+    import ast
+    import ref_import
+    path = os.path.join(ref_import.REFERENCE_ROOT, relpath)
+    if not os.path.exists(path):
+        pytest.skip('reference tree not present')
+    tree = ast.parse(open(path).read())
+    node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
+    node.returns = None
+    for arg in node.args.args:
+        arg.annotation = None
+    import torch
+    scope = {'np': np, 'torch': torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), scope)
+    return scope[name]
+
+
+def test_mask_nms_restatement_equals_reference_method():
+    """oracle nms_mask_instances against ProcessFeaturesStep.__nms_mask_instances (process_features_step.py:63-113) on random
+    overlapping boxes, empty masks and the chain case where the reference differs from textbook greedy NMS."""
+    import torch
+    ref_nms = _reference_function('moseq2_detectron_extract/pipeline/process_features_step.py', '__nms_mask_instances')
+
+    class Fake:                                   # the slice of detectron2's Instances the method touches
+        def __init__(self, masks, scores):
+            self.pred_masks, self.scores = masks, scores
+
+        def __len__(self):
+            return len(self.scores)
+
+        def __getitem__(self, k):
+            k = torch.tensor(k, dtype=torch.long) if isinstance(k, list) else k
+            return Fake(self.pred_masks[k], self.scores[k])
+
+    def run(masks, scores):
+        out = ref_nms(None, Fake(torch.from_numpy(masks), torch.from_numpy(scores)))
+        want = [masks[i] for i in O.nms_mask_instances(masks, scores)]
+        got = list(out.pred_masks.numpy())
+        assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+        return len(got)
+
+    def box(x0, x1):
+        m = np.zeros((40, 40), bool)
+        m[10:30, x0:x1] = True
+        return m
+    # A-B and B-C overlap (IoU 0.6), A-C do not (0.33): textbook NMS keeps A and C, the reference keeps only A
+    assert run(np.stack([box(0, 20), box(5, 25), box(10, 30)]), np.array([.9, .8, .7], np.float32)) == 1
+    rng = np.random.default_rng(0)
+    suppressed = 0
+    for trial in range(200):
+        n = int(rng.integers(2, 8))
+        masks = np.zeros((n, 32, 32), bool)
+        for i in range(n):
+            x0, y0 = int(rng.integers(0, 14)), int(rng.integers(0, 14))
+            masks[i, y0:y0 + int(rng.integers(6, 18)), x0:x0 + int(rng.integers(6, 18))] = True
+        if trial % 5 == 0:
+            masks[int(rng.integers(0, n))] = False
+        suppressed += run(masks, rng.random(n).astype(np.float32)) < n
+    assert suppressed > 50
