@@ -278,6 +278,7 @@ def _reference_function(relpath, name):
     return scope[name]
 
 
+@pytest.mark.filterwarnings('ignore::DeprecationWarning')          # the reference's np.matmul on torch tensors under NumPy 2
 def test_mask_nms_restatement_equals_reference_method():
     """oracle nms_mask_instances against ProcessFeaturesStep.__nms_mask_instances (process_features_step.py:63-113) on random
     overlapping boxes, empty masks and the chain case where the reference differs from textbook greedy NMS."""
