@@ -517,7 +517,8 @@ def secondary_figures(args, geom, cfg, roi, bg):
             feats.process(infer.process(data))
         ms_full = timed(full, iters=2)
         out['full_extract_rcnn'] = {
-            'workload': 'configs[2]: prep -> scale -> Keypoint+Mask R-CNN R50-FPN (random init, torchvision graph, bf16 autocast, '
+            'workload': 'configs[2]: prep -> scale/normalise/resize (one kernel) -> Keypoint+Mask R-CNN R50-FPN (random init, torchvision graph with '
+                        'BatchNorm folded, cuDNN fused conv epilogues, batched heads + our NMS / RoIAlign / keypoint kernels, bf16 autocast, '
                         f'batch {args.rcnn_batch}, 100 proposals, 1 detection/frame) -> batched paste of the first instance -> features -> crops',
             'frames': n, 'ms': ms_full, 'frames_per_s': n / (ms_full * 1e-3)}
     return out
