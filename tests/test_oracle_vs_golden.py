@@ -273,7 +273,8 @@ def _reference_function(relpath, name):
     for arg in node.args.args:
         arg.annotation = None
     import torch
-    scope = {'np': np, 'torch': torch}
+    import cv2
+    scope = {'np': np, 'torch': torch, 'cv2': cv2}
     exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), scope)
     return scope[name]
 
@@ -321,3 +322,32 @@ def test_mask_nms_restatement_equals_reference_method():
             masks[int(rng.integers(0, n))] = False
         suppressed += run(masks, rng.random(n).astype(np.float32)) < n
     assert suppressed > 50
+
+
+def test_chunk_ranges_equal_reference_gen_batch_sequence():
+    """shard.chunk_ranges against the reference's gen_batch_sequence (io/util.py:24-35, offset 0) compiled from its source."""
+    from moseq2_detectron_extract_b200.shard import chunk_ranges
+    gen = _reference_function('moseq2_detectron_extract/io/util.py', 'gen_batch_sequence')
+    for nframes in (0, 1, 9, 10, 11, 25, 70, 1000, 54000):
+        for chunk_size, overlap in ((10, 0), (10, 3), (30, 10), (1000, 0), (1000, 100), (7, 6)):
+            want = [list(r) for r in gen(nframes, chunk_size, overlap)]
+            got = [list(r) for r in chunk_ranges(nframes, chunk_size, overlap)]
+            assert got == want, (nframes, chunk_size, overlap)
+
+
+def test_roi_host_helpers_equal_reference_functions():
+    """proc.plane_fit3 / proc.select_strel (host helpers of the session ROI set-up) against the reference's functions compiled
+    from source (proc/roi.py:106-130, proc/util.py:9-26)."""
+    from moseq2_detectron_extract_b200.proc.roi import plane_fit3
+    from moseq2_detectron_extract_b200.proc.util import select_strel
+    ref_fit = _reference_function('moseq2_detectron_extract/proc/roi.py', 'plane_fit3')
+    ref_strel = _reference_function('moseq2_detectron_extract/proc/util.py', 'select_strel')
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        pts = np.column_stack([rng.integers(0, 512, 3), rng.integers(0, 424, 3), rng.integers(600, 720, 3)]).astype(np.float64)
+        np.testing.assert_allclose(plane_fit3(pts), ref_fit(pts), rtol=1e-13, atol=1e-13, equal_nan=True)
+    line = np.array([[0., 0., 1.], [1., 1., 2.], [2., 2., 3.]])
+    assert np.isnan(plane_fit3(line)).all() and np.isnan(ref_fit(line)).all()
+    for shape in ('ellipse', 'rect', 'e', 'r', 'other'):
+        for size in ((10, 10), (15, 15), (7, 3), (1, 1), (4, 9)):
+            assert np.array_equal(select_strel(shape, size), ref_strel(shape, size)), (shape, size)
