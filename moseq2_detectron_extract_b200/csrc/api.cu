@@ -42,7 +42,7 @@ struct TimerState {
 } g_timer;
 const char *const kKernelNames[K_COUNT] = {"prep_frames", "scale_frames", "clean_frames", "frame_features",
                                            "angles_flips_filter", "masked_sums", "scalars_keypoints", "crop_rotate",
-                                           "paste_masks", "inpaint", "kalman_tracking", "bground_median", "session_roi"};
+                                           "paste_masks", "inpaint", "kalman_tracking", "bground_median", "session_roi", "detector_glue"};
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kernel_id, cudaStream_t stream) : slot(-1), st(stream) {

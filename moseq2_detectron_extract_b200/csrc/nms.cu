@@ -65,7 +65,7 @@ extern "C" int msq_nms_sorted(const float *boxes, const uint8_t *valid, int n, i
     MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "msq_nms_sorted: max_keep %d is too large", max_keep);
     if (smem > 48 * 1024)
         MSQ_CUDA_OK(cudaFuncSetAttribute(nms_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TimedLaunch timed(K_PASTE, (cudaStream_t)stream);          // counted with the other R-CNN glue kernel
+    TimedLaunch timed(K_DETECTOR_GLUE, (cudaStream_t)stream);
     nms_sorted_kernel<<<(n + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(boxes), valid, n, K, iou_threshold, max_keep, keep, count);
     MSQ_LAUNCH_OK("nms_sorted");
@@ -169,7 +169,7 @@ extern "C" int msq_keypoints_from_heatmaps(const float *maps, const float *rois,
     MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "msq_keypoints_from_heatmaps: %dx%d heatmaps are too large", Hm, Wm);
     if (smem > 48 * 1024)
         MSQ_CUDA_OK(cudaFuncSetAttribute(msq::keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msq::TimedLaunch timed(msq::K_PASTE, (cudaStream_t)stream);
+    msq::TimedLaunch timed(msq::K_DETECTOR_GLUE, (cudaStream_t)stream);
     msq::keypoint_decode_kernel<<<n_rois * K, msq::kKpThreads, smem, (cudaStream_t)stream>>>(maps, rois, K, Hm, Wm, round_bf16, xyv, scores);
     MSQ_LAUNCH_OK("keypoint_decode");
     return MSQ_OK;

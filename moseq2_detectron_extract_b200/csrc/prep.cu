@@ -410,7 +410,7 @@ extern "C" int msq_detector_input(const uint8_t *in, void *out, int out_is_bf16,
     }
     const size_t work = (size_t)n * ph * pw;
     const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 16);
-    TimedLaunch timed(K_SCALE, (cudaStream_t)stream);
+    TimedLaunch timed(K_DETECTOR_GLUE, (cudaStream_t)stream);
     if (out_is_bf16)
         detector_input_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16 *>(out), n, h, w, oh, ow,
                                                                                        ph, pw, norm, vmin, vmax, vmin_is_int);

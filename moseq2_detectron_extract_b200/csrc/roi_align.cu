@@ -165,7 +165,7 @@ extern "C" int msq_roi_align_levels(const void *const *feat_dev, const int *heig
     // one instantiation per (dtype, sampling ratio); launched through a type-erased trampoline
     auto launch = [&](auto kernel, auto *typed_out) -> int {
         if (smem > 48 * 1024) MSQ_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TimedLaunch timed(K_PASTE, st);
+        TimedLaunch timed(K_DETECTOR_GLUE, st);
         kernel<<<n_rois, kAlignThreads, smem, st>>>(pyr, C, rois_dev, levels_dev, P, typed_out);
         return MSQ_OK;
     };
