@@ -407,3 +407,20 @@ def test_raw_session_archive_metadata_timestamps_and_trim(tmp_path):
     (tmp_path / 'plain' / 'timestamps.csv').unlink()
     with pytest.raises(ValueError):
         RawDepthSession(str(tmp_path / 'plain' / 'depth.dat'), frame_dims=(W, H), pinned=False).load_timestamps()
+
+
+def test_ransac_triples_reproduce_the_reference_draws():
+    """One randint call for all RANSAC iterations == the reference's per-iteration np.random.choice(n, 3, replace=True)
+    (proc/roi.py:170): same numbers, same generator state afterwards."""
+    from moseq2_detectron_extract_b200.proc.roi import _ransac_triples
+    for npoints in (1, 2, 7, 45225, 217088, 368640, 5_000_000):
+        for seed, iters in ((0, 1), (3, 5), (11, 1000)):
+            np.random.seed(seed)
+            want = np.stack([np.random.choice(npoints, 3, replace=True) for _ in range(iters)])
+            state_want = np.random.get_state()
+            np.random.seed(seed)
+            got = _ransac_triples(npoints, iters)
+            state_got = np.random.get_state()
+            assert got.dtype == want.dtype and np.array_equal(got, want)
+            assert np.array_equal(state_got[1], state_want[1]) and state_got[2] == state_want[2]
+    assert _ransac_triples(10, 0).shape == (0, 3)
