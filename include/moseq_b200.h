@@ -138,6 +138,43 @@ MSQ_API int msq_roi_align_levels(const void *const *feat_dev, const int *heights
                          int n_levels, int C, int is_bf16, const float *rois_dev, const long long *levels_dev, int n_rois,
                          int P, int sampling_ratio, void *out_dev, void *stream);
 
+/* ---- a4  glue kernels of the repo's own detectron2-configuration graph (model/rcnn.py; ref: model/config.py:21-94 on top of
+ *      detectron2's COCO-Keypoints/keypoint_rcnn_R_50_FPN_3x.yaml; export contract ref: model/deploy.py:65-110) -----------
+ * GroupNorm of the FPN convolutions (FPN.NORM = 'GN', ref: model/config.py:82) on a channels-last map (n,H,W,C) of bf16
+ * (is_bf16 != 0) or float32, fused with the top-down path (FPN.FUSE_TYPE = 'avg', ref: model/config.py:83):
+ *   out = (GroupNorm(x; groups, eps, gamma, beta) + nearest_upsample_x2(top)) * scale        top (n,ceil(H/2),ceil(W/2),C) or NULL
+ * gamma / beta: (C) float32 on the device.  Channels per group must be a multiple of 8.  x and out may alias.
+ * scratch_dev: msq_group_norm_scratch_bytes(n,H,W,C) bytes, 16-byte aligned. */
+MSQ_API size_t msq_group_norm_scratch_bytes(int n, int H, int W, int C);
+MSQ_API int msq_group_norm_nhwc(const void *x_dev, int is_bf16, int n, int H, int W, int C, int groups, float eps,
+                        const float *gamma_dev, const float *beta_dev, const void *top_dev, float scale, void *out_dev,
+                        void *scratch_dev, size_t scratch_bytes, void *stream);
+
+/* detectron2 ROIPooler with ROIAlignV2 (torchvision.ops.roi_align(aligned=True); sampling_ratio 0 = adaptive grid
+ * ceil(roi / P), the detectron2 default) over n_levels channels-last maps (n, H_l, W_l, C), level of a box =
+ * clamp(floor(canonical_level + log2(sqrt(area) / canonical_size + 1e-8)), min_level, min_level + n_levels - 1) as in
+ * detectron2.modeling.poolers.assign_boxes_to_levels.  boxes_dev (n_rois,4) float32 x1,y1,x2,y2; box r belongs to image
+ * r / rois_per_image.  out_dev (n_rois, P, P, C) CHANNELS-LAST in the dtype of the maps.  Host arrays as in
+ * msq_roi_align_levels. */
+MSQ_API int msq_roi_align_v2(const void *const *feat_dev, const int *heights, const int *widths, const float *scales, int n_levels,
+                     int C, int is_bf16, const float *boxes_dev, int n_rois, int rois_per_image, int P, int sampling_ratio,
+                     int min_level, int canonical_level, float canonical_size, void *out_dev, void *stream);
+
+/* detectron2 fast_rcnn_inference with TEST.DETECTIONS_PER_IMAGE = 1 (ref: model/config.py:75) and one foreground class: per
+ * image the proposal with the best soft-max foreground score above score_thresh (it always survives its class's NMS),
+ * decoded with Box2BoxTransform(weights4_host) and clipped to the image.  pred_dev (n*k, pred_stride) float32 rows
+ * [logit_fg, logit_bg, dx, dy, dw, dh, ...]; proposals_dev (n,k,4); counts_dev (n) int32 valid proposals per image or NULL.
+ * box_dev (n,4), score_dev (n), has_dev (n) u8 (0: no detection, box = 0), index_dev (n) int32 or NULL. */
+MSQ_API int msq_fastrcnn_top1(const float *pred_dev, int pred_stride, const float *proposals_dev, const int32_t *counts_dev, int n,
+                      int k, int img_h, int img_w, float score_thresh, const float *weights4_host, float *box_dev,
+                      float *score_dev, uint8_t *has_dev, int32_t *index_dev, void *stream);
+
+/* detectron2.structures.keypoints.heatmaps_to_keypoints for a batch: as msq_keypoints_from_heatmaps, but the third column
+ * of xyp_dev (R,K,3) is detectron2's score exp(max) / sum(exp(pool-resolution map)); logit_dev (R,K) or NULL receives the
+ * heatmap value at the arg-max. */
+MSQ_API int msq_keypoints_from_heatmaps_d2(const float *maps_dev, const float *rois_dev, int n_rois, int K, int Hm, int Wm,
+                                   float *xyp_dev, float *logit_dev, void *stream);
+
 /* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
 MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);

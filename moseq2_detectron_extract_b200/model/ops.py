@@ -1,0 +1,245 @@
+"""`torch.ops.msq.*`: the operators the repo's own R-CNN graph (model/rcnn.py) is made of.
+
+They are registered with the PyTorch dispatcher (torch.library) so that a TorchScript export of the graph can name them;
+every implementation is CUDA-only and goes through the C ABI of libmoseq_b200.so (ctypes) or a cuDNN / cuBLAS library call
+for the dense contractions.  There is no CPU implementation: on a CPU tensor the dispatcher raises.
+
+Importing this module registers the operators; `Predictor.from_torchscript` imports it before `torch.jit.load`.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .. import _dev, _lib
+
+_LIB = torch.library.Library('msq', 'DEF')
+_LIB.define('detector_input(Tensor chunk_u8, float vmin, float vmax, bool int_limits, float[] mean, float[] std, int ph, int pw, '
+            'bool bf16) -> Tensor')
+_LIB.define('conv2d(Tensor x, Tensor w, Tensor? b, Tensor? z, bool relu, int stride, int pad) -> Tensor')
+_LIB.define('linear(Tensor x, Tensor w, Tensor? b, bool relu) -> Tensor')
+_LIB.define('group_norm_nhwc(Tensor x, Tensor gamma, Tensor beta, int groups, float eps, Tensor? top, float scale) -> Tensor')
+_LIB.define('rpn_proposals(Tensor[] preds, int[] strides, float[] sizes, float[] ratios, int img_h, int img_w, int pre_topk, '
+            'int post_topk, float nms_thresh) -> (Tensor, Tensor, Tensor)')
+_LIB.define('roi_align_v2(Tensor[] feats, float[] scales, Tensor boxes, int rois_per_image, int pooled, int sampling_ratio, '
+            'int min_level, int canonical_level, float canonical_size) -> Tensor')
+_LIB.define('fastrcnn_top1(Tensor pred, Tensor proposals, Tensor counts, int img_h, int img_w, float score_thresh, float[] weights) '
+            '-> (Tensor, Tensor, Tensor)')
+_LIB.define('keypoints_from_heatmaps_d2(Tensor heatmaps, Tensor boxes) -> Tensor')
+
+# implementation switches (bench / tests): which engine runs the dense contractions
+CONV_ENGINE = {'mode': 'cudnn'}          # 'cudnn' | 'tcgen05' (csrc/conv_tc.cu, where the shape is served)
+
+
+def _is_cl(x: torch.Tensor) -> bool:
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    return x if _is_cl(x) else x.contiguous(memory_format=torch.channels_last)
+
+
+# ---- detector input -----------------------------------------------------------------------------------------------------
+def _detector_input(chunk_u8, vmin, vmax, int_limits, mean, std, ph, pw, bf16):
+    n, h, w = (int(v) for v in chunk_u8.shape)
+    x = torch.empty((n, 3, ph, pw), dtype=torch.bfloat16 if bf16 else torch.float32, device=chunk_u8.device,
+                    memory_format=torch.channels_last)
+    _lib.call('msq_detector_input', _dev.ptr(chunk_u8.contiguous()), _dev.ptr(x), int(bf16), n, h, w, h, w, ph, pw,
+              (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std]),
+              float(vmin), float(vmax), int(int_limits), _dev.stream())
+    return x
+
+
+# ---- dense contractions -------------------------------------------------------------------------------------------------
+def _conv2d(x, w, b, z, relu, stride, pad):
+    if CONV_ENGINE['mode'] == 'tcgen05':
+        from . import conv_tc
+        y = conv_tc.try_conv2d(x, w, b, z, relu, stride, pad)
+        if y is not None:
+            return y
+    x = _cl(x)
+    st, pd, dl = [stride, stride], [pad, pad], [1, 1]
+    if relu and b is not None and x.dtype == w.dtype:
+        if z is None:
+            return torch.cudnn_convolution_relu(x, w, b, st, pd, dl, 1)
+        return torch.cudnn_convolution_add_relu(x, w, _cl(z), 1.0, b, st, pd, dl, 1)
+    y = F.conv2d(x, w, b, st, pd)
+    if z is not None:
+        y = y + z
+    return F.relu(y) if relu else y
+
+
+def _linear(x, w, b, relu):
+    if CONV_ENGINE['mode'] == 'tcgen05':
+        from . import conv_tc
+        y = conv_tc.try_linear(x, w, b, relu)
+        if y is not None:
+            return y
+    y = F.linear(x, w, b)
+    return F.relu_(y) if relu else y
+
+
+# ---- GroupNorm (+ top-down merge) on channels-last maps -------------------------------------------------------------------
+def _group_norm_nhwc(x, gamma, beta, groups, eps, top, scale):
+    x = _cl(x)
+    n, c, h, w = (int(v) for v in x.shape)
+    if top is not None:
+        top = _cl(top)
+        if (int(top.shape[2]), int(top.shape[3])) != ((h + 1) // 2, (w + 1) // 2) or h % 2 or w % 2:
+            raise ValueError(f'group_norm_nhwc: top-down map {tuple(top.shape)} is not half of {tuple(x.shape)}')
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    nbytes = int(_lib.load().msq_group_norm_scratch_bytes(n, h, w, c))
+    scratch = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    _lib.call('msq_group_norm_nhwc', _dev.ptr(x), int(x.dtype == torch.bfloat16), n, h, w, c, int(groups), float(eps),
+              _dev.ptr(gamma), _dev.ptr(beta), _dev.ptr(top), float(scale), _dev.ptr(out), _dev.ptr(scratch), nbytes, _dev.stream())
+    return out
+
+
+# ---- RPN: detectron2 find_top_rpn_proposals for a batch of equally sized images ---------------------------------------------
+_ANCHOR_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def cell_anchors(size: float, ratios) -> torch.Tensor:
+    """detectron2 DefaultAnchorGenerator.generate_cell_anchors for one size."""
+    out = []
+    for ar in ratios:
+        area = size ** 2.0
+        w = math.sqrt(area / ar)
+        h = ar * w
+        out.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
+    return torch.tensor(out, dtype=torch.float32)
+
+
+def grid_anchors(gh: int, gw: int, stride: int, size: float, ratios, device) -> torch.Tensor:
+    """(gh * gw * A, 4) anchors of one pyramid level in detectron2's (y, x, anchor) order, offset 0."""
+    key = (gh, gw, stride, float(size), tuple(float(r) for r in ratios), str(device))
+    hit = _ANCHOR_CACHE.get(key)
+    if hit is None:
+        sx = torch.arange(0, gw * stride, step=stride, dtype=torch.float32)
+        sy = torch.arange(0, gh * stride, step=stride, dtype=torch.float32)
+        yy, xx = torch.meshgrid(sy, sx, indexing='ij')
+        shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), dim=1)
+        hit = (shifts.view(-1, 1, 4) + cell_anchors(size, ratios).view(1, -1, 4)).reshape(-1, 4).to(device)
+        _ANCHOR_CACHE[key] = hit
+    return hit
+
+
+_SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+def apply_deltas(deltas: torch.Tensor, boxes: torch.Tensor, weights=(1.0, 1.0, 1.0, 1.0)) -> torch.Tensor:
+    """detectron2 Box2BoxTransform.apply_deltas on (..., 4) tensors."""
+    deltas = deltas.float()
+    boxes = boxes.to(deltas.dtype)
+    widths = boxes[..., 2] - boxes[..., 0]
+    heights = boxes[..., 3] - boxes[..., 1]
+    ctr_x = boxes[..., 0] + 0.5 * widths
+    ctr_y = boxes[..., 1] + 0.5 * heights
+    wx, wy, ww, wh = weights
+    dx, dy = deltas[..., 0] / wx, deltas[..., 1] / wy
+    dw = torch.clamp(deltas[..., 2] / ww, max=_SCALE_CLAMP)
+    dh = torch.clamp(deltas[..., 3] / wh, max=_SCALE_CLAMP)
+    pcx, pcy = dx * widths + ctr_x, dy * heights + ctr_y
+    pw, ph = torch.exp(dw) * widths, torch.exp(dh) * heights
+    return torch.stack((pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph), dim=-1)
+
+
+def _rpn_proposals(preds, strides, sizes, ratios, img_h, img_w, pre_topk, post_topk, nms_thresh):
+    """preds[l]: (n, 16, H_l, W_l) channels-last, channels [A objectness logits, A x 4 anchor deltas, padding] (A = 3).
+    Returns proposals (n, post_topk, 4) float32 (zero boxes beyond the count), their logits (n, post_topk), counts (n) int32."""
+    n = int(preds[0].shape[0])
+    dev = preds[0].device
+    A = len(ratios)
+    boxes_l, scores_l, level_l = [], [], []
+    for lvl, p in enumerate(preds):
+        gh, gw = int(p.shape[2]), int(p.shape[3])
+        p = _cl(p).permute(0, 2, 3, 1)                                   # (n, H, W, 16) view of the channels-last memory
+        logits = p[..., :A].reshape(n, -1).float()                       # (h, w, a) order, as detectron2 flattens it
+        deltas = p[..., A:5 * A].reshape(n, -1, 4).float()
+        anchors = grid_anchors(gh, gw, int(strides[lvl]), float(sizes[lvl]), ratios, dev)
+        k = min(int(pre_topk), gh * gw * A)
+        top, idx = logits.topk(k, dim=1)
+        sel = torch.gather(deltas, 1, idx[..., None].expand(-1, -1, 4))
+        boxes_l.append(apply_deltas(sel, anchors[idx]))
+        scores_l.append(top)
+        level_l.append(torch.full((k,), lvl, dtype=torch.float32, device=dev))
+    boxes = torch.cat(boxes_l, 1)
+    scores = torch.cat(scores_l, 1)
+    levels = torch.cat(level_l)[None].expand(n, -1)
+    finite = torch.isfinite(boxes).all(-1) & torch.isfinite(scores)
+    boxes = torch.stack([boxes[..., 0].clamp(0, img_w), boxes[..., 1].clamp(0, img_h),
+                         boxes[..., 2].clamp(0, img_w), boxes[..., 3].clamp(0, img_h)], dim=-1)
+    valid = finite & ((boxes[..., 2] - boxes[..., 0]) > 0) & ((boxes[..., 3] - boxes[..., 1]) > 0)
+    order = torch.sort(torch.where(valid, scores, scores.new_full((), float('-inf'))), dim=1, descending=True, stable=True).indices
+    boxes = torch.gather(boxes, 1, order[..., None].expand(-1, -1, 4))
+    scores = torch.gather(scores, 1, order)
+    levels = torch.gather(levels, 1, order)
+    valid = torch.gather(valid, 1, order)
+    # torchvision batched_nms' coordinate trick (what detectron2's batched_nms runs for < 40 000 boxes): shift every level by
+    # (largest coordinate of the image's boxes + 1) so that levels never suppress each other
+    max_coord = torch.where(valid[..., None], boxes, boxes.new_full((), float('-inf'))).amax(dim=(1, 2))
+    max_coord = torch.where(torch.isfinite(max_coord), max_coord, torch.zeros_like(max_coord))
+    shifted = (boxes + (levels * (max_coord[:, None] + 1))[..., None]).contiguous()
+    K = int(boxes.shape[1])
+    keep = torch.empty((n, int(post_topk)), dtype=torch.int32, device=dev)
+    count = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.call('msq_nms_sorted', _dev.ptr(shifted), _dev.ptr(valid.to(torch.uint8).contiguous()), n, K, float(nms_thresh), int(post_topk),
+              _dev.ptr(keep), _dev.ptr(count), _dev.stream())
+    ok = keep >= 0
+    idx = keep.clamp(min=0).long()
+    out_boxes = torch.gather(boxes, 1, idx[..., None].expand(-1, -1, 4)) * ok[..., None]
+    out_scores = torch.where(ok, torch.gather(scores, 1, idx), scores.new_full((), float('-inf')))
+    return out_boxes.contiguous(), out_scores.contiguous(), count
+
+
+# ---- ROIAlignV2 over the pyramid -------------------------------------------------------------------------------------------
+def _roi_align_v2(feats, scales, boxes, rois_per_image, pooled, sampling_ratio, min_level, canonical_level, canonical_size):
+    """feats[l] (n, C, H_l, W_l) channels-last; boxes (R, 4) float32, box r on image r // rois_per_image.  Returns (R, C, P, P)
+    in channels-last memory (= (R, P, P, C) contiguous) in the dtype of the maps."""
+    feats = [_cl(f) for f in feats]
+    k = len(feats)
+    c = int(feats[0].shape[1])
+    boxes = boxes.reshape(-1, 4).float().contiguous()
+    r = int(boxes.shape[0])
+    out = torch.empty((r, c, int(pooled), int(pooled)), dtype=feats[0].dtype, device=feats[0].device, memory_format=torch.channels_last)
+    if r == 0:
+        return out
+    _lib.call('msq_roi_align_v2', (ctypes.c_void_p * k)(*[f.data_ptr() for f in feats]), (ctypes.c_int * k)(*[int(f.shape[2]) for f in feats]),
+              (ctypes.c_int * k)(*[int(f.shape[3]) for f in feats]), (ctypes.c_float * k)(*[float(s) for s in scales]), k, c,
+              int(feats[0].dtype == torch.bfloat16), _dev.ptr(boxes), r, int(rois_per_image), int(pooled), int(sampling_ratio),
+              int(min_level), int(canonical_level), float(canonical_size), _dev.ptr(out), _dev.stream())
+    return out
+
+
+# ---- Fast R-CNN outputs, one detection per image ----------------------------------------------------------------------------
+def _fastrcnn_top1(pred, proposals, counts, img_h, img_w, score_thresh, weights):
+    n, k = int(proposals.shape[0]), int(proposals.shape[1])
+    pred = pred.float().contiguous()
+    proposals = proposals.float().contiguous()
+    dev = pred.device
+    box = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    score = torch.empty((n,), dtype=torch.float32, device=dev)
+    has = torch.empty((n,), dtype=torch.uint8, device=dev)
+    _lib.call('msq_fastrcnn_top1', _dev.ptr(pred), int(pred.shape[1]), _dev.ptr(proposals), _dev.ptr(counts.to(torch.int32).contiguous()), n, k,
+              int(img_h), int(img_w), float(score_thresh), (ctypes.c_float * 4)(*[float(v) for v in weights]), _dev.ptr(box),
+              _dev.ptr(score), _dev.ptr(has), None, _dev.stream())
+    return box, score, has
+
+
+def _keypoints_from_heatmaps_d2(heatmaps, boxes):
+    r, k, hm, wm = (int(v) for v in heatmaps.shape)
+    xyp = torch.empty((r, k, 3), dtype=torch.float32, device=heatmaps.device)
+    if r:
+        _lib.call('msq_keypoints_from_heatmaps_d2', _dev.ptr(heatmaps.float().contiguous()), _dev.ptr(boxes.float().contiguous()), r, k, hm, wm,
+                  _dev.ptr(xyp), None, _dev.stream())
+    return xyp
+
+
+for _name, _fn in (('detector_input', _detector_input), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
+                   ('rpn_proposals', _rpn_proposals), ('roi_align_v2', _roi_align_v2), ('fastrcnn_top1', _fastrcnn_top1),
+                   ('keypoints_from_heatmaps_d2', _keypoints_from_heatmaps_d2)):
+    _LIB.impl(_name, _fn, 'CUDA')

@@ -17,7 +17,11 @@ class InferenceStep(ProcessPipelineStep):
         if isinstance(model_path, str) and os.path.isfile(model_path) and model_path.endswith('.ts'):
             self.predictor = Predictor.from_torchscript(model_path)
         elif model_path is None or model_path == 'random':
-            self.predictor = Predictor.from_random_init(device=self.config.get('device', 'cuda'), amp=bool(self.config.get('amp', False)))
+            import torch as _torch
+            kw = {k: self.config[k] for k in ('post_nms_topk', 'pre_nms_topk') if k in self.config}
+            self.predictor = Predictor.from_random_init(device=self.config.get('device', 'cuda'),
+                                                        dtype=_torch.bfloat16 if self.config.get('amp', True) else _torch.float32,
+                                                        scripted=bool(self.config.get('scripted', False)), **kw)
         else:
             raise NotImplementedError('InferenceStep: only TorchScript (.ts) models or model="random" are supported; '
                                       'detectron2 checkpoints need detectron2 (not part of this build)')

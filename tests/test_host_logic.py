@@ -342,28 +342,6 @@ def test_select_strel_and_sobel_kernels_equal_opencv():
     assert np.isnan(plane_fit3(np.zeros((3, 3)))).all()
 
 
-def test_batchnorm_folding_preserves_backbone_outputs():
-    pytest.importorskip('torchvision')
-    import torch
-    from moseq2_detectron_extract_b200.model.predict import build_random_keypoint_mask_rcnn, fold_batchnorm_into_convs
-    torch.manual_seed(0)
-    backbone = build_random_keypoint_mask_rcnn().eval().backbone
-    for mod in backbone.modules():
-        if isinstance(mod, torch.nn.BatchNorm2d):              # non-trivial statistics, as a trained model would have
-            mod.running_mean.normal_(0, 0.1)
-            mod.running_var.uniform_(0.5, 1.5)
-            mod.weight.data.uniform_(0.5, 1.5)
-            mod.bias.data.normal_(0, 0.1)
-    x = torch.rand(1, 3, 64, 64)
-    with torch.no_grad():
-        want = backbone(x)
-        assert fold_batchnorm_into_convs(backbone) == 53       # stem + 16 bottlenecks x 3 + 4 downsample branches
-        got = backbone(x)
-    assert not any(isinstance(mod, torch.nn.BatchNorm2d) for mod in backbone.modules())
-    for k in want:
-        assert float((want[k] - got[k]).abs().max()) <= 1e-5 * float(want[k].abs().max())
-
-
 def test_raw_session_archive_metadata_timestamps_and_trim(tmp_path):
     """RawDepthSession over a .tar.gz session archive (ref io/session.py:50-178): depth.dat member, DepthResolution from
     metadata.json, depth_ts.txt / timestamps.csv, frame_trim like __trim_frames."""
@@ -424,3 +402,59 @@ def test_ransac_triples_reproduce_the_reference_draws():
             assert got.dtype == want.dtype and np.array_equal(got, want)
             assert np.array_equal(state_got[1], state_want[1]) and state_got[2] == state_want[2]
     assert _ransac_triples(10, 0).shape == (0, 3)
+
+
+def test_rcnn_graph_scripts_and_keeps_export_contract(tmp_path):
+    """model/rcnn.py: the graph is TorchScript-scriptable, survives save / load, carries the reference's export contract
+    (ref model/deploy.py:91-97: forward(List[Dict[str, Tensor]]) -> List[Dict[str, Tensor]]) plus the batched `forward_dense`
+    entry, and fails loudly on CPU tensors (no CPU implementation of torch.ops.msq.*)."""
+    import torch
+    from moseq2_detectron_extract_b200.model import rcnn
+    model = rcnn.finalize(rcnn.MoseqRCNN(post_nms_topk=100), torch.float32, 'cpu')
+    path = str(tmp_path / 'model.ts')
+    rcnn.export_torchscript(model, path)
+    loaded = torch.jit.load(path)
+    assert int(loaded.graph_version) == rcnn.GRAPH_VERSION and loaded.input_format == 'RGB' and int(loaded.post_nms_topk) == 100
+    schema = str(loaded.forward.schema)
+    assert 'Dict(str, Tensor)[] inputs' in schema and schema.endswith('-> Dict(str, Tensor)[]')
+    assert hasattr(loaded, 'forward_dense')
+    for op in ('conv2d', 'group_norm_nhwc', 'rpn_proposals', 'roi_align_v2', 'fastrcnn_top1', 'keypoints_from_heatmaps_d2', 'linear'):
+        assert f'msq::{op}' in str(loaded.inlined_graph) or f'msq::{op}' in str(loaded.forward_dense.inlined_graph), op
+    with pytest.raises(Exception):
+        loaded([{'image': torch.zeros((3, 64, 64), dtype=torch.uint8)}])
+    with pytest.raises(NotImplementedError):
+        rcnn.MoseqRCNN(detections_per_image=2)
+
+
+def test_detectron2_state_dict_rewrites_are_exact_on_cpu():
+    """from_detectron2_state_dict's rewrites checked with plain torch on the CPU: FrozenBN folding == conv + FrozenBN, the fc1
+    column permutation == flatten of (C, 7, 7) vs (7, 7, C), the merged RPN predictor == the two 1x1 convolutions."""
+    import torch
+    import torch.nn.functional as F
+    import d2_rcnn_oracle as D
+    from moseq2_detectron_extract_b200.model import rcnn
+    st = D.make_random_state(1)
+    model = rcnn.from_detectron2_state_dict(st, dtype=torch.float32, device='cpu')
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 64, 20, 20), generator=g)
+    blk = model.res2[0]
+    p = 'backbone.bottom_up.res2.0.'
+    for conv, name, stride, pad in ((blk.conv1, 'conv1', 1, 0), (blk.shortcut, 'shortcut', 1, 0)):
+        want = D.conv_frozen_bn(x, st, p + name, stride, pad)
+        got = F.conv2d(x, conv.weight, conv.bias, stride, pad)
+        assert float((want - got).abs().max()) <= 1e-5 * float(want.abs().max())
+    assert model.res3[0].conv1.stride == 2 and model.res3[0].conv2.stride == 1 and model.res3[0].shortcut.stride == 2    # STRIDE_IN_1X1
+    roi = torch.randn((5, 256, 7, 7), generator=g)
+    want = F.linear(roi.flatten(1), st['roi_heads.box_head.fc1.weight'], st['roi_heads.box_head.fc1.bias'])
+    got = F.linear(roi.permute(0, 2, 3, 1).reshape(5, -1), model.fc1_w, model.fc1_b)
+    assert float((want - got).abs().max()) <= 1e-4 * float(want.abs().max())
+    t = torch.randn((2, 256, 6, 6), generator=g)
+    rp = 'proposal_generator.rpn_head.'
+    both = F.conv2d(t, model.rpn_pred.weight, model.rpn_pred.bias)
+    assert torch.allclose(both[:, :3], F.conv2d(t, st[rp + 'objectness_logits.weight'], st[rp + 'objectness_logits.bias']), atol=1e-6)
+    assert torch.allclose(both[:, 3:15], F.conv2d(t, st[rp + 'anchor_deltas.weight'], st[rp + 'anchor_deltas.bias']), atol=1e-6)
+    assert float(both[:, 15].abs().max()) == 0
+    pred = F.linear(torch.randn((3, 1024), generator=g), model.box_pred_w, model.box_pred_b)
+    assert pred.shape == (3, 8) and float(pred[:, 6:].abs().max()) == 0
+    assert model.pixel_mean == pytest.approx([1.12] * 3) and model.pixel_std == pytest.approx([5.79] * 3)
+    assert tuple(model.kp_deconv_w.shape) == (512, 8, 4, 4) and model.keypoint_pooler == 7 and model.post_nms_topk == 1000
