@@ -113,6 +113,17 @@ MSQ_API int msq_detector_input(const uint8_t *in_dev, void *out_dev, int out_is_
                        int ph, int pw, const float *mean_host, const float *std_host, double vmin, double vmax,
                        int vmin_is_int, void *stream);
 
+/* The detector's stem in one kernel (ref: model/predict.py:74-77 grey -> 3 identical channels; detectron2 BasicStem of the
+ * graph ref model/config.py configures): a3 scaling -> (x - mean) / std -> zero padding to (ph, pw) -> 7x7 stride-2 convolution
+ * + bias -> ReLU -> 3x3 stride-2 max-pool.  Valid when PIXEL_MEAN / PIXEL_STD are the same for the three channels: the
+ * 3-channel convolution of a replicated grey image is the 1-channel convolution with the weights summed over the input
+ * channels.  in_dev (n,h,w) u8 prepared frames; w49x64_dev (49, 64) float32 = sum over input channels of the (folded) stem
+ * weight, [tap r*7+s][output channel]; bias64_dev (64) float32; out_dev (n, PH, PW, 64) channels-last bf16 / float32 with
+ * PH = ((ph-1)/2+1 - 1)/2 + 1 (64 for ph = 256). */
+MSQ_API int msq_stem_conv_pool(const uint8_t *in_dev, int n, int h, int w, int ph, int pw, double vmin, double vmax, int vmin_is_int,
+                       float mean, float std, const float *w49x64_dev, const float *bias64_dev, void *out_dev, int out_is_bf16,
+                       void *stream);
+
 /* Segmented greedy NMS for the RPN proposal filtering of a whole batch (replaces the per-image box_ops.batched_nms calls of
  * torchvision's RegionProposalNetwork.filter_proposals behind Predictor; the reference's detectron2 RPN does the same
  * per-image loop).  boxes_dev (n,K,4) float32, per image sorted by descending score and already shifted per pyramid level
@@ -120,6 +131,14 @@ MSQ_API int msq_detector_input(const uint8_t *in_dev, void *out_dev, int out_is_
  * survivors (-1 padded), count_dev (n) their number.  boxes_dev 16-byte aligned. */
 MSQ_API int msq_nms_sorted(const float *boxes_dev, const uint8_t *valid_dev, int n, int K, float iou_threshold, int max_keep,
                    int32_t *keep_dev, int32_t *count_dev, void *stream);
+
+/* The same greedy NMS for long keep lists (detectron2's RPN keeps the first POST_NMS_TOPK_TEST = 1000 survivors of ~3000
+ * candidates per image): the K x K overlap matrix is evaluated in parallel as bit rows, then one warp per image walks the
+ * candidates in order.  Same arguments and results as msq_nms_sorted; K <= 6144; scratch_dev: msq_nms_scratch_bytes(n, K)
+ * bytes, 8-byte aligned. */
+MSQ_API size_t msq_nms_scratch_bytes(int n, int K);
+MSQ_API int msq_nms_sorted_long(const float *boxes_dev, const uint8_t *valid_dev, int n, int K, float iou_threshold, int max_keep,
+                        int32_t *keep_dev, int32_t *count_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
 
 /* Keypoint decoding for a batch (replaces the per-RoI loop of torchvision's heatmaps_to_keypoints / detectron2's keypoint
  * head inference): for every RoI and keypoint, the arg-max of the heatmap (maps_dev (R,K,Hm,Wm) float32) bicubically

@@ -73,6 +73,100 @@ extern "C" int msq_nms_sorted(const float *boxes, const uint8_t *valid, int n, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same greedy rule for LONG keep lists (detectron2's RPN keeps the first 1000 survivors of ~3000 candidates per image:
+// the walk above would compare every candidate with up to 1000 kept boxes, 41 ms per 250 images).  Two kernels:
+//   nms_mask_kernel   every (64 candidates) x (64 later candidates) block of the K x K overlap matrix in parallel, one bit
+//                     per pair (upper triangle only);
+//   nms_scan_kernel   a warp per image walks the candidates in score order: candidate i survives when its bit is clear in
+//                     the running `removed` set (K / 64 words spread over the lanes), then ORs row i into the set.  Rows
+//                     do not depend on the walk, so the rows of the next candidates are prefetched into L2.
+// Results are identical to nms_sorted_kernel (greedy NMS either way).
+// ---------------------------------------------------------------------------------------------------------------
+namespace msq {
+namespace {
+
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4 *__restrict__ boxes, const uint8_t *__restrict__ valid, int K, int words, float thr,
+                unsigned long long *__restrict__ mask /* (n, K, words) */) {
+    const int img = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;                                           // only later candidates can be suppressed
+    __shared__ float4 col[64];
+    __shared__ uint8_t col_ok[64];
+    const float4 *b = boxes + (size_t)img * K;
+    const uint8_t *v = valid + (size_t)img * K;
+    const int c = cb * 64 + threadIdx.x;
+    col[threadIdx.x] = c < K ? b[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    col_ok[threadIdx.x] = c < K ? v[c] : 0;
+    __syncthreads();
+    const int r = rb * 64 + threadIdx.x;
+    if (r >= K) return;
+    unsigned long long bits = 0ull;
+    if (v[r]) {
+        const float4 box = b[r];
+        const int start = cb == rb ? threadIdx.x + 1 : 0;
+        for (int j = start; j < 64; ++j)
+            if (col_ok[j] && iou_above(box, col[j], thr)) bits |= 1ull << j;
+    }
+    mask[((size_t)img * K + r) * words + cb] = bits;
+}
+
+__global__ void __launch_bounds__(kNmsWarps * 32)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, const uint8_t *__restrict__ valid, int n, int K, int words, int max_keep,
+                int *__restrict__ keep, int *__restrict__ count) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.x * kNmsWarps + warp;
+    if (img >= n) return;
+    const unsigned long long *m = mask + (size_t)img * K * words;
+    const uint8_t *v = valid + (size_t)img * K;
+    int *out = keep + (size_t)img * max_keep;
+    // lane l owns words l, l + 32, l + 64 (K <= 6144); row words left of the diagonal were never written: masked below
+    unsigned long long rem0 = 0ull, rem1 = 0ull, rem2 = 0ull;
+    int kc = 0;
+    for (int i = 0; i < K && kc < max_keep; ++i) {
+        const int w = i >> 6;
+        const unsigned long long word = w < 32 ? rem0 : (w < 64 ? rem1 : rem2);
+        const unsigned long long mine = __shfl_sync(0xffffffffu, word, w & 31);
+        if (i + 6 < K && lane < words) asm volatile("prefetch.global.L2 [%0];" :: "l"(m + (size_t)(i + 6) * words + lane));
+        if (!v[i] || ((mine >> (i & 63)) & 1ull)) continue;
+        if (lane == 0) out[kc] = i;
+        ++kc;
+        const unsigned long long *row = m + (size_t)i * words;
+        if (lane >= w && lane < words) rem0 |= row[lane];
+        if (lane + 32 >= w && lane + 32 < words) rem1 |= row[lane + 32];
+        if (lane + 64 >= w && lane + 64 < words) rem2 |= row[lane + 64];
+    }
+    for (int j = kc + lane; j < max_keep; j += 32) out[j] = -1;
+    if (lane == 0) count[img] = kc;
+}
+
+}  // namespace
+}  // namespace msq
+
+extern "C" size_t msq_nms_scratch_bytes(int n, int K) {
+    if (n <= 0 || K <= 0) return 0;
+    return (size_t)n * K * ((K + 63) / 64) * sizeof(unsigned long long);
+}
+
+extern "C" int msq_nms_sorted_long(const float *boxes, const uint8_t *valid, int n, int K, float iou_threshold, int max_keep,
+                                   int32_t *keep, int32_t *count, void *scratch, size_t scratch_bytes, void *stream) {
+    MSQ_REQUIRE(n >= 0 && K >= 0 && max_keep > 0, MSQ_EINVAL, "msq_nms_sorted_long: bad sizes n=%d K=%d max_keep=%d", n, K, max_keep);
+    if (n == 0) return MSQ_OK;
+    MSQ_REQUIRE(boxes && valid && keep && count && scratch, MSQ_EINVAL, "msq_nms_sorted_long: null pointer");
+    MSQ_REQUIRE((uintptr_t)boxes % 16 == 0 && (uintptr_t)scratch % 8 == 0, MSQ_EINVAL, "msq_nms_sorted_long: boxes must be 16-byte, scratch 8-byte aligned");
+    MSQ_REQUIRE(K <= 6144, MSQ_EUNSUPPORTED, "msq_nms_sorted_long: at most 6144 candidates per image (got %d)", K);
+    MSQ_REQUIRE(scratch_bytes >= msq_nms_scratch_bytes(n, K), MSQ_ENOMEM, "msq_nms_sorted_long: scratch too small");
+    const int words = (K + 63) / 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    TimedLaunch timed(K_DETECTOR_GLUE, st);
+    nms_mask_kernel<<<dim3(words, words, n), 64, 0, st>>>(reinterpret_cast<const float4 *>(boxes), valid, K, words, iou_threshold,
+                                                          static_cast<unsigned long long *>(scratch));
+    nms_scan_kernel<<<(n + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, 0, st>>>(static_cast<const unsigned long long *>(scratch), valid, n, K,
+                                                                                 words, max_keep, keep, count);
+    MSQ_LAUNCH_OK("nms_sorted_long");
+    return MSQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Keypoint decoding for a whole batch: torchvision's heatmaps_to_keypoints (the reference's detectron2 keypoint head does
 // the same) resizes every RoI's K heatmaps to the RoI's size with bicubic interpolation and takes the arg-max -- one
 // F.interpolate + arg-max + two host synchronisations per RoI.  Here one CTA per (RoI, keypoint) holds the heatmap in

@@ -390,6 +390,143 @@ detector_input_kernel(const uint8_t *__restrict__ in, T *__restrict__ out, int n
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The R-CNN's stem in one kernel: a3 intensity scaling -> (x - mean) / std -> zero padding -> 7x7 stride-2 convolution
+// (+ folded FrozenBN bias) -> ReLU -> 3x3 stride-2 max-pool, from the prepared uint8 chunk to the (n, 64, 64, 64)
+// channels-last input of res2 (ref: model/predict.py:74-77 replicates the grey channel three times; detectron2 BasicStem).
+// The three input channels are copies of one grey image and PIXEL_MEAN / PIXEL_STD are the same for all of them, so the
+// 3-channel convolution equals a 1-channel convolution with the weights summed over the input channels (K = 49 instead of
+// 147; exact algebra): cuDNN needs 2.9 ms + 0.9 ms (pool) per 250 frames for the 3-channel form, bound by the C = 3 layout.
+// Direct convolution on the FP32 pipe: a CTA owns 8x8 pooled pixels = 17x17 convolution outputs = a 39x39 input patch (kept
+// as even / odd column planes so that stride-2 reads are conflict-free); a warp owns 16 output channels (weights are warp
+// broadcasts) and half of the pixels, a thread 5 pixels x 16 channels = 80 accumulators.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kStemPool = 8;                         // pooled pixels per tile side
+constexpr int kStemConv = 2 * kStemPool + 1;         // 17 convolution outputs per tile side
+constexpr int kStemIn = 2 * (kStemConv - 1) + 7;     // 39 input pixels per tile side
+constexpr int kStemHalf = (kStemIn + 1) / 2;         // 20 columns per parity plane
+constexpr int kStemPix = kStemConv * kStemConv;      // 289
+constexpr int kStemPixPerThread = 5;
+constexpr int kStemCstride = 72;                     // channels per stored pixel (64 + padding against bank conflicts)
+
+template <typename T> struct StemStore;
+template <> struct StemStore<float> {
+    static __device__ __forceinline__ float make(float v) { return v; }
+    static __device__ __forceinline__ float get(float v) { return v; }
+};
+template <> struct StemStore<__nv_bfloat16> {
+    static __device__ __forceinline__ __nv_bfloat16 make(float v) { return __float2bfloat16_rn(v); }
+    static __device__ __forceinline__ float get(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_conv_pool_kernel(const uint8_t *__restrict__ in, int h, int w, int conv_h, int conv_w, int pool_h, int pool_w, int tiles_x,
+                      float mean, float stdv, double vmin, double vmax, int vmin_is_int, const float *__restrict__ w49x64,
+                      const float *__restrict__ bias64, T *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char stem_smem[];
+    float *wsm = reinterpret_cast<float *>(stem_smem);                         // [49][64]
+    float *even = wsm + 49 * 64;                                                // [39][20] input columns 0, 2, 4, ...
+    float *odd = even + kStemIn * kStemHalf;                                    // [39][20] input columns 1, 3, 5, ...
+    float *lutf = odd + kStemIn * kStemHalf;                                    // [256] normalised value of every grey level
+    T *conv = reinterpret_cast<T *>(lutf + 256);                                // [289][72]
+    __shared__ uint8_t lut8[256];
+    build_scale_lut(lut8, vmin, vmax, vmin_is_int);
+    for (int i = threadIdx.x; i < 256; i += 256) lutf[i] = ((float)lut8[i] - mean) / stdv;
+    for (int i = threadIdx.x; i < 49 * 64; i += 256) wsm[i] = w49x64[i];
+    __syncthreads();
+    const int img = blockIdx.y, ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int py0 = ty * kStemPool, px0 = tx * kStemPool;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;                             // first convolution output of the tile
+    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;                             // first input pixel of the tile
+    const uint8_t *src = in + (size_t)img * h * w;
+    for (int i = threadIdx.x; i < kStemIn * kStemIn; i += 256) {
+        const int j = i / kStemIn, k = i - j * kStemIn;
+        const int gy = iy0 + j, gx = ix0 + k;
+        const float v = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? lutf[src[(size_t)gy * w + gx]] : 0.f;   // padding is 0 after normalisation
+        ((k & 1) ? odd : even)[j * kStemHalf + (k >> 1)] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = (warp & 3) * 16;                                             // this warp's 16 output channels
+    const int pbase = (warp >> 2) * (kStemPixPerThread * 32);                   // pixels 0..159 / 160..319 (289 in use)
+    int off[kStemPixPerThread];
+#pragma unroll
+    for (int k = 0; k < kStemPixPerThread; ++k) {
+        const int p = min(pbase + k * 32 + lane, kStemPix - 1);
+        const int oy = p / kStemConv, ox = p - oy * kStemConv;
+        off[k] = 2 * oy * kStemHalf + ox;
+    }
+    float acc[kStemPixPerThread][16];
+#pragma unroll
+    for (int k = 0; k < kStemPixPerThread; ++k)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[k][c] = 0.f;
+#pragma unroll 1
+    for (int r = 0; r < 7; ++r) {
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const float *plane = (t & 1) ? odd : even;
+            const int shift = r * kStemHalf + (t >> 1);
+            float xin[kStemPixPerThread];
+#pragma unroll
+            for (int k = 0; k < kStemPixPerThread; ++k) xin[k] = plane[off[k] + shift];
+            const float4 *wv = reinterpret_cast<const float4 *>(wsm + (r * 7 + t) * 64 + cg);
+            float wt[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 v4 = wv[q]; wt[4 * q] = v4.x; wt[4 * q + 1] = v4.y; wt[4 * q + 2] = v4.z; wt[4 * q + 3] = v4.w; }
+#pragma unroll
+            for (int k = 0; k < kStemPixPerThread; ++k)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[k][c] = fmaf(xin[k], wt[c], acc[k][c]);
+        }
+    }
+    // bias + ReLU; convolution outputs outside the map count as 0 (every pool window holds a real output, and those are >= 0)
+#pragma unroll
+    for (int k = 0; k < kStemPixPerThread; ++k) {
+        const int p = pbase + k * 32 + lane;
+        if (p >= kStemPix) continue;
+        const int oy = p / kStemConv, ox = p - oy * kStemConv;
+        const int gy = cy0 + oy, gx = cx0 + ox;
+        const bool inside = gy >= 0 && gy < conv_h && gx >= 0 && gx < conv_w;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            conv[p * kStemCstride + cg + c] = StemStore<T>::make(inside ? fmaxf(acc[k][c] + bias64[cg + c], 0.f) : 0.f);
+    }
+    __syncthreads();
+    // 3x3 stride-2 max-pool of the tile, 8 channels per thread, written as contiguous channels-last rows
+    for (int i = threadIdx.x; i < kStemPool * kStemPool * 8; i += 256) {
+        const int v = i & 7, pp = i >> 3, py = pp / kStemPool, px = pp - py * kStemPool;
+        const int gy = py0 + py, gx = px0 + px;
+        if (gy >= pool_h || gx >= pool_w) continue;
+        float m[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[c] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const T *cp = conv + ((2 * py + dy) * kStemConv + 2 * px + dx) * kStemCstride + v * 8;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) m[c] = fmaxf(m[c], StemStore<T>::get(cp[c]));
+            }
+        T *dst = out + (((size_t)img * pool_h + gy) * pool_w + gx) * 64 + v * 8;
+        if constexpr (sizeof(T) == 2) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(m[2 * c], m[2 * c + 1]);
+                pk[c] = *reinterpret_cast<const uint32_t *>(&h2);
+            }
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {
+            *reinterpret_cast<float4 *>(dst) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(m[4], m[5], m[6], m[7]);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace msq
 
@@ -418,6 +555,35 @@ extern "C" int msq_detector_input(const uint8_t *in, void *out, int out_is_bf16,
         detector_input_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<float *>(out), n, h, w, oh, ow, ph, pw, norm,
                                                                                vmin, vmax, vmin_is_int);
     MSQ_LAUNCH_OK("detector_input");
+    return MSQ_OK;
+}
+
+extern "C" int msq_stem_conv_pool(const uint8_t *in, int n, int h, int w, int ph, int pw, double vmin, double vmax, int vmin_is_int,
+                                  float mean, float stdv, const float *w49x64, const float *bias64, void *out, int out_is_bf16,
+                                  void *stream) {
+    MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && ph >= h && pw >= w, MSQ_EINVAL, "msq_stem_conv_pool: bad sizes n=%d %dx%d in %dx%d", n, h, w, ph, pw);
+    MSQ_REQUIRE(vmax != vmin && stdv != 0.f, MSQ_EINVAL, "msq_stem_conv_pool: vmax == vmin or std == 0");
+    if (n == 0) return MSQ_OK;
+    MSQ_REQUIRE(in && w49x64 && bias64 && out, MSQ_EINVAL, "msq_stem_conv_pool: null pointer");
+    MSQ_REQUIRE((uintptr_t)out % 16 == 0, MSQ_EINVAL, "msq_stem_conv_pool: output must be 16-byte aligned");
+    const int conv_h = (ph + 6 - 7) / 2 + 1, conv_w = (pw + 6 - 7) / 2 + 1;
+    const int pool_h = (conv_h + 2 - 3) / 2 + 1, pool_w = (conv_w + 2 - 3) / 2 + 1;
+    const int tiles_x = (pool_w + kStemPool - 1) / kStemPool, tiles_y = (pool_h + kStemPool - 1) / kStemPool;
+    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_stem_conv_pool: at most 65535 frames per call (got %d)", n);
+    const size_t fixed = (size_t)(49 * 64 + 2 * kStemIn * kStemHalf + 256) * sizeof(float);
+    const size_t smem = fixed + (size_t)kStemPix * kStemCstride * (out_is_bf16 ? 2 : 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    TimedLaunch timed(K_DETECTOR_GLUE, st);
+    if (out_is_bf16) {
+        MSQ_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv_pool_kernel<__nv_bfloat16><<<dim3(tiles_x * tiles_y, n), 256, smem, st>>>(in, h, w, conv_h, conv_w, pool_h, pool_w, tiles_x, mean,
+            stdv, vmin, vmax, vmin_is_int, w49x64, bias64, static_cast<__nv_bfloat16 *>(out));
+    } else {
+        MSQ_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv_pool_kernel<float><<<dim3(tiles_x * tiles_y, n), 256, smem, st>>>(in, h, w, conv_h, conv_w, pool_h, pool_w, tiles_x, mean, stdv,
+            vmin, vmax, vmin_is_int, w49x64, bias64, static_cast<float *>(out));
+    }
+    MSQ_LAUNCH_OK("stem_conv_pool");
     return MSQ_OK;
 }
 

@@ -20,6 +20,8 @@ from .. import _dev, _lib
 _LIB = torch.library.Library('msq', 'DEF')
 _LIB.define('detector_input(Tensor chunk_u8, float vmin, float vmax, bool int_limits, float[] mean, float[] std, int ph, int pw, '
             'bool bf16) -> Tensor')
+_LIB.define('stem_conv_pool(Tensor chunk_u8, float vmin, float vmax, bool int_limits, float mean, float std, int ph, int pw, '
+            'Tensor w49x64, Tensor bias64, bool bf16) -> Tensor')
 _LIB.define('conv2d(Tensor x, Tensor w, Tensor? b, Tensor? z, bool relu, int stride, int pad) -> Tensor')
 _LIB.define('linear(Tensor x, Tensor w, Tensor? b, bool relu) -> Tensor')
 _LIB.define('group_norm_nhwc(Tensor x, Tensor gamma, Tensor beta, int groups, float eps, Tensor? top, float scale) -> Tensor')
@@ -52,6 +54,17 @@ def _detector_input(chunk_u8, vmin, vmax, int_limits, mean, std, ph, pw, bf16):
               (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std]),
               float(vmin), float(vmax), int(int_limits), _dev.stream())
     return x
+
+
+def _stem_conv_pool(chunk_u8, vmin, vmax, int_limits, mean, std, ph, pw, w49x64, bias64, bf16):
+    n, h, w = (int(v) for v in chunk_u8.shape)
+    conv_h, conv_w = (ph - 1) // 2 + 1, (pw - 1) // 2 + 1
+    pool_h, pool_w = (conv_h - 1) // 2 + 1, (conv_w - 1) // 2 + 1
+    out = torch.empty((n, 64, pool_h, pool_w), dtype=torch.bfloat16 if bf16 else torch.float32, device=chunk_u8.device,
+                      memory_format=torch.channels_last)
+    _lib.call('msq_stem_conv_pool', _dev.ptr(chunk_u8.contiguous()), n, h, w, int(ph), int(pw), float(vmin), float(vmax), int(int_limits),
+              float(mean), float(std), _dev.ptr(w49x64), _dev.ptr(bias64), _dev.ptr(out), int(bf16), _dev.stream())
+    return out
 
 
 # ---- dense contractions -------------------------------------------------------------------------------------------------
@@ -187,8 +200,15 @@ def _rpn_proposals(preds, strides, sizes, ratios, img_h, img_w, pre_topk, post_t
     K = int(boxes.shape[1])
     keep = torch.empty((n, int(post_topk)), dtype=torch.int32, device=dev)
     count = torch.empty((n,), dtype=torch.int32, device=dev)
-    _lib.call('msq_nms_sorted', _dev.ptr(shifted), _dev.ptr(valid.to(torch.uint8).contiguous()), n, K, float(nms_thresh), int(post_topk),
-              _dev.ptr(keep), _dev.ptr(count), _dev.stream())
+    valid_u8 = valid.to(torch.uint8).contiguous()
+    if int(post_topk) > 128 and K <= 6144:       # long keep lists: overlap matrix as bit rows + one ordered walk per image
+        nbytes = int(_lib.load().msq_nms_scratch_bytes(n, K))
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        _lib.call('msq_nms_sorted_long', _dev.ptr(shifted), _dev.ptr(valid_u8), n, K, float(nms_thresh), int(post_topk), _dev.ptr(keep),
+                  _dev.ptr(count), _dev.ptr(scratch), nbytes, _dev.stream())
+    else:
+        _lib.call('msq_nms_sorted', _dev.ptr(shifted), _dev.ptr(valid_u8), n, K, float(nms_thresh), int(post_topk), _dev.ptr(keep),
+                  _dev.ptr(count), _dev.stream())
     ok = keep >= 0
     idx = keep.clamp(min=0).long()
     out_boxes = torch.gather(boxes, 1, idx[..., None].expand(-1, -1, 4)) * ok[..., None]
@@ -239,7 +259,7 @@ def _keypoints_from_heatmaps_d2(heatmaps, boxes):
     return xyp
 
 
-for _name, _fn in (('detector_input', _detector_input), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
+for _name, _fn in (('detector_input', _detector_input), ('stem_conv_pool', _stem_conv_pool), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
                    ('rpn_proposals', _rpn_proposals), ('roi_align_v2', _roi_align_v2), ('fastrcnn_top1', _fastrcnn_top1),
                    ('keypoints_from_heatmaps_d2', _keypoints_from_heatmaps_d2)):
     _LIB.impl(_name, _fn, 'CUDA')

@@ -105,6 +105,11 @@ class MoseqRCNN(nn.Module):
         self.pool_scales: List[float] = [1.0 / 4, 1.0 / 8, 1.0 / 16, 1.0 / 32]
         # ---- bottom-up ResNet-50 ----
         self.stem = ConvBias(3, 64, 7, stride=2, pad=3, relu=True)
+        # grey input replicated to 3 channels + channel-uniform mean / std: the stem is a 1-channel convolution (K = 49) and runs
+        # fused with the input staging and the max-pool (csrc/prep.cu stem_conv_pool_kernel); buffers filled by finalize()
+        self.stem_uniform = len(set(self.pixel_mean)) == 1 and len(set(self.pixel_std)) == 1
+        self.register_buffer('stem_w49', torch.zeros((49, 64)))
+        self.register_buffer('stem_b64', torch.zeros((64,)))
         self.res2 = _stage(64, 64, 256, 3, 1)
         self.res3 = _stage(256, 128, 512, 4, 2)
         self.res4 = _stage(512, 256, 1024, 6, 2)
@@ -157,7 +162,11 @@ class MoseqRCNN(nn.Module):
     def backbone(self, x: Tensor) -> List[Tensor]:
         """x (n, 3, H, W) normalised, padded, channels-last, compute dtype -> [p2, p3, p4, p5, p6]."""
         x = self.stem(x)
-        x = torch.max_pool2d(x, 3, 2, 1)
+        x = torch.max_pool2d(x, [3, 3], [2, 2], [1, 1])
+        return self.pyramid(x)
+
+    def pyramid(self, x: Tensor) -> List[Tensor]:
+        """x (n, 64, H/4, W/4): the pooled stem output -> [p2, p3, p4, p5, p6]."""
         c2 = self.res2(x)
         c3 = self.res3(c2)
         c4 = self.res4(c3)
@@ -170,7 +179,7 @@ class MoseqRCNN(nn.Module):
         p4 = self.output4(i4, None, 1.0)
         p3 = self.output3(i3, None, 1.0)
         p2 = self.output2(i2, None, 1.0)
-        p6 = torch.max_pool2d(p5, 1, 2, 0)                                    # LastLevelMaxPool
+        p6 = torch.max_pool2d(p5, [1, 1], [2, 2], [0, 0])                                    # LastLevelMaxPool
         return [p2, p3, p4, p5, p6]
 
     def rpn(self, feats: List[Tensor], img_h: int, img_w: int) -> Tuple[Tensor, Tensor, Tensor]:
@@ -203,7 +212,9 @@ class MoseqRCNN(nn.Module):
         return torch.ops.msq.keypoints_from_heatmaps_d2(heat, boxes), heat
 
     def detect(self, x: Tensor, img_h: int, img_w: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-        feats = self.backbone(x)
+        return self.detect_from_pyramid(self.backbone(x), img_h, img_w)
+
+    def detect_from_pyramid(self, feats: List[Tensor], img_h: int, img_w: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
         proposals, _, counts = self.rpn(feats, img_h, img_w)
         boxes, scores, has = self.box_head(feats, proposals, counts, img_h, img_w)
         soft = self.mask_head(feats, boxes)
@@ -219,6 +230,10 @@ class MoseqRCNN(nn.Module):
         h, w = chunk_u8.shape[1], chunk_u8.shape[2]
         d = self.size_divisibility
         ph, pw = (h + d - 1) // d * d, (w + d - 1) // d * d
+        if self.stem_uniform:
+            x = torch.ops.msq.stem_conv_pool(chunk_u8, vmin, vmax, int_limits, self.pixel_mean[0], self.pixel_std[0], ph, pw, self.stem_w49,
+                                             self.stem_b64, self._compute_bf16())
+            return self.detect_from_pyramid(self.pyramid(x), h, w)
         x = torch.ops.msq.detector_input(chunk_u8, vmin, vmax, int_limits, self.pixel_mean, self.pixel_std, ph, pw, self._compute_bf16())
         return self.detect(x, h, w)
 
@@ -261,6 +276,9 @@ def finalize(model: MoseqRCNN, dtype: torch.dtype, device: str) -> MoseqRCNN:
     """Move to `device`, cast every dense-contraction operand to the compute dtype (GroupNorm affine stays float32) and put
     the convolution weights in channels-last memory."""
     model = model.to(device).eval()
+    with torch.no_grad():       # 1-channel form of the stem (float32 whatever the compute dtype): weights summed over the input channels
+        model.stem_w49 = model.stem.weight.detach().float().sum(dim=1).permute(1, 2, 0).reshape(49, 64).contiguous()
+        model.stem_b64 = model.stem.bias.detach().float().contiguous()
     for name, p in model.named_parameters():
         if name.endswith('gamma') or name.endswith('beta'):
             p.data = p.data.float().contiguous()
