@@ -153,10 +153,55 @@ struct RoiPyramid {
     int n_levels;
 };
 
+// One axis of torchvision's roi_align_forward_kernel_impl (aligned = true) for pooled bin `p`: the `grid` sample positions
+// start + p * bin + (i + .5) * bin / grid, each bilinear between two neighbouring rows (columns).  Bilinear weights are products
+// of a row term and a column term and the samples form a product grid, so the pooled value is
+//     out[ph][pw] = sum_rows sum_cols WY[ph][row] * WX[pw][col] * F[row][col]
+// with per-axis weights that already hold the 1 / grid of the average.  Rows touched by one bin are consecutive: (first, count).
+constexpr int kRoiMaxTaps = 12;
+struct AxisTaps {
+    int first, count;
+    float w[kRoiMaxTaps];
+};
+
+__device__ __forceinline__ bool build_axis_taps(float start, float bin, int p, int grid, int size, AxisTaps &t) {
+    t.first = 0; t.count = 0;
+    int lo = INT_MAX, hi = -1;
+    for (int i = 0; i < grid; ++i) {                                  // extent first
+        float y = start + p * bin + ((float)i + .5f) * bin / (float)grid;
+        if (y < -1.0f || y > (float)size) continue;
+        if (y <= 0.f) y = 0.f;
+        int y_low = (int)y, y_high;
+        if (y_low >= size - 1) { y_high = y_low = size - 1; } else y_high = y_low + 1;
+        lo = min(lo, y_low); hi = max(hi, y_high);
+    }
+    if (hi < 0) return true;                                          // every sample outside: the bin is 0
+    if (hi - lo + 1 > kRoiMaxTaps) return false;
+    t.first = lo; t.count = hi - lo + 1;
+#pragma unroll
+    for (int k = 0; k < kRoiMaxTaps; ++k) t.w[k] = 0.f;
+    const float inv = 1.f / (float)grid;
+    for (int i = 0; i < grid; ++i) {
+        float y = start + p * bin + ((float)i + .5f) * bin / (float)grid;
+        if (y < -1.0f || y > (float)size) continue;
+        if (y <= 0.f) y = 0.f;
+        int y_low = (int)y, y_high;
+        if (y_low >= size - 1) { y_high = y_low = size - 1; y = (float)y_low; } else y_high = y_low + 1;
+        const float l = y - y_low, h = 1.f - l;
+        t.w[y_low - lo] += h * inv;
+        t.w[y_high - lo] += l * inv;
+    }
+    return true;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRoiThreads)
 roi_align_v2_kernel(RoiPyramid pyr, int C, const float *__restrict__ boxes, int rois_per_image, int P, int sampling_ratio,
                     int min_level, int canonical_level, float canonical_size, T *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char roi_smem[];
+    AxisTaps *taps_y = reinterpret_cast<AxisTaps *>(roi_smem);       // [P]
+    AxisTaps *taps_x = taps_y + P;                                    // [P]
+    __shared__ int s_direct;
     const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 b = *reinterpret_cast<const float4 *>(boxes + (size_t)r * 4);
     // detectron2.modeling.poolers.assign_boxes_to_levels
@@ -165,8 +210,8 @@ roi_align_v2_kernel(RoiPyramid pyr, int C, const float *__restrict__ boxes, int 
         const float size = sqrtf((b.z - b.x) * (b.w - b.y));
         const float l = floorf((float)canonical_level + log2f(size / canonical_size + 1e-8f));
         const float lo = (float)min_level, hi = (float)(min_level + pyr.n_levels - 1);
-        lvl = (int)fminf(fmaxf(l, lo), hi) - min_level;           // NaN sizes (degenerate boxes) land on the lowest level
-        if (!(l == l)) lvl = 0;
+        lvl = (int)fminf(fmaxf(l, lo), hi) - min_level;
+        if (!(l == l)) lvl = 0;                                       // NaN sizes (degenerate boxes) land on the lowest level
     }
     const int H = pyr.H[lvl], W = pyr.W[lvl];
     const float scale = pyr.scale[lvl];
@@ -177,9 +222,45 @@ roi_align_v2_kernel(RoiPyramid pyr, int C, const float *__restrict__ boxes, int 
     const float bin_h = roi_h / (float)P, bin_w = roi_w / (float)P;
     const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_h / (float)P);
     const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_w / (float)P);
-    const float count = (float)max(gh * gw, 1);
+    if (threadIdx.x == 0) s_direct = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * P) {
+        const bool is_y = (int)threadIdx.x < P;
+        const int p = is_y ? threadIdx.x : threadIdx.x - P;
+        AxisTaps t;
+        const bool ok = is_y ? build_axis_taps(y0, bin_h, p, gh, H, t) : build_axis_taps(x0, bin_w, p, gw, W, t);
+        if (!ok) s_direct = 1;
+        (is_y ? taps_y : taps_x)[p] = t;
+    }
+    __syncthreads();
     const int bins = P * P, vecs = C >> 3;
     T *dst = out + (size_t)r * bins * C;
+    if (!s_direct) {
+        for (int bin = warp; bin < bins; bin += kRoiThreads / 32) {
+            const int ph = bin / P, pw = bin - ph * P;
+            const AxisTaps &ty = taps_y[ph], &tx = taps_x[pw];
+            for (int v = lane; v < vecs; v += 32) {
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+                for (int j = 0; j < ty.count; ++j) {
+                    const float wy = ty.w[j];
+                    const T *row = feat + ((size_t)(ty.first + j) * W + tx.first) * C + v * 8;
+                    for (int i = 0; i < tx.count; ++i) {
+                        const float wgt = wy * tx.w[i];
+                        float val[8];
+                        Ch8<T>::load(row + (size_t)i * C, val);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] = __fmaf_rn(wgt, val[k], acc[k]);
+                    }
+                }
+                Ch8<T>::store(dst + (size_t)bin * C + v * 8, acc);
+            }
+        }
+        return;
+    }
+    // very elongated boxes (more than kRoiMaxTaps rows under one bin): sample by sample, as torchvision loops
+    const float count = (float)max(gh * gw, 1);
     for (int bin = warp; bin < bins; bin += kRoiThreads / 32) {
         const int ph = bin / P, pw = bin - ph * P;
         for (int v = lane; v < vecs; v += 32) {
@@ -416,12 +497,14 @@ extern "C" int msq_roi_align_v2(const void *const *feat_dev, const int *heights,
         pyr.feat[l] = feat_dev[l]; pyr.H[l] = heights[l]; pyr.W[l] = widths[l]; pyr.scale[l] = scales[l];
     }
     cudaStream_t st = (cudaStream_t)stream;
+    MSQ_REQUIRE(2 * P <= kRoiThreads && (size_t)2 * P * sizeof(AxisTaps) <= 48 * 1024, MSQ_EUNSUPPORTED, "msq_roi_align_v2: pooled size %d is too large", P);
+    const size_t taps_smem = (size_t)2 * P * sizeof(AxisTaps);
     TimedLaunch timed(K_DETECTOR_GLUE, st);
     if (is_bf16)
-        roi_align_v2_kernel<__nv_bfloat16><<<n_rois, kRoiThreads, 0, st>>>(pyr, C, boxes_dev, rois_per_image, P, sampling_ratio, min_level,
+        roi_align_v2_kernel<__nv_bfloat16><<<n_rois, kRoiThreads, taps_smem, st>>>(pyr, C, boxes_dev, rois_per_image, P, sampling_ratio, min_level,
                                                                           canonical_level, canonical_size, static_cast<__nv_bfloat16 *>(out_dev));
     else
-        roi_align_v2_kernel<float><<<n_rois, kRoiThreads, 0, st>>>(pyr, C, boxes_dev, rois_per_image, P, sampling_ratio, min_level,
+        roi_align_v2_kernel<float><<<n_rois, kRoiThreads, taps_smem, st>>>(pyr, C, boxes_dev, rois_per_image, P, sampling_ratio, min_level,
                                                                   canonical_level, canonical_size, static_cast<float *>(out_dev));
     MSQ_LAUNCH_OK("roi_align_v2");
     return MSQ_OK;

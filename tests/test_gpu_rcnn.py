@@ -89,6 +89,7 @@ def test_roi_align_v2_matches_detectron2_pooler(dtype, pooled):
         b[3] = torch.tensor([200., 10., 240., 200.])
         b[4] = torch.tensor([10., 20., 130., 150.])                                            # level 3 (112 <= sqrt(area) < 224)
         b[5] = torch.tensor([100., 100., 170., 180.])                                          # level 2
+        b[6] = torch.tensor([0., 100., 240., 140.])                                            # elongated: > 12 columns under one bin
         boxes.append(b)
     want = D.roi_pooler([f.float() for f in feats], boxes, pooled)
     got = msq.roi_align_v2(feats, [1 / 4, 1 / 8, 1 / 16, 1 / 32], torch.cat(boxes), k, pooled, 0, 2, 4, 224.0)
@@ -96,9 +97,10 @@ def test_roi_align_v2_matches_detectron2_pooler(dtype, pooled):
     assert len(set(D.assign_boxes_to_levels(torch.cat(boxes)).tolist())) >= 3
     scale = max(1.0, float(want.abs().max()))
     if dtype == torch.float32:
-        # torchvision's kernel contracts multiply-adds nvcc's way; sample positions agree to an ulp of float32
+        # same samples and bilinear weights as torchvision's kernel, summed per row / column instead of per sample (the
+        # weights factorise): float32 rounding differs in the last bits
         assert float((got - want).abs().max()) <= 2e-4 * scale
-        assert float(((got - want).abs() <= 4e-6 * scale).float().mean()) > 0.99
+        assert float(((got - want).abs() <= 1e-5 * scale).float().mean()) > 0.99
     else:
         ref = want.to(torch.bfloat16)
         assert float((got == ref).float().mean()) > 0.99
@@ -127,7 +129,8 @@ def test_fastrcnn_top1_matches_detectron2_inference():
         if len(wb):
             assert torch.allclose(box[i], wb[0], rtol=1e-5, atol=1e-4) and abs(float(score[i]) - float(ws[0])) <= 1e-6
         else:
-            assert i == 4 and float(box[i].abs().sum()) == 0
+            assert float(box[i].abs().sum()) == 0 and float(score[i]) == 0
+    assert int(has[4]) == 0 and int(has[:4].sum()) == 4
 
 
 def test_keypoint_decode_matches_detectron2():

@@ -46,6 +46,8 @@ with torch.no_grad():
     c5 = timed('res5', lambda: model.res5(c4))
     feats = timed('backbone_total(stem..fpn)', lambda: model.backbone(x))
     times['fpn'] = times['backbone_total(stem..fpn)'] - sum(times[k] for k in ('stem', 'maxpool', 'res2', 'res3', 'res4', 'res5'))
+    timed('fused_stem(input+conv+relu+pool)', lambda: msq.stem_conv_pool(prep, 0.0, 100.0, True, model.pixel_mean[0], model.pixel_std[0], 256, 256,
+                                                                          model.stem_w49, model.stem_b64, True))
     preds = timed('rpn_head_convs', lambda: [model.rpn_pred(model.rpn_conv(f)) for f in feats])
     props = timed('rpn_proposals(topk+decode+nms)', lambda: msq.rpn_proposals(preds, model.anchor_strides, model.anchor_sizes, model.anchor_ratios,
                                                                              240, 240, model.pre_nms_topk, model.post_nms_topk, 0.7))
