@@ -1,12 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the extract hot path (BASELINE.json metric: extract frames/s + kernel HBM GB/s vs peak).
 
-Workload (config.workload): BASELINE.json configs[1] -- preprocess + crop/rotate kernels only (no R-CNN) on a
-30-minute synthetic session (54,000 Kinect-v2-shaped 512x424 int16 frames, ROI box 240x240, 80x80 crops,
-1000-frame chunks, use_tracking=False; instance masks + keypoints given).  One "step" = one pass over the whole
-session.  `value` = frames/s with the session resident in HBM; `e2e` = the same metric with HOST (pinned) frames,
-masks and keypoints copied to the GPU and the results (crops, scalars, keypoint table, flips) copied back inside
-the timed region.  Under torchrun every rank extracts its own session (weak scaling, no collective).
+Headline workload (config.workload): BASELINE.json configs[1] -- preprocess + crop/rotate kernels only (no R-CNN) on a
+30-minute synthetic session (54,000 Kinect-v2-shaped 512x424 int16 frames, ROI box 240x240, 80x80 crops, 1000-frame chunks,
+use_tracking=False; instance masks + keypoints given).  One "step" = one pass over the whole session.  `value` = frames/s
+with the session resident in HBM; `e2e` = the same metric with HOST (pinned) frames, bit-packed masks and keypoints copied
+to the GPU and the results (crops, scalars, keypoint table, flips) copied back inside the timed region, the host frames
+cycling through a pool far larger than any CPU cache.  Under torchrun the global chunk list (N sessions) is sharded
+contiguously over the ranks (shard.shard_chunks; weak scaling, no collective).
+
+Further measured workloads carried in the same JSON line (each with its own e2e / roofline):
+  full_extract_rcnn        BASELINE configs[2]: prep -> the repo's own detectron2-configuration Keypoint/Mask R-CNN (bf16, the
+                           reference's 1000 test proposals) -> paste -> features -> crops, >= 20 chunks
+  full_extract_rcnn_topk100  the same graph exported with RPN.POST_NMS_TOPK_TEST = 100
+  azure                    BASELINE configs[4] geometry: 640x576 frames, 400x400 ROI box, 128x128 crops
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -25,6 +32,7 @@ for p in (ROOT, os.path.join(ROOT, 'oracle')):
 
 METRIC = 'extract_frames_per_s'
 UNIT = 'frames/s'
+CHUNK = 1000
 
 
 def parse_args():
@@ -36,12 +44,15 @@ def parse_args():
     ap.add_argument('--frames', type=int, default=54000, help='frames per session (per GPU)')
     ap.add_argument('--launch-chunks', type=int, default=6, help='1000-frame chunks processed per kernel launch')
     ap.add_argument('--pool-frames', type=int, default=1000, help='distinct synthetic frames generated on the host')
+    ap.add_argument('--host-pool-gb', type=float, default=6.0, help='pinned host frame pool the end-to-end pass cycles through (per rank)')
     ap.add_argument('--geometry', default='kinect_v2', choices=['kinect_v2', 'azure'])
     ap.add_argument('--cpu-frames-per-worker', type=int, default=250)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--rcnn-frames', type=int, default=2000, help='frames for the secondary full-extract (R-CNN) figure; 0 = skip')
+    ap.add_argument('--rcnn-frames', type=int, default=20000, help='frames of the full-extract (R-CNN) workloads; 0 = skip')
     ap.add_argument('--rcnn-batch', type=int, default=500)
+    ap.add_argument('--azure-frames', type=int, default=12000, help='frames of the Azure-geometry workload; 0 = skip')
+    ap.add_argument('--no-secondary', action='store_true', help='skip in-painting / tracking side figures')
     return ap.parse_args()
 
 
@@ -49,8 +60,8 @@ def workload_config(args, geom, n_gpus):
     return {
         'workload': f'configs[1]: prep + clean + features + angles/flips/filter + scalars/keypoints + crop/rotate, no R-CNN, '
                     f'{args.frames}-frame synthetic session per GPU',
-        'frame': f'{geom.width}x{geom.height} int16', 'roi_box': None, 'crop': list(geom.crop_size), 'chunk_size': 1000,
-        'frames_per_session': args.frames, 'sessions': n_gpus, 'frames_per_launch': args.launch_chunks * 1000,
+        'frame': f'{geom.width}x{geom.height} int16', 'roi_box': None, 'crop': list(geom.crop_size), 'chunk_size': CHUNK,
+        'frames_per_session': args.frames, 'sessions': n_gpus, 'frames_per_launch': args.launch_chunks * CHUNK,
         'use_tracking': False, 'parallelism': f'chunk-sharded x{n_gpus}, no collective',
         'l2_policy': 'inputs (23 GB session) far larger than the 126 MB L2; every frame is read from HBM once per step',
     }
@@ -160,7 +171,234 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# one geometry's no-R-CNN workload: resident pass + end-to-end pass (used for Kinect-v2 and Azure)
+# ------------------------------------------------------------------------------------------------
+class ExtractWorkload:
+    """The configs[1] work for one sensor geometry on this rank's GPU: synthetic session resident in HBM, and the 4-stream
+    host -> GPU -> host pipeline."""
+
+    def __init__(self, args, geom, n_frames, rank, world, host_pool_gb):
+        import numpy as np
+        import torch
+        from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+        from moseq2_detectron_extract_b200.engine import ChunkEngine
+        from moseq2_detectron_extract_b200.shard import shard_chunks
+        self.args, self.geom, self.n_frames, self.rank, self.world = args, geom, n_frames, rank, world
+        self.torch, self._dev, self._lib, self.ChunkEngine = torch, _dev, _lib, ChunkEngine
+        self.cfg = synthetic.default_config(geom)
+        roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+        self.roi_np, self.bg_np = roi, bg
+        self.y0, self.x0, y1, x1 = synthetic.roi_bbox(roi)
+        self.h, self.w = y1 - self.y0, x1 - self.x0
+        self.H, self.W = geom.height, geom.width
+        self.launch = args.launch_chunks * CHUNK
+        # this rank's chunks of the global job (world sessions of n_frames each, sharded contiguously by chunk)
+        per_session = (n_frames + CHUNK - 1) // CHUNK
+        self.my_chunks = shard_chunks(per_session * world, rank, world)
+        # ---- synthetic session: `pool` distinct frames generated on the host, cycled (with a per-chunk roll) on the GPU
+        npool = min(args.pool_frames, n_frames)
+        pool = synthetic.generate_chunk(npool, seed=rank, geom=geom, t0=0)
+        self.npool = npool
+        self.pool_frames = torch.from_numpy(pool.frames).pin_memory()
+        self.pool_masks = torch.from_numpy(pool.masks).pin_memory()
+        self.pool_bits = torch.from_numpy(np.packbits(pool.masks, axis=-1, bitorder='little')).pin_memory()
+        self.pool_kpts = torch.from_numpy(pool.keypoints).pin_memory()
+        # compulsory bytes of the masked sums: the mask, plus the frame bytes under 16-pixel groups that carry a mask byte
+        groups = pool.masks.reshape(npool, -1)
+        groups = groups[:, : groups.shape[1] // 16 * 16].reshape(npool, -1, 16).any(axis=2).mean()
+        self.masked_group_fraction = float(groups)
+        d_pool_f, d_pool_m, d_pool_k = self.pool_frames.cuda(), self.pool_masks.cuda(), self.pool_kpts.cuda()
+        idx = torch.cat([(torch.arange(min(CHUNK, n_frames - c), device='cuda') + 37 * (self.my_chunks.start + c // CHUNK)) % npool
+                         for c in range(0, n_frames, CHUNK)])
+        self.frames = torch.empty((n_frames, self.H, self.W), dtype=torch.int16, device='cuda')
+        for s in range(0, n_frames, 2000):
+            self.frames[s:s + 2000] = d_pool_f[idx[s:s + 2000]]
+        self.masks = d_pool_m[idx].contiguous()
+        self.kpts = d_pool_k[idx].contiguous()
+        del d_pool_f, d_pool_m, d_pool_k
+        self.bg_d, self.roi_d = _dev.as_device(bg), _dev.as_device(roi.astype(np.uint8))
+        self.prep_buf = _dev.empty((self.launch, self.h, self.w), torch.uint8)
+        self.invalid = _dev.empty((self.launch,), torch.int32)
+        self.engine = ChunkEngine()
+        self.kw = dict(chunk_size=CHUNK, min_height=self.cfg['min_height'], max_height=self.cfg['max_height'],
+                       true_depth=self.cfg['true_depth'], crop_size=self.cfg['crop_size'])
+        self.flags = _lib.MSQ_PREP_HAS_VMIN | _lib.MSQ_PREP_HAS_VMAX
+        self.host_pool = None
+        self.host_pool_gb = host_pool_gb
+
+    def prep(self, src, n, out, invalid, stream=None):
+        _dev, _lib = self._dev, self._lib
+        _lib.call('msq_prep_frames', _dev.ptr(src), n, self.H, self.W, _dev.ptr(self.bg_d), _lib.MSQ_BG_F32, _dev.ptr(self.roi_d),
+                  self.y0, self.x0, self.h, self.w, float(self.cfg['min_height']), float(self.cfg['max_height']), self.flags,
+                  _dev.ptr(out), _dev.ptr(invalid), None, stream if stream is not None else _dev.stream())
+
+    def resident_step(self):
+        for s in range(0, self.n_frames, self.launch):
+            n = min(self.launch, self.n_frames - s)
+            self.prep(self.frames[s:s + n], n, self.prep_buf, self.invalid)
+            self.engine.extract(self.prep_buf[:n], self.masks[s:s + n], self.kpts[s:s + n], **self.kw)
+
+    # ---- end to end ---------------------------------------------------------------------------------------------
+    def build_host_pool(self):
+        """A pinned host frame pool far larger than any CPU cache (the chunks of an e2e pass walk through it), filled with
+        rolled copies of the distinct synthetic frames."""
+        torch = self.torch
+        frame_bytes = self.H * self.W * 2
+        n_pool_chunks = max(1, min(int(self.host_pool_gb * 1e9 / (frame_bytes * CHUNK)), (self.n_frames + CHUNK - 1) // CHUNK))
+        if self.npool < CHUNK:
+            n_pool_chunks = 1
+        self.host_pool = torch.empty((n_pool_chunks, min(CHUNK, self.npool), self.H, self.W), dtype=torch.int16, pin_memory=True)
+        for c in range(n_pool_chunks):
+            self.host_pool[c].copy_(self.pool_frames[:self.host_pool.shape[1]])
+        return self.host_pool.numel() * 2
+
+    def h2d_bandwidth(self, repeats=3):
+        """Plain pinned host -> device copy rate of this rank (GB/s) over the e2e pool, CUDA events."""
+        torch = self.torch
+        dst = torch.empty_like(self.host_pool[0], device='cuda')
+        dst.copy_(self.host_pool[0], non_blocking=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nbytes = 0
+        a.record()
+        for _ in range(repeats):
+            for c in range(self.host_pool.shape[0]):
+                dst.copy_(self.host_pool[c], non_blocking=True)
+                nbytes += dst.numel() * 2
+        b.record()
+        torch.cuda.synchronize()
+        return nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
+
+    def setup_e2e(self):
+        torch, _dev, _lib = self.torch, self._dev, self._lib
+        chunk = self.host_pool.shape[1]
+        self.e2e_chunk = chunk
+        self.streams = [torch.cuda.Stream() for _ in range(4)]            # H2D, prep, extract, D2H
+        slots = 2
+        h, w, H, W = self.h, self.w, self.H, self.W
+        wb = (w + 7) // 8
+        self.in_f = [_dev.empty((chunk, H, W), torch.int16) for _ in range(slots)]
+        self.in_bits = [_dev.empty((chunk, h, wb), torch.uint8) for _ in range(slots)]
+        self.in_m = [_dev.empty((chunk, h, w), torch.uint8) for _ in range(slots)]
+        self.in_k = [_dev.empty((chunk, 8, 3), torch.float32) for _ in range(slots)]
+        self.engines = [self.ChunkEngine() for _ in range(slots)]
+        self.preps = [_dev.empty((chunk, h, w), torch.uint8) for _ in range(slots)]
+        self.invs = [_dev.empty((chunk,), torch.int32) for _ in range(slots)]
+        cw, ch = self.cfg['crop_size']
+        self.host_out = [{'depth_crops': torch.empty((chunk, ch, cw), dtype=torch.uint8).pin_memory(),
+                          'mask_crops': torch.empty((chunk, ch, cw), dtype=torch.uint8).pin_memory(),
+                          'scalars': torch.empty((_lib.NUM_SCALARS, chunk), dtype=torch.float64).pin_memory(),
+                          'kpt_cols': torch.empty((_lib.NUM_KPT_COLS, chunk), dtype=torch.float64).pin_memory(),
+                          'flips': torch.empty((chunk,), dtype=torch.uint8).pin_memory(),
+                          'invalid': torch.empty((chunk,), dtype=torch.int32).pin_memory()} for _ in range(slots)]
+        self.small_chunk_bytes = self.pool_bits[:chunk].numel() + self.pool_kpts[:chunk].numel() * 4
+        self.d2h_chunk_bytes = sum(v.numel() * v.element_size() for v in self.host_out[0].values())
+
+    def e2e_step(self, zero_copy):
+        """One pass over the session from pinned host buffers.  zero_copy=True: the prep kernel reads the ROI box of the raw
+        frames straight out of pinned host memory (UVA), so only the bytes the path needs cross PCIe; bit-packed masks and
+        keypoints go through cudaMemcpyAsync.  zero_copy=False: whole frames are copied."""
+        torch, _dev, _lib = self.torch, self._dev, self._lib
+        copy_in, prep_st, compute, copy_out = self.streams
+        slots, chunk = 2, self.e2e_chunk
+        n_chunks = (self.n_frames + chunk - 1) // chunk
+        ev_h2d, ev_comp, ev_d2h = [None] * slots, [None] * slots, [None] * slots
+        n_pool = self.host_pool.shape[0]
+        for c in range(n_chunks):
+            b = c % slots
+            src_host = self.host_pool[c % n_pool]
+            with torch.cuda.stream(copy_in):
+                if ev_comp[b] is not None:
+                    copy_in.wait_event(ev_comp[b])          # input slot consumed by the previous user
+                if not zero_copy:
+                    self.in_f[b].copy_(src_host, non_blocking=True)
+                self.in_bits[b].copy_(self.pool_bits[:chunk], non_blocking=True)
+                self.in_k[b].copy_(self.pool_kpts[:chunk], non_blocking=True)
+                _lib.call('msq_unpack_mask_bits', _dev.ptr(self.in_bits[b]), chunk, self.h, self.w, _dev.ptr(self.in_m[b]), _dev.stream())
+                ev_h2d[b] = torch.cuda.Event()
+                ev_h2d[b].record(copy_in)
+            # prep is PCIe-bound in zero-copy mode (it pulls the ROI box from host memory) and needs few SMs; on its own
+            # stream it overlaps the SM-bound extract kernels of the previous chunk
+            with torch.cuda.stream(prep_st):
+                if not zero_copy:
+                    prep_st.wait_event(ev_h2d[b])
+                if ev_comp[b] is not None:
+                    prep_st.wait_event(ev_comp[b])          # preps[b] consumed by the previous user of the slot
+                self.prep(src_host if zero_copy else self.in_f[b], chunk, self.preps[b], self.invs[b], _dev.stream())
+                ev_prep = torch.cuda.Event()
+                ev_prep.record(prep_st)
+            with torch.cuda.stream(compute):
+                compute.wait_event(ev_h2d[b])
+                compute.wait_event(ev_prep)
+                if ev_d2h[b] is not None:
+                    compute.wait_event(ev_d2h[b])           # output slot drained
+                res = self.engines[b].extract(self.preps[b], self.in_m[b], self.in_k[b], **self.kw)
+                ev_comp[b] = torch.cuda.Event()
+                ev_comp[b].record(compute)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(ev_comp[b])
+                for key in ('depth_crops', 'mask_crops', 'scalars', 'kpt_cols', 'flips'):
+                    self.host_out[b][key].copy_(res[key], non_blocking=True)
+                self.host_out[b]['invalid'].copy_(self.invs[b], non_blocking=True)
+                ev_d2h[b] = torch.cuda.Event()
+                ev_d2h[b].record(copy_out)
+        for st in (copy_out, compute, prep_st):
+            torch.cuda.current_stream().wait_stream(st)
+
+    def bytes_per_frame(self):
+        A, C = self.h * self.w, self.cfg['crop_size'][0] * self.cfg['crop_size'][1]
+        # algorithmic bytes per frame (DESIGN.md section 4): only the ROI box of the raw frame is ever needed; the masked sums
+        # read the mask and the frame bytes under 16-pixel groups that carry a mask byte (a masked-out pixel contributes 0)
+        return {'prep_frames': 3 * A, 'clean_frames': 2 * A, 'frame_features': 2 * A + 40,
+                'masked_sums': A + self.masked_group_fraction * A,
+                'scalars_keypoints': 113 * 8 + 24 * 4 + 8 * 1 + 64, 'crop_rotate': 2 * 2 * C + 2 * C,
+                'angles_flips_filter': 8 * 8 + 96 + 9}
+
+
+def timed_steps(torch, fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def peak_numbers():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        pk = json.load(open(peaks_path))
+        return float(pk['hbm_gbs']), float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops', 1375.4))), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1400.0, 'fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)'
+
+
+def kernel_roofline(wl, ktimes, n_frames_total, peak, peak_src):
+    bytes_per_frame = wl.bytes_per_frame()
+    kernel_ms = {k: v[0] for k, v in ktimes.items() if v[1] > 0 and k in bytes_per_frame}
+    dominant = max(kernel_ms, key=kernel_ms.get)
+    total_kernel_ms = sum(kernel_ms.values())
+    d_ms, d_cnt = ktimes[dominant]
+    frames_per_launch_avg = n_frames_total / d_cnt
+    achieved = bytes_per_frame[dominant] * frames_per_launch_avg / (d_ms / d_cnt * 1e-3) / 1e9
+    return {
+        'bound': 'hbm', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+        'traffic': None, 'peak_source': peak_src, 'avg_launch_ms': d_ms / d_cnt,
+        'algorithmic_bytes_per_frame': bytes_per_frame[dominant], 'frames_per_launch': frames_per_launch_avg,
+        'share_of_kernel_time': d_ms / total_kernel_ms,
+        'per_kernel': {k: {'ms_total': v, 'share': v / total_kernel_ms, 'launches': ktimes[k][1],
+                           'bytes_per_frame': bytes_per_frame[k],
+                           'GBps': bytes_per_frame[k] * n_frames_total / (v * 1e-3) / 1e9,
+                           'frac_of_peak': bytes_per_frame[k] * n_frames_total / (v * 1e-3) / 1e9 / peak}
+                       for k, v in kernel_ms.items()},
+    }
 
 
 # ------------------------------------------------------------------------------------------------
@@ -176,21 +414,16 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
-    from moseq2_detectron_extract_b200.engine import ChunkEngine
-    from moseq2_detectron_extract_b200.proc import proc as P
 
     torch.cuda.set_device(local_rank)
     _dev.require_cuda()
     from moseq2_detectron_extract_b200.shard import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: host buffers land on the GPU's NUMA node
     if world > 1:
-        # NCCL carries only the barrier and the max-over-ranks of two timing scalars (no data-path collective);
-        # keep its banner off stdout so that the single JSON line is the only output
-        os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL carries only the barrier and the max / sum of a few timing scalars: there is NO data-path collective
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     def barrier():
@@ -198,46 +431,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce(values, op):
+        t = torch.tensor(values, dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return [float(v) for v in t]
+
+    MAX, SUM, MIN = (dist.ReduceOp.MAX, dist.ReduceOp.SUM, dist.ReduceOp.MIN)
+    peak, tensor_peak, peak_src = peak_numbers()
     geom = getattr(synthetic.SessionGeometry, args.geometry)()
-    cfg = synthetic.default_config(geom)
-    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
-    y0, x0, y1, x1 = synthetic.roi_bbox(roi)
-    h, w = y1 - y0, x1 - x0
-    H, W = geom.height, geom.width
-    chunk = 1000
-    n_frames = args.frames
-    launch = args.launch_chunks * chunk
-
-    # ---- synthetic session: `pool` distinct frames generated on the host, cycled (with a per-chunk roll) on the GPU
-    pool = synthetic.generate_chunk(args.pool_frames, seed=rank, geom=geom, t0=0)
-    pool_frames = torch.from_numpy(pool.frames).pin_memory()
-    pool_masks = torch.from_numpy(pool.masks).pin_memory()
-    pool_kpts = torch.from_numpy(pool.keypoints).pin_memory()
-    d_pool_f, d_pool_m, d_pool_k = pool_frames.cuda(), pool_masks.cuda(), pool_kpts.cuda()
-    idx = torch.cat([(torch.arange(min(chunk, n_frames - c), device='cuda') + 37 * (c // chunk)) % args.pool_frames
-                     for c in range(0, n_frames, chunk)])
-    frames = torch.empty((n_frames, H, W), dtype=torch.int16, device='cuda')
-    for s in range(0, n_frames, 2000):
-        frames[s:s + 2000] = d_pool_f[idx[s:s + 2000]]
-    masks = d_pool_m[idx].contiguous()
-    kpts = d_pool_k[idx].contiguous()
-    del d_pool_f, d_pool_m, d_pool_k
-    bg_d, roi_d = _dev.as_device(bg), _dev.as_device(roi.astype(np.uint8))
-    prep_buf = _dev.empty((launch, h, w), torch.uint8)
-    invalid = _dev.empty((launch,), torch.int32)
-    engine = ChunkEngine()
-    kw = dict(chunk_size=chunk, min_height=cfg['min_height'], max_height=cfg['max_height'], true_depth=cfg['true_depth'],
-              crop_size=cfg['crop_size'])
-    flags = _lib.MSQ_PREP_HAS_VMIN | _lib.MSQ_PREP_HAS_VMAX
-
-    def resident_step():
-        st = _dev.stream()
-        for s in range(0, n_frames, launch):
-            n = min(launch, n_frames - s)
-            _lib.call('msq_prep_frames', _dev.ptr(frames[s:s + n]), n, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32, _dev.ptr(roi_d),
-                      y0, x0, h, w, float(cfg['min_height']), float(cfg['max_height']), flags, _dev.ptr(prep_buf),
-                      _dev.ptr(invalid), None, st)
-            engine.extract(prep_buf[:n], masks[s:s + n], kpts[s:s + n], **kw)
+    wl = ExtractWorkload(args, geom, args.frames, rank, world, args.host_pool_gb)
 
     # ---- device-resident throughput ------------------------------------------------------------------
     # the clock sampler is started BEFORE the warm-up and must have delivered a line before timing starts (nvidia-smi
@@ -248,7 +451,7 @@ def run_ours(args):
         sampler.wait_first(3.0)
     barrier()
     for _ in range(args.warmup):
-        resident_step()
+        wl.resident_step()
     barrier()
     launches_before = sum(_lib.kernel_launches().values())
     _lib.kernel_timing(True)
@@ -257,7 +460,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        resident_step()
+        wl.resident_step()
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -266,192 +469,293 @@ def run_ours(args):
     _lib.kernel_timing(False)
     ktimes = _lib.kernel_timing_collect()
     gpu_launches = sum(_lib.kernel_launches().values()) - launches_before
-    assert int(invalid.sum().item()) == 0
+    assert int(wl.invalid.sum().item()) == 0
+    roofline = kernel_roofline(wl, ktimes, args.frames * args.steps, peak, peak_src)
 
-    # ---- end to end: pinned host inputs -> GPU -> pinned host results, 3-stage stream pipeline ----------------
-    e2e_ms, h2d_bytes, d2h_bytes = None, 0, 0
-    e2e_copy_ms = e2e_zc_ms = None
-    e2e_mode = None
+    # ---- end to end: pinned host inputs -> GPU -> pinned host results, 4-stream double-buffered pipeline ----------------
+    e2e = None
     if not args.no_e2e:
-        n_e2e_chunks = (n_frames + chunk - 1) // chunk
-        copy_in, compute, copy_out, prep_st = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-        slots = 2
-        in_f = [_dev.empty((chunk, H, W), torch.int16) for _ in range(slots)]
-        in_m = [_dev.empty((chunk, h, w), torch.uint8) for _ in range(slots)]
-        in_k = [_dev.empty((chunk, 8, 3), torch.float32) for _ in range(slots)]
-        engines = [ChunkEngine() for _ in range(slots)]
-        preps = [_dev.empty((chunk, h, w), torch.uint8) for _ in range(slots)]
-        invs = [_dev.empty((chunk,), torch.int32) for _ in range(slots)]
-        cw, ch = cfg['crop_size']
-        host_out = [{'depth_crops': torch.empty((chunk, ch, cw), dtype=torch.uint8).pin_memory(),
-                     'mask_crops': torch.empty((chunk, ch, cw), dtype=torch.uint8).pin_memory(),
-                     'scalars': torch.empty((_lib.NUM_SCALARS, chunk), dtype=torch.float64).pin_memory(),
-                     'kpt_cols': torch.empty((_lib.NUM_KPT_COLS, chunk), dtype=torch.float64).pin_memory(),
-                     'flips': torch.empty((chunk,), dtype=torch.uint8).pin_memory(),
-                     'invalid': torch.empty((chunk,), dtype=torch.int32).pin_memory()} for _ in range(slots)]
-        h2d_chunk = pool_frames[:chunk].numel() * 2 + pool_masks[:chunk].numel() + pool_kpts[:chunk].numel() * 4
-        d2h_chunk = sum(v.numel() * v.element_size() for v in host_out[0].values())
+        pool_bytes = wl.build_host_pool()
+        wl.setup_e2e()
+        barrier()
+        h2d_gbs = wl.h2d_bandwidth()
+        h2d_sum, = reduce([h2d_gbs], SUM)
+        h2d_min, = reduce([h2d_gbs], MIN)
+        w3 = min(args.warmup, 3)
+        ms_copy = timed_steps(torch, lambda: wl.e2e_step(False), args.steps, w3, barrier)
+        ms_zc = timed_steps(torch, lambda: wl.e2e_step(True), args.steps, w3, barrier)
+        assert float(wl.host_out[0]['scalars'][6].sum()) > 0          # area_px really came back
+        ms_copy_max, ms_zc_max = reduce([ms_copy, ms_zc], MAX)
+        n_chunks = (args.frames + wl.e2e_chunk - 1) // wl.e2e_chunk
+        zc = ms_zc_max <= ms_copy_max
+        e2e_ms = ms_zc_max if zc else ms_copy_max
+        frame_bytes_chunk = wl.e2e_chunk * (wl.h * wl.w * 2 if zc else wl.H * wl.W * 2)
+        h2d_step = (frame_bytes_chunk + wl.small_chunk_bytes) * n_chunks
+        total = args.frames * world * args.steps
+        e2e = {'value': total / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_step),
+               'd2h_bytes_per_step': int(wl.d2h_chunk_bytes * n_chunks), 'ms_per_step': e2e_ms / args.steps,
+               'mode': 'zero-copy' if zc else 'copy',
+               'frames_per_s_full_frame_copy': total / (ms_copy_max * 1e-3), 'frames_per_s_zero_copy_roi': total / (ms_zc_max * 1e-3),
+               'h2d_GBps_sustained_all_ranks': h2d_step * args.steps / (e2e_ms * 1e-3) / 1e9 * world,
+               'host_pool_bytes_per_rank': int(pool_bytes),
+               'pinned_h2d_copy_GBps': {'sum_over_ranks': h2d_sum, 'min_rank': h2d_min,
+                                        'how': 'cudaMemcpyAsync of the pinned frame pool, all ranks at once, CUDA events'},
+               'mask_format': 'bit rows (numpy.packbits little) expanded on the GPU by msq_unpack_mask_bits',
+               'path': 'pinned host int16 frames (pool >> CPU caches, cycled) + bit-packed masks + f32 keypoints -> msq_prep_frames + '
+                       'msq_unpack_mask_bits + msq_extract_chunk -> pinned host crops/scalars/keypoint table/flips; 4-stream (H2D, prep, '
+                       'extract, D2H) double-buffered pipeline; in zero-copy mode the prep kernel reads the ROI box of the raw frames '
+                       'directly from pinned host memory'}
+        del wl.host_pool
+        wl.host_pool = None
 
-        def e2e_step(zero_copy):
-            """One pass over the session from pinned host buffers.  zero_copy=True: the prep kernel reads the ROI box
-            of the raw frames straight out of pinned host memory (UVA), so only the bytes the path needs cross
-            PCIe; masks / keypoints still go through cudaMemcpyAsync.  zero_copy=False: whole frames are copied."""
-            ev_h2d = [None] * slots
-            ev_comp = [None] * slots
-            ev_d2h = [None] * slots
-            for c in range(n_e2e_chunks):
-                b = c % slots
-                with torch.cuda.stream(copy_in):
-                    if ev_comp[b] is not None:
-                        copy_in.wait_event(ev_comp[b])          # input slot consumed by the previous user
-                    if not zero_copy:
-                        in_f[b].copy_(pool_frames[:chunk], non_blocking=True)
-                    in_m[b].copy_(pool_masks[:chunk], non_blocking=True)
-                    in_k[b].copy_(pool_kpts[:chunk], non_blocking=True)
-                    ev_h2d[b] = torch.cuda.Event()
-                    ev_h2d[b].record(copy_in)
-                # prep is PCIe-bound in zero-copy mode (it pulls the ROI box from host memory) and needs few SMs; on its
-                # own stream it overlaps the SM-bound extract kernels of the previous chunk
-                with torch.cuda.stream(prep_st):
-                    if not zero_copy:
-                        prep_st.wait_event(ev_h2d[b])
-                    if ev_comp[b] is not None:
-                        prep_st.wait_event(ev_comp[b])          # preps[b] consumed by the previous user of the slot
-                    src = pool_frames[:chunk] if zero_copy else in_f[b]
-                    _lib.call('msq_prep_frames', _dev.ptr(src), chunk, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32,
-                              _dev.ptr(roi_d), y0, x0, h, w, float(cfg['min_height']), float(cfg['max_height']), flags,
-                              _dev.ptr(preps[b]), _dev.ptr(invs[b]), None, _dev.stream())
-                    ev_prep = torch.cuda.Event()
-                    ev_prep.record(prep_st)
-                with torch.cuda.stream(compute):
-                    compute.wait_event(ev_h2d[b])
-                    compute.wait_event(ev_prep)
-                    if ev_d2h[b] is not None:
-                        compute.wait_event(ev_d2h[b])           # output slot drained
-                    res = engines[b].extract(preps[b], in_m[b], in_k[b], **kw)
-                    ev_comp[b] = torch.cuda.Event()
-                    ev_comp[b].record(compute)
-                with torch.cuda.stream(copy_out):
-                    copy_out.wait_event(ev_comp[b])
-                    for key in ('depth_crops', 'mask_crops', 'scalars', 'kpt_cols', 'flips'):
-                        host_out[b][key].copy_(res[key], non_blocking=True)
-                    host_out[b]['invalid'].copy_(invs[b], non_blocking=True)
-                    ev_d2h[b] = torch.cuda.Event()
-                    ev_d2h[b].record(copy_out)
-            torch.cuda.current_stream().wait_stream(copy_out)
-            torch.cuda.current_stream().wait_stream(compute)
-            torch.cuda.current_stream().wait_stream(prep_st)
+    ms_max, = reduce([ms], MAX)
+    launches_sum, = reduce([float(gpu_launches)], SUM)
 
-        def time_e2e(zero_copy):
-            for _ in range(min(args.warmup, 3)):
-                e2e_step(zero_copy)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                e2e_step(zero_copy)
-            e1.record()
-            barrier()
-            assert float(host_out[0]['scalars'][6].sum()) > 0          # area_px really came back
-            return e0.elapsed_time(e1)
-
-        e2e_copy_ms = time_e2e(False)
-        e2e_zc_ms = time_e2e(True)
-        roi_bytes_chunk = chunk * h * w * 2          # int16 ROI-box pixels the prep kernel pulls over PCIe
-        small_chunk = pool_masks[:chunk].numel() + pool_kpts[:chunk].numel() * 4
-        if e2e_zc_ms <= e2e_copy_ms:
-            e2e_ms, e2e_mode, h2d_chunk = e2e_zc_ms, 'zero-copy', roi_bytes_chunk + small_chunk
-        else:
-            e2e_ms, e2e_mode, h2d_chunk = e2e_copy_ms, 'copy', pool_frames[:chunk].numel() * 2 + small_chunk
-        h2d_bytes, d2h_bytes = h2d_chunk * n_e2e_chunks, d2h_chunk * n_e2e_chunks
-    # ---- secondary figures (rank 0, not part of `value`): in-painting cost and the full extract with the R-CNN ------
+    # ---- the other measured workloads: Azure geometry, full extract with the R-CNN ------------------------------------
     extras = {}
-    if rank == 0 and world == 1:
+    frames_main = wl.frames
+    del wl.frames, wl.masks, wl.kpts
+    del frames_main
+    torch.cuda.empty_cache()
+    try:
+        if args.azure_frames > 0 and args.geometry != 'azure':
+            extras['azure'] = azure_workload(args, rank, world, barrier, reduce, (MAX, SUM, MIN), peak, peak_src)
+    except Exception as exc:       # never let a further workload break the contract line
+        extras['azure'] = {'error': repr(exc)[:300]}
+    torch.cuda.empty_cache()
+    try:
+        if args.rcnn_frames > 0:
+            extras.update(rcnn_workloads(args, geom, rank, world, barrier, reduce, (MAX, SUM, MIN), tensor_peak, peak_src))
+    except Exception as exc:
+        extras['full_extract_rcnn'] = {'error': repr(exc)[:300]}
+    if rank == 0 and world == 1 and not args.no_secondary:
         try:
-            extras.update(secondary_figures(args, geom, cfg, roi, bg))
-        except Exception as exc:       # never let a secondary figure break the contract line
+            extras.update(secondary_figures(args, geom, wl.cfg, wl.roi_np, wl.bg_np))
+        except Exception as exc:
             extras['secondary_error'] = repr(exc)[:300]
-
-    # ---- reduce over ranks (max time) --------------------------------------------------------------------
-    times = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device='cuda')
-    launches_all = torch.tensor([float(gpu_launches)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(launches_all, op=dist.ReduceOp.SUM)
-    ms, e2e_ms_max = float(times[0]), float(times[1])
-    gpu_launches = int(launches_all[0])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    total_frames = n_frames * world * args.steps
-    value = total_frames / (ms * 1e-3)
-
-    # ---- roofline of the dominant kernel (largest share of device time in the timed region) -----------------
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
-    A, C = h * w, cfg['crop_size'][0] * cfg['crop_size'][1]
-    # algorithmic bytes per frame (DESIGN.md section 4): only the ROI box of the raw frame is ever needed
-    bytes_per_frame = {'prep_frames': 3 * A, 'clean_frames': 2 * A, 'frame_features': 2 * A + 40, 'masked_sums': 2 * A,
-                       'scalars_keypoints': 113 * 8 + 24 * 4 + 8 * 1 + 64, 'crop_rotate': 2 * 2 * C + 2 * C,
-                       'angles_flips_filter': 8 * 8 + 96 + 9}
-    kernel_ms = {k: v[0] for k, v in ktimes.items() if v[1] > 0}
-    dominant = max(kernel_ms, key=kernel_ms.get)
-    total_kernel_ms = sum(kernel_ms.values())
-    d_ms, d_cnt = ktimes[dominant]
-    frames_per_launch_avg = n_frames * args.steps / d_cnt
-    achieved = bytes_per_frame[dominant] * frames_per_launch_avg / (d_ms / d_cnt * 1e-3) / 1e9
-    roofline = {
-        'bound': 'hbm', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-        'traffic': None, 'peak_source': peak_src, 'avg_launch_ms': d_ms / d_cnt,
-        'algorithmic_bytes_per_frame': bytes_per_frame[dominant], 'frames_per_launch': frames_per_launch_avg,
-        'share_of_kernel_time': d_ms / total_kernel_ms,
-        'per_kernel': {k: {'ms_total': v, 'share': v / total_kernel_ms, 'launches': ktimes[k][1],
-                           'GBps': bytes_per_frame.get(k, 0) * n_frames * args.steps / (v * 1e-3) / 1e9}
-                       for k, v in kernel_ms.items()},
-    }
+    total_frames = args.frames * world * args.steps
     traffic_file = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
     if os.path.exists(traffic_file):
         try:
             t = json.load(open(traffic_file))
-            if t.get('kernel') == dominant:
+            if t.get('kernel') == roofline['kernel']:
                 roofline['traffic'] = t.get('dram_bytes_per_launch')
                 roofline['traffic_source'] = t.get('source')
         except Exception:
             pass
-
     cfg_out = workload_config(args, geom, world)
-    cfg_out['roi_box'] = [y0, x0, y1, x1]
-    cfg_out['host_numa_binding'] = numa if numa else 'unavailable'      # rank 0's; every rank binds to its own GPU's node
+    cfg_out['roi_box'] = [wl.y0, wl.x0, wl.y0 + wl.h, wl.x0 + wl.w]
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u8 / int16 (pixels), int64 (moments), f64 (features)', 'data': 'synthetic', 'config': cfg_out,
-        'clocks': clocks, 'gpu_launches': int(gpu_launches),
-        'e2e': ({'value': total_frames / (e2e_ms_max * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_bytes),
-                 'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': e2e_ms_max / args.steps,
-                 'mode': e2e_mode,
-                 'frames_per_s_full_frame_copy': n_frames * args.steps / (e2e_copy_ms * 1e-3),
-                 'frames_per_s_zero_copy_roi': n_frames * args.steps / (e2e_zc_ms * 1e-3),
-                 'path': 'pinned host int16 frames + u8 masks + f32 keypoints -> msq_prep_frames + msq_extract_chunk -> '
-                         'pinned host crops/scalars/keypoint table/flips; 4-stream (H2D, prep, extract, D2H) double-buffered pipeline; in zero-copy '
-                         'mode the prep kernel reads the ROI box of the raw frames directly from pinned host memory'}
-                if e2e_ms is not None else None),
-        'roofline': roofline, 'cpu_baseline': cpu_base,
+        'metric': METRIC, 'value': total_frames / (ms_max * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8 / int16 (pixels), int64 (moments), f64 (features)', 'data': 'synthetic',
+        'config': cfg_out, 'clocks': clocks, 'gpu_launches': int(launches_sum), 'e2e': e2e, 'roofline': roofline,
+        'cpu_baseline': cpu_base,
+        'collective': 'none on the data path (chunks shard; NCCL carries the timing barrier and MAX / SUM of a few scalars only)',
+        'host': {'numa_binding': numa if numa else 'unavailable (NVML / sysfs report no NUMA node for the GPU)', 'cpus': os.cpu_count()},
     }
     line.update(extras)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def azure_workload(args, rank, world, barrier, reduce, ops, peak, peak_src):
+    """BASELINE configs[4] geometry on this rank: 640x576 int16 frames, 400x400 ROI box, 128x128 crops; resident + end to end,
+    per-kernel roofline (the multi-tile clean path and the 128-pixel crop staging run here)."""
+    import torch
+    from moseq2_detectron_extract_b200 import _lib, synthetic
+    MAX, SUM, MIN = ops
+    geom = synthetic.SessionGeometry.azure()
+    sub = argparse.Namespace(**vars(args))
+    sub.pool_frames = min(args.pool_frames, 500)
+    sub.launch_chunks = min(args.launch_chunks, 3)
+    wl = ExtractWorkload(sub, geom, args.azure_frames, rank, world, min(args.host_pool_gb, 3.0))
+    steps = max(2, args.steps // 2)
+    for _ in range(2):
+        wl.resident_step()
+    barrier()
+    _lib.kernel_timing(True)
+    ms = timed_steps(torch, wl.resident_step, steps, 0, barrier)
+    _lib.kernel_timing(False)
+    ktimes = _lib.kernel_timing_collect()
+    roofline = kernel_roofline(wl, ktimes, args.azure_frames * steps, peak, peak_src)
+    out = {'workload': f'configs[4] geometry: {geom.width}x{geom.height} int16, ROI box {wl.h}x{wl.w}, crops {list(geom.crop_size)}, '
+                       f'{args.azure_frames} frames per GPU, batch 64 is the R-CNN batch of that config (no R-CNN in this pass)',
+           'frames': args.azure_frames, 'steps': steps}
+    ms_max, = reduce([ms], MAX)
+    out['frames_per_s'] = args.azure_frames * world * steps / (ms_max * 1e-3)
+    out['ms_per_step'] = ms_max / steps
+    out['roofline'] = roofline
+    if not args.no_e2e:
+        wl.build_host_pool()
+        wl.setup_e2e()
+        ms_zc = timed_steps(torch, lambda: wl.e2e_step(True), steps, 1, barrier)
+        ms_zc_max, = reduce([ms_zc], MAX)
+        n_chunks = (args.azure_frames + wl.e2e_chunk - 1) // wl.e2e_chunk
+        out['e2e'] = {'value': args.azure_frames * world * steps / (ms_zc_max * 1e-3), 'unit': UNIT, 'mode': 'zero-copy',
+                      'h2d_bytes_per_step': int((wl.e2e_chunk * wl.h * wl.w * 2 + wl.small_chunk_bytes) * n_chunks),
+                      'd2h_bytes_per_step': int(wl.d2h_chunk_bytes * n_chunks)}
+    return out
+
+
+def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, peak_src):
+    """BASELINE configs[2]: the full extract with the repo's own Keypoint/Mask R-CNN graph between the pre- and post-processing
+    kernels, random weights, bf16.  Measured twice: with detectron2's 1000 test proposals (the reference's configuration) and with
+    the graph built for 100.  Resident (frames in HBM) and end to end (pinned host int16 frames in, pinned host crops / scalars /
+    keypoint table / flips out; masks never cross PCIe on this path)."""
+    import numpy as np
+    import torch
+    from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+    from moseq2_detectron_extract_b200.engine import ChunkEngine
+    from moseq2_detectron_extract_b200.model import rcnn
+    from moseq2_detectron_extract_b200.model.predict import Predictor
+    MAX, SUM, MIN = ops
+    n = args.rcnn_frames
+    B = args.rcnn_batch
+    cfg = synthetic.default_config(geom)
+    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+    y0, x0, y1, x1 = synthetic.roi_bbox(roi)
+    h, w, H, W = y1 - y0, x1 - x0, geom.height, geom.width
+    npool = min(1000, n)
+    pool = synthetic.generate_chunk(npool, seed=12 + rank, geom=geom)
+    host_frames = torch.from_numpy(pool.frames).pin_memory()
+    n_pool_chunks = max(1, min(int(args.host_pool_gb * 1e9 / (H * W * 2 * npool)), (n + npool - 1) // npool))
+    host_pool = torch.empty((n_pool_chunks, npool, H, W), dtype=torch.int16, pin_memory=True)
+    for c in range(n_pool_chunks):
+        host_pool[c].copy_(host_frames)
+    dev_pool = host_frames.cuda()
+    bg_d, roi_d = _dev.as_device(bg), _dev.as_device(roi.astype(np.uint8))
+    flags = _lib.MSQ_PREP_HAS_VMIN | _lib.MSQ_PREP_HAS_VMAX
+    kw = dict(chunk_size=CHUNK, min_height=cfg['min_height'], max_height=cfg['max_height'], true_depth=cfg['true_depth'],
+              crop_size=cfg['crop_size'])
+    cw, ch = cfg['crop_size']
+    out = {}
+    for key, topk in (('full_extract_rcnn', 1000), ('full_extract_rcnn_topk100', 100)):
+        pred = Predictor.from_random_init(post_nms_topk=topk, scripted=True)
+        engine = ChunkEngine()
+        prep_buf = [_dev.empty((npool, h, w), torch.uint8) for _ in range(2)]
+        invalid = _dev.empty((npool,), torch.int32)
+        host_out = {'depth_crops': torch.empty((npool, ch, cw), dtype=torch.uint8).pin_memory(),
+                    'mask_crops': torch.empty((npool, ch, cw), dtype=torch.uint8).pin_memory(),
+                    'scalars': torch.empty((_lib.NUM_SCALARS, npool), dtype=torch.float64).pin_memory(),
+                    'kpt_cols': torch.empty((_lib.NUM_KPT_COLS, npool), dtype=torch.float64).pin_memory(),
+                    'flips': torch.empty((npool,), dtype=torch.uint8).pin_memory()}
+        stage_ms = {}
+
+        def prep_chunk(src, dst, stream=None):
+            _lib.call('msq_prep_frames', _dev.ptr(src), npool, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32, _dev.ptr(roi_d), y0, x0, h, w,
+                      float(cfg['min_height']), float(cfg['max_height']), flags, _dev.ptr(dst), _dev.ptr(invalid), None,
+                      stream if stream is not None else _dev.stream())
+
+        def infer_and_extract(chunk):
+            parts = [pred.predict_dense(chunk[i:i + B], cfg['min_height'], cfg['max_height']) for i in range(0, npool, B)]
+            masks, kpts = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+            return engine.extract(chunk, masks, kpts, **kw)
+
+        def resident_pass():
+            for c in range((n + npool - 1) // npool):
+                prep_chunk(dev_pool, prep_buf[0])
+                infer_and_extract(prep_buf[0])
+
+        prep_st, d2h_st = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def e2e_pass():
+            """prep of chunk c+1 (zero-copy read of the ROI box from pinned host memory) overlaps the graph of chunk c; results of
+            chunk c go back on a third stream."""
+            n_chunks = (n + npool - 1) // npool
+            main = torch.cuda.current_stream()
+            ev_prep, ev_free, ev_out = [None, None], [None, None], None
+            with torch.cuda.stream(prep_st):
+                prep_chunk(host_pool[0], prep_buf[0], _dev.stream())
+                ev_prep[0] = torch.cuda.Event(); ev_prep[0].record(prep_st)
+            for c in range(n_chunks):
+                b = c % 2
+                if c + 1 < n_chunks:
+                    with torch.cuda.stream(prep_st):
+                        if ev_free[1 - b] is not None:
+                            prep_st.wait_event(ev_free[1 - b])
+                        prep_chunk(host_pool[(c + 1) % n_pool_chunks], prep_buf[1 - b], _dev.stream())
+                        ev_prep[1 - b] = torch.cuda.Event(); ev_prep[1 - b].record(prep_st)
+                main.wait_event(ev_prep[b])
+                if ev_out is not None:
+                    main.wait_event(ev_out)                 # the engine's result buffers were drained
+                res = infer_and_extract(prep_buf[b])
+                ev_free[b] = torch.cuda.Event(); ev_free[b].record(main)
+                with torch.cuda.stream(d2h_st):
+                    d2h_st.wait_event(ev_free[b])
+                    for k2 in host_out:
+                        host_out[k2].copy_(res[k2], non_blocking=True)
+                    ev_out = torch.cuda.Event(); ev_out.record(d2h_st)
+            main.wait_stream(d2h_st)
+            main.wait_stream(prep_st)
+
+        launches0 = sum(_lib.kernel_launches().values())
+        ms_res = timed_steps(torch, resident_pass, 1, 1, barrier)
+        launches = sum(_lib.kernel_launches().values()) - launches0
+        ms_e2e = timed_steps(torch, e2e_pass, 1, 1, barrier)
+        assert float(host_out['scalars'][6].sum()) >= 0
+        # per-stage device times of one batch (CUDA events around each stage of the graph)
+        model = pred.model
+        chunk = prep_buf[0][:B]
+
+        def t(name, fn):
+            fn()
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b2.record()
+            torch.cuda.synchronize()
+            stage_ms[name] = a.elapsed_time(b2)
+            return r
+        with torch.no_grad():
+            msq = torch.ops.msq
+            ph = (h + 31) // 32 * 32
+            pw = (w + 31) // 32 * 32
+            x = t('stem (input staging + 7x7 conv + ReLU + max-pool, one kernel)',
+                  lambda: msq.stem_conv_pool(chunk, float(cfg['min_height']), float(cfg['max_height']), True, model.pixel_mean[0],
+                                             model.pixel_std[0], ph, pw, model.stem_w49, model.stem_b64, True))
+            feats = t('res2-res5 + FPN (GN, avg fusion)', lambda: model.pyramid(x))
+            props = t('RPN head + proposals (top-k, decode, NMS)', lambda: model.rpn(feats, h, w))
+            det = t('box head (ROIAlignV2 + 2 FC + top-1)', lambda: model.box_head(feats, props[0], props[2], h, w))
+            t('mask head', lambda: model.mask_head(feats, det[0]))
+            t('keypoint head + decode', lambda: model.keypoint_head(feats, det[0]))
+            masks_kp = t('whole graph + paste (predict_dense)', lambda: pred.predict_dense(chunk, cfg['min_height'], cfg['max_height']))
+            t('clean + features + angles + scalars + crops (msq_extract_chunk)', lambda: engine.extract(chunk, masks_kp[0], masks_kp[1], **kw))
+        ms_res_max, ms_e2e_max = reduce([ms_res, ms_e2e], MAX)
+        flops = rcnn.dense_flops_per_frame(h, w, topk)
+        graph_ms = stage_ms['whole graph + paste (predict_dense)']
+        achieved = flops * B / (graph_ms * 1e-3) / 1e12
+        out[key] = {
+            'workload': f'configs[2]: prep -> stem kernel -> Keypoint+Mask R-CNN R50-FPN of the reference configuration (own TorchScript graph: '
+                        f'GN FPN with avg fusion, stride-in-1x1 ResNet, ROIAlignV2, keypoint pooler 7; random init, bf16, batch {B}, '
+                        f'{topk} proposals per image, 1 detection per frame) -> batched paste -> clean/features/angles/scalars -> crops',
+            'frames': n * world, 'chunks': (n + npool - 1) // npool, 'post_nms_topk': topk,
+            'frames_per_s': n * world / (ms_res_max * 1e-3), 'ms_per_1000_frames': ms_res_max / n * 1000,
+            'e2e': {'value': n * world / (ms_e2e_max * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(n * h * w * 2),
+                    'd2h_bytes_per_step': int(sum(v.numel() * v.element_size() for v in host_out.values()) * ((n + npool - 1) // npool)),
+                    'path': 'pinned host int16 frames (pool >> CPU caches) -> zero-copy msq_prep_frames -> graph -> msq_paste_masks -> '
+                            'msq_extract_chunk -> pinned host crops / scalars / keypoint table / flips; masks never cross PCIe'},
+            'stage_ms_per_batch': {k2: round(v, 3) for k2, v in stage_ms.items()}, 'batch': B,
+            'gpu_launches_own_kernels': int(launches),
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
+                         'peak_source': peak_src + ' bf16_tflops_sustained', 'dense_flops_per_frame': flops,
+                         'what': 'FLOPs of every convolution / Linear of the graph (2 x MACs, executed shapes) x batch / device time of the '
+                                 'whole graph call incl. its glue kernels'},
+        }
+        del pred, engine
+        torch.cuda.empty_cache()
+    return out
+
+
 def secondary_figures(args, geom, cfg, roi, bg):
-    """(1) prep with Kinect-like invalid pixels (rate 0.002) incl. the GPU in-paint, (2) BASELINE configs[2]: the full
-    extract path with a random-init Keypoint+Mask R-CNN R50-FPN (torchvision graph, bf16 autocast) between our kernels."""
+    """(1) prep with Kinect-like invalid pixels (rate 0.002) incl. the GPU in-paint, (2) use_tracking=True: the Kalman branch."""
     import numpy as np
     import torch
     from moseq2_detectron_extract_b200 import _dev, synthetic
@@ -476,8 +780,6 @@ def secondary_figures(args, geom, cfg, roi, bg):
     out['prep_with_invalid_pixels'] = {'frames': int(fr.shape[0]), 'invalid_rate': 0.002, 'ms_prep_only': ms_raw,
                                        'ms_prep_plus_inpaint': ms_fix, 'frames_per_s': fr.shape[0] / (ms_fix * 1e-3)}
     del fr
-    # (3) use_tracking=True: the Kalman branch (a14) -- EM initialisation once, then 1000-frame chunks of one session in
-    # sequence (the running state makes chunks of a session sequential; other sessions would run beside them)
     try:
         from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
         tcfg = dict(cfg, use_tracking=True, results_to_host=False, expected_instances=1)
@@ -501,26 +803,6 @@ def secondary_figures(args, geom, cfg, roi, bg):
                                   'frames_per_s': 1000 / (ms_next * 1e-3)}
     except Exception as exc:      # secondary figure only
         out['tracking_branch'] = {'error': repr(exc)}
-    if args.rcnn_frames > 0:
-        from moseq2_detectron_extract_b200.pipeline import InferenceStep, ProcessFeaturesStep
-        n = args.rcnn_frames
-        cfg2 = dict(cfg, batch_size=args.rcnn_batch, model='random', nframes=n, results_to_host=False, amp=True, dense_inference=True)
-        infer, feats = InferenceStep(cfg2, 'infer'), ProcessFeaturesStep(cfg2, 'features')
-        infer.initialize()
-        feats.initialize()
-        ch = synthetic.generate_chunk(min(n, 500), seed=12, geom=geom)
-        raw = torch.from_numpy(np.tile(ch.frames, ((n + len(ch.frames) - 1) // len(ch.frames), 1, 1))[:n]).cuda()
-
-        def full():
-            chunk = prep_raw_frames(raw, bground_im=bg, roi=roi, vmin=cfg['min_height'], vmax=cfg['max_height'])
-            data = {'batch': 0, 'chunk': chunk, 'frame_idxs': list(range(n)), 'offset': 0}
-            feats.process(infer.process(data))
-        ms_full = timed(full, iters=2)
-        out['full_extract_rcnn'] = {
-            'workload': 'configs[2]: prep -> scale/normalise/resize (one kernel) -> Keypoint+Mask R-CNN R50-FPN (random init, torchvision graph with '
-                        'BatchNorm folded, cuDNN fused conv epilogues, batched heads + our NMS / RoIAlign / keypoint kernels, bf16 autocast, '
-                        f'batch {args.rcnn_batch}, 100 proposals, 1 detection/frame) -> batched paste of the first instance -> features -> crops',
-            'frames': n, 'ms': ms_full, 'frames_per_s': n / (ms_full * 1e-3)}
     return out
 
 

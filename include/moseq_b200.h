@@ -85,6 +85,11 @@ MSQ_API int msq_prep_frames(const int16_t *frames_dev, int n, int H, int W,
                     int y0, int x0, int h, int w, double vmin, double vmax, int flags,
                     uint8_t *out_dev, int32_t *invalid_count_dev, uint8_t *invalid_bits_dev, void *stream);
 
+/* Instance masks handed over from the host as bit rows (the reference passes bool images, ref: proc/proc.py:672-684; one bit per
+ * pixel is the same information in 1/8 of the PCIe bytes): bits_dev (n, h, ceil(w/8)), bit b of byte B of a row = pixel 8B+b
+ * (numpy.packbits(..., axis=-1, bitorder='little')) -> out_dev (n,h,w) u8 in {0,1}, the mask format of every entry point. */
+MSQ_API int msq_unpack_mask_bits(const uint8_t *bits_dev, int n, int h, int w, uint8_t *out_dev, void *stream);
+
 /* ---- a2  fill_invalid_pixels (ref: proc/proc.py:189-210): cv2.inpaint(frame, mask, radius, INPAINT_NS), bit-exact.
  * frames_dev (n_total,h,w) u8 updated IN PLACE; invalid_bits_dev as written by msq_prep_frames; frame_idx_dev (m) int32
  * indices of the frames to in-paint (NULL = frames 0..m-1); radius 1..4 (the reference uses 3).

@@ -527,6 +527,28 @@ stem_conv_pool_kernel(const uint8_t *__restrict__ in, int h, int w, int conv_h, 
     }
 }
 
+
+// Host-side instance masks travel as bit rows (1/8 of the bytes over PCIe); the extract kernels read {0,1} bytes.
+// bits (n, h, ceil(w/8)) with bit b of byte B of a row = pixel 8B + b  ->  out (n, h, w) u8.  A thread expands one byte.
+__global__ void __launch_bounds__(256)
+unpack_mask_bits_kernel(const uint8_t *__restrict__ bits, size_t rows, int w, int wb, uint8_t *__restrict__ out) {
+    const size_t total = rows * (size_t)wb;
+    const bool vec = (w % 8 == 0) && ((uintptr_t)out % 8 == 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / wb;
+        const int B = (int)(i - row * wb);
+        const uint32_t v = bits[i];
+        uint8_t *dst = out + row * (size_t)w + (size_t)B * 8;
+        if (vec) {
+            // spread 8 bits to 8 bytes: multiply trick on two nibbles
+            const uint32_t lo = ((v & 0xfu) * 0x00204081u) & 0x01010101u, hi = (((v >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
+        } else {
+            for (int b = 0; b < 8 && B * 8 + b < w; ++b) dst[b] = (v >> b) & 1u;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace msq
 
@@ -584,6 +606,19 @@ extern "C" int msq_stem_conv_pool(const uint8_t *in, int n, int h, int w, int ph
             vmin, vmax, vmin_is_int, w49x64, bias64, static_cast<float *>(out));
     }
     MSQ_LAUNCH_OK("stem_conv_pool");
+    return MSQ_OK;
+}
+
+extern "C" int msq_unpack_mask_bits(const uint8_t *bits, int n, int h, int w, uint8_t *out, void *stream) {
+    MSQ_REQUIRE(n >= 0 && h > 0 && w > 0, MSQ_EINVAL, "msq_unpack_mask_bits: bad sizes");
+    if (n == 0) return MSQ_OK;
+    MSQ_REQUIRE(bits && out, MSQ_EINVAL, "msq_unpack_mask_bits: null pointer");
+    const int wb = (w + 7) / 8;
+    const size_t rows = (size_t)n * h, work = rows * wb;
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)sm_count() * 16);
+    TimedLaunch timed(K_PREP, (cudaStream_t)stream);
+    unpack_mask_bits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, rows, w, wb, out);
+    MSQ_LAUNCH_OK("unpack_mask_bits");
     return MSQ_OK;
 }
 

@@ -53,7 +53,7 @@ def read_frames_raw(filename: Union[str, tarfile.TarInfo], frames: Optional[Unio
     shape = (len(frames), frame_dims[1], frame_dims[0])
     if pinned:
         import torch
-        holder = torch.empty(shape, dtype=torch.int16).pin_memory()
+        holder = torch.empty(shape, dtype=torch.int16, pin_memory=True)      # page-locked from the start: no pageable copy
         out = holder.numpy().view(dt)
     else:
         out = np.empty(shape, dtype=dt)

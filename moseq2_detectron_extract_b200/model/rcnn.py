@@ -371,3 +371,34 @@ def export_torchscript(model: MoseqRCNN, path: str) -> torch.jit.ScriptModule:
     scripted = torch.jit.script(model)
     torch.jit.save(scripted, path)
     return scripted
+
+
+def dense_flops_per_frame(h: int, w: int, proposals: int, num_keypoints: int = 8, keypoint_pooler: int = 7) -> float:
+    """FLOPs (2 x multiply-accumulates) of every convolution / Linear the graph executes for one (h, w) frame: the 1-channel stem
+    (K = 49), res2..res5 with the stride in the first 1x1, FPN laterals / outputs, the RPN head on p2..p6, the box head on
+    `proposals` RoIs, mask and keypoint heads on one detection.  The tensor-pipe roofline of bench.py divides by this."""
+    ph, pw = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    macs = 0.0
+    ch, cw = (ph - 1) // 2 + 1, (pw - 1) // 2 + 1
+    macs += ch * cw * 64 * 49
+    fh, fw = (ch - 1) // 2 + 1, (cw - 1) // 2 + 1
+    cin = 64
+    sizes = []
+    for blocks, mid, cout, stride in ((3, 64, 256, 1), (4, 128, 512, 2), (6, 256, 1024, 2), (3, 512, 2048, 2)):
+        for i in range(blocks):
+            if i == 0:
+                fh, fw = (fh - 1) // stride + 1, (fw - 1) // stride + 1
+                macs += fh * fw * cin * cout                                   # shortcut
+            macs += fh * fw * (cin * mid + 9 * mid * mid + mid * cout)
+            cin = cout
+        sizes.append((fh, fw, cout))
+    for fh_, fw_, c in sizes:
+        macs += fh_ * fw_ * (c * 256 + 9 * 256 * 256)                          # lateral + output
+    levels = [(a, b) for a, b, _ in sizes] + [((sizes[-1][0] - 1) // 2 + 1, (sizes[-1][1] - 1) // 2 + 1)]
+    for a, b in levels:
+        macs += a * b * (9 * 256 * 256 + 256 * 16)                             # RPN head
+    macs += proposals * (49 * 256 * 1024 + 1024 * 1024 + 1024 * 8)             # box head
+    macs += 4 * 196 * 9 * 256 * 256 + 196 * 4 * 256 * 256 + 784 * 256          # mask head
+    p2 = keypoint_pooler * keypoint_pooler
+    macs += p2 * 9 * 256 * 512 + 7 * p2 * 9 * 512 * 512 + p2 * 16 * 512 * num_keypoints
+    return 2.0 * macs

@@ -120,3 +120,71 @@ def concat_results(parts: Sequence[Dict[str, np.ndarray]]) -> Dict[str, np.ndarr
         return {}
     keys = parts[0].keys()
     return {k: np.concatenate([np.asarray(p[k]) for p in parts], axis=0) for k in keys}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the GPU runner: one process per GPU, the real step classes on this rank's chunks
+# ---------------------------------------------------------------------------------------------------------------------
+PER_FRAME_KEYS = ('depth_frames', 'mask_frames', 'flips', 'centroid', 'orientation', 'axis_length', 'num_instances')
+
+
+def run_session_shard(session, config: dict, rank: int = 0, world: int = 1, inference: str = 'synthetic',
+                      device_index: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """This rank's contiguous chunk range of `session` through ProduceFramesStep -> InferenceStep -> ProcessFeaturesStep (the
+    step classes of ref pipeline/*.py) on one GPU, results as per-frame numpy arrays in frame order.
+
+    Chunks follow the reference's sequence (ref: io/util.py:24-35, incl. `chunk_overlap`); like the reference's writer (ref:
+    pipeline/write_results_step.py:54-73, io/result.py:105-130) the first `offset` frames of every chunk but the session's
+    first are dropped, so the concatenation over ranks holds every frame exactly once and equals the single-rank result.
+    `inference`: 'synthetic' (ground-truth instances of a synthetic session: BASELINE configs[1]) or 'model' (R-CNN:
+    config['model'] = 'random' or a .ts path).  No collective: ranks never talk to each other here."""
+    import torch
+    from .pipeline import InferenceStep, Pipeline, PipelineStep, ProcessFeaturesStep, ProduceFramesStep, SyntheticInferenceStep
+    if device_index is not None:
+        torch.cuda.set_device(device_index)
+    cfg = dict(config)
+    cfg['chunk_shard'] = (int(rank), int(world))
+    cfg.setdefault('results_to_host', True)
+    parts: List[Dict[str, np.ndarray]] = []
+
+    def host(x):
+        return x.detach().cpu().numpy() if hasattr(x, 'detach') else np.asarray(x)
+
+    class Collect(PipelineStep):
+        def process(self, data):
+            off = int(data['offset'])
+            feats = data['features']
+            part = {'frame_idxs': np.asarray(data['frame_idxs'])[off:],
+                    'depth_frames': host(data['depth_frames'])[off:], 'mask_frames': host(data['mask_frames'])[off:],
+                    'flips': host(feats['flips'])[off:], 'centroid': host(feats['features']['centroid'])[off:],
+                    'orientation': host(feats['features']['orientation'])[off:],
+                    'axis_length': host(feats['features']['axis_length'])[off:], 'num_instances': np.asarray(feats['num_instances'])[off:]}
+            for k, v in data['scalars'].items():
+                part['scalars/' + k] = host(v)[off:]
+            for k, v in data['keypoints'].items():
+                part['keypoints/' + k] = host(v)[off:]
+            parts.append(part)
+            return data
+
+    pipe = Pipeline()
+    infer = SyntheticInferenceStep(cfg, 'infer') if inference == 'synthetic' else InferenceStep(cfg, 'infer')
+    steps = [pipe.add_step(ProduceFramesStep(session, cfg, 'produce')), pipe.add_step(infer),
+             pipe.add_step(ProcessFeaturesStep(cfg, 'features')), pipe.add_step(Collect(cfg, 'collect'))]
+    for a, b in zip(steps[:-1], steps[1:]):
+        pipe.link(a, b)
+    pipe.run()
+    return concat_results(parts)
+
+
+def gather_shards(local: Dict[str, np.ndarray], rank: int, world: int) -> Optional[Dict[str, np.ndarray]]:
+    """Control-plane gather of the per-frame tables to rank 0 in frame order (None elsewhere); not on the data path."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object(local, bucket, dst=0)
+    if rank != 0:
+        return None
+    merged = concat_results([b for b in bucket if b])
+    order = np.argsort(merged['frame_idxs'], kind='stable')
+    return {k: v[order] for k, v in merged.items()}

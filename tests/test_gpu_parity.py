@@ -474,3 +474,18 @@ def test_bground_im_rejects_unsupported(P):
         P.get_bground_im(frames.astype(np.float32))
     with pytest.raises(ValueError):
         P.get_bground_im(frames[0])
+
+
+def test_unpack_mask_bits_matches_numpy():
+    """msq_unpack_mask_bits: bit rows (numpy.packbits little) -> {0,1} bytes, widths that are and are not multiples of 8."""
+    import numpy as np
+    import torch
+    from moseq2_detectron_extract_b200 import _dev, _lib
+    rng = np.random.default_rng(3)
+    for h, w in ((240, 240), (17, 43), (400, 400), (5, 8)):
+        mask = (rng.random((6, h, w)) < 0.3).astype(np.uint8)
+        bits = np.packbits(mask, axis=-1, bitorder='little')
+        d_bits = torch.from_numpy(bits).cuda()
+        out = torch.full((6, h, w), 7, dtype=torch.uint8, device='cuda')
+        _lib.call('msq_unpack_mask_bits', _dev.ptr(d_bits), 6, h, w, _dev.ptr(out), _dev.stream())
+        assert np.array_equal(out.cpu().numpy(), mask)
