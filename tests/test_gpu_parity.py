@@ -159,6 +159,53 @@ def test_clean_matches_opencv_on_random_frames(P, shape):
     assert np.array_equal(P.clean_frames(fr, iters_tail=3), O.clean_frames_cv2(fr)), shape
 
 
+@pytest.mark.parametrize('shape', [(240, 240), (120, 64), (400, 400), (90, 488), (64, 248), (300, 256)])
+def test_clean_row_skipping_matches_opencv(P, shape):
+    """The streaming kernel only sends rows through the full median / erosion / dilation pipeline when a bit-level pre-pass
+    finds a nine-run of positive medians within reach; everything else is written as zeros.  Sparse frames exercise that
+    decision: blobs at every border and corner, across the 240-column tile seam, thin (8-wide, never survives) and just-wide-
+    enough (9..11) bars, Kinect-like floor noise (31 % positive pixels), empty frames, frames cut across CTA row ranges."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    h, w = shape
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = []
+
+    def noise():
+        return np.clip(np.rint(-rng.normal(0, 1, shape)), 0, 255).astype(np.uint8)
+
+    def blob(cy, cx, ry, rx, val=40):
+        f = noise()
+        m = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
+        f[m] = np.clip(val + rng.integers(-5, 6, size=int(m.sum())), 1, 255)
+        return f
+
+    frames.append(np.zeros(shape, np.uint8))
+    frames.append(noise())
+    for cy, cx in ((0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1), (h // 2, 0), (0, w // 2), (h - 1, w // 2), (h // 2, w - 1),
+                   (h // 2, min(w - 1, 239)), (h // 2, min(w - 1, 244)), (3, 3), (h - 4, w - 4)):
+        frames.append(blob(cy, cx, 14, 30))
+    two = blob(h // 5, w // 4, 8, 12)
+    m2 = ((yy - 4 * h // 5) / 9) ** 2 + ((xx - 3 * w // 4) / 20) ** 2 <= 1
+    two[m2] = 60
+    frames.append(two)
+    for width in (8, 9, 10, 11):                                   # horizontal bars: the ellipse's centre row is 9 wide
+        f = np.zeros(shape, np.uint8)
+        f[h // 3:h // 3 + 12, 5:5 + width] = 50
+        f[2 * h // 3:2 * h // 3 + width, w // 2:w // 2 + 14] = 70
+        frames.append(f)
+    full = np.full(shape, 9, np.uint8)
+    full[h // 2, :] = 0                                            # one zero row: the band logic sees two halves
+    frames.append(full)
+    edge = np.zeros(shape, np.uint8)
+    edge[:, :5] = 30; edge[:6, :] = 30; edge[:, -5:] = 30; edge[-6:, :] = 30   # strips along the borders (outside pixels are ignored)
+    frames.append(edge)
+    fr = np.stack(frames)
+    got, want = P.clean_frames(fr, iters_tail=3), O.clean_frames_cv2(fr)
+    assert want[2:].any()                                           # the blobs do survive the opening
+    for i in range(len(fr)):
+        assert np.array_equal(got[i], want[i]), (shape, i)
+
+
 def test_clean_rejects_unsupported_configs(P):
     fr = np.zeros((1, 8, 8), np.uint8)
     with pytest.raises(NotImplementedError):
