@@ -92,20 +92,102 @@ template <class OP> __device__ __forceinline__ uint4 op3_4(const uint4 &a, const
 }
 
 // ---- pass 1: which rows of a strip can hold a non-zero output at all? -----------------------------------------------------
-// The opening's erosion E(x, e) is the minimum of the median image M over the 9x9 ellipse around (x, e); its centre row is 9
-// wide, so E(x, e) > 0 needs M > 0 on the nine pixels (x-4..x+4, e) -- pixels outside the image do not take part in the
-// minimum and count as positive.  And M(p) > 0 exactly when at least 5 of the 9 raw pixels around p (replicate border) are
-// positive.  Both tests only need ONE BIT per pixel: 8 pixels of a lane become an 8-bit mask, the 3x3 counts are bit-sliced
-// adders (a handful of LOP3 for 8 pixels at once), the nine-run an AND of shifted masks.  ~45 ALU instructions per row and
-// lane against ~160 for the full median + erosion + dilation, and on a prepared depth frame (floor noise: 31 % positive
-// pixels -> 12 % positive medians -> a nine-run every ~10^8 positions) only the rows under the animal pass.  Rows with no
-// such run within 4 rows produce zeros and are never sent through the full pipeline: exact, not a heuristic -- every
-// uncertainty (pixels beyond the ends of the warp-row) is resolved as "positive".
-struct RowBits { uint32_t s0, s1; };   // per pixel: number of positive pixels among (left, self, right), as two bit planes
+// The opening's erosion E(x, e) is the minimum of the median image M over the 9x9 ellipse around (x, e) -- rows of width
+// 1,7,7,9,9,9,7,7,1; pixels outside the image take no part in it.  So E(x, e) > 0 exactly when M > 0 on every in-image pixel
+// of that ellipse, and M(p) > 0 exactly when at least 5 of the 9 raw pixels around p (replicate border) are positive.  Both
+// statements are about ONE BIT per pixel: a lane turns 32 pixels of a row into a 32-bit mask, the 3x3 counts are bit-sliced
+// adders (a dozen LOP3 for 32 pixels), horizontal runs are ANDs of funnel-shifted masks, the ellipse an AND over nine rows.
+// The warp's four 8-lane groups each walk a quarter of the strip's rows with their vertical history in registers:
+// ~30 instructions per 256-pixel row against ~230 for the full median + erosion + dilation.  On a prepared depth frame the
+// floor is noise (about half of the pixels positive) and only the rows under the animal come out positive; every other row
+// of the result is zero and is never sent through the full pipeline.  Exact, not a heuristic: the one uncertainty (pixels
+// beyond the ends of the warp-row on images wider than one tile) is resolved as "positive".
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t x, int shift) {       // 4 bytes -> 4 bits placed at bit `shift`
+    const uint32_t m = (bytes_nonzero(x) >> 7) * 0x00204081u;                      // bits 21..24
+    return shift >= 21 ? (m << (shift - 21)) & (0xfu << shift) : (m >> (21 - shift)) & (0xfu << shift);
+}
 
-__device__ __forceinline__ uint32_t positive_bits8(uint2 v) {                 // 8 bytes -> 8 bits (bit k: byte k != 0)
-    const uint32_t a = bytes_nonzero(v.x) >> 7, b = bytes_nonzero(v.y) >> 7;  // 0x01 per non-zero byte
-    return ((a * 0x00204081u) >> 21 & 0xfu) | (((b * 0x00204081u) >> 21 & 0xfu) << 4);
+struct BandScan {
+    const uint8_t *src;
+    int h, w, xb, j;                 // image, first column of this lane's 32-pixel block, block index 0..7 in the row
+    uint32_t out_mask;               // bits of the block that lie outside the image
+
+    __device__ __forceinline__ uint32_t positive_bits(int y) const {              // raw row y (clamped): bit k = pixel xb + k > 0
+        const uint8_t *row = src + (size_t)min(max(y, 0), h - 1) * w;
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xg = xb + 8 * k;
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + min(max(xg, 0), w - 8)));
+            uint32_t b8 = (nonzero_nibble(v.x, 0) | nonzero_nibble(v.y, 4));
+            if (xg < 0) b8 = (b8 & 1u) ? 0xffu : 0u;                               // replicate border
+            else if (xg >= w) b8 = (b8 & 0x80u) ? 0xffu : 0u;
+            bits |= b8 << (8 * k);
+        }
+        return bits;
+    }
+    // per pixel the number of positive pixels among (left, self, right) as two bit planes
+    __device__ __forceinline__ void row_counts(int y, uint32_t &s0, uint32_t &s1) const {
+        const uint32_t P = positive_bits(y);
+        const uint32_t pl = __shfl_up_sync(kFull, P, 1, 8), pr = __shfl_down_sync(kFull, P, 1, 8);
+        // beyond either end of the warp-row: the image border replicates the lane's own edge pixel, anything else is unknown (1)
+        const uint32_t left = j == 0 ? ((xb - 1 < 0) ? ((P & 1u) << 31) : 0x80000000u) : pl;
+        const uint32_t right = j == 7 ? ((xb + 32 >= w) ? (P >> 31) : 1u) : pr;
+        const uint32_t L = __funnelshift_l(left, P, 1), R = __funnelshift_r(P, right, 1);
+        s0 = L ^ P ^ R;
+        s1 = (L & P) | (L & R) | (P & R);
+    }
+};
+
+// rows e in [e_first, e_last] (in-image) on which the erosion is non-zero somewhere in this warp-row: [lo, hi] or hi < lo
+__device__ __forceinline__ void scan_band(const uint8_t *src, int h, int w, int x_span0, int e_first, int e_last, int lane,
+                                          int &band_lo, int &band_hi) {
+    BandScan sc;
+    sc.src = src; sc.h = h; sc.w = w; sc.j = lane & 7; sc.xb = x_span0 + 32 * sc.j;
+    sc.out_mask = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((unsigned)(sc.xb + 8 * k) >= (unsigned)w) sc.out_mask |= 0xffu << (8 * k);
+    const int rows = e_last - e_first + 1, per = (rows + 3) >> 2, grp = lane >> 3;
+    const int q0 = e_first + grp * per, q1 = min(e_last, q0 + per - 1);            // centre rows of this 8-lane group
+    int lo = INT_MAX, hi = -1;
+    // median row m needs raw rows m-1..m+1; centre e needs median rows e-4..e+4: raw rows q0-5 .. q1+5
+    uint32_t a0, a1, b0, b1;
+    sc.row_counts(q0 - 5, a0, a1);
+    sc.row_counts(q0 - 4, b0, b1);
+    // acc[i]: the ellipse AND of the centre row that completes i rows from now (acc0 completes with the current median row)
+    uint32_t acc0 = ~0u, acc1 = ~0u, acc2 = ~0u, acc3 = ~0u, acc4 = ~0u, acc5 = ~0u, acc6 = ~0u, acc7 = ~0u, acc8 = ~0u;
+    const int steps = per + 8;                                                      // the same for every group (warp-uniform loop)
+    for (int i = 0; i < steps; ++i) {
+        const int m = q0 - 4 + i;                                                   // median row of this step
+        uint32_t c0, c1;
+        sc.row_counts(m + 1, c0, c1);
+        // total = t0 + 2 u0 + 4 v0 + 8 v1 of the three rows' 2-bit counts; median positive <=> total >= 5
+        const uint32_t t0 = a0 ^ b0 ^ c0, k0 = (a0 & b0) | (a0 & c0) | (b0 & c0);
+        const uint32_t t1 = a1 ^ b1 ^ c1, k1 = (a1 & b1) | (a1 & c1) | (b1 & c1);
+        const uint32_t u0 = k0 ^ t1, u1 = k0 & t1, v0 = u1 ^ k1, v1 = u1 & k1;
+        uint32_t M = v1 | (v0 & (u0 | t0));
+        M |= sc.out_mask;                                                           // outside the image: not part of the minimum
+        if ((unsigned)m >= (unsigned)h) M = ~0u;
+        const uint32_t ml = __shfl_up_sync(kFull, M, 1, 8), mr = __shfl_down_sync(kFull, M, 1, 8);
+        const uint32_t ML = sc.j == 0 ? ~0u : ml, MR = sc.j == 7 ? ~0u : mr;
+        const uint32_t c3 = M & __funnelshift_r(M, MR, 1) & __funnelshift_l(ML, M, 1);
+        const uint32_t c5 = c3 & __funnelshift_r(M, MR, 2) & __funnelshift_l(ML, M, 2);
+        const uint32_t c7 = c5 & __funnelshift_r(M, MR, 3) & __funnelshift_l(ML, M, 3);
+        const uint32_t c9 = c7 & __funnelshift_r(M, MR, 4) & __funnelshift_l(ML, M, 4);
+        // row m is row e+4 of centre e = m-4 (acc0), e+3 of m-3 (acc1), ... e-4 of m+4 (acc8): widths 1,7,7,9,9,9,7,7,1
+        acc0 &= M; acc1 &= c7; acc2 &= c7; acc3 &= c9; acc4 &= c9; acc5 &= c9; acc6 &= c7; acc7 &= c7; acc8 &= M;
+        const int e = m - 4;
+        if ((acc0 & ~sc.out_mask) != 0u && e >= q0 && e <= q1) { lo = min(lo, e); hi = max(hi, e); }
+        acc0 = acc1; acc1 = acc2; acc2 = acc3; acc3 = acc4; acc4 = acc5; acc5 = acc6; acc6 = acc7; acc7 = acc8; acc8 = ~0u;
+        a0 = b0; a1 = b1; b0 = c0; b1 = c1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
+        hi = max(hi, __shfl_xor_sync(kFull, hi, o));
+    }
+    band_lo = lo; band_hi = hi;
 }
 
 struct StreamGeom {
@@ -164,47 +246,9 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
             return r;
         };
 
-        // ---- pass 1 (see RowBits above): rows of this strip that can be non-zero ----
+        // ---- pass 1 (scan_band above): rows of this strip on which the erosion is non-zero ----
         int band_lo = INT_MAX, band_hi = -1;
-        {
-            const int e_first = max(0, y_out0 - 4), e_last = min(h, y_out1 + 4) - 1;       // erosion rows that reach this strip
-            const bool left_out = x_lane < 0, right_out = x_lane >= w;
-            auto row_bits = [&](int y) {
-                const uint8_t *row = src + (size_t)min(max(y, 0), h - 1) * w;
-                uint32_t b = positive_bits8(__ldg(reinterpret_cast<const uint2 *>(row + xg)));
-                if (left_out) b = (b & 1u) ? 0xffu : 0u;                                   // replicate border, as decode() does
-                else if (right_out) b = (b & 0x80u) ? 0xffu : 0u;
-                const uint32_t from_l = __shfl_up_sync(kFull, b, 1), from_r = __shfl_down_sync(kFull, b, 1);
-                // the pixel beyond either end of the warp-row: the lane's own edge pixel when that is the image border
-                // (replicate), otherwise unknown -> positive
-                const uint32_t lbit = lane == 0 ? (left_out ? (b & 1u) : 1u) : (from_l >> 7);
-                const uint32_t rbit = lane == 31 ? (right_out ? (b >> 7) : 1u) : (from_r & 1u);
-                const uint32_t L = ((b << 1) | lbit) & 0xffu, R = (b >> 1) | (rbit << 7);
-                RowBits o;
-                o.s0 = L ^ b ^ R;
-                o.s1 = (L & b) | (L & R) | (b & R);
-                return o;
-            };
-            RowBits ra = row_bits(e_first - 1), rb = row_bits(e_first);
-            for (int e = e_first; e <= e_last; ++e) {
-                const RowBits rc = row_bits(e + 1);
-                // bit-sliced sum of three 2-bit counts: total = t0 + 2 u0 + 4 v0 + 8 v1 >= 5 ?
-                const uint32_t t0 = ra.s0 ^ rb.s0 ^ rc.s0, c0 = (ra.s0 & rb.s0) | (ra.s0 & rc.s0) | (rb.s0 & rc.s0);
-                const uint32_t t1 = ra.s1 ^ rb.s1 ^ rc.s1, c1 = (ra.s1 & rb.s1) | (ra.s1 & rc.s1) | (rb.s1 & rc.s1);
-                const uint32_t u0 = c0 ^ t1, u1 = c0 & t1, v0 = u1 ^ c1, v1 = u1 & c1;
-                uint32_t med = (v1 | (v0 & (u0 | t0))) & 0xffu;                             // bit k: median of pixel k is positive
-                if (!col_in) med = 0xffu;                                                   // outside the image: not part of the minimum
-                const uint32_t ml = __shfl_up_sync(kFull, med, 1), mr = __shfl_down_sync(kFull, med, 1);
-                const uint32_t W = (lane == 0 ? 0xffu : ml) | (med << 8) | ((lane == 31 ? 0xffu : mr) << 16);
-                uint32_t r = W & (W >> 1);
-                r &= r >> 2;
-                r &= r >> 4;                                                                // bit i: W[i .. i+7] all set
-                r &= W >> 8;                                                                // bit i: W[i .. i+8] all set, centre i + 4
-                const bool hit = col_in && ((r >> 4) & 0xffu) != 0u;                        // centred on one of this lane's pixels
-                if (__any_sync(kFull, hit)) { band_lo = min(band_lo, e); band_hi = e; }
-                ra = rb; rb = rc;
-            }
-        }
+        scan_band(src, h, w, tx * kOutCols - 8, max(0, y_out0 - 4), min(h, y_out1 + 4) - 1, lane, band_lo, band_hi);
         // rows outside [band_lo - 4, band_hi + 4] are zero
         const int act0 = band_hi < 0 ? y_out1 : max(y_out0, band_lo - 4), act1 = band_hi < 0 ? y_out1 : min(y_out1, band_hi + 5);
         if (writes) {
