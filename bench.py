@@ -786,6 +786,36 @@ def secondary_figures(args, geom, cfg, roi, bg):
     out['prep_with_invalid_pixels'] = {'frames': int(fr.shape[0]), 'invalid_rate': 0.002, 'ms_prep_only': ms_raw,
                                        'ms_prep_plus_inpaint': ms_fix, 'frames_per_s': fr.shape[0] / (ms_fix * 1e-3)}
     del fr
+    # (3) a7 on a less convenient animal: bent body, tail, pasted-28x28 mask outlines.  Which share of the frames does the
+    # streaming (row-convex, hole-free) feature kernel settle, and what do both regimes cost?
+    try:
+        import ctypes
+        from moseq2_detectron_extract_b200 import _lib
+        regimes = {}
+        for name, kw in (('ellipsoid (headline workload)', {}), ('bent body + tail + pasted 28x28 mask', {'realistic': True})):
+            ch = synthetic.generate_chunk(300, seed=21, geom=geom, **kw)
+            reps = 10
+            prep = prep_raw_frames(torch.from_numpy(np.tile(ch.frames, (reps, 1, 1))).cuda(), bground_im=bg, roi=roi, vmin=0, vmax=100)
+            masks = torch.from_numpy(np.tile(ch.masks, (reps, 1, 1))).cuda()
+            n, h, w = (int(v) for v in prep.shape)
+            cleaned = torch.empty_like(prep)
+            _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, _dev.stream())
+            cen, ori, ax = _dev.empty((n, 2), torch.float64), _dev.empty((n,), torch.float64), _dev.empty((n, 2), torch.float64)
+            flist = _dev.empty((n + 1,), torch.int32)
+
+            def feats(scratch=True):
+                _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(cen), _dev.ptr(ori), _dev.ptr(ax),
+                          None, _dev.ptr(flist) if scratch else None, flist.numel() * 4 if scratch else 0, _dev.stream())
+            ms_mixed = timed(feats, iters=5)
+            passed_on = int(flist[0].item())
+            ms_general = timed(lambda: feats(False), iters=5)
+            ms_clean = timed(lambda: _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, _dev.stream()), iters=5)
+            regimes[name] = {'frames': n, 'fast_path_hit_rate': 1.0 - passed_on / n, 'ms_streaming_plus_general_for_the_rest': ms_mixed,
+                             'ms_general_kernel_on_every_frame': ms_general, 'GBps_mixed': (2 * h * w + 40) * n / (ms_mixed * 1e-3) / 1e9,
+                             'ms_clean_frames': ms_clean, 'GBps_clean': 2 * h * w * n / (ms_clean * 1e-3) / 1e9}
+        out['features_regimes'] = regimes
+    except Exception as exc:
+        out['features_regimes'] = {'error': repr(exc)[:300]}
     try:
         from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
         tcfg = dict(cfg, use_tracking=True, results_to_host=False, expected_instances=1)

@@ -112,14 +112,20 @@ struct BandScan {
     int h, w, xb, j;                 // image, first column of this lane's 32-pixel block, block index 0..7 in the row
     uint32_t out_mask;               // bits of the block that lie outside the image
 
-    __device__ __forceinline__ uint32_t positive_bits(int y) const {              // raw row y (clamped): bit k = pixel xb + k > 0
+    struct Raw { uint2 v[4]; };
+    __device__ __forceinline__ Raw load_row(int y) const {                         // raw row y (clamped), this lane's 32 pixels
         const uint8_t *row = src + (size_t)min(max(y, 0), h - 1) * w;
+        Raw r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.v[k] = __ldg(reinterpret_cast<const uint2 *>(row + min(max(xb + 8 * k, 0), w - 8)));
+        return r;
+    }
+    __device__ __forceinline__ uint32_t positive_bits(const Raw &r) const {        // bit k = pixel xb + k > 0
         uint32_t bits = 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int xg = xb + 8 * k;
-            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + min(max(xg, 0), w - 8)));
-            uint32_t b8 = (nonzero_nibble(v.x, 0) | nonzero_nibble(v.y, 4));
+            uint32_t b8 = (nonzero_nibble(r.v[k].x, 0) | nonzero_nibble(r.v[k].y, 4));
             if (xg < 0) b8 = (b8 & 1u) ? 0xffu : 0u;                               // replicate border
             else if (xg >= w) b8 = (b8 & 0x80u) ? 0xffu : 0u;
             bits |= b8 << (8 * k);
@@ -127,8 +133,8 @@ struct BandScan {
         return bits;
     }
     // per pixel the number of positive pixels among (left, self, right) as two bit planes
-    __device__ __forceinline__ void row_counts(int y, uint32_t &s0, uint32_t &s1) const {
-        const uint32_t P = positive_bits(y);
+    __device__ __forceinline__ void row_counts(const Raw &r, uint32_t &s0, uint32_t &s1) const {
+        const uint32_t P = positive_bits(r);
         const uint32_t pl = __shfl_up_sync(kFull, P, 1, 8), pr = __shfl_down_sync(kFull, P, 1, 8);
         // beyond either end of the warp-row: the image border replicates the lane's own edge pixel, anything else is unknown (1)
         const uint32_t left = j == 0 ? ((xb - 1 < 0) ? ((P & 1u) << 31) : 0x80000000u) : pl;
@@ -153,15 +159,18 @@ __device__ __forceinline__ void scan_band(const uint8_t *src, int h, int w, int 
     int lo = INT_MAX, hi = -1;
     // median row m needs raw rows m-1..m+1; centre e needs median rows e-4..e+4: raw rows q0-5 .. q1+5
     uint32_t a0, a1, b0, b1;
-    sc.row_counts(q0 - 5, a0, a1);
-    sc.row_counts(q0 - 4, b0, b1);
+    sc.row_counts(sc.load_row(q0 - 5), a0, a1);
+    sc.row_counts(sc.load_row(q0 - 4), b0, b1);
+    BandScan::Raw p0 = sc.load_row(q0 - 3), p1 = sc.load_row(q0 - 2);              // raw rows are requested two steps ahead
     // acc[i]: the ellipse AND of the centre row that completes i rows from now (acc0 completes with the current median row)
     uint32_t acc0 = ~0u, acc1 = ~0u, acc2 = ~0u, acc3 = ~0u, acc4 = ~0u, acc5 = ~0u, acc6 = ~0u, acc7 = ~0u, acc8 = ~0u;
     const int steps = per + 8;                                                      // the same for every group (warp-uniform loop)
     for (int i = 0; i < steps; ++i) {
         const int m = q0 - 4 + i;                                                   // median row of this step
         uint32_t c0, c1;
-        sc.row_counts(m + 1, c0, c1);
+        const BandScan::Raw p2 = sc.load_row(m + 3);
+        sc.row_counts(p0, c0, c1);                                                  // raw row m + 1
+        p0 = p1; p1 = p2;
         // total = t0 + 2 u0 + 4 v0 + 8 v1 of the three rows' 2-bit counts; median positive <=> total >= 5
         const uint32_t t0 = a0 ^ b0 ^ c0, k0 = (a0 & b0) | (a0 & c0) | (b0 & c0);
         const uint32_t t1 = a1 ^ b1 ^ c1, k1 = (a1 & b1) | (a1 & c1) | (b1 & c1);

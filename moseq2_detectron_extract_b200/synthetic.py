@@ -99,8 +99,13 @@ def _body_keypoints(cx, cy, theta, a, b):
 
 def generate_chunk(n_frames: int, seed: int = 0, geom: Optional[SessionGeometry] = None, t0: int = 0,
                    invalid_rate: float = 0.0, missing_every: int = 0, noise_sigma: float = 1.0,
-                   mask_holes: bool = False) -> SyntheticChunk:
+                   mask_holes: bool = False, realistic: bool = False) -> SyntheticChunk:
     """Generate `n_frames` consecutive frames starting at session time index `t0`.
+
+    realistic    : a less convenient animal -- the body bends into a banana (curvature swings with time: concave outlines, rows
+                   with two runs at many headings), it drags a thin curved tail, and the instance mask is what a Mask R-CNN
+                   would hand over: the ground-truth silhouette averaged down to a 28x28 soft mask inside its box, pasted back
+                   bilinearly and thresholded at 0.5 (ragged, box-clipped outline; the tail mostly falls below 0.5).
 
     invalid_rate : probability for a pixel to be a Kinect "invalid" (value 0) pixel.
     missing_every: if >0, every `missing_every`-th frame (offset 7) has no instance (NaN path).
@@ -123,7 +128,7 @@ def generate_chunk(n_frames: int, seed: int = 0, geom: Optional[SessionGeometry]
     centers = np.empty((n_frames, 2), dtype=np.float64)
 
     a, b = geom.mouse_axes
-    reach = int(np.ceil(a)) + 2
+    reach = int(np.ceil(a * (1.9 if realistic else 1.0))) + 2
     bx, by = geom.bucket_center
     for i in range(n_frames):
         t = t0 + i
@@ -140,10 +145,20 @@ def generate_chunk(n_frames: int, seed: int = 0, geom: Optional[SessionGeometry]
         ya, yb = max(int(cy) - reach, 0), min(int(cy) + reach + 1, H)
         yy, xx = np.mgrid[ya:yb, xa:xb]
         dx, dy = xx - cx, yy - cy
-        u = (dx * np.cos(th) + dy * np.sin(th)) / a
-        v = (-dx * np.sin(th) + dy * np.cos(th)) / b
+        along = dx * np.cos(th) + dy * np.sin(th)
+        across = -dx * np.sin(th) + dy * np.cos(th)
+        kappa = (np.sin(0.031 * t) / 45.0) if realistic else 0.0          # body axis bent into a parabola across = kappa s^2 / 2
+        u = along / a
+        v = (across - 0.5 * kappa * along * along) / b
         rr = u * u + v * v
         body = np.where(rr < 1.0, geom.mouse_height * np.sqrt(np.clip(1.0 - rr, 0.0, 1.0)), 0.0)
+        tail = np.zeros_like(body, dtype=bool)
+        if realistic:                                                     # 3 px wide, 8 mm high, curling the other way
+            ts = np.linspace(-a - 0.85 * a, -a + 2.0, 60)
+            tl = 0.5 * kappa * a * a - 0.02 * np.cos(0.017 * t) * (ts + a) ** 2
+            d2 = (along[..., None] - ts) ** 2 + (across[..., None] - tl) ** 2
+            tail = (d2.min(axis=-1) <= 1.5 ** 2) & (rr >= 1.0)
+            body = np.where(tail, 8.0, body)
         depth[ya:yb, xa:xb] -= body.astype(np.float32)
         frames[i] = np.rint(depth).astype(np.int16)
 
@@ -152,10 +167,18 @@ def generate_chunk(n_frames: int, seed: int = 0, geom: Optional[SessionGeometry]
             continue
 
         # instance mask in ROI-bbox space: slightly generous ellipse support
-        blob = (rr < 1.08)
+        blob = (rr < 1.08) | tail
         full = np.zeros((H, W), dtype=np.uint8)
         full[ya:yb, xa:xb] = blob
         m = full[y0:y1, x0:x1].copy()
+        if realistic and m.any():
+            import cv2
+            ys, xs = np.nonzero(m)
+            by0, by1, bx0, bx1 = ys.min(), ys.max() + 1, xs.min(), xs.max() + 1
+            soft = cv2.resize(m[by0:by1, bx0:bx1].astype(np.float32), (28, 28), interpolation=cv2.INTER_AREA)
+            pasted = cv2.resize(soft, (int(bx1 - bx0), int(by1 - by0)), interpolation=cv2.INTER_LINEAR) >= 0.5
+            m = np.zeros_like(m)
+            m[by0:by1, bx0:bx1] = pasted
         if mask_holes and (i % 5) == 3:
             hx, hy = int(cx) - x0, int(cy) - y0
             if 2 <= hy < h - 2 and 2 <= hx < w - 2:
