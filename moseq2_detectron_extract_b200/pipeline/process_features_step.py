@@ -14,6 +14,7 @@ from .. import _lib
 from ..proc.kalman import KalmanTracker, KalmanTrackerAngle, KalmanTrackerNPoints2D, KalmanTrackerPoint2D
 from ..proc.proc import _gather_instances, _tracked_angles_and_flips, crop_and_rotate_frames_batch
 from ..proc.scalars import scalars_from_table
+from ..proc.sort_tracker import Detection, Tracker
 from .pipeline_step import ProcessPipelineStep
 
 
@@ -28,6 +29,8 @@ class ProcessFeaturesStep(ProcessPipelineStep):
         else:
             self.point_tracker = None
             self.angle_tracker = None
+        # ref: process_features_step.py:35-38 -- identities of individuals across frames (norfair's configuration, restated)
+        self.instance_tracker = Tracker(distance_function='euclidean', distance_threshold=50, initialization_delay=0, hit_counter_max=3)
         self.engine = ChunkEngine()
         self.to_host = bool(self.config.get('results_to_host', True))
 
@@ -60,15 +63,49 @@ class ProcessFeaturesStep(ProcessPipelineStep):
             idxs = np.delete(idxs, np.unique(np.concatenate(([last], rows))))
         return instances[picked]
 
+    @staticmethod
+    def _instances_to_detections(instances: Instances) -> List[Detection]:
+        """ref: process_features_step.py:115-129 -- one Detection per instance at the centre of mass of its mask (row, column),
+        the box centre when the mask is empty.  Centres are computed on the device in one pass; the tracker is host-side."""
+        n = len(instances)
+        if n == 0:
+            return []
+        masks = instances.pred_masks.float()
+        area = masks.sum(dim=(1, 2))
+        ys = torch.arange(masks.shape[1], device=masks.device, dtype=torch.float32)
+        xs = torch.arange(masks.shape[2], device=masks.device, dtype=torch.float32)
+        cy = (masks.sum(dim=2) * ys).sum(dim=1) / area
+        cx = (masks.sum(dim=1) * xs).sum(dim=1) / area
+        centres = torch.stack([cy, cx], dim=1).cpu().numpy()
+        boxes = instances.pred_boxes.get_centers().cpu().numpy()
+        out = []
+        for i in range(n):
+            centre = centres[i] if np.isfinite(centres[i]).all() else boxes[i]
+            out.append(Detection(np.asarray(centre, dtype=float), data={'index': i, 'instance': instances[i]}))
+        return out
+
     def _select_instances(self, data: dict) -> dict:
+        """ref: process_features_step.py:132-160 -- mask-IoU suppression, then SORT-style identity tracking: when more than one
+        tracked object is alive, keep the `expected_instances` OLDEST ones that are live in this frame.  The dense hand-over
+        (one detection per frame by construction, TEST.DETECTIONS_PER_IMAGE = 1) has nothing to select."""
         if '_dense_instances' in data:
             return data
+        expected = int(self.config.get('expected_instances', 1))
         for frame in data['inference']:
             inst = self._nms_mask_instances(frame['instances'])
-            if len(inst) > self.config['expected_instances']:
-                top = torch.argsort(inst.scores, descending=True)[: self.config['expected_instances']]
-                inst = inst[top.tolist()]
             frame['instances'] = inst
+            tracked = self.instance_tracker.update(detections=self._instances_to_detections(inst))
+            if len(tracked) <= 1:
+                continue
+            by_age = sorted((t for t in tracked if t.live_points.any()), key=lambda t: t.age)
+            selected = []
+            while len(selected) < expected and len(by_age) > 0:
+                selected.append(by_age.pop().last_detection.data['instance'])
+            if selected:
+                frame['instances'] = Instances.cat(selected)
+            else:
+                h, w = inst.image_size
+                frame['instances'] = create_empty_instances(w, h, _lib.NUM_KEYPOINTS, device='cuda')
         return data
 
     # ---- use_tracking=True: the same outputs through the Kalman branch (ref: proc/proc.py:730-826) ---------------

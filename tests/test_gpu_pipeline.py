@@ -240,3 +240,43 @@ def test_mask_iou_suppression_matches_reference_semantics():
         if trial % 4 == 0:
             masks[int(rng.integers(0, n))] = False
         run(masks, rng.random(n).astype(np.float32))
+
+
+def test_select_instances_keeps_the_oldest_tracked_identity():
+    """ProcessFeaturesStep._select_instances (ref: process_features_step.py:132-160): after the mask-IoU suppression the SORT
+    tracker decides -- with expected_instances = 1 the OLDEST identity that is live in the frame is kept, not the best score."""
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.model.instances import Boxes, Instances
+    from moseq2_detectron_extract_b200.pipeline import ProcessFeaturesStep
+    cfg = dict(synthetic.default_config(), expected_instances=1, results_to_host=False)
+    step = ProcessFeaturesStep(cfg, 'features')
+    step.initialize()
+    h = w = 120
+
+    def disk(cy, cx, r=9):
+        yy, xx = np.mgrid[0:h, 0:w]
+        return (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+
+    def inst(masks, scores, tags):
+        n = len(masks)
+        return Instances((h, w), pred_boxes=Boxes(torch.zeros((n, 4), device='cuda')), scores=torch.tensor(scores, device='cuda'),
+                         pred_classes=torch.zeros((n,), dtype=torch.int64, device='cuda'),
+                         pred_masks=torch.from_numpy(np.stack(masks)).cuda() if n else torch.zeros((0, h, w), dtype=torch.bool, device='cuda'),
+                         pred_keypoints=torch.tensor(tags, device='cuda', dtype=torch.float32)[:, None, None].expand(n, 8, 3).contiguous())
+    frames = []
+    for t in range(8):
+        a = disk(30 + 3 * t, 30 + 2 * t)                           # animal A from the first frame on (tag 1)
+        if t < 3:
+            frames.append({'instances': inst([a], [0.6], [1.0])})
+        elif t == 6:
+            frames.append({'instances': inst([disk(90, 90 - 4 * t)], [0.99], [2.0])})      # A missed by the detector once
+        else:
+            b = disk(90, 90 - 4 * t)                                # animal B appears later with the better score (tag 2)
+            frames.append({'instances': inst([b, a], [0.99, 0.6], [2.0, 1.0])})
+    data = step._select_instances({'inference': frames, 'frame_idxs': list(range(8))})
+    tags = [int(f['instances'].pred_keypoints[0, 0, 0]) if len(f['instances']) else 0 for f in data['inference']]
+    counts = [len(f['instances']) for f in data['inference']]
+    assert counts == [1] * 8
+    # frames 3-5: both alive -> the older A; frame 6: only B is detected, A is alive but B is what the frame holds ... the
+    # reference takes the oldest LIVE object's last detection, which is A's detection of frame 5; frame 7: A again
+    assert tags[:6] == [1, 1, 1, 1, 1, 1] and tags[7] == 1 and tags[6] == 1

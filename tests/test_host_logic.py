@@ -458,3 +458,49 @@ def test_detectron2_state_dict_rewrites_are_exact_on_cpu():
     assert pred.shape == (3, 8) and float(pred[:, 6:].abs().max()) == 0
     assert model.pixel_mean == pytest.approx([1.12] * 3) and model.pixel_std == pytest.approx([5.79] * 3)
     assert tuple(model.kp_deconv_w.shape) == (512, 8, 4, 4) and model.keypoint_pooler == 7 and model.post_nms_topk == 1000
+
+
+def test_sort_tracker_follows_norfair_semantics():
+    """proc/sort_tracker.py (a15; norfair's Tracker for the reference's configuration, ref process_features_step.py:35-38):
+    greedy nearest matching below the threshold, hit counters (+2 on a hit capped at 3, -1 per frame, dropped below 0), ages,
+    live points, constant-velocity prediction, identity kept through a crossing and through a short occlusion."""
+    from moseq2_detectron_extract_b200.proc.sort_tracker import Detection, TrackedObject, Tracker
+    TrackedObject._next_id = 0
+    trk = Tracker(distance_function='euclidean', distance_threshold=50, initialization_delay=0, hit_counter_max=3)
+    assert trk.update(detections=[]) == []
+    # frame 0: one animal -> initialised at once (initialization_delay = 0), returned as active
+    out = trk.update(detections=[Detection(np.array([100.0, 100.0]), data='a0')])
+    assert len(out) == 1 and out[0].id == 0 and out[0].age == 0 and out[0].hit_counter == 1 and out[0].live_points.all()
+    # frames 1..3: it moves 5 px per frame; a second animal appears at frame 2 far away
+    for t in range(1, 4):
+        dets = [Detection(np.array([100.0 + 5 * t, 100.0]), data=f'a{t}')]
+        if t >= 2:
+            dets.insert(0, Detection(np.array([30.0, 200.0]), data=f'b{t}'))
+        out = trk.update(detections=dets)
+    assert sorted(o.id for o in out) == [0, 1]
+    a = next(o for o in out if o.id == 0)
+    b = next(o for o in out if o.id == 1)
+    assert a.age == 3 and b.age == 1 and a.hit_counter == 3 and a.last_detection.data == 'a3' and b.last_detection.data == 'b3'
+    assert 108.0 < a.estimate[0, 0] <= 115.0 and a.estimate[0, 1] == 100.0      # the filter follows the motion (it starts at rest)
+    # the reference keeps the OLDEST live object: sorted by age, pop from the end
+    oldest = sorted((o for o in out if o.live_points.any()), key=lambda o: o.age).pop()
+    assert oldest.id == 0
+    # a detection beyond the threshold starts a new object instead of moving an old one
+    out = trk.update(detections=[Detection(np.array([120.0, 100.0])), Detection(np.array([30.0, 200.0])), Detection(np.array([230.0, 20.0]))])
+    assert sorted(o.id for o in out) == [0, 1, 2]
+    # occlusion: object 0 unseen for 3 frames keeps its identity (hit counter 3 -> 2 -> 1 -> 0), the 4th miss ends it
+    for t in range(3):
+        out = trk.update(detections=[Detection(np.array([30.0, 200.0]))])
+        assert 0 in [o.id for o in out]
+    a = next(o for o in out if o.id == 0)
+    assert a.hit_counter == 0 and int(a.point_hit_counter[0]) == 1 and a.live_points.any()   # point counters are capped at 4, object counters at 3
+    out = trk.update(detections=[Detection(np.array([30.0, 200.0]))])
+    assert 0 not in [o.id for o in out]
+    # greedy matching: smallest distance first, one detection per object
+    d = np.array([[10.0, 12.0], [11.0, 60.0]])
+    det_idxs, obj_idxs = Tracker.match_dets_and_objs(d, 50.0)
+    assert (det_idxs, obj_idxs) == ([0], [0])
+    det_idxs, obj_idxs = Tracker.match_dets_and_objs(np.array([[10.0, 12.0], [11.0, 40.0]]), 50.0)
+    assert (det_idxs, obj_idxs) == ([0, 1], [0, 1])
+    with pytest.raises(ValueError):
+        trk._update_objects_in_place(trk.tracked_objects[:1], [Detection(np.array([np.nan, 1.0]))], 1)
