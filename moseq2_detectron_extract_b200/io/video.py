@@ -182,25 +182,50 @@ class RawDepthSession:
     def find_roi(self, bg_roi_dilate: Tuple[int, int] = (10, 10), bg_roi_shape: str = 'ellipse', bg_roi_index: int = 0,
                  bg_roi_weights=(1, .1, 1), bg_roi_depth_range: Tuple[int, int] = (650, 750), bg_roi_gradient_filter: bool = False,
                  bg_roi_gradient_threshold: int = 3000, bg_roi_gradient_kernel: int = 7, bg_roi_fill_holes: bool = True,
-                 use_plane_bground: bool = False, verbose: bool = False, frame_stride: int = 500):
-        """Per-session set-up (ref: io/session.py:181-264 without its tiff cache): first frame, background image
-        (unless one was given to the constructor), arena ROI = the `bg_roi_index`-th ranked region of `proc.get_roi`, and
-        `true_depth` = median background depth inside the ROI.  Stores `.bground_im`, `.roi`, `.true_depth` and returns
-        `(first_frame, bground_im, roi, true_depth)`.  Background and ROI are computed on the GPU."""
+                 use_plane_bground: bool = False, verbose: bool = False, frame_stride: int = 500, cache_dir: Optional[str] = None):
+        """Per-session set-up (ref: io/session.py:181-264): first frame, background image (unless one was given to the
+        constructor), arena ROI = the `bg_roi_index`-th ranked region of `proc.get_roi`, and `true_depth` = median background
+        depth inside the ROI.  Stores `.bground_im`, `.roi`, `.true_depth` and returns `(first_frame, bground_im, roi,
+        true_depth)`.  Background and ROI are computed on the GPU.  With `cache_dir` the reference's tiff cache is kept
+        (`first_frame.tiff`, `bground.tiff`, `roi_XX.tiff`, ref :194-257): existing files are loaded instead of recomputed --
+        the background then comes back as uint16, as in the reference (SURVEY trap 8)."""
         from ..proc.roi import get_roi
         from ..proc.util import select_strel
-        first_frame = self.read_frames([0], pinned=False)
-        if self.bground_im is None:
-            self.compute_bground(frame_stride=frame_stride)
+        from .image import read_tiff_image, write_image
+        use_cache = cache_dir is not None
+        cache_dir = cache_dir or ''
+        ff_filename = os.path.join(cache_dir, 'first_frame.tiff')
+        if use_cache and os.path.exists(ff_filename):
+            first_frame = read_tiff_image(ff_filename, scale=True)[None]
+        else:
+            first_frame = self.read_frames([0], pinned=False)
+            if use_cache:
+                write_image(ff_filename, first_frame[0], scale=True, scale_factor=tuple(bg_roi_depth_range))
+        bg_filename = os.path.join(cache_dir, 'bground.tiff')
+        if use_cache and os.path.exists(bg_filename):
+            self.bground_im = read_tiff_image(bg_filename, scale=True)
+        else:
+            if self.bground_im is None:
+                self.compute_bground(frame_stride=frame_stride)
+            if use_cache and not use_plane_bground:
+                write_image(bg_filename, np.asarray(self.bground_im), scale=True)
         bground_im = np.asarray(self.bground_im)
-        rois, plane, _, _, _, _ = get_roi(bground_im, strel_dilate=select_strel(bg_roi_shape, bg_roi_dilate), weights=bg_roi_weights,
-                                          depth_range=bg_roi_depth_range, gradient_filter=bg_roi_gradient_filter,
-                                          gradient_threshold=bg_roi_gradient_threshold, gradient_kernel=bg_roi_gradient_kernel,
-                                          fill_holes=bg_roi_fill_holes, progress_bar=verbose)
-        if use_plane_bground:                               # io/session.py:245-252: the fitted plane replaces the median image
-            yy, xx = np.mgrid[:bground_im.shape[0], :bground_im.shape[1]]
-            bground_im = ((xx * plane[0] + yy * plane[1]) + plane[3]) / -plane[2]
-        roi = rois[bg_roi_index]
+        roi_filename = os.path.join(cache_dir, f'roi_{int(bg_roi_index):02d}.tiff')
+        if use_cache and os.path.exists(roi_filename):
+            roi = read_tiff_image(roi_filename, scale=True) > 0
+        else:
+            rois, plane, _, _, _, _ = get_roi(bground_im, strel_dilate=select_strel(bg_roi_shape, bg_roi_dilate), weights=bg_roi_weights,
+                                              depth_range=bg_roi_depth_range, gradient_filter=bg_roi_gradient_filter,
+                                              gradient_threshold=bg_roi_gradient_threshold, gradient_kernel=bg_roi_gradient_kernel,
+                                              fill_holes=bg_roi_fill_holes, progress_bar=verbose)
+            if use_plane_bground:                           # io/session.py:245-252: the fitted plane replaces the median image
+                yy, xx = np.mgrid[:bground_im.shape[0], :bground_im.shape[1]]
+                bground_im = ((xx * plane[0] + yy * plane[1]) + plane[3]) / -plane[2]
+                if use_cache:
+                    write_image(bg_filename, bground_im, scale=True)
+            roi = rois[bg_roi_index]
+            if use_cache:
+                write_image(roi_filename, roi, scale=True, dtype='uint8')
         self.bground_im, self.roi = bground_im, roi
         self.true_depth = float(np.median(bground_im[roi > 0]))
         return first_frame, bground_im, roi, self.true_depth

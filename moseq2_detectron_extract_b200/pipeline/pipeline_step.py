@@ -52,8 +52,16 @@ class PipelineStep(threading.Thread):
 
     # ---- queues (ref: pipeline_step.py:72-96) ----------------------------------------------------
     def set_outputs(self, data) -> None:
+        """Blocks while a consumer's queue is full, but gives up when the pipeline is shutting down (a consumer that died can no
+        longer drain its queue: the producer must not hang on it holding CUDA tensors)."""
         for q in self.out_queue:
-            q.put(data)
+            while True:
+                try:
+                    q.put(data, timeout=0.1)
+                    break
+                except queue.Full:
+                    if self.shutdown_event is not None and self.shutdown_event.is_set():
+                        return
 
     def is_output_empty(self) -> bool:
         return all(q.empty() for q in self.out_queue)

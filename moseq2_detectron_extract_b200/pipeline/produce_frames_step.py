@@ -61,6 +61,6 @@ class ProduceFramesStep(ProducerPipelineStep):
         self.update_progress(int(raw_frames.shape[0]))
         return out
 
-    def finalize(self):
+    def shutdown(self):
         while getattr(self, '_inflight', None):
             self._inflight.popleft()[1].synchronize()

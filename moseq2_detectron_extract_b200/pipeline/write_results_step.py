@@ -22,6 +22,19 @@ except Exception:                       # pylint: disable=broad-except
     h5py = None
 
 
+def _plain(obj):
+    """numpy / tuple values -> plain Python for YAML."""
+    if isinstance(obj, dict):
+        return {str(k): _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    if isinstance(obj, np.ndarray):
+        return obj.tolist()
+    if isinstance(obj, np.generic):
+        return obj.item()
+    return obj if isinstance(obj, (str, int, float, bool)) or obj is None else str(obj)
+
+
 def _host(x):
     return x.detach().cpu().numpy() if hasattr(x, 'detach') else np.asarray(x)
 
@@ -50,8 +63,21 @@ class ResultStore:
                 self.arrays[path] = _host(config[key])
                 self.attrs[path] = text
         self.arrays['metadata/extraction/extract_version'] = np.array('moseq2-detectron-extract_b200')
+        # ref: io/result.py:31,88-102 -- uuid, the extraction parameters and the acquisition metadata of the session
+        status = config.get('status_dict') or {}
+        if status.get('uuid') is not None:
+            self.arrays['metadata/uuid'] = np.array(str(status['uuid']))
+        for key, value in (status.get('parameters') or {}).items():
+            if value is not None and not callable(value):
+                try:
+                    self.arrays[f'metadata/extraction/parameters/{key}'] = np.asarray(value)
+                except Exception:          # pylint: disable=broad-except
+                    self.arrays[f'metadata/extraction/parameters/{key}'] = np.array(str(value))
+        for key, value in (status.get('metadata') or {}).items():
+            self.arrays[f'metadata/acquisition/{key}'] = np.asarray([] if value is None else value)
         self.path = path_without_ext + ('.h5' if h5py is not None else '.npz')
         self.closed = False
+        self.frames_written = 0
 
     def _create(self, path, shape, dtype, description):
         self.arrays[path] = np.zeros(shape, dtype=dtype)
@@ -68,10 +94,17 @@ class ResultStore:
         self.arrays['metadata/extraction/flips'][rng] = _host(results['features']['flips'])[off:]
         for name, col in results['keypoints'].items():
             self.arrays[f'keypoints/{name}'][rng] = _host(col)[off:]
+        self.frames_written += len(rng)
 
-    def close(self) -> str:
+    def close(self, complete: bool = True) -> str:
+        """Write the file.  A run that did not reach its end (an upstream step failed, the pipeline was shut down) is NOT written
+        under the result's name: its partial contents go to `<name>.partial<ext>` so that a zero-padded file can never be
+        mistaken for a finished extraction."""
         if self.closed:
             return self.path
+        if not complete:
+            root, ext = os.path.splitext(self.path)
+            self.path = root + '.partial' + ext
         if h5py is not None:            # pragma: no cover
             with h5py.File(self.path, 'w') as f:
                 for path, arr in self.arrays.items():
@@ -93,6 +126,7 @@ class ResultWriterStep(ProcessPipelineStep):
         os.makedirs(out_dir, exist_ok=True)
         self.store = ResultStore(os.path.join(out_dir, f'results_{idx:02d}'), self.config)
         self.keypoint_data_dest = os.path.join(out_dir, f'keypoints_{idx:02d}.tsv')
+        self.status_filename = os.path.join(out_dir, f'results_{idx:02d}.yaml')
         self._tsv_header: Optional[list] = None
 
     def process(self, data):
@@ -102,11 +136,29 @@ class ResultWriterStep(ProcessPipelineStep):
         return data
 
     def finalize(self):
+        """After an error in this step."""
         if getattr(self, 'store', None) is not None:
-            self.store.close()
+            self.store.close(complete=False)
+            self._write_status(False)
 
     def shutdown(self):
-        self.finalize()
+        """End of the step's loop: a complete result only when the end-of-stream sentinel arrived and nothing failed."""
+        if getattr(self, 'store', None) is not None and not self.store.closed:
+            complete = self.is_complete.is_set() and self.error is None
+            self.store.close(complete=complete)
+            self._write_status(complete)
+
+    def _write_status(self, complete: bool) -> None:
+        """results_XX.yaml (ref: extract.py:55-62,131-132): uuid, parameters, acquisition metadata and the `complete` flag."""
+        status = dict(self.config.get('status_dict') or {})
+        status['complete'] = bool(complete)
+        status['frames_written'] = int(self.store.frames_written)
+        try:
+            import yaml
+            with open(self.status_filename, 'w', encoding='utf-8') as fh:
+                yaml.safe_dump(_plain(status), fh)
+        except Exception:              # pylint: disable=broad-except
+            pass
 
     # ---- keypoints_XX.tsv: Frame_Idx, Flip, Centroid_X, Centroid_Y, Angle, then the 96 keypoint columns -------------------
     def _write_tsv(self, data) -> None:

@@ -320,6 +320,65 @@ def test_result_writer_step_layout_and_offsets(tmp_path):
     header = lines[0].split('\t')
     assert header[:5] == ['Frame_Idx', 'Flip', 'Centroid_X', 'Centroid_Y', 'Angle'] and len(header) == 5 + 96
     assert len(lines) == 1 + 8 and lines[1].split('\t')[:3] == ['0', 'True', '0.0']
+    # uuid / parameters / acquisition metadata (ref io/result.py:31,88-102) and the status file with its `complete` flag
+    import yaml
+    cfg2 = dict(cfg, output_dir=str(tmp_path / 'second'),
+                status_dict={'uuid': 'abc-123', 'parameters': {'chunk_size': 1000, 'crop_size': (80, 80), 'fn': None},
+                             'metadata': {'SubjectName': 'mouse1', 'DepthResolution': [512, 424], 'Empty': None}})
+    step2 = ResultWriterStep(cfg2, 'writer')
+    step2.shutdown_event = threading.Event()
+    step2.in_queue = _queue.Queue()
+    step2.in_queue.put(chunk([0, 1, 2, 3], 0))
+    step2.in_queue.put(None)
+    step2.run()
+    assert step2.store.path.endswith(('results_00.npz', 'results_00.h5'))
+    status = yaml.safe_load(open(step2.status_filename))
+    assert status['complete'] is True and status['uuid'] == 'abc-123' and status['frames_written'] == 4
+    if step2.store.path.endswith('.npz'):
+        out2 = np.load(step2.store.path)
+        assert str(out2['metadata/uuid']) == 'abc-123' and int(out2['metadata/extraction/parameters/chunk_size']) == 1000
+        assert out2['metadata/acquisition/DepthResolution'].tolist() == [512, 424] and str(out2['metadata/acquisition/SubjectName']) == 'mouse1'
+    # a run that is shut down before the end-of-stream sentinel must not leave a file that looks finished
+    cfg3 = dict(cfg, output_dir=str(tmp_path / 'third'))
+    step3 = ResultWriterStep(cfg3, 'writer')
+    step3.shutdown_event = threading.Event()
+    step3.in_queue = _queue.Queue()
+    step3.in_queue.put(chunk([0, 1, 2, 3], 0))
+    t = threading.Thread(target=step3.run)
+    t.start()
+    import time as _time
+    while step3.in_queue.qsize() > 0:
+        _time.sleep(0.01)
+    _time.sleep(0.2)
+    step3.shutdown_event.set()                          # an upstream failure shuts the pipeline down
+    t.join(timeout=10)
+    assert '.partial.' in os.path.basename(step3.store.path) and not os.path.exists(os.path.join(str(tmp_path / 'third'), 'results_00.npz'))
+    assert yaml.safe_load(open(step3.status_filename))['complete'] is False
+
+
+def test_tiff_cache_round_trip_and_find_roi_cache_files(tmp_path):
+    """io/image.py (ref io/image.py:13-103): scaled uint16 / uint8 TIFFs with the scale factor in the ImageDescription, readable by
+    an independent decoder (OpenCV); the three cache files of find_roi (ref io/session.py:194-257) carry those conventions."""
+    import cv2
+    from moseq2_detectron_extract_b200.io.image import read_tiff_image, write_image
+    rng = np.random.default_rng(0)
+    bg = rng.uniform(600, 700, (48, 64))
+    path = str(tmp_path / 'cache' / 'bground.tiff')
+    write_image(path, bg, scale=True)
+    back = read_tiff_image(path, scale=True)
+    assert back.dtype == np.uint16 and np.array_equal(back, bg.astype('uint16'))          # the uint16 background of SURVEY trap 8
+    raw = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    factor = int(65535 / bg.astype('uint16').max())
+    assert raw.dtype == np.uint16 and np.array_equal(raw, bg.astype('uint16') * factor)
+    ff = rng.integers(500, 800, (48, 64)).astype('int16')
+    write_image(str(tmp_path / 'ff.tiff'), ff, scale=True, scale_factor=(650, 750))
+    got = read_tiff_image(str(tmp_path / 'ff.tiff')).astype(float)
+    assert np.abs(got - np.clip(ff, 650, 750)).max() <= 1.0
+    roi = rng.random((48, 64)) > 0.5
+    write_image(str(tmp_path / 'roi_00.tiff'), roi, scale=True, dtype='uint8')
+    assert np.array_equal(read_tiff_image(str(tmp_path / 'roi_00.tiff'), scale=True) > 0, roi)
+    with pytest.raises(NotImplementedError):
+        write_image(str(tmp_path / 'x.tiff'), roi, compress=3)
 
 
 def test_select_strel_and_sobel_kernels_equal_opencv():
