@@ -163,6 +163,17 @@ def test_raw_session_find_roi_from_file(tmp_path):
         assert abs(true_depth - 673.0) < 2.0
         # the detected arena covers the synthetic bucket floor the generator masks with
         assert (roi & synthetic.make_roi(geom)).sum() > 0.95 * synthetic.make_roi(geom).sum()
+    # the tiff cache (ref io/session.py:194-257): first call writes first_frame / bground / roi_00, the second one loads them
+    cache = str(tmp_path / 'cache')
+    sess = RawDepthSession(str(path), pinned=False)
+    np.random.seed(4)
+    _, bg1, roi1, depth1 = sess.find_roi(frame_stride=2, cache_dir=cache)
+    for name in ('first_frame.tiff', 'bground.tiff', 'roi_00.tiff'):
+        assert (tmp_path / 'cache' / name).exists(), name
+    sess2 = RawDepthSession(str(path), pinned=False)
+    first2, bg2, roi2, depth2 = sess2.find_roi(frame_stride=2, cache_dir=cache)
+    assert np.array_equal(roi2, roi1) and bg2.dtype == np.uint16 and np.array_equal(bg2, bg1.astype('uint16'))   # SURVEY trap 8
+    assert abs(depth2 - depth1) <= 1.0 and np.abs(first2[0].astype(float) - np.clip(ch.frames[0], 650, 750)).max() <= 1.0
 
 
 def test_pipeline_with_result_writer(tmp_path):
