@@ -12,7 +12,8 @@
  *   - "dev" pointers are CUDA device pointers on the current device; "host" pointers are host memory
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
  *   - device entry points never allocate device memory, never synchronise with the host and are re-entrant per
- *     stream (msq_extract_chunk lazily creates one side stream + two events per host thread);
+ *     stream (msq_extract_chunk keeps one msq_engine -- a side stream + two events -- per host thread and device; callers
+ *     that want no library-held state create their own with msq_engine_create and call msq_extract_chunk_engine);
  *     scratch memory is passed in by the caller (sizes from the *_scratch_bytes helpers)
  *   - return 0 on success, a negative MSQ_E* code otherwise; msq_last_error() gives the message of
  *     the last failure on the calling thread (Python raises from it)
@@ -275,7 +276,7 @@ MSQ_API int msq_scalars_and_keypoints_f64(const uint8_t *chunk_dev, const uint8_
  * angle_deg[i] into out[i] (crop_h,crop_w) u8; NaN / negative centre -> zeros.  src2/out2 optional
  * second plane (the mask) warped with the same transform.  scratch_dev: msq_crop_scratch_bytes(n) bytes,
  * 16-byte aligned (per-frame float64 rotation coefficients + OpenCV's fixed-point row/column tables).
- * Crops up to 512x512; n <= 65535 per call only when the 4-byte-aligned fast path does not apply (w, crop_w % 4, bases). */
+ * Crops up to 512x512; any number of frames per call. */
 MSQ_API size_t msq_crop_scratch_bytes(int n);
 MSQ_API int msq_crop_rotate(const uint8_t *src_dev, const uint8_t *src2_dev, int n, int h, int w,
                     const double *centroid_dev, const double *angle_deg_dev, int crop_w, int crop_h,
@@ -387,6 +388,16 @@ typedef struct msq_chunk_outputs {
 } msq_chunk_outputs;
 
 MSQ_API size_t msq_extract_scratch_bytes(int n, int h, int w);
+/* The side stream + fork / join events msq_extract_chunk runs its general feature kernel on, as an explicit object of the
+ * CURRENT device: create once per (thread, GPU), pass to msq_extract_chunk_engine, destroy at the end.  msq_extract_chunk is
+ * the same call with an engine the library keeps per (host thread, device) -- the only state the library ever holds. */
+typedef struct msq_engine msq_engine;
+MSQ_API int msq_engine_create(msq_engine **engine);
+MSQ_API int msq_engine_destroy(msq_engine *engine);
+MSQ_API int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *keypoints_dev,
+                      int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
+                      int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch_dev,
+                      size_t scratch_bytes, void *stream);
 MSQ_API int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *keypoints_dev,
                       int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
                       int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch_dev,

@@ -104,6 +104,10 @@ SIGNATURES = {
     'msq_region_props': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'msq_region_rois': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'msq_engine_create': (c_int, [POINTER(c_void_p)]),
+    'msq_engine_destroy': (c_int, [c_void_p]),
+    'msq_extract_chunk_engine': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
+                                         c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),
     'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),
 }

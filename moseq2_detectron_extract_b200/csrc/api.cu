@@ -1,5 +1,8 @@
 // Error plumbing, version and device queries of the C ABI.
 #include "common.cuh"
+#include <atomic>
+#include <mutex>
+#include <algorithm>
 #include <string.h>
 
 namespace msq {
@@ -32,10 +35,11 @@ int sm_count() {
 namespace {
 constexpr int kTimerSlots = 4096;
 struct TimerState {
-    bool enabled = false;
-    int used = 0;
-    int dropped = 0;
-    long long launches[K_COUNT] = {0};
+    std::atomic<bool> enabled{false};
+    std::atomic<int> used{0};            // steps of the pipeline are threads of one process: slots are claimed atomically
+    std::atomic<int> dropped{0};
+    std::atomic<long long> launches[K_COUNT];
+    std::mutex collect_lock;             // enable / collect against each other
     cudaEvent_t start[kTimerSlots], stop[kTimerSlots];
     int kernel[kTimerSlots];
     bool created = false;
@@ -46,10 +50,11 @@ const char *const kKernelNames[K_COUNT] = {"prep_frames", "scale_frames", "clean
 }  // namespace
 
 TimedLaunch::TimedLaunch(int kernel_id, cudaStream_t stream) : slot(-1), st(stream) {
-    g_timer.launches[kernel_id]++;
-    if (!g_timer.enabled) return;
-    if (g_timer.used >= kTimerSlots) { g_timer.dropped++; return; }
-    slot = g_timer.used++;
+    g_timer.launches[kernel_id].fetch_add(1, std::memory_order_relaxed);
+    if (!g_timer.enabled.load(std::memory_order_acquire)) return;
+    const int claimed = g_timer.used.fetch_add(1, std::memory_order_acq_rel);
+    if (claimed >= kTimerSlots) { g_timer.dropped.fetch_add(1, std::memory_order_relaxed); return; }
+    slot = claimed;
     g_timer.kernel[slot] = kernel_id;
     cudaEventRecord(g_timer.start[slot], st);
 }
@@ -61,6 +66,7 @@ TimedLaunch::~TimedLaunch() {
 
 extern "C" int msq_kernel_timing_enable(int enable) {
     using namespace msq;
+    std::lock_guard<std::mutex> guard(g_timer.collect_lock);
     if (enable && !g_timer.created) {
         for (int i = 0; i < kTimerSlots; ++i) {
             MSQ_CUDA_OK(cudaEventCreate(&g_timer.start[i]));
@@ -68,7 +74,7 @@ extern "C" int msq_kernel_timing_enable(int enable) {
         }
         g_timer.created = true;
     }
-    g_timer.enabled = enable != 0;
+    g_timer.enabled.store(enable != 0, std::memory_order_release);
     return MSQ_OK;
 }
 
@@ -76,21 +82,24 @@ extern "C" int msq_kernel_timing_enable(int enable) {
 extern "C" int msq_kernel_timing_collect(double *total_ms, long long *timed, int capacity) {
     using namespace msq;
     MSQ_REQUIRE(total_ms && timed && capacity >= K_COUNT, MSQ_EINVAL, "msq_kernel_timing_collect: need %d slots", (int)K_COUNT);
-    for (int i = 0; i < g_timer.used; ++i) {
+    // call with timing disabled (or from the only launching thread): a launch in flight on another thread may still be recording
+    std::lock_guard<std::mutex> guard(g_timer.collect_lock);
+    const int used = std::min(g_timer.used.load(std::memory_order_acquire), kTimerSlots);
+    for (int i = 0; i < used; ++i) {
         MSQ_CUDA_OK(cudaEventSynchronize(g_timer.stop[i]));
         float ms = 0.f;
         MSQ_CUDA_OK(cudaEventElapsedTime(&ms, g_timer.start[i], g_timer.stop[i]));
         total_ms[g_timer.kernel[i]] += ms;
         timed[g_timer.kernel[i]] += 1;
     }
-    g_timer.used = 0;
+    g_timer.used.store(0, std::memory_order_release);
     return MSQ_OK;
 }
 
 extern "C" int msq_kernel_count(void) { return msq::K_COUNT; }
 extern "C" const char *msq_kernel_name(int id) { return (id >= 0 && id < msq::K_COUNT) ? msq::kKernelNames[id] : nullptr; }
 // number of kernel launches issued by this library since load (per kernel id), for `gpu_launches`
-extern "C" long long msq_kernel_launches(int id) { return (id >= 0 && id < msq::K_COUNT) ? msq::g_timer.launches[id] : -1; }
+extern "C" long long msq_kernel_launches(int id) { return (id >= 0 && id < msq::K_COUNT) ? msq::g_timer.launches[id].load() : -1; }
 
 extern "C" int msq_version(void) { return MSQ_VERSION; }
 

@@ -89,9 +89,9 @@ crop_rotate_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__
                    uint8_t *__restrict__ out0, uint8_t *__restrict__ out1) {
     // a CTA covers a 16x16 output tile; each warp an 8x4 patch, so that under rotation the 32 lanes of a
     // gather touch a compact source footprint (a 32x1 line would hit up to 32 different source rows)
-    const int f = blockIdx.y;
+    const int f = blockIdx.x;                                  // frames on grid.x (2^31 - 1), tiles on grid.y
     const int tiles_x = (cw + 15) >> 4;
-    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const int tile_y = blockIdx.y / tiles_x, tile_x = blockIdx.y - tile_y * tiles_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = (tile_x << 4) + ((warp & 1) << 3) + (lane & 7);
     const int y = (tile_y << 4) + ((warp >> 1) << 2) + (lane >> 3);
@@ -288,13 +288,12 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
         MSQ_LAUNCH_OK("crop_rotate (staged)");
         return MSQ_OK;
     }
-    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_crop_rotate: at most 65535 frames per call for unaligned shapes (got %d)", n);
     WarpCoeffs *coeffs = reinterpret_cast<WarpCoeffs *>(scratch);
     int *tables = reinterpret_cast<int *>(reinterpret_cast<char *>(scratch) + (size_t)n * sizeof(WarpCoeffs));
     TimedLaunch timed(K_CROP, st);          // the coefficient kernel is part of the crop step
     crop_coeffs_kernel<<<n, 128, 0, st>>>(centroid, angle_deg, n, cw, ch, w, h, coeffs, tables);
     MSQ_LAUNCH_OK("crop_coeffs");
-    dim3 grid(((cw + 15) / 16) * ((ch + 15) / 16), n);
+    dim3 grid(n, ((cw + 15) / 16) * ((ch + 15) / 16));
     crop_rotate_kernel<<<grid, kCropThreads, 0, st>>>(src, two ? src2 : nullptr, h, w, coeffs, tables, cw, ch, out,
                                                       two ? out2 : nullptr);
     MSQ_LAUNCH_OK("crop_rotate");

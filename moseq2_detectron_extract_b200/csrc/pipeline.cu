@@ -13,10 +13,44 @@ extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
            align_up((nn + 1) * sizeof(int), 256);
 }
 
-extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,
-                                 int h, int w, int chunk, double min_height, double max_height, double true_depth,
-                                 int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch,
-                                 size_t scratch_bytes, void *stream) {
+// The one piece of state the whole-chunk entry point needs: a side stream + two events on one device, so that the few
+// frames the streaming feature kernel leaves to the general one run beside the masked sums.  Explicit object (create /
+// destroy) for callers that manage their own resources; msq_extract_chunk() keeps one per (host thread, device) for callers
+// that do not.
+struct msq_engine {
+    int device;
+    cudaStream_t side;
+    cudaEvent_t fork, join;
+};
+
+extern "C" int msq_engine_create(msq_engine **engine) {
+    MSQ_REQUIRE(engine, MSQ_EINVAL, "msq_engine_create: null pointer");
+    msq_engine *e = new msq_engine();
+    if (cudaGetDevice(&e->device) != cudaSuccess || cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("msq_engine_create: %s", cudaGetErrorString(cudaGetLastError()));
+        delete e;
+        return MSQ_ECUDA;
+    }
+    *engine = e;
+    return MSQ_OK;
+}
+
+extern "C" int msq_engine_destroy(msq_engine *e) {
+    if (!e) return MSQ_OK;
+    cudaEventDestroy(e->fork);
+    cudaEventDestroy(e->join);
+    cudaStreamDestroy(e->side);
+    delete e;
+    return MSQ_OK;
+}
+
+extern "C" int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev,
+                                        int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
+                                        int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch, size_t scratch_bytes,
+                                        void *stream) {
+    MSQ_REQUIRE(engine, MSQ_EINVAL, "msq_extract_chunk_engine: null engine");
     MSQ_REQUIRE(chunk_dev && mask_dev && kpts_dev && out, MSQ_EINVAL, "msq_extract_chunk: null input pointer");
     MSQ_REQUIRE(out->cleaned && out->centroid && out->angle_deg && out->axis_length && out->flips && out->scalars &&
                     out->kpt_cols && out->depth_crops && out->mask_crops,
@@ -24,7 +58,9 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0 && chunk > 0 && crop_w > 0 && crop_h > 0, MSQ_EINVAL,
                 "msq_extract_chunk: bad sizes n=%d h=%d w=%d chunk=%d crop=%dx%d", n, h, w, chunk, crop_w, crop_h);
     if (n == 0) return MSQ_OK;
-    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_extract_chunk: at most 65535 frames per call (got %d)", n);
+    int dev = -1;
+    MSQ_CUDA_OK(cudaGetDevice(&dev));
+    MSQ_REQUIRE(dev == engine->device, MSQ_EINVAL, "msq_extract_chunk: engine belongs to device %d, current device is %d", engine->device, dev);
     MSQ_REQUIRE(scratch && (uintptr_t)scratch % 256 == 0 && scratch_bytes >= msq_extract_scratch_bytes(n, h, w), MSQ_ENOMEM,
                 "msq_extract_chunk: scratch must be 256-byte aligned and >= %zu bytes", msq_extract_scratch_bytes(n, h, w));
     cudaStream_t st = (cudaStream_t)stream;
@@ -33,23 +69,13 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
     int2 *sums = reinterpret_cast<int2 *>(base + align_up((size_t)n * sizeof(double), 256));
     void *crop_scratch = base + align_up((size_t)n * sizeof(double), 256) + align_up((size_t)n * sizeof(int2), 256);
     int *feature_list = reinterpret_cast<int *>(reinterpret_cast<char *>(crop_scratch) + align_up(msq_crop_scratch_bytes(n), 256));
-
-    // a side stream for the few frames the streaming feature kernel leaves to the general one: their long sequential
-    // chains run beside the masked sums (which do not depend on the features).  Created once per host thread.
-    static thread_local cudaStream_t side = nullptr;
-    static thread_local cudaEvent_t fork = nullptr, join = nullptr;
-    if (!side) {
-        MSQ_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-        MSQ_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        MSQ_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    }
     int rc;
     if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st)) != MSQ_OK) return rc;
     // frame_threshold = 3 (ref proc/proc.py:716)
     if ((rc = launch_frame_features(out->cleaned, mask_dev, n, h, w, 3.0, out->centroid, orientation, out->axis_length,
-                                    nullptr, feature_list, st, side, fork, join)) != MSQ_OK) return rc;
+                                    nullptr, feature_list, st, engine->side, engine->fork, engine->join)) != MSQ_OK) return rc;
     if ((rc = launch_masked_sums(chunk_dev, mask_dev, n, h, w, min_height, max_height, sums, st)) != MSQ_OK) return rc;
-    MSQ_CUDA_OK(cudaStreamWaitEvent(st, join, 0));
+    MSQ_CUDA_OK(cudaStreamWaitEvent(st, engine->join, 0));
     if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
                                       out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
     if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,
@@ -57,4 +83,22 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
                                            true_depth, out->scalars, out->kpt_cols, sums, st, true)) != MSQ_OK) return rc;
     return launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
                               out->depth_crops, out->mask_crops, crop_scratch, st);
+}
+
+extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,
+                                 int h, int w, int chunk, double min_height, double max_height, double true_depth,
+                                 int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch,
+                                 size_t scratch_bytes, void *stream) {
+    // one lazily created engine per (host thread, device): a thread that moves to another GPU gets a fresh one there
+    constexpr int kMaxDevices = 64;
+    static thread_local msq_engine *engines[kMaxDevices] = {nullptr};
+    int dev = 0;
+    MSQ_CUDA_OK(cudaGetDevice(&dev));
+    MSQ_REQUIRE(dev >= 0 && dev < kMaxDevices, MSQ_EUNSUPPORTED, "msq_extract_chunk: device index %d", dev);
+    if (!engines[dev]) {
+        const int rc = msq_engine_create(&engines[dev]);
+        if (rc != MSQ_OK) return rc;
+    }
+    return msq_extract_chunk_engine(engines[dev], chunk_dev, mask_dev, kpts_dev, n, h, w, chunk, min_height, max_height, true_depth,
+                                    crop_w, crop_h, out, scratch, scratch_bytes, stream);
 }

@@ -436,7 +436,7 @@ stem_conv_pool_kernel(const uint8_t *__restrict__ in, int h, int w, int conv_h, 
     for (int i = threadIdx.x; i < 256; i += 256) lutf[i] = ((float)lut8[i] - mean) / stdv;
     for (int i = threadIdx.x; i < 49 * 64; i += 256) wsm[i] = w49x64[i];
     __syncthreads();
-    const int img = blockIdx.y, ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int img = blockIdx.x, ty = blockIdx.y / tiles_x, tx = blockIdx.y - ty * tiles_x;
     const int py0 = ty * kStemPool, px0 = tx * kStemPool;
     const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;                             // first convolution output of the tile
     const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;                             // first input pixel of the tile
@@ -591,18 +591,17 @@ extern "C" int msq_stem_conv_pool(const uint8_t *in, int n, int h, int w, int ph
     const int conv_h = (ph + 6 - 7) / 2 + 1, conv_w = (pw + 6 - 7) / 2 + 1;
     const int pool_h = (conv_h + 2 - 3) / 2 + 1, pool_w = (conv_w + 2 - 3) / 2 + 1;
     const int tiles_x = (pool_w + kStemPool - 1) / kStemPool, tiles_y = (pool_h + kStemPool - 1) / kStemPool;
-    MSQ_REQUIRE(n <= 65535, MSQ_EUNSUPPORTED, "msq_stem_conv_pool: at most 65535 frames per call (got %d)", n);
     const size_t fixed = (size_t)(49 * 64 + 2 * kStemIn * kStemHalf + 256) * sizeof(float);
     const size_t smem = fixed + (size_t)kStemPix * kStemCstride * (out_is_bf16 ? 2 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     TimedLaunch timed(K_DETECTOR_GLUE, st);
     if (out_is_bf16) {
         MSQ_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stem_conv_pool_kernel<__nv_bfloat16><<<dim3(tiles_x * tiles_y, n), 256, smem, st>>>(in, h, w, conv_h, conv_w, pool_h, pool_w, tiles_x, mean,
+        stem_conv_pool_kernel<__nv_bfloat16><<<dim3(n, tiles_x * tiles_y), 256, smem, st>>>(in, h, w, conv_h, conv_w, pool_h, pool_w, tiles_x, mean,
             stdv, vmin, vmax, vmin_is_int, w49x64, bias64, static_cast<__nv_bfloat16 *>(out));
     } else {
         MSQ_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stem_conv_pool_kernel<float><<<dim3(tiles_x * tiles_y, n), 256, smem, st>>>(in, h, w, conv_h, conv_w, pool_h, pool_w, tiles_x, mean, stdv,
+        stem_conv_pool_kernel<float><<<dim3(n, tiles_x * tiles_y), 256, smem, st>>>(in, h, w, conv_h, conv_w, pool_h, pool_w, tiles_x, mean, stdv,
             vmin, vmax, vmin_is_int, w49x64, bias64, static_cast<float *>(out));
     }
     MSQ_LAUNCH_OK("stem_conv_pool");

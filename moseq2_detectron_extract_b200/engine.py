@@ -21,6 +21,19 @@ class ChunkEngine:
         _dev.require_cuda()
         self._cap: Tuple[int, int, int, int, int] = (0, 0, 0, 0, 0)
         self._buf: Dict[str, torch.Tensor] = {}
+        # the library-side state of the whole-chunk call (a side stream + two events on the current device), owned here
+        self._handle = ctypes.c_void_p()
+        _lib.call('msq_engine_create', ctypes.byref(self._handle))
+        self._destroy = _lib.load().msq_engine_destroy
+
+    def __del__(self):
+        handle = getattr(self, '_handle', None)
+        if handle:
+            try:
+                self._destroy(handle)
+            except Exception:      # interpreter shutdown; pylint: disable=broad-except
+                pass
+            self._handle = None
 
     @classmethod
     def shared(cls) -> "ChunkEngine":
@@ -67,7 +80,7 @@ class ChunkEngine:
         outs = _lib.ChunkOutputs(*(b[k].data_ptr() for k in ('cleaned', 'centroid', 'angle_deg', 'axis_length', 'flips',
                                                              'scalars', 'kpt_cols', 'depth_crops', 'mask_crops',
                                                              'filter_passes')))
-        _lib.call('msq_extract_chunk', _dev.ptr(chunk), _dev.ptr(masks), _dev.ptr(keypoints), n, h, w, int(chunk_size),
+        _lib.call('msq_extract_chunk_engine', self._handle, _dev.ptr(chunk), _dev.ptr(masks), _dev.ptr(keypoints), n, h, w, int(chunk_size),
                   float(min_height), float(max_height), float(true_depth), cw, ch, ctypes.byref(outs),
                   _dev.ptr(b['scratch']), b['scratch'].numel(), _dev.stream())
         return {

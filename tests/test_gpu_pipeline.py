@@ -291,3 +291,66 @@ def test_select_instances_keeps_the_oldest_tracked_identity():
     # frames 3-5: both alive -> the older A; frame 6: only B is detected, A is alive but B is what the frame holds ... the
     # reference takes the oldest LIVE object's last detection, which is A's detection of frame 5; frame 7: A again
     assert tags[:6] == [1, 1, 1, 1, 1, 1] and tags[7] == 1 and tags[6] == 1
+
+
+def test_pinned_multi_chunk_session_without_inpainting(tmp_path):
+    """The zero-copy producer path over several chunks with fix_invalid_pixels=False (no synchronising step after the prep
+    launch): every pinned chunk buffer must stay alive until its kernel has read it.  Frames carry their index so that a
+    recycled buffer would show."""
+    from moseq2_detectron_extract_b200 import synthetic
+    from moseq2_detectron_extract_b200.io import RawDepthSession
+    from moseq2_detectron_extract_b200.pipeline import Pipeline, PipelineStep, ProduceFramesStep
+    geom = synthetic.SessionGeometry()
+    n, chunk = 96, 8
+    ch = synthetic.generate_chunk(n, seed=8, geom=geom, invalid_rate=0.001)
+    path = str(tmp_path / 'depth.dat')
+    ch.frames.astype('<i2').tofile(path)
+    roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+    sess = RawDepthSession(path, bg, roi, geom.floor_depth, frame_dims=(geom.width, geom.height), pinned=True)
+    cfg = dict(synthetic.default_config(geom), chunk_size=chunk, chunk_overlap=0, nframes=n, fix_invalid_pixels=False)
+    got = {}
+
+    class Sink(PipelineStep):
+        def process(self, data):
+            got[data['batch']] = data['chunk']             # keep device tensors; look at them only after the whole run
+            return data
+
+    pipe = Pipeline(queue_depth=8)
+    a, b = pipe.add_step(ProduceFramesStep(sess, cfg, 'produce')), pipe.add_step(Sink(cfg, 'sink'))
+    pipe.link(a, b)
+    pipe.run()
+    torch.cuda.synchronize()
+    assert sorted(got) == list(range(n // chunk))
+    want = O.prep_frames(ch.frames, bg, roi, 0, 100, fix_invalid=False)
+    assert (ch.frames == 0).any()
+    for i in range(n // chunk):
+        assert np.array_equal(got[i].cpu().numpy(), want[i * chunk:(i + 1) * chunk]), i
+
+
+def test_explicit_engine_equals_library_held_engine():
+    """msq_extract_chunk_engine with a caller-owned msq_engine == msq_extract_chunk with the library's per-thread one."""
+    import ctypes
+    from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+    from moseq2_detectron_extract_b200.engine import ChunkEngine
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(24, seed=2, geom=geom, missing_every=7, mask_holes=True)
+    prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom), roi=synthetic.make_roi(geom), vmin=0, vmax=100)
+    masks, kpts = _dev.as_device(ch.masks), _dev.as_device(ch.keypoints, torch.float32)
+    eng = ChunkEngine()
+    kw = dict(chunk_size=1000, min_height=0, max_height=100, true_depth=673.0, crop_size=(80, 80))
+    a = {k: v.clone() for k, v in eng.extract(prep, masks, kpts, **kw).items()}
+    b = eng._buf
+    n, h, w = prep.shape
+    outs = _lib.ChunkOutputs(*(b[k].data_ptr() for k in ('cleaned', 'centroid', 'angle_deg', 'axis_length', 'flips', 'scalars', 'kpt_cols',
+                                                         'depth_crops', 'mask_crops', 'filter_passes')))
+    for key in ('depth_crops', 'scalars', 'centroid'):
+        b[key].zero_()
+    _lib.call('msq_extract_chunk', _dev.ptr(prep), _dev.ptr(masks), _dev.ptr(kpts), n, h, w, 1000, 0.0, 100.0, 673.0, 80, 80, ctypes.byref(outs),
+              _dev.ptr(b['scratch']), b['scratch'].numel(), _dev.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(b['depth_crops'][:n], a['depth_crops']) and torch.equal(b['cleaned'][:n], a['cleaned'])
+    assert torch.allclose(b['centroid'][:n], a['centroid'], rtol=0, atol=0, equal_nan=True)
+    with pytest.raises(_lib.MoseqB200Error):
+        _lib.call('msq_extract_chunk_engine', None, _dev.ptr(prep), _dev.ptr(masks), _dev.ptr(kpts), n, h, w, 1000, 0.0, 100.0, 673.0, 80, 80,
+                  ctypes.byref(outs), _dev.ptr(b['scratch']), b['scratch'].numel(), _dev.stream())
