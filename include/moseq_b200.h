@@ -146,6 +146,19 @@ MSQ_API size_t msq_nms_scratch_bytes(int n, int K);
 MSQ_API int msq_nms_sorted_long(const float *boxes_dev, const uint8_t *valid_dev, int n, int K, float iou_threshold, int max_keep,
                         int32_t *keep_dev, int32_t *count_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
 
+/* detectron2 find_top_rpn_proposals up to the NMS for a batch of equally sized images, one launch: per-level top-k of the
+ * objectness logits (exact k-th largest by radix select; ties in anchor order), Box2BoxTransform decoding of the selected
+ * anchors (weights 1, anchors from the level's stride and its three cell anchors), clipping to (img_h, img_w), validity
+ * (finite, non-empty), one sort of all levels' candidates by descending logit (invalid last, ties in (level, anchor) order).
+ * pred_dev[l]: HOST array of device pointers to (n, H_l, W_l, 16) channels-last head outputs of bf16 / float32 -- channels
+ * [3 logits, 3 x 4 deltas, 1 padding]; heights / widths / strides: HOST int arrays; cell_anchors: HOST float array
+ * (n_levels, 3, 4).  Outputs, K = sum over levels of min(pre_topk, 3 H_l W_l) <= 4096 candidates per image in sorted order:
+ * boxes_dev (n,K,4), shifted_dev (n,K,4) = boxes + level * (largest valid coordinate of the image + 1) (torchvision's
+ * batched_nms coordinate trick), scores_dev (n,K) (-inf where invalid), valid_dev (n,K) u8: the inputs of msq_nms_sorted*. */
+MSQ_API int msq_rpn_select(const void *const *pred_dev, const int *heights, const int *widths, const int *strides,
+                   const float *cell_anchors, int n_levels, int is_bf16, int n, int pre_topk, int img_h, int img_w,
+                   float *boxes_dev, float *shifted_dev, float *scores_dev, uint8_t *valid_dev, void *stream);
+
 /* Keypoint decoding for a batch (replaces the per-RoI loop of torchvision's heatmaps_to_keypoints / detectron2's keypoint
  * head inference): for every RoI and keypoint, the arg-max of the heatmap (maps_dev (R,K,Hm,Wm) float32) bicubically
  * resized to the RoI's ceil(width) x ceil(height), mapped back to image coordinates.  rois_dev (R,4) float32 x1,y1,x2,y2;

@@ -55,6 +55,8 @@ SIGNATURES = {
                                    c_void_p, c_int, c_void_p]),
     'msq_nms_scratch_bytes': (c_size_t, [c_int, c_int]),
     'msq_nms_sorted_long': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'msq_rpn_select': (c_int, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'msq_keypoints_from_heatmaps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'msq_angles_and_flips': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),

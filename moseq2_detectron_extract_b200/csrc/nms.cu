@@ -7,6 +7,8 @@
 // Boxes arrive sorted by score and already shifted per pyramid level (torchvision's "coordinate trick", so that levels
 // never suppress each other and the float32 arithmetic is the one torchvision does); IoU as in torchvision's devIoU.
 #include "common.cuh"
+#include <cuda_bf16.h>
+#include <algorithm>
 #include <limits.h>
 #include <math.h>
 
@@ -266,5 +268,239 @@ extern "C" int msq_keypoints_from_heatmaps(const float *maps, const float *rois,
     msq::TimedLaunch timed(msq::K_DETECTOR_GLUE, (cudaStream_t)stream);
     msq::keypoint_decode_kernel<<<n_rois * K, msq::kKpThreads, smem, (cudaStream_t)stream>>>(maps, rois, K, Hm, Wm, round_bf16, xyv, scores);
     MSQ_LAUNCH_OK("keypoint_decode");
+    return MSQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// detectron2 find_top_rpn_proposals up to (not including) the NMS, for a whole batch in ONE launch (model/ops.py ran it as
+// ~40 PyTorch operators: per-level top-k = a full sort of every row, gathers, decode, clip, a second sort: 3 ms per 500
+// images).  A CTA owns one image:
+//   per pyramid level   objectness logits -> order-preserving 32-bit keys in shared memory; levels with more anchors than
+//                       PRE_NMS_TOPK get an exact k-th largest by 4-pass radix select (warp-aggregated histogram votes), ties at
+//                       the threshold are taken in anchor order; every selected anchor is decoded on the spot
+//                       (Box2BoxTransform, weights 1) and clipped to the image;
+//   across levels       candidates are sorted by descending logit with a bitonic network on 64-bit words
+//                       (key | reversed (level, anchor) order | slot): invalid boxes (not finite, empty after clipping) sink
+//                       to the end, equal logits keep (level, anchor) order;
+//   output              boxes, logits, validity and the boxes shifted per level by (largest coordinate + 1) -- torchvision's
+//                       batched_nms coordinate trick -- in sorted order, ready for msq_nms_sorted / msq_nms_sorted_long.
+// ---------------------------------------------------------------------------------------------------------------
+namespace msq {
+namespace {
+
+constexpr int kSelThreads = 512;
+constexpr int kSelMaxLevels = 8;
+constexpr int kSelMaxCand = 4096;
+
+struct RpnLevelsArg {
+    const void *pred[kSelMaxLevels];          // (n, H, W, 16) channels-last: 3 logits, 12 deltas, 1 padding channel
+    int H[kSelMaxLevels], W[kSelMaxLevels], stride[kSelMaxLevels], take[kSelMaxLevels], offset[kSelMaxLevels];
+    float cell[kSelMaxLevels][3][4];          // the three cell anchors of the level (x1, y1, x2, y2 around 0)
+    int n_levels, total;                      // candidates per image = sum of take[]
+};
+
+__device__ __forceinline__ uint32_t float_key(float x) {                 // larger float <=> larger key; NaN lowest
+    if (x != x) return 0u;
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kSelThreads)
+rpn_select_kernel(RpnLevelsArg L, float img_w, float img_h, float scale_clamp, int sort_len,
+                  float4 *__restrict__ boxes_out, float4 *__restrict__ shifted_out, float *__restrict__ scores_out,
+                  uint8_t *__restrict__ valid_out) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long *sort_keys = reinterpret_cast<unsigned long long *>(sel_smem);                   // [sort_len]
+    float4 *cand_box = reinterpret_cast<float4 *>(sort_keys + sort_len);                                // [total]
+    uint32_t *keys = reinterpret_cast<uint32_t *>(cand_box + L.total);                                   // [largest level]
+    __shared__ int hist[256];
+    __shared__ int counts[kSelThreads];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining, s_greater;
+    __shared__ float s_max[kSelThreads / 32];
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+
+    for (int lvl = 0; lvl < L.n_levels; ++lvl) {
+        const int H = L.H[lvl], W = L.W[lvl], N = H * W * 3, take = L.take[lvl];
+        const T *pred = static_cast<const T *>(L.pred[lvl]) + (size_t)img * H * W * 16;
+        for (int i = tid; i < N; i += kSelThreads) keys[i] = float_key(to_f32(pred[(size_t)(i / 3) * 16 + (i % 3)]));
+        __syncthreads();
+        uint32_t thr = 0u;
+        int take_equal = N;                                   // anchors equal to the threshold that are still taken
+        if (take < N) {
+            // ---- exact k-th largest key: most significant byte first ----
+            uint32_t prefix = 0u, mask = 0u;
+            int remaining = take;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+                __syncthreads();
+                for (int i0 = 0; i0 < N; i0 += kSelThreads) {
+                    const int i = i0 + tid;
+                    int bin = 256;                            // lanes without a vote agree among themselves
+                    if (i < N && (keys[i] & mask) == prefix) bin = (keys[i] >> shift) & 255;
+                    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                    if (bin < 256 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int above = 0, b = 255;
+                    for (; b > 0; --b) {
+                        if (above + hist[b] >= remaining) break;
+                        above += hist[b];
+                    }
+                    s_prefix = prefix | ((uint32_t)b << shift);
+                    s_remaining = remaining - above;
+                }
+                __syncthreads();
+                prefix = s_prefix; remaining = s_remaining; mask |= 0xffu << shift;
+                __syncthreads();
+            }
+            thr = prefix;
+            take_equal = remaining;
+        }
+        // ---- anchors above the threshold, then the first `take_equal` at the threshold in anchor order ----
+        const int per = (N + kSelThreads - 1) / kSelThreads, i_lo = min(N, tid * per), i_hi = min(N, i_lo + per);
+        int n_gt = 0, n_eq = 0;
+        for (int i = i_lo; i < i_hi; ++i) { n_gt += keys[i] > thr; n_eq += keys[i] == thr; }
+        counts[tid] = n_gt;
+        __syncthreads();
+        if (tid == 0) { int run = 0; for (int t = 0; t < kSelThreads; ++t) { const int c = counts[t]; counts[t] = run; run += c; } s_greater = run; }
+        __syncthreads();
+        int pos_gt = counts[tid];
+        const int greater_total = s_greater;
+        __syncthreads();
+        counts[tid] = n_eq;
+        __syncthreads();
+        if (tid == 0) { int run = 0; for (int t = 0; t < kSelThreads; ++t) { const int c = counts[t]; counts[t] = run; run += c; } }
+        __syncthreads();
+        int pos_eq = counts[tid];
+        __syncthreads();
+        const int base = L.offset[lvl];
+        const float stride = (float)L.stride[lvl];
+        for (int i = i_lo; i < i_hi; ++i) {
+            const uint32_t k = keys[i];
+            int slot = -1;
+            if (k > thr) slot = pos_gt++;
+            else if (k == thr) { if (pos_eq < take_equal) slot = greater_total + pos_eq; ++pos_eq; }
+            if (slot < 0 || slot >= take) continue;
+            // decode anchor i = (y * W + x) * 3 + a with its deltas (detectron2 Box2BoxTransform.apply_deltas, weights 1)
+            const int a = i % 3, pix = i / 3, y = pix / W, x = pix - y * W;
+            const float sx = (float)x * stride, sy = (float)y * stride;
+            const float ax1 = sx + L.cell[lvl][a][0], ay1 = sy + L.cell[lvl][a][1], ax2 = sx + L.cell[lvl][a][2], ay2 = sy + L.cell[lvl][a][3];
+            const T *d = pred + (size_t)pix * 16 + 3 + 4 * a;
+            const float dx = to_f32(d[0]), dy = to_f32(d[1]), dw = fminf(to_f32(d[2]), scale_clamp), dh = fminf(to_f32(d[3]), scale_clamp);
+            const float wa = ax2 - ax1, ha = ay2 - ay1, cx = ax1 + 0.5f * wa, cy = ay1 + 0.5f * ha;
+            const float pcx = dx * wa + cx, pcy = dy * ha + cy, pw = expf(dw) * wa, ph = expf(dh) * ha;
+            float4 b = make_float4(pcx - 0.5f * pw, pcy - 0.5f * ph, pcx + 0.5f * pw, pcy + 0.5f * ph);
+            const bool finite = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w) && k != 0u && isfinite(key_float(k));
+            b.x = fminf(fmaxf(b.x, 0.f), img_w); b.y = fminf(fmaxf(b.y, 0.f), img_h);
+            b.z = fminf(fmaxf(b.z, 0.f), img_w); b.w = fminf(fmaxf(b.w, 0.f), img_h);
+            const bool ok = finite && (b.z - b.x) > 0.f && (b.w - b.y) > 0.f;
+            const int c = base + slot;
+            cand_box[c] = b;
+            // descending sort: valid boxes by logit, then (level, anchor) ascending; invalid ones last
+            const unsigned long long order = 0xfffffull - (((unsigned long long)lvl << 14) | (unsigned long long)i);
+            sort_keys[c] = ((unsigned long long)(ok ? k : 0u) << 32) | (order << 12) | (unsigned long long)c;
+        }
+        __syncthreads();
+    }
+    for (int i = L.total + tid; i < sort_len; i += kSelThreads) sort_keys[i] = 0ull;       // padding sinks below everything
+    __syncthreads();
+    // ---- bitonic sort, descending ----
+    for (int k = 2; k <= sort_len; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < sort_len; i += kSelThreads) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long a = sort_keys[i], b = sort_keys[p];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { sort_keys[i] = b; sort_keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- largest coordinate of the image's valid boxes (torchvision batched_nms offsets) ----
+    float mx = -INFINITY;
+    for (int i = tid; i < L.total; i += kSelThreads) {
+        const unsigned long long w = sort_keys[i];
+        if ((w >> 32) != 0ull) {
+            const float4 b = cand_box[(int)(w & 0xfffull)];
+            mx = fmaxf(fmaxf(mx, fmaxf(b.x, b.y)), fmaxf(b.z, b.w));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_max[tid >> 5] = mx;
+    __syncthreads();
+    mx = s_max[0];
+    for (int wv = 1; wv < kSelThreads / 32; ++wv) mx = fmaxf(mx, s_max[wv]);
+    if (!isfinite(mx)) mx = 0.f;
+    const size_t o0 = (size_t)img * L.total;
+    for (int i = tid; i < L.total; i += kSelThreads) {
+        const unsigned long long w = sort_keys[i];
+        const uint32_t k = (uint32_t)(w >> 32);
+        const int c = (int)(w & 0xfffull);
+        const int lvl = (int)((0xfffffull - ((w >> 12) & 0xfffffull)) >> 14);
+        const float4 b = cand_box[c];
+        const float off = (float)lvl * (mx + 1.f);
+        boxes_out[o0 + i] = b;
+        shifted_out[o0 + i] = make_float4(b.x + off, b.y + off, b.z + off, b.w + off);
+        scores_out[o0 + i] = k ? key_float(k) : -INFINITY;
+        valid_out[o0 + i] = k ? 1 : 0;
+    }
+}
+
+}  // namespace
+}  // namespace msq
+
+extern "C" int msq_rpn_select(const void *const *pred_dev, const int *heights, const int *widths, const int *strides, const float *cell_anchors,
+                              int n_levels, int is_bf16, int n, int pre_topk, int img_h, int img_w, float *boxes_dev, float *shifted_dev,
+                              float *scores_dev, uint8_t *valid_dev, void *stream) {
+    MSQ_REQUIRE(n_levels >= 1 && n_levels <= kSelMaxLevels && n >= 0 && pre_topk >= 1, MSQ_EINVAL, "msq_rpn_select: bad sizes");
+    if (n == 0) return MSQ_OK;
+    MSQ_REQUIRE(pred_dev && heights && widths && strides && cell_anchors && boxes_dev && shifted_dev && scores_dev && valid_dev, MSQ_EINVAL,
+                "msq_rpn_select: null pointer");
+    RpnLevelsArg L;
+    L.n_levels = n_levels;
+    int total = 0, largest = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        MSQ_REQUIRE(pred_dev[l] && heights[l] > 0 && widths[l] > 0, MSQ_EINVAL, "msq_rpn_select: level %d", l);
+        const int N = heights[l] * widths[l] * 3;
+        MSQ_REQUIRE(N < (1 << 14), MSQ_EUNSUPPORTED, "msq_rpn_select: at most 16383 anchors per level (level %d has %d)", l, N);
+        L.pred[l] = pred_dev[l]; L.H[l] = heights[l]; L.W[l] = widths[l]; L.stride[l] = strides[l];
+        L.take[l] = std::min(pre_topk, N); L.offset[l] = total;
+        for (int a = 0; a < 3; ++a) for (int k = 0; k < 4; ++k) L.cell[l][a][k] = cell_anchors[(l * 3 + a) * 4 + k];
+        total += L.take[l];
+        largest = std::max(largest, N);
+    }
+    MSQ_REQUIRE(total <= kSelMaxCand, MSQ_EUNSUPPORTED, "msq_rpn_select: at most %d candidates per image (got %d)", kSelMaxCand, total);
+    L.total = total;
+    int sort_len = 2;
+    while (sort_len < total) sort_len <<= 1;
+    const size_t smem = (size_t)sort_len * 8 + (size_t)total * 16 + (size_t)largest * 4;
+    MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "msq_rpn_select: %zu bytes of shared memory needed", smem);
+    MSQ_REQUIRE((uintptr_t)boxes_dev % 16 == 0 && (uintptr_t)shifted_dev % 16 == 0, MSQ_EINVAL, "msq_rpn_select: outputs must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    TimedLaunch timed(K_DETECTOR_GLUE, st);
+    const float clamp = logf(1000.f / 16.f);
+    if (is_bf16) {
+        MSQ_CUDA_OK(cudaFuncSetAttribute(rpn_select_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rpn_select_kernel<__nv_bfloat16><<<n, kSelThreads, smem, st>>>(L, (float)img_w, (float)img_h, clamp, sort_len, reinterpret_cast<float4 *>(boxes_dev),
+                                                                      reinterpret_cast<float4 *>(shifted_dev), scores_dev, valid_dev);
+    } else {
+        MSQ_CUDA_OK(cudaFuncSetAttribute(rpn_select_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rpn_select_kernel<float><<<n, kSelThreads, smem, st>>>(L, (float)img_w, (float)img_h, clamp, sort_len, reinterpret_cast<float4 *>(boxes_dev),
+                                                              reinterpret_cast<float4 *>(shifted_dev), scores_dev, valid_dev);
+    }
+    MSQ_LAUNCH_OK("rpn_select");
     return MSQ_OK;
 }

@@ -34,6 +34,7 @@ _LIB.define('fastrcnn_top1(Tensor pred, Tensor proposals, Tensor counts, int img
 _LIB.define('keypoints_from_heatmaps_d2(Tensor heatmaps, Tensor boxes) -> Tensor')
 
 # implementation switches (bench / tests): which engine runs the dense contractions
+RPN_ENGINE = {'mode': 'fused'}            # 'fused' (msq_rpn_select) | 'torch' (operator by operator)
 CONV_ENGINE = {'mode': 'cudnn'}          # 'cudnn' | 'tcgen05' (csrc/conv_tc.cu, where the shape is served)
 
 
@@ -167,6 +168,10 @@ def _rpn_proposals(preds, strides, sizes, ratios, img_h, img_w, pre_topk, post_t
     n = int(preds[0].shape[0])
     dev = preds[0].device
     A = len(ratios)
+    fused = _rpn_select_fused(preds, strides, sizes, ratios, img_h, img_w, pre_topk) if RPN_ENGINE['mode'] == 'fused' else None
+    if fused is not None:
+        boxes, shifted, scores, valid_u8 = fused
+        return _nms_and_gather(boxes, shifted, scores, valid_u8, post_topk, nms_thresh)
     boxes_l, scores_l, level_l = [], [], []
     for lvl, p in enumerate(preds):
         gh, gw = int(p.shape[2]), int(p.shape[3])
@@ -197,10 +202,39 @@ def _rpn_proposals(preds, strides, sizes, ratios, img_h, img_w, pre_topk, post_t
     max_coord = torch.where(valid[..., None], boxes, boxes.new_full((), float('-inf'))).amax(dim=(1, 2))
     max_coord = torch.where(torch.isfinite(max_coord), max_coord, torch.zeros_like(max_coord))
     shifted = (boxes + (levels * (max_coord[:, None] + 1))[..., None]).contiguous()
-    K = int(boxes.shape[1])
+    return _nms_and_gather(boxes, shifted, scores, valid.to(torch.uint8).contiguous(), post_topk, nms_thresh)
+
+
+def _rpn_select_fused(preds, strides, sizes, ratios, img_h, img_w, pre_topk):
+    """Everything of find_top_rpn_proposals before the NMS in one launch (`msq_rpn_select`, csrc/nms.cu); None when the shapes are
+    not the ones that kernel serves (then the operator-by-operator path below runs)."""
+    k = len(preds)
+    if len(ratios) != 3 or k > 8 or any(int(p.shape[1]) != 16 for p in preds) or preds[0].dtype not in (torch.bfloat16, torch.float32):
+        return None
+    if any(p.dtype != preds[0].dtype for p in preds) or any(int(p.shape[2]) * int(p.shape[3]) * 3 >= (1 << 14) for p in preds):
+        return None
+    total = sum(min(int(pre_topk), int(p.shape[2]) * int(p.shape[3]) * 3) for p in preds)
+    if total > 4096:
+        return None
+    preds = [_cl(p) for p in preds]
+    n, dev = int(preds[0].shape[0]), preds[0].device
+    cells = torch.stack([cell_anchors(float(sizes[i]), ratios) for i in range(k)]).reshape(-1).tolist()
+    boxes = torch.empty((n, total, 4), dtype=torch.float32, device=dev)
+    shifted = torch.empty((n, total, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n, total), dtype=torch.float32, device=dev)
+    valid = torch.empty((n, total), dtype=torch.uint8, device=dev)
+    _lib.call('msq_rpn_select', (ctypes.c_void_p * k)(*[p.data_ptr() for p in preds]), (ctypes.c_int * k)(*[int(p.shape[2]) for p in preds]),
+              (ctypes.c_int * k)(*[int(p.shape[3]) for p in preds]), (ctypes.c_int * k)(*[int(v) for v in strides]),
+              (ctypes.c_float * len(cells))(*cells), k, int(preds[0].dtype == torch.bfloat16), n, int(pre_topk), int(img_h), int(img_w),
+              _dev.ptr(boxes), _dev.ptr(shifted), _dev.ptr(scores), _dev.ptr(valid), _dev.stream())
+    return boxes, shifted, scores, valid
+
+
+def _nms_and_gather(boxes, shifted, scores, valid_u8, post_topk, nms_thresh):
+    n, K = int(boxes.shape[0]), int(boxes.shape[1])
+    dev = boxes.device
     keep = torch.empty((n, int(post_topk)), dtype=torch.int32, device=dev)
     count = torch.empty((n,), dtype=torch.int32, device=dev)
-    valid_u8 = valid.to(torch.uint8).contiguous()
     if int(post_topk) > 128 and K <= 6144:       # long keep lists: overlap matrix as bit rows + one ordered walk per image
         nbytes = int(_lib.load().msq_nms_scratch_bytes(n, K))
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)

@@ -149,10 +149,13 @@ def test_keypoint_decode_matches_detectron2():
     assert float(((got[..., 2] - want[..., 2]).abs() / want[..., 2])[close].max()) <= 1e-4
 
 
-def test_rpn_proposals_match_detectron2(state):
+@pytest.mark.parametrize('engine', ['fused', 'torch'])
+def test_rpn_proposals_match_detectron2(state, engine):
     """find_top_rpn_proposals for a batch (per-level top-k, decode, clip, non-empty, per-level NMS 0.7 via the coordinate trick,
     first 1000 / 100 survivors) against the per-image loop over torchvision.ops.batched_nms, on the same head outputs."""
     msq = _ops()
+    from moseq2_detectron_extract_b200.model import ops as _o
+    _o.RPN_ENGINE['mode'] = engine          # 'fused': msq_rpn_select (one launch); 'torch': operator by operator
     g = torch.Generator(device='cuda').manual_seed(2)
     feats = [torch.randn((3, 256, s, s), device='cuda', generator=g) * 3 for s in (64, 32, 16, 8, 4)]
     st = dict(state)
@@ -174,6 +177,18 @@ def test_rpn_proposals_match_detectron2(state):
             assert float(same.float().mean()) >= 0.99, float(same.float().mean())
             assert torch.allclose(scores[i, :c][same], ws[same], rtol=1e-5, atol=1e-5)
             assert float(boxes[i, c:].abs().sum()) == 0
+    # bf16 head outputs (what the graph produces): many equal logits -- both engines must agree on the proposals up to tie order
+    preds16 = [p.to(torch.bfloat16) for p in preds]
+    _o.RPN_ENGINE['mode'] = 'fused'
+    b1, s1, c1 = msq.rpn_proposals(preds16, [4, 8, 16, 32, 64], [32.0, 64.0, 128.0, 256.0, 512.0], [0.5, 1.0, 2.0], 240, 240, 1000, 1000, 0.7)
+    _o.RPN_ENGINE['mode'] = 'torch'
+    b2, s2, c2 = msq.rpn_proposals(preds16, [4, 8, 16, 32, 64], [32.0, 64.0, 128.0, 256.0, 512.0], [0.5, 1.0, 2.0], 240, 240, 1000, 1000, 0.7)
+    _o.RPN_ENGINE['mode'] = 'fused'
+    assert (c1 - c2).abs().max() <= 8
+    for i in range(3):
+        c = int(min(c1[i], c2[i]))
+        assert torch.equal(s1[i, :c], s2[i, :c])                        # the same multiset of logits in the same order
+        assert float(((b1[i, :c] - b2[i, :c]).abs().amax(dim=1) <= 1e-3).float().mean()) >= 0.9
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
