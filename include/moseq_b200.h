@@ -216,11 +216,11 @@ MSQ_API int msq_keypoints_from_heatmaps_d2(const float *maps_dev, const float *r
 /* The graph's 1x1 / 3x3 convolutions and Linear layers on the 5th-generation tensor cores (csrc/conv_tc.cu): implicit GEMM,
  * TMA-fed (the 3x3 taps are shifted reads of one 4-D tensor map, out-of-image rows / columns zero-filled by the TMA unit),
  * tcgen05.mma with fp32 accumulators in TMEM, fused epilogue out = act(conv + bias + residual).
- * x_dev (n,H,W,cin) channels-last bf16; w_dev (cout,k,k,cin) bf16; bias_dev (cout) float32 or NULL; residual_dev like out or
+ * x_dev (n,H,W,cin) channels-last bf16; w_dev (cout,k,k,cin) bf16; bias_dev (cout) float32 / bf16 (bias_is_bf16) or NULL; residual_dev like out or
  * NULL; out_dev (n,Ho,Wo,cout) bf16, Ho = (H-1)/stride + 1.  k = 1 (stride 1 or 2) or k = 3 (stride 1, padding 1); cin, cout
  * multiples of 64.  A Linear layer y = x W^T + b is the call with n = H = 1, W = rows. */
 MSQ_API int msq_conv_tc(const void *x_dev, int n, int H, int W, int cin, const void *w_dev, int cout, int ksize, int stride,
-                const float *bias_dev, const void *residual_dev, int relu, void *out_dev, void *stream);
+                const void *bias_dev, int bias_is_bf16, const void *residual_dev, int relu, void *out_dev, void *stream);
 
 /* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */

@@ -90,7 +90,7 @@ SIGNATURES = {
     'msq_get_bground_im': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_detector_input': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_double, c_double, c_int, c_void_p]),
     'msq_roi_align_levels': (c_int, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    'msq_conv_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'msq_conv_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'msq_group_norm_scratch_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'msq_group_norm_nhwc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_float,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace msq {
 namespace {
@@ -35,8 +36,8 @@ struct ConvTcParams {
     int n_img, Ho, Wo;                         // output pixels
     int bw, bh, bn;                            // pixel box of a tile, bw * bh * bn == 128
     int tiles_x, tiles_y, tiles_n, tiles_c;    // tile grid: pixels (x, y, image) and output-channel blocks
-    int cout, relu, num_tiles;
-    const float *bias;
+    int cout, relu, num_tiles, bias_bf16;
+    const void *bias;                          // (cout) float32 or bf16, may be null
     const __nv_bfloat16 *residual;
     __nv_bfloat16 *out;
 };
@@ -206,9 +207,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * g + k]);
                         if (p.bias) {
-                            const float4 b0 = *reinterpret_cast<const float4 *>(p.bias + c0 + c + 8 * g);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(p.bias + c0 + c + 8 * g + 4);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            if (p.bias_bf16) {
+                                const uint4 bv = *reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(p.bias) + c0 + c + 8 * g);
+                                const uint32_t bw4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) { f[2 * k] += __uint_as_float(bw4[k] << 16); f[2 * k + 1] += __uint_as_float(bw4[k] & 0xffff0000u); }
+                            } else {
+                                const float *bf = static_cast<const float *>(p.bias) + c0 + c + 8 * g;
+                                const float4 b0 = *reinterpret_cast<const float4 *>(bf), b1 = *reinterpret_cast<const float4 *>(bf + 4);
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
                         }
                         if (res) {
                             const uint4 rv = *reinterpret_cast<const uint4 *>(res + c + 8 * g);
@@ -263,6 +271,10 @@ EncodeTiledFn encode_tiled_fn() {
 void choose_box(int W, int H, int N, int &bw, int &bh, int &bn) {
     long long best = -1;
     bw = 128; bh = 1; bn = 1;
+    if (const char *e = getenv("MSQ_TC_BOX")) {                   // development aid: "bw,bh,bn"
+        int a = 0, b = 0, c = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a * b * c == 128) { bw = a; bh = b; bn = c; return; }
+    }
     for (int w = 1; w <= 128; w <<= 1)
         for (int h = 1; w * h <= 128; h <<= 1) {
             const int n = 128 / (w * h);
@@ -281,8 +293,8 @@ using namespace msq;
 
 // x (n, H, W, cin) channels-last bf16; w (cout, ksize, ksize, cin) bf16 (= a channels-last (cout, cin, k, k) tensor's memory);
 // out (n, Ho, Wo, cout) bf16 with Ho = (H - 1) / stride + 1.  ksize 1 (stride 1 or 2, pad 0) or 3 (stride 1, pad 1).
-extern "C" int msq_conv_tc(const void *x, int n, int H, int W, int cin, const void *w, int cout, int ksize, int stride, const float *bias,
-                           const void *residual, int relu, void *out, void *stream) {
+extern "C" int msq_conv_tc(const void *x, int n, int H, int W, int cin, const void *w, int cout, int ksize, int stride, const void *bias,
+                           int bias_is_bf16, const void *residual, int relu, void *out, void *stream) {
     MSQ_REQUIRE(n >= 0 && H > 0 && W > 0 && cin > 0 && cout > 0, MSQ_EINVAL, "msq_conv_tc: bad sizes");
     MSQ_REQUIRE((ksize == 1 && (stride == 1 || stride == 2)) || (ksize == 3 && stride == 1), MSQ_EUNSUPPORTED,
                 "msq_conv_tc: 1x1 (stride 1, 2) and 3x3 (stride 1, padding 1) convolutions only (got k=%d stride=%d)", ksize, stride);
@@ -300,7 +312,7 @@ extern "C" int msq_conv_tc(const void *x, int n, int H, int W, int cin, const vo
     choose_box(Wo, Ho, n, p.bw, p.bh, p.bn);
     p.tiles_x = (Wo + p.bw - 1) / p.bw; p.tiles_y = (Ho + p.bh - 1) / p.bh; p.tiles_n = (n + p.bn - 1) / p.bn;
     const int BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-    p.tiles_c = cout / BN; p.cout = cout; p.relu = relu; p.bias = bias;
+    p.tiles_c = cout / BN; p.cout = cout; p.relu = relu; p.bias = bias; p.bias_bf16 = bias_is_bf16;
     p.residual = static_cast<const __nv_bfloat16 *>(residual); p.out = static_cast<__nv_bfloat16 *>(out);
     const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_c;
     MSQ_REQUIRE(tiles < (1ll << 31), MSQ_EUNSUPPORTED, "msq_conv_tc: too many tiles");

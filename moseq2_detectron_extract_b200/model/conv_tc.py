@@ -3,25 +3,19 @@ shape is one that kernel serves (bf16, channels-last, channel counts multiples o
 return None otherwise so that model/ops.py falls through to the cuDNN / cuBLAS call."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Optional
 
 import torch
 
 from .. import _dev, _lib
 
-_BIAS_F32: Dict[int, torch.Tensor] = {}
-
-
-def _bias_f32(b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """The kernel adds the bias in float32; the graph keeps it in the compute dtype for cuDNN.  Converted once per tensor."""
+def _bias(b: Optional[torch.Tensor]):
+    """(pointer, is_bf16) of a bias vector the kernel can read as it is (float32 or bf16), or None when it cannot."""
     if b is None:
+        return _dev.ptr(None), 0
+    if b.dtype not in (torch.float32, torch.bfloat16) or not b.is_contiguous() or b.data_ptr() % 16:
         return None
-    key = b.data_ptr()
-    hit = _BIAS_F32.get(key)
-    if hit is None or hit.numel() != b.numel():
-        hit = b.detach().float().contiguous()
-        _BIAS_F32[key] = hit
-    return hit
+    return _dev.ptr(b), int(b.dtype == torch.bfloat16)
 
 
 def try_conv2d(x, w, b, z, relu, stride, pad) -> Optional[torch.Tensor]:
@@ -43,7 +37,10 @@ def try_conv2d(x, w, b, z, relu, stride, pad) -> Optional[torch.Tensor]:
             return None
         if not z.is_contiguous(memory_format=torch.channels_last):
             z = z.contiguous(memory_format=torch.channels_last)
-    _lib.call('msq_conv_tc', _dev.ptr(x), n, h, wd, cin, _dev.ptr(w), cout, k, int(stride), _dev.ptr(_bias_f32(b)), _dev.ptr(z), int(bool(relu)),
+    bias = _bias(b)
+    if bias is None:
+        return None
+    _lib.call('msq_conv_tc', _dev.ptr(x), n, h, wd, cin, _dev.ptr(w), cout, k, int(stride), bias[0], bias[1], _dev.ptr(z), int(bool(relu)),
               _dev.ptr(out), _dev.stream())
     return out
 
@@ -56,6 +53,9 @@ def try_linear(x, w, b, relu) -> Optional[torch.Tensor]:
     if kdim % 64 or nout % 64 or rows == 0:
         return None
     out = torch.empty((rows, nout), dtype=torch.bfloat16, device=x.device)
-    _lib.call('msq_conv_tc', _dev.ptr(x), 1, 1, rows, kdim, _dev.ptr(w), nout, 1, 1, _dev.ptr(_bias_f32(b)), None, int(bool(relu)), _dev.ptr(out),
+    bias = _bias(b)
+    if bias is None:
+        return None
+    _lib.call('msq_conv_tc', _dev.ptr(x), 1, 1, rows, kdim, _dev.ptr(w), nout, 1, 1, bias[0], bias[1], None, int(bool(relu)), _dev.ptr(out),
               _dev.stream())
     return out
