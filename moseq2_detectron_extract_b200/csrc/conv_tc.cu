@@ -16,8 +16,9 @@
 //            completion on mbarriers (cp.async.bulk.tensor + mbarrier::complete_tx)
 //   warp 1   allocates TMEM (2 x BN columns: two accumulator tiles) and issues tcgen05.mma (M = 128, N = BN, K = 16 per
 //            instruction, fp32 accumulation in TMEM); tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld their 32 TMEM lanes (= 32 pixels), add bias and residual, ReLU, convert to bf16 and store the
-//            pixel's channels -- while warp 1 already accumulates the next tile into the other half of TMEM.
+//   warps 2-9  epilogue: tcgen05.ld their 32 TMEM lanes (= 32 pixels) x half of the columns, add bias and residual (requested one
+//            column group ahead), ReLU, convert to bf16 and store the pixel's channels -- while warp 1 already accumulates the
+//            next tile into the other half of TMEM.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -28,7 +29,8 @@ namespace {
 
 constexpr int kTcM = 128;                      // pixels per tile (UMMA M, cta_group::1)
 constexpr int kTcK = 64;                       // bf16 per K block: 128 bytes = one swizzle-128B row
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 8;                 // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 constexpr int kTcABytes = kTcM * kTcK * 2;     // 16 KB
 
 struct ConvTcParams {
@@ -117,7 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(accf0 + 8 * i, 1); mbar_init(acce0 + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accf0 + 8 * i, 1); mbar_init(acce0 + 8 * i, 32 * kTcEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -179,27 +181,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ================= epilogue: 4 warps, one TMEM lane quarter (32 pixels) each =================
-        const int q = warp & 3;                                                // warps 2,3,4,5 -> lane quarters 2,3,0,1
+        // ================= epilogue: 8 warps; warp w reads TMEM lane quarter w % 4 (32 pixels) and half of the columns ==========
+        const int q = warp & 3;                                                // warps 2..9 -> lane quarters 2,3,0,1,2,3,0,1
+        const int half = (warp - 2) >> 2;                                      // which half of the tile's BN columns
         const int m = q * 32 + lane;                                           // pixel of the tile this thread owns
         const int ix = m % p.bw, iy = (m / p.bw) % p.bh, in = m / (p.bw * p.bh);
+        constexpr int kCols = BN / 2;                                          // columns per warp: 32, 64 or 128
         uint32_t acc_phase = 0;
         int acc = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int ct = tile % p.tiles_c, mt = tile / p.tiles_c;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-            const int x = tx * p.bw + ix, y = ty * p.bh + iy, n = tn * p.bn + in, c0 = ct * BN;
+            const int x = tx * p.bw + ix, y = ty * p.bh + iy, n = tn * p.bn + in, c0 = ct * BN + half * kCols;
             const bool valid = x < p.Wo && y < p.Ho && n < p.n_img;
-            const size_t pix = ((size_t)n * p.Ho + y) * p.Wo + x;
+            const size_t pix = valid ? ((size_t)n * p.Ho + y) * p.Wo + x : 0;
             __nv_bfloat16 *dst = p.out + pix * p.cout + c0;
             const __nv_bfloat16 *res = p.residual ? p.residual + pix * p.cout + c0 : nullptr;
+            // the residual of the first 32 columns is requested before the accumulator is even complete, the next group's
+            // while the current one is converted: the loads' latency stays off the critical path
+            uint4 rnext[4];
+            if (res && valid) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) rnext[g] = ldg_stream_u4(res + 8 * g);
+            }
             mbar_wait(accf0 + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * kCols);
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < kCols; c += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c, v);
+                uint4 rcur[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                if (res && valid && c + 32 < kCols) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) rnext[g] = ldg_stream_u4(res + c + 32 + 8 * g);
+                }
                 if (valid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {                              // 8 channels = one 16-byte store
@@ -219,8 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                         if (res) {
-                            const uint4 rv = *reinterpret_cast<const uint4 *>(res + c + 8 * g);
-                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                            const uint32_t rw[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) { f[2 * k] += __uint_as_float(rw[k] << 16); f[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u); }
                         }
@@ -234,12 +251,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
                             o[k] = *reinterpret_cast<const uint32_t *>(&h2);
                         }
-                        *reinterpret_cast<uint4 *>(dst + c + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
+                        stg_stream_u4(dst + c + 8 * g, make_uint4(o[0], o[1], o[2], o[3]));
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(acce0 + 8 * acc);                                      // 128 arrivals hand the accumulator back
+            mbar_arrive(acce0 + 8 * acc);                                      // all epilogue threads hand the accumulator back
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }

@@ -35,7 +35,7 @@ _LIB.define('keypoints_from_heatmaps_d2(Tensor heatmaps, Tensor boxes) -> Tensor
 
 # implementation switches (bench / tests): which engine runs the dense contractions
 RPN_ENGINE = {'mode': 'fused'}            # 'fused' (msq_rpn_select) | 'torch' (operator by operator)
-CONV_ENGINE = {'mode': 'cudnn'}          # 'cudnn' | 'tcgen05' (csrc/conv_tc.cu, where the shape is served)
+CONV_ENGINE = {'mode': 'auto'}           # 'auto' (per layer shape, the faster of the two) | 'cudnn' | 'tcgen05' (csrc/conv_tc.cu)
 
 
 def _is_cl(x: torch.Tensor) -> bool:
@@ -69,12 +69,29 @@ def _stem_conv_pool(chunk_u8, vmin, vmax, int_limits, mean, std, ph, pw, w49x64,
 
 
 # ---- dense contractions -------------------------------------------------------------------------------------------------
-def _conv2d(x, w, b, z, relu, stride, pad):
-    if CONV_ENGINE['mode'] == 'tcgen05':
-        from . import conv_tc
-        y = conv_tc.try_conv2d(x, w, b, z, relu, stride, pad)
-        if y is not None:
-            return y
+# Two engines run the convolutions / Linear layers of the graph: cuDNN / cuBLAS (library calls) and csrc/conv_tc.cu (the repo's
+# tcgen05 + TMA implicit GEMM).  CONV_ENGINE['mode']: 'cudnn', 'tcgen05' (wherever the shape is served), or 'auto': the first
+# time a layer shape is seen both engines are timed on it (CUDA events, 3 runs each) and the faster one keeps the shape.
+_ENGINE_CHOICE: Dict[tuple, str] = {}
+
+
+def engine_choices() -> Dict[tuple, str]:
+    """Layer shape -> engine picked by 'auto' so far (bench.py prints the split)."""
+    return dict(_ENGINE_CHOICE)
+
+
+def _time_call(fn, runs: int = 3) -> float:
+    fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(runs):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / runs
+
+
+def _conv2d_cudnn(x, w, b, z, relu, stride, pad):
     x = _cl(x)
     st, pd, dl = [stride, stride], [pad, pad], [1, 1]
     if relu and b is not None and x.dtype == w.dtype:
@@ -87,14 +104,55 @@ def _conv2d(x, w, b, z, relu, stride, pad):
     return F.relu(y) if relu else y
 
 
-def _linear(x, w, b, relu):
-    if CONV_ENGINE['mode'] == 'tcgen05':
+def _conv2d(x, w, b, z, relu, stride, pad):
+    mode = CONV_ENGINE['mode']
+    if mode != 'cudnn' and x.dtype == torch.bfloat16:
         from . import conv_tc
-        y = conv_tc.try_linear(x, w, b, relu)
-        if y is not None:
-            return y
+        if mode == 'tcgen05':
+            y = conv_tc.try_conv2d(x, w, b, z, relu, stride, pad)
+            if y is not None:
+                return y
+        else:                                                    # 'auto'
+            key = ('conv', tuple(x.shape), tuple(w.shape), int(stride), int(pad), z is not None, bool(relu), b is not None)
+            choice = _ENGINE_CHOICE.get(key)
+            if choice is None:
+                choice = 'cudnn'
+                if conv_tc.try_conv2d(x, w, b, z, relu, stride, pad) is not None:
+                    t_tc = _time_call(lambda: conv_tc.try_conv2d(x, w, b, z, relu, stride, pad))
+                    t_cd = _time_call(lambda: _conv2d_cudnn(x, w, b, z, relu, stride, pad))
+                    choice = 'tcgen05' if t_tc < t_cd else 'cudnn'
+                _ENGINE_CHOICE[key] = choice
+            if choice == 'tcgen05':
+                return conv_tc.try_conv2d(x, w, b, z, relu, stride, pad)
+    return _conv2d_cudnn(x, w, b, z, relu, stride, pad)
+
+
+def _linear_cublas(x, w, b, relu):
     y = F.linear(x, w, b)
     return F.relu_(y) if relu else y
+
+
+def _linear(x, w, b, relu):
+    mode = CONV_ENGINE['mode']
+    if mode != 'cudnn' and x.dtype == torch.bfloat16:
+        from . import conv_tc
+        if mode == 'tcgen05':
+            y = conv_tc.try_linear(x, w, b, relu)
+            if y is not None:
+                return y
+        else:
+            key = ('linear', tuple(x.shape), tuple(w.shape), bool(relu), b is not None)
+            choice = _ENGINE_CHOICE.get(key)
+            if choice is None:
+                choice = 'cudnn'
+                if conv_tc.try_linear(x, w, b, relu) is not None:
+                    t_tc = _time_call(lambda: conv_tc.try_linear(x, w, b, relu))
+                    t_cd = _time_call(lambda: _linear_cublas(x, w, b, relu))
+                    choice = 'tcgen05' if t_tc < t_cd else 'cudnn'
+                _ENGINE_CHOICE[key] = choice
+            if choice == 'tcgen05':
+                return conv_tc.try_linear(x, w, b, relu)
+    return _linear_cublas(x, w, b, relu)
 
 
 # ---- GroupNorm (+ top-down merge) on channels-last maps -------------------------------------------------------------------

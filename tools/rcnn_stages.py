@@ -65,5 +65,11 @@ with torch.no_grad():
     timed('graph_total(forward_dense)', lambda: model.forward_dense(prep, 0.0, 100.0, True))
     print('mean proposals per image:', float(counts.float().mean()))
 tot = times['graph_total(forward_dense)']
+if ENGINE == 'auto':
+    ch = ops.engine_choices()
+    print('auto engine split:', {e: sum(1 for v in ch.values() if v == e) for e in ('tcgen05', 'cudnn')})
+    for k, v in ch.items():
+        if v == 'tcgen05':
+            print('  tcgen05:', k[:5])
 print(json.dumps({'batch': B, 'post_nms_topk': TOPK, 'engine': ENGINE, 'ms': {k: round(v, 3) for k, v in times.items()},
                   'frames_per_s_graph_only': B / tot * 1e3}))
