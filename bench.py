@@ -749,6 +749,7 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
                     'path': 'pinned host int16 frames (pool >> CPU caches) -> zero-copy msq_prep_frames -> graph -> msq_paste_masks -> '
                             'msq_extract_chunk -> pinned host crops / scalars / keypoint table / flips; masks never cross PCIe'},
             'stage_ms_per_batch': {k2: round(v, 3) for k2, v in stage_ms.items()}, 'batch': B,
+            'dense_engine': engine_report(),
             'gpu_launches_own_kernels': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
                          'peak_source': peak_src + ' bf16_tflops_sustained', 'dense_flops_per_frame': flops,
@@ -758,6 +759,16 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
         del pred, engine
         torch.cuda.empty_cache()
     return out
+
+
+def engine_report():
+    """Which engine runs the graph's convolutions / Linear layers: per layer shape the faster of cuDNN / cuBLAS and the repo's
+    tcgen05 + TMA implicit GEMM (csrc/conv_tc.cu), timed once per shape (model/ops.py 'auto')."""
+    from moseq2_detectron_extract_b200.model import ops
+    ch = ops.engine_choices()
+    tc = sorted({f'{k[0]} {list(k[2])} on {list(k[1])}' + (f' stride {k[3]}' if k[0] == 'conv' and k[3] != 1 else '') for k, v in ch.items() if v == 'tcgen05'})
+    return {'mode': ops.CONV_ENGINE['mode'], 'layer_shapes_on_tcgen05': sum(1 for v in ch.values() if v == 'tcgen05'),
+            'layer_shapes_on_cudnn_cublas': sum(1 for v in ch.values() if v == 'cudnn'), 'tcgen05_layers': tc}
 
 
 def secondary_figures(args, geom, cfg, roi, bg):
