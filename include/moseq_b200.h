@@ -130,6 +130,13 @@ MSQ_API int msq_stem_conv_pool(const uint8_t *in_dev, int n, int h, int w, int p
                        float mean, float std, const float *w49x64_dev, const float *bias64_dev, void *out_dev, int out_is_bf16,
                        void *stream);
 
+/* The same stem on the tensor cores (csrc/stem_tc.cu; bf16 output): the 49 taps are one 64-wide K block, the im2col operand is
+ * written into shared memory in the swizzle-128B layout and multiplied by tcgen05.mma.  b_tile_dev: 8192 bytes = the summed stem
+ * weight as bf16 [64 output channels][64 k] in that layout: element (n, k) at byte n*128 + (((k>>3) ^ (n&7))<<4) + (k&7)*2,
+ * k = r*7+s < 49, zero beyond (model/rcnn.py stem_b_tile builds it). */
+MSQ_API int msq_stem_conv_pool_tc(const uint8_t *in_dev, int n, int h, int w, int ph, int pw, double vmin, double vmax, int vmin_is_int,
+                          float mean, float std, const void *b_tile_dev, const float *bias64_dev, void *out_dev, void *stream);
+
 /* Segmented greedy NMS for the RPN proposal filtering of a whole batch (replaces the per-image box_ops.batched_nms calls of
  * torchvision's RegionProposalNetwork.filter_proposals behind Predictor; the reference's detectron2 RPN does the same
  * per-image loop).  boxes_dev (n,K,4) float32, per image sorted by descending score and already shifted per pyramid level

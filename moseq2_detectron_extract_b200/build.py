@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmoseq_b200.so')
-SOURCES = ['api.cu', 'prep.cu', 'clean.cu', 'clean_stream.cu', 'features.cu', 'epilogue.cu', 'crop.cu', 'paste.cu', 'nms.cu', 'roi_align.cu', 'rcnn.cu', 'conv_tc.cu', 'inpaint.cu', 'kalman.cu', 'bground.cu', 'roi.cu', 'pipeline.cu']
+SOURCES = ['api.cu', 'prep.cu', 'clean.cu', 'clean_stream.cu', 'features.cu', 'epilogue.cu', 'crop.cu', 'paste.cu', 'nms.cu', 'roi_align.cu', 'rcnn.cu', 'conv_tc.cu', 'stem_tc.cu', 'inpaint.cu', 'kalman.cu', 'bground.cu', 'roi.cu', 'pipeline.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '--fmad=false', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--threads', '0']
 

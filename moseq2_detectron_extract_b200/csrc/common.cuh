@@ -124,6 +124,19 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t c, const ByteTest &t) {
 __device__ __forceinline__ uint32_t bytes_nonzero(uint32_t m) {
     return (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u;
 }
+// ref proc/proc.py:214-234: float64 affine map then truncation.  256 possible inputs -> each CTA
+// builds the table in shared memory with the reference's exact float64 operation order.
+__device__ __forceinline__ void build_scale_lut(uint8_t *lut, double vmin, double vmax, int vmin_is_int) {
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) {
+        const double gain = __ddiv_rn(255.0 - 0.0, __dsub_rn(vmax, vmin));
+        double xv;
+        if (vmin_is_int) xv = (double)(uint8_t)(x - (int)vmin);   // uint8 array - Python int wraps in uint8
+        else xv = __dsub_rn((double)x, vmin);
+        const double v = __dadd_rn(__dmul_rn(xv, gain), 0.0);
+        lut[x] = (uint8_t)(long long)v;
+    }
+    __syncthreads();
+}
 #endif  // __CUDACC__
 }  // namespace msq
 

@@ -282,20 +282,7 @@ int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground,
 }
 
 // ------------------------------- scale ---------------------------------------------------------
-// ref proc/proc.py:214-234: float64 affine map then truncation.  256 possible inputs -> each CTA
-// builds the table in shared memory with the reference's exact float64 operation order.
-__device__ __forceinline__ void build_scale_lut(uint8_t *lut, double vmin, double vmax, int vmin_is_int) {
-    for (int x = threadIdx.x; x < 256; x += blockDim.x) {
-        const double gain = __ddiv_rn(255.0 - 0.0, __dsub_rn(vmax, vmin));
-        double xv;
-        if (vmin_is_int) xv = (double)(uint8_t)(x - (int)vmin);   // uint8 array - Python int wraps in uint8
-        else xv = __dsub_rn((double)x, vmin);
-        const double v = __dadd_rn(__dmul_rn(xv, gain), 0.0);
-        lut[x] = (uint8_t)(long long)v;
-    }
-    __syncthreads();
-}
-
+// (build_scale_lut lives in common.cuh: the stem kernels share it)
 __global__ void __launch_bounds__(256)
 scale_u8_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t count, double vmin,
                 double vmax, int vmin_is_int, int vec_ok) {

@@ -22,6 +22,8 @@ _LIB.define('detector_input(Tensor chunk_u8, float vmin, float vmax, bool int_li
             'bool bf16) -> Tensor')
 _LIB.define('stem_conv_pool(Tensor chunk_u8, float vmin, float vmax, bool int_limits, float mean, float std, int ph, int pw, '
             'Tensor w49x64, Tensor bias64, bool bf16) -> Tensor')
+_LIB.define('stem_conv_pool_tc(Tensor chunk_u8, float vmin, float vmax, bool int_limits, float mean, float std, int ph, int pw, '
+            'Tensor b_tile, Tensor bias64) -> Tensor')
 _LIB.define('conv2d(Tensor x, Tensor w, Tensor? b, Tensor? z, bool relu, int stride, int pad) -> Tensor')
 _LIB.define('linear(Tensor x, Tensor w, Tensor? b, bool relu) -> Tensor')
 _LIB.define('group_norm_nhwc(Tensor x, Tensor gamma, Tensor beta, int groups, float eps, Tensor? top, float scale) -> Tensor')
@@ -65,6 +67,16 @@ def _stem_conv_pool(chunk_u8, vmin, vmax, int_limits, mean, std, ph, pw, w49x64,
                       memory_format=torch.channels_last)
     _lib.call('msq_stem_conv_pool', _dev.ptr(chunk_u8.contiguous()), n, h, w, int(ph), int(pw), float(vmin), float(vmax), int(int_limits),
               float(mean), float(std), _dev.ptr(w49x64), _dev.ptr(bias64), _dev.ptr(out), int(bf16), _dev.stream())
+    return out
+
+
+def _stem_conv_pool_tc(chunk_u8, vmin, vmax, int_limits, mean, std, ph, pw, b_tile, bias64):
+    n, h, w = (int(v) for v in chunk_u8.shape)
+    conv_h, conv_w = (ph - 1) // 2 + 1, (pw - 1) // 2 + 1
+    pool_h, pool_w = (conv_h - 1) // 2 + 1, (conv_w - 1) // 2 + 1
+    out = torch.empty((n, 64, pool_h, pool_w), dtype=torch.bfloat16, device=chunk_u8.device, memory_format=torch.channels_last)
+    _lib.call('msq_stem_conv_pool_tc', _dev.ptr(chunk_u8.contiguous()), n, h, w, int(ph), int(pw), float(vmin), float(vmax), int(int_limits),
+              float(mean), float(std), _dev.ptr(b_tile), _dev.ptr(bias64), _dev.ptr(out), _dev.stream())
     return out
 
 
@@ -351,7 +363,7 @@ def _keypoints_from_heatmaps_d2(heatmaps, boxes):
     return xyp
 
 
-for _name, _fn in (('detector_input', _detector_input), ('stem_conv_pool', _stem_conv_pool), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
+for _name, _fn in (('detector_input', _detector_input), ('stem_conv_pool', _stem_conv_pool), ('stem_conv_pool_tc', _stem_conv_pool_tc), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
                    ('rpn_proposals', _rpn_proposals), ('roi_align_v2', _roi_align_v2), ('fastrcnn_top1', _fastrcnn_top1),
                    ('keypoints_from_heatmaps_d2', _keypoints_from_heatmaps_d2)):
     _LIB.impl(_name, _fn, 'CUDA')

@@ -110,6 +110,8 @@ class MoseqRCNN(nn.Module):
         self.stem_uniform = len(set(self.pixel_mean)) == 1 and len(set(self.pixel_std)) == 1
         self.register_buffer('stem_w49', torch.zeros((49, 64)))
         self.register_buffer('stem_b64', torch.zeros((64,)))
+        self.register_buffer('stem_btile', torch.zeros((4096,), dtype=torch.int16))     # the same weights as a tcgen05 B operand
+        self.stem_tc = True                                                    # bf16 graph: stem on the tensor cores (csrc/stem_tc.cu)
         self.res2 = _stage(64, 64, 256, 3, 1)
         self.res3 = _stage(256, 128, 512, 4, 2)
         self.res4 = _stage(512, 256, 1024, 6, 2)
@@ -230,6 +232,10 @@ class MoseqRCNN(nn.Module):
         h, w = chunk_u8.shape[1], chunk_u8.shape[2]
         d = self.size_divisibility
         ph, pw = (h + d - 1) // d * d, (w + d - 1) // d * d
+        if self.stem_uniform and self.stem_tc and self._compute_bf16():
+            x = torch.ops.msq.stem_conv_pool_tc(chunk_u8, vmin, vmax, int_limits, self.pixel_mean[0], self.pixel_std[0], ph, pw, self.stem_btile,
+                                                self.stem_b64)
+            return self.detect_from_pyramid(self.pyramid(x), h, w)
         if self.stem_uniform:
             x = torch.ops.msq.stem_conv_pool(chunk_u8, vmin, vmax, int_limits, self.pixel_mean[0], self.pixel_std[0], ph, pw, self.stem_w49,
                                              self.stem_b64, self._compute_bf16())
@@ -279,6 +285,7 @@ def finalize(model: MoseqRCNN, dtype: torch.dtype, device: str) -> MoseqRCNN:
     with torch.no_grad():       # 1-channel form of the stem (float32 whatever the compute dtype): weights summed over the input channels
         model.stem_w49 = model.stem.weight.detach().float().sum(dim=1).permute(1, 2, 0).reshape(49, 64).contiguous()
         model.stem_b64 = model.stem.bias.detach().float().contiguous()
+        model.stem_btile = stem_b_tile(model.stem_w49).to(model.stem_w49.device)
     for name, p in model.named_parameters():
         if name.endswith('gamma') or name.endswith('beta'):
             p.data = p.data.float().contiguous()
@@ -286,6 +293,20 @@ def finalize(model: MoseqRCNN, dtype: torch.dtype, device: str) -> MoseqRCNN:
             t = p.data.to(dtype)
             p.data = t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 and 'deconv' not in name else t.contiguous()
     return model
+
+
+def stem_b_tile(w49x64: Tensor) -> Tensor:
+    """(49, 64) float32 summed stem weight -> the 8 KB B operand of csrc/stem_tc.cu: bf16 [64 n][64 k], K-major rows of 128 bytes
+    with the 128-byte swizzle (16-byte chunk index XOR row-in-atom), k >= 49 zero.  Returned as 4096 int16 (bf16 bit patterns)."""
+    w = torch.zeros((64, 64), dtype=torch.float32)
+    w[:, :49] = w49x64.detach().float().cpu().t()
+    bits = w.to(torch.bfloat16).view(torch.int16)                             # [n][k]
+    n = torch.arange(64)[:, None].expand(64, 64)
+    k = torch.arange(64)[None, :].expand(64, 64)
+    pos = n * 64 + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)                        # in 2-byte units
+    tile = torch.zeros((4096,), dtype=torch.int16)
+    tile[pos.reshape(-1)] = bits.reshape(-1)
+    return tile
 
 
 def _fold(state: Dict[str, Tensor], name: str) -> Tuple[Tensor, Tensor]:

@@ -215,6 +215,35 @@ def test_stem_conv_pool_matches_torch(dtype, h, w):
     assert float((got.float() - want).abs().max()) <= tol * float(want.abs().max())
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('h,w', [(240, 240), (200, 236), (250, 250), (64, 48)])
+def test_stem_on_tensor_cores_matches_torch(h, w):
+    """csrc/stem_tc.cu (im2col written in the swizzle-128B layout + tcgen05.mma + TMEM read-back + pool) against the float32
+    reference of the same steps.  Operands are bf16 (normalised input, summed weights), accumulation float32: the result agrees
+    with the float32 convolution to bf16 operand rounding (2^-8 relative per product, 49 products)."""
+    msq = _ops()
+    from moseq2_detectron_extract_b200.model import rcnn
+    g = torch.Generator(device='cuda').manual_seed(h + w)
+    chunk = torch.randint(0, 120, (5, h, w), dtype=torch.uint8, device='cuda', generator=g)
+    chunk[0, : h // 4] = 0
+    model = rcnn.build_random(seed=1, dtype=torch.bfloat16)
+    with torch.no_grad():
+        model.stem.bias.normal_(0, 0.5)
+        model = rcnn.finalize(model, torch.bfloat16, 'cuda')
+        ph, pw = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+        x = msq.detector_input(chunk, 0.0, 100.0, True, model.pixel_mean, model.pixel_std, ph, pw, False)
+        w1 = model.stem_w49.t().reshape(64, 1, 7, 7)
+        want = F.max_pool2d(F.relu(F.conv2d(x[:, :1], w1, model.stem_b64, 2, 3)), 3, 2, 1)
+        got = msq.stem_conv_pool_tc(chunk, 0.0, 100.0, True, model.pixel_mean[0], model.pixel_std[0], ph, pw, model.stem_btile, model.stem_b64)
+        ref32 = msq.stem_conv_pool(chunk, 0.0, 100.0, True, model.pixel_mean[0], model.pixel_std[0], ph, pw, model.stem_w49, model.stem_b64, True)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    scale = float(want.abs().max())
+    assert float((got.float() - want).abs().max()) <= 0.03 * scale
+    assert float((got.float() - want).abs().mean()) <= 0.004 * scale
+    assert float((got.float() - ref32.float()).abs().max()) <= 0.03 * scale            # and with the CUDA-core kernel
+
+
 # ---- the whole graph ------------------------------------------------------------------------------------------------------
 def test_graph_float32_matches_detectron2_restatement(state, images):
     """from_detectron2_state_dict (FrozenBN folded, fused epilogues, merged RPN predictor, permuted fc1, channels-last, batched

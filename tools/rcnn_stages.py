@@ -46,6 +46,8 @@ with torch.no_grad():
     c5 = timed('res5', lambda: model.res5(c4))
     feats = timed('backbone_total(stem..fpn)', lambda: model.backbone(x))
     times['fpn'] = times['backbone_total(stem..fpn)'] - sum(times[k] for k in ('stem', 'maxpool', 'res2', 'res3', 'res4', 'res5'))
+    timed('stem_tc(tcgen05: input+im2col+mma+relu+pool)', lambda: msq.stem_conv_pool_tc(prep, 0.0, 100.0, True, model.pixel_mean[0], model.pixel_std[0], 256,
+                                                                                      256, model.stem_btile, model.stem_b64))
     timed('fused_stem(input+conv+relu+pool)', lambda: msq.stem_conv_pool(prep, 0.0, 100.0, True, model.pixel_mean[0], model.pixel_std[0], 256, 256,
                                                                           model.stem_w49, model.stem_b64, True))
     preds = timed('rpn_head_convs', lambda: [model.rpn_pred(model.rpn_conv(f)) for f in feats])
