@@ -724,9 +724,9 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
             msq = torch.ops.msq
             ph = (h + 31) // 32 * 32
             pw = (w + 31) // 32 * 32
-            x = t('stem (input staging + 7x7 conv + ReLU + max-pool, one kernel)',
-                  lambda: msq.stem_conv_pool(chunk, float(cfg['min_height']), float(cfg['max_height']), True, model.pixel_mean[0],
-                                             model.pixel_std[0], ph, pw, model.stem_w49, model.stem_b64, True))
+            x = t('stem (input staging + im2col + tcgen05 7x7 conv + ReLU + max-pool, one kernel)',
+                  lambda: msq.stem_conv_pool_tc(chunk, float(cfg['min_height']), float(cfg['max_height']), True, model.pixel_mean[0],
+                                                model.pixel_std[0], ph, pw, model.stem_btile, model.stem_b64))
             feats = t('res2-res5 + FPN (GN, avg fusion)', lambda: model.pyramid(x))
             props = t('RPN head + proposals (top-k, decode, NMS)', lambda: model.rpn(feats, h, w))
             det = t('box head (ROIAlignV2 + 2 FC + top-1)', lambda: model.box_head(feats, props[0], props[2], h, w))
@@ -739,7 +739,7 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
         graph_ms = stage_ms['whole graph + paste (predict_dense)']
         achieved = flops * B / (graph_ms * 1e-3) / 1e12
         out[key] = {
-            'workload': f'configs[2]: prep -> stem kernel -> Keypoint+Mask R-CNN R50-FPN of the reference configuration (own TorchScript graph: '
+            'workload': f'configs[2]: prep -> stem kernel (tcgen05) -> Keypoint+Mask R-CNN R50-FPN of the reference configuration (own TorchScript graph: '
                         f'GN FPN with avg fusion, stride-in-1x1 ResNet, ROIAlignV2, keypoint pooler 7; random init, bf16, batch {B}, '
                         f'{topk} proposals per image, 1 detection per frame) -> batched paste -> clean/features/angles/scalars -> crops',
             'frames': n * world, 'chunks': (n + npool - 1) // npool, 'post_nms_topk': topk,
