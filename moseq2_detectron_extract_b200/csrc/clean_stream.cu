@@ -266,19 +266,11 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
         }
         if (act0 >= act1) continue;
         const int ys0 = act0, ys1 = act1;                              // the rows that go through the full pipeline
-        // The erosion is zero above band_lo, so the pipeline starts right there: the first median row anyone needs is band_lo - 4
-        // (raw rows from band_lo - 5 on), and the dilation's history -- erosion rows before band_lo -- is all zeros, which is
-        // what its delay lines are reset to.  (Starting 9 rows above the first OUTPUT row, as a strip without this knowledge
-        // must, costs 8 more trips of the whole pipeline per strip.)
-        const int y_first = band_lo - 5;                               // first input row of the strip
-#pragma unroll
-        for (int k = 0; k < kDelayM; ++k) ring_e[k][lane] = splat(0u);
-#pragma unroll
-        for (int k = 0; k < kDelayV; ++k) { ring_w[k][lane] = splat(0u); ring_b[k][lane] = splat(0u); }
+        const int y_first = ys0 - 9;                                   // first input row of the strip
         // The three stages are software-pipelined across iterations: iteration s computes the median row s-1, the
         // erosion from the median row of iteration s-1 and the dilation from the erosion row of iteration s-2, so the
         // stages inside one iteration are mutually independent instruction streams (ILP for the ~10 resident warps).
-        const int steps = ys1 - y_first + 11;                          // the dilation row of trip s is y_first + s - 11
+        const int steps = (ys1 - ys0) + 20;
         const uint32_t one = G.one, neg1 = G.neg1;
         uint2 pf_v[kPrefetch];
         uint32_t pf_e[kPrefetch];
@@ -339,7 +331,7 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
                     E_next = op3_4<MinOp>(a_old, v7_prev, M_cur);               // E[m-4] = min(A[m-4], V7[m-2], M[m])
                     h7_prev = h7; h9_prev2 = h9_prev; h9_prev = h9; v7_prev = v7;
                     const int ye = y_first + m - 4;
-                    if (!(col_in && (unsigned)ye < (unsigned)h) || ye < band_lo) E_next = splat(0u);   // outside the image / above the band: 0
+                    if (!(col_in && (unsigned)ye < (unsigned)h)) E_next = splat(0u);               // dilation identity outside the image
                 }
                 // ================= stage 1: median row m = s-1 (image row y_first + s - 1), centre row r1 =================
                 uint4 M_next;
