@@ -810,7 +810,7 @@ def secondary_figures(args, geom, cfg, roi, bg):
             masks = torch.from_numpy(np.tile(ch.masks, (reps, 1, 1))).cuda()
             n, h, w = (int(v) for v in prep.shape)
             cleaned = torch.empty_like(prep)
-            _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, _dev.stream())
+            _dev.clean_frames_ws(prep, cleaned)
             cen, ori, ax = _dev.empty((n, 2), torch.float64), _dev.empty((n,), torch.float64), _dev.empty((n, 2), torch.float64)
             flist = _dev.empty((n + 1,), torch.int32)
 
@@ -820,7 +820,7 @@ def secondary_figures(args, geom, cfg, roi, bg):
             ms_mixed = timed(feats, iters=5)
             passed_on = int(flist[0].item())
             ms_general = timed(lambda: feats(False), iters=5)
-            ms_clean = timed(lambda: _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(cleaned), n, h, w, _dev.stream()), iters=5)
+            ms_clean = timed(lambda: _dev.clean_frames_ws(prep, cleaned), iters=5)
             regimes[name] = {'frames': n, 'fast_path_hit_rate': 1.0 - passed_on / n, 'ms_streaming_plus_general_for_the_rest': ms_mixed,
                              'ms_general_kernel_on_every_frame': ms_general, 'GBps_mixed': (2 * h * w + 40) * n / (ms_mixed * 1e-3) / 1e9,
                              'ms_clean_frames': ms_clean, 'GBps_clean': 2 * h * w * n / (ms_clean * 1e-3) / 1e9}

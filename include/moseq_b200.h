@@ -232,6 +232,11 @@ MSQ_API int msq_conv_tc(const void *x_dev, int n, int H, int W, int cin, const v
 /* ---- a6  clean_frames(iters_tail=3) (ref: proc/proc.py:480-515) -------------------------------------
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
 MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);
+/* The same with scratch memory (msq_clean_scratch_bytes(n,h,w) bytes, 8-byte aligned): the row pre-pass that finds where the
+ * opening can be non-zero runs as its own lean launch instead of inside the pipeline kernel (faster; msq_extract_chunk uses it). */
+MSQ_API size_t msq_clean_scratch_bytes(int n, int h, int w);
+MSQ_API int msq_clean_frames_ws(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *scratch_dev, size_t scratch_bytes,
+                        void *stream);
 
 /* ---- a7  get_frame_features + im_moment_features (ref: proc/proc.py:237-302, 518-549) ----------------
  * fm = (cleaned > frame_threshold) & (mask != 0); polygon moments of the largest outer contour.

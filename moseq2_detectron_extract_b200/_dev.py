@@ -62,3 +62,11 @@ def give_back(t: torch.Tensor, like: Any):
     if isinstance(like, torch.Tensor):
         return t
     return t.cpu().numpy()
+
+
+def clean_frames_ws(src: torch.Tensor, out: torch.Tensor) -> None:
+    """`msq_clean_frames_ws` with a torch-owned scratch buffer (the row pre-pass runs as its own launch)."""
+    n, h, w = (int(v) for v in src.shape)
+    nbytes = int(_lib.load().msq_clean_scratch_bytes(n, h, w))
+    scratch = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=src.device)
+    _lib.call('msq_clean_frames_ws', ptr(src), ptr(out), n, h, w, ptr(scratch), nbytes, stream())

@@ -46,6 +46,8 @@ SIGNATURES = {
     'msq_scale_frames': (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_double, c_int, c_void_p]),
     'msq_scale_frames_chw3_f32': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int, c_void_p]),
     'msq_clean_frames': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'msq_clean_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'msq_clean_frames_ws': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     'msq_frame_features_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_frame_features': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),

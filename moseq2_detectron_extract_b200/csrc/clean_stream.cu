@@ -204,8 +204,24 @@ struct StreamGeom {
     uint32_t one, neg1;        // 1 and -1, opaque to the compiler (see med3_of_sorted)
 };
 
+// Pass 1 as its own launch (msq_clean_frames_ws / msq_extract_chunk, which have scratch memory for its result): one warp per
+// (frame, 240-column tile) scans the whole height and writes the band [lo, hi] of rows with a non-zero erosion.  ~50 registers:
+// 48 warps per SM hide the load latency that the same scan suffers inside the 128-register pipeline kernel (ncu: long-scoreboard
+// stalls 2.3 per issue there).
+constexpr int kBandWarps = 4;
+__global__ void __launch_bounds__(32 * kBandWarps)
+clean_band_kernel(const uint8_t *__restrict__ in, int n, int h, int w, int tiles_x, int2 *__restrict__ bands) {
+    const int item = blockIdx.x * kBandWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n * tiles_x) return;
+    const int f = item / tiles_x, tx = item - f * tiles_x;
+    int lo = INT_MAX, hi = -1;
+    scan_band(in + (size_t)f * h * w, h, w, tx * kOutCols - 8, 0, h - 1, lane, lo, hi);
+    if (lane == 0) bands[item] = make_int2(lo, hi);
+}
+
+template <bool kBandsGiven>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, 16)
-clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, StreamGeom G) {
+clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, StreamGeom G, const int2 *__restrict__ bands) {
     // per-lane delay lines: [row slot][lane] uint4
     __shared__ uint4 ring_m[kDelayM][32], ring_v[kDelayV][32], ring_a[kDelayA][32];
     __shared__ uint4 ring_e[kDelayM][32], ring_w[kDelayV][32], ring_b[kDelayA][32];
@@ -257,9 +273,14 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
 
         // ---- pass 1 (scan_band above): rows of this strip on which the erosion is non-zero ----
         int band_lo = INT_MAX, band_hi = -1;
-        scan_band(src, h, w, tx * kOutCols - 8, max(0, y_out0 - 4), min(h, y_out1 + 4) - 1, lane, band_lo, band_hi);
+        if (kBandsGiven) {                                             // the band of the whole (frame, tile), found by clean_band_kernel
+            const int2 b = bands[(size_t)f * G.tiles_x + tx];
+            band_lo = b.x; band_hi = b.y;
+        } else {
+            scan_band(src, h, w, tx * kOutCols - 8, max(0, y_out0 - 4), min(h, y_out1 + 4) - 1, lane, band_lo, band_hi);
+        }
         // rows outside [band_lo - 4, band_hi + 4] are zero
-        const int act0 = band_hi < 0 ? y_out1 : max(y_out0, band_lo - 4), act1 = band_hi < 0 ? y_out1 : min(y_out1, band_hi + 5);
+        const int act0 = band_hi < 0 ? y_out1 : min(y_out1, max(y_out0, band_lo - 4)), act1 = band_hi < 0 ? y_out1 : max(act0, min(y_out1, band_hi + 5));
         if (writes) {
             for (int y = y_out0; y < act0; ++y) *reinterpret_cast<uint2 *>(dst + ((size_t)y * w + x_lane)) = make_uint2(0u, 0u);
             for (int y = act1; y < y_out1; ++y) *reinterpret_cast<uint2 *>(dst + ((size_t)y * w + x_lane)) = make_uint2(0u, 0u);
@@ -373,8 +394,9 @@ clean_stream_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, i
 
 }  // namespace
 
-// returns MSQ_EUNSUPPORTED-like negative hint (-100) when the streaming kernel cannot serve the shape
-int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st) {
+// returns MSQ_EUNSUPPORTED-like negative hint (-100) when the streaming kernel cannot serve the shape.
+// bands: n * tiles_x int2 of scratch for the separate pre-pass launch, or nullptr (then every strip scans its own rows).
+int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands) {
     const bool vec = (w % 8 == 0) && w >= 8 && ((uintptr_t)in % 8 == 0) && ((uintptr_t)out % 8 == 0);
     if (!vec) return -100;
     StreamGeom G;
@@ -383,7 +405,7 @@ int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cu
     static thread_local int resident = 0;          // co-resident CTAs per SM (shared-memory limited, ~10)
     if (resident == 0) {
         int r = 0;
-        MSQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, clean_stream_kernel, 32 * kWarpsPerCta, 0));
+        MSQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, clean_stream_kernel<false>, 32 * kWarpsPerCta, 0));
         resident = std::max(1, r);
     }
     // persistent grid: every CTA is resident and gets the same number of rows; at least ~120 rows each so that the
@@ -394,7 +416,13 @@ int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cu
     G.rows_per_cta = (int)((total_rows + ctas - 1) / ctas);
     const int grid = (int)((total_rows + G.rows_per_cta - 1) / G.rows_per_cta);
     TimedLaunch timed(K_CLEAN, st);
-    clean_stream_kernel<<<grid, 32 * kWarpsPerCta, 0, st>>>(in, out, n, G);
+    if (bands) {
+        const int items = n * G.tiles_x;
+        clean_band_kernel<<<(items + kBandWarps - 1) / kBandWarps, 32 * kBandWarps, 0, st>>>(in, n, h, w, G.tiles_x, bands);
+        clean_stream_kernel<true><<<grid, 32 * kWarpsPerCta, 0, st>>>(in, out, n, G, bands);
+    } else {
+        clean_stream_kernel<false><<<grid, 32 * kWarpsPerCta, 0, st>>>(in, out, n, G, nullptr);
+    }
     MSQ_LAUNCH_OK("clean_frames (streaming)");
     return MSQ_OK;
 }

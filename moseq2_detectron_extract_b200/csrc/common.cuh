@@ -142,8 +142,9 @@ __device__ __forceinline__ void build_scale_lut(uint8_t *lut, double vmin, doubl
 
 // ---- internal launchers shared with the whole-chunk pipeline (pipeline.cu) ---------------------
 namespace msq {
-int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);
-int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st);   // -100: shape not served
+int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands = nullptr);   // bands: clean_scratch_bytes() or null
+int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands);   // -100: shape not served
+size_t clean_scratch_bytes(int n, int w);
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
                           double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
                           cudaStream_t st, cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join);

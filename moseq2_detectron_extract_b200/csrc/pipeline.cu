@@ -10,7 +10,7 @@ using namespace msq;
 extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
     const size_t nn = (size_t)(n > 0 ? n : 0);
     return align_up(nn * sizeof(double), 256) + align_up(nn * sizeof(int2), 256) + align_up(msq_crop_scratch_bytes((int)nn), 256) +
-           align_up((nn + 1) * sizeof(int), 256);
+           align_up((nn + 1) * sizeof(int), 256) + align_up(clean_scratch_bytes((int)nn, 4096), 256);
 }
 
 // The one piece of state the whole-chunk entry point needs: a side stream + two events on one device, so that the few
@@ -69,8 +69,10 @@ extern "C" int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk
     int2 *sums = reinterpret_cast<int2 *>(base + align_up((size_t)n * sizeof(double), 256));
     void *crop_scratch = base + align_up((size_t)n * sizeof(double), 256) + align_up((size_t)n * sizeof(int2), 256);
     int *feature_list = reinterpret_cast<int *>(reinterpret_cast<char *>(crop_scratch) + align_up(msq_crop_scratch_bytes(n), 256));
+    int2 *clean_bands = reinterpret_cast<int2 *>(reinterpret_cast<char *>(feature_list) + align_up((size_t)(n + 1) * sizeof(int), 256));
+    MSQ_REQUIRE(w <= 4096, MSQ_EUNSUPPORTED, "msq_extract_chunk: frames wider than 4096 pixels (got %d)", w);
     int rc;
-    if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st)) != MSQ_OK) return rc;
+    if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st, clean_bands)) != MSQ_OK) return rc;
     // frame_threshold = 3 (ref proc/proc.py:716)
     if ((rc = launch_frame_features(out->cleaned, mask_dev, n, h, w, 3.0, out->centroid, orientation, out->axis_length,
                                     nullptr, feature_list, st, engine->side, engine->fork, engine->join)) != MSQ_OK) return rc;

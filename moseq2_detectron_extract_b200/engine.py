@@ -100,7 +100,7 @@ class ChunkEngine:
         centroid, orientation, axis = e((n, 2), torch.float64), e((n,), torch.float64), e((n, 2), torch.float64)
         flist = e((n + 1,), torch.int32)            # msq_frame_features scratch: frames left to the general kernel
         st = _dev.stream()
-        _lib.call('msq_clean_frames', _dev.ptr(chunk), _dev.ptr(cleaned), n, h, w, st)
+        _dev.clean_frames_ws(chunk, cleaned)
         _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(centroid),
                   _dev.ptr(orientation), _dev.ptr(axis), ctypes.c_void_p(0), _dev.ptr(flist), flist.numel() * 4, st)
         return {'cleaned': cleaned, 'centroid': centroid, 'orientation_rad': orientation, 'axis_length': axis}
@@ -118,7 +118,7 @@ class ChunkEngine:
         passes = e(((n + chunk_size - 1) // chunk_size,), torch.int32)
         flist = e((n + 1,), torch.int32)            # msq_frame_features scratch: frames left to the general kernel
         st = _dev.stream()
-        _lib.call('msq_clean_frames', _dev.ptr(chunk), _dev.ptr(cleaned), n, h, w, st)
+        _dev.clean_frames_ws(chunk, cleaned)
         _lib.call('msq_frame_features', _dev.ptr(cleaned), _dev.ptr(masks), n, h, w, 3.0, _dev.ptr(centroid),
                   _dev.ptr(orientation), _dev.ptr(axis), ctypes.c_void_p(0), _dev.ptr(flist), flist.numel() * 4, st)
         _lib.call('msq_angles_and_flips', _dev.ptr(orientation), _dev.ptr(axis), _dev.ptr(centroid), _dev.ptr(keypoints),

@@ -167,7 +167,7 @@ def clean_frames(frames, prefilter_space=(3,), prefilter_time=None, strel_tail=_
     src = _dev.as_device(frames, torch.uint8)
     n, h, w = (int(v) for v in src.shape)
     out = torch.empty_like(src)
-    _lib.call('msq_clean_frames', _dev.ptr(src), _dev.ptr(out), n, h, w, _dev.stream())
+    _dev.clean_frames_ws(src, out)
     return _dev.give_back(out, frames)
 
 

@@ -206,6 +206,22 @@ def test_clean_row_skipping_matches_opencv(P, shape):
         assert np.array_equal(got[i], want[i]), (shape, i)
 
 
+def test_clean_single_launch_entry_point_agrees(P):
+    """msq_clean_frames (no scratch: every strip scans its own rows inside the pipeline kernel) == msq_clean_frames_ws (separate
+    pre-pass launch), on a sparse frame set cut across CTA row ranges."""
+    import torch
+    from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+    geom = synthetic.SessionGeometry()
+    ch = synthetic.generate_chunk(40, seed=5, geom=geom, realistic=True)
+    prep = P.prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=synthetic.make_background(geom), roi=synthetic.make_roi(geom), vmin=0, vmax=100)
+    a, b = torch.empty_like(prep), torch.empty_like(prep)
+    n, h, w = prep.shape
+    _lib.call('msq_clean_frames', _dev.ptr(prep), _dev.ptr(a), n, h, w, _dev.stream())
+    _dev.clean_frames_ws(prep, b)
+    assert torch.equal(a, b) and np.array_equal(a.cpu().numpy(), O.clean_frames_cv2(prep.cpu().numpy()))
+    assert int(a.any(dim=(1, 2)).sum()) == n
+
+
 def test_clean_rejects_unsupported_configs(P):
     fr = np.zeros((1, 8, 8), np.uint8)
     with pytest.raises(NotImplementedError):
