@@ -91,6 +91,12 @@ MSQ_API int msq_prep_frames(const int16_t *frames_dev, int n, int H, int W,
  * (numpy.packbits(..., axis=-1, bitorder='little')) -> out_dev (n,h,w) u8 in {0,1}, the mask format of every entry point. */
 MSQ_API int msq_unpack_mask_bits(const uint8_t *bits_dev, int n, int h, int w, uint8_t *out_dev, void *stream);
 
+/* Host -> device staging of the ROI box only, as ONE strided DMA transfer per chunk (host side: no kernel): frames_host
+ * (n,H,W) int16 in pinned host memory -> out_dev (n,h,w) int16 = rows [y0,y0+h) x columns [x0,x0+w) of every frame.  Feed the
+ * result to msq_prep_frames with H = h, W = w, y0 = x0 = 0 and the background / ROI cropped to the same box. */
+MSQ_API int msq_copy_roi_rows(const int16_t *frames_host, int n, int H, int W, int y0, int x0, int h, int w, int16_t *out_dev,
+                      void *stream);
+
 /* ---- a2  fill_invalid_pixels (ref: proc/proc.py:189-210): cv2.inpaint(frame, mask, radius, INPAINT_NS), bit-exact.
  * frames_dev (n_total,h,w) u8 updated IN PLACE; invalid_bits_dev as written by msq_prep_frames; frame_idx_dev (m) int32
  * indices of the frames to in-paint (NULL = frames 0..m-1); radius 1..4 (the reference uses 3).

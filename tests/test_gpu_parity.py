@@ -552,3 +552,28 @@ def test_unpack_mask_bits_matches_numpy():
         out = torch.full((6, h, w), 7, dtype=torch.uint8, device='cuda')
         _lib.call('msq_unpack_mask_bits', _dev.ptr(d_bits), 6, h, w, _dev.ptr(out), _dev.stream())
         assert np.array_equal(out.cpu().numpy(), mask)
+
+
+def test_roi_box_dma_then_prep_equals_prep_of_full_frames(P):
+    """msq_copy_roi_rows (one strided DMA of the ROI box per chunk from pinned host memory) + msq_prep_frames on the dense box
+    with the cropped background / ROI == msq_prep_frames on the full frames (and the oracle)."""
+    import torch
+    from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+    for geom in (synthetic.SessionGeometry(), synthetic.SessionGeometry.azure()):
+        ch = synthetic.generate_chunk(9, seed=2, geom=geom, invalid_rate=0.001)
+        roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+        y0, x0, y1, x1 = synthetic.roi_bbox(roi)
+        h, w = y1 - y0, x1 - x0
+        host = torch.from_numpy(ch.frames).pin_memory()
+        box = torch.empty((9, h, w), dtype=torch.int16, device='cuda')
+        _lib.call('msq_copy_roi_rows', _dev.ptr(host), 9, geom.height, geom.width, y0, x0, h, w, _dev.ptr(box), _dev.stream())
+        torch.cuda.synchronize()
+        assert np.array_equal(box.cpu().numpy(), ch.frames[:, y0:y1, x0:x1])
+        out = torch.empty((9, h, w), dtype=torch.uint8, device='cuda')
+        inv = torch.empty((9,), dtype=torch.int32, device='cuda')
+        _lib.call('msq_prep_frames', _dev.ptr(box), 9, h, w, _dev.ptr(_dev.as_device(np.ascontiguousarray(bg[y0:y1, x0:x1]))), _lib.MSQ_BG_F32,
+                  _dev.ptr(_dev.as_device(np.ascontiguousarray(roi[y0:y1, x0:x1].astype(np.uint8)))), 0, 0, h, w, 0.0, 100.0,
+                  _lib.MSQ_PREP_HAS_VMIN | _lib.MSQ_PREP_HAS_VMAX, _dev.ptr(out), _dev.ptr(inv), None, _dev.stream())
+        want = O.prep_frames(ch.frames, bg, roi, 0, 100, fix_invalid=False)
+        assert np.array_equal(out.cpu().numpy(), want)
+        assert int(inv.sum()) == int(((ch.frames[:, y0:y1, x0:x1] == 0) & roi[y0:y1, x0:x1]).sum())
