@@ -571,8 +571,9 @@ def test_roi_box_dma_then_prep_equals_prep_of_full_frames(P):
         assert np.array_equal(box.cpu().numpy(), ch.frames[:, y0:y1, x0:x1])
         out = torch.empty((9, h, w), dtype=torch.uint8, device='cuda')
         inv = torch.empty((9,), dtype=torch.int32, device='cuda')
-        _lib.call('msq_prep_frames', _dev.ptr(box), 9, h, w, _dev.ptr(_dev.as_device(np.ascontiguousarray(bg[y0:y1, x0:x1]))), _lib.MSQ_BG_F32,
-                  _dev.ptr(_dev.as_device(np.ascontiguousarray(roi[y0:y1, x0:x1].astype(np.uint8)))), 0, 0, h, w, 0.0, 100.0,
+        bg_box = _dev.as_device(np.ascontiguousarray(bg[y0:y1, x0:x1]))      # named: the device arrays must outlive the call
+        roi_box = _dev.as_device(np.ascontiguousarray(roi[y0:y1, x0:x1].astype(np.uint8)))
+        _lib.call('msq_prep_frames', _dev.ptr(box), 9, h, w, _dev.ptr(bg_box), _lib.MSQ_BG_F32, _dev.ptr(roi_box), 0, 0, h, w, 0.0, 100.0,
                   _lib.MSQ_PREP_HAS_VMIN | _lib.MSQ_PREP_HAS_VMAX, _dev.ptr(out), _dev.ptr(inv), None, _dev.stream())
         want = O.prep_frames(ch.frames, bg, roi, 0, 100, fix_invalid=False)
         assert np.array_equal(out.cpu().numpy(), want)
