@@ -222,6 +222,7 @@ class ExtractWorkload:
         del d_pool_f, d_pool_m, d_pool_k
         self.bg_d, self.roi_d = _dev.as_device(bg), _dev.as_device(roi.astype(np.uint8))
         self.prep_buf = _dev.empty((self.launch, self.h, self.w), torch.uint8)
+        self.pos_buf = _dev.positive_bits_like(self.prep_buf)      # the prep kernel's bit rows for the cleaning pass
         self.invalid = _dev.empty((self.launch,), torch.int32)
         self.engine = ChunkEngine()
         self.kw = dict(chunk_size=CHUNK, min_height=self.cfg['min_height'], max_height=self.cfg['max_height'],
@@ -230,17 +231,17 @@ class ExtractWorkload:
         self.host_pool = None
         self.host_pool_gb = host_pool_gb
 
-    def prep(self, src, n, out, invalid, stream=None):
+    def prep(self, src, n, out, invalid, positive, stream=None):
         _dev, _lib = self._dev, self._lib
-        _lib.call('msq_prep_frames', _dev.ptr(src), n, self.H, self.W, _dev.ptr(self.bg_d), _lib.MSQ_BG_F32, _dev.ptr(self.roi_d),
+        _lib.call('msq_prep_frames_bits', _dev.ptr(src), n, self.H, self.W, _dev.ptr(self.bg_d), _lib.MSQ_BG_F32, _dev.ptr(self.roi_d),
                   self.y0, self.x0, self.h, self.w, float(self.cfg['min_height']), float(self.cfg['max_height']), self.flags,
-                  _dev.ptr(out), _dev.ptr(invalid), None, stream if stream is not None else _dev.stream())
+                  _dev.ptr(out), _dev.ptr(invalid), None, _dev.ptr(positive), stream if stream is not None else _dev.stream())
 
     def resident_step(self):
         for s in range(0, self.n_frames, self.launch):
             n = min(self.launch, self.n_frames - s)
-            self.prep(self.frames[s:s + n], n, self.prep_buf, self.invalid)
-            self.engine.extract(self.prep_buf[:n], self.masks[s:s + n], self.kpts[s:s + n], **self.kw)
+            self.prep(self.frames[s:s + n], n, self.prep_buf, self.invalid, self.pos_buf)
+            self.engine.extract(self.prep_buf[:n], self.masks[s:s + n], self.kpts[s:s + n], positive_bits=self.pos_buf[:n], **self.kw)
 
     # ---- end to end ---------------------------------------------------------------------------------------------
     def build_host_pool(self):
@@ -291,6 +292,7 @@ class ExtractWorkload:
         self.in_k = [_dev.empty((chunk, 8, 3), torch.float32) for _ in range(slots)]
         self.engines = [self.ChunkEngine() for _ in range(slots)]
         self.preps = [_dev.empty((chunk, h, w), torch.uint8) for _ in range(slots)]
+        self.poss = [_dev.positive_bits_like(p) for p in self.preps]
         self.invs = [_dev.empty((chunk,), torch.int32) for _ in range(slots)]
         cw, ch = self.cfg['crop_size']
         self.host_out = [{'depth_crops': torch.empty((chunk, ch, cw), dtype=torch.uint8).pin_memory(),
@@ -337,11 +339,11 @@ class ExtractWorkload:
                 if ev_comp[b] is not None:
                     prep_st.wait_event(ev_comp[b])          # preps[b] consumed by the previous user of the slot
                 if roi_dma:
-                    _lib.call('msq_prep_frames', _dev.ptr(self.in_roi[b]), chunk, self.h, self.w, _dev.ptr(self.bg_box), _lib.MSQ_BG_F32,
+                    _lib.call('msq_prep_frames_bits', _dev.ptr(self.in_roi[b]), chunk, self.h, self.w, _dev.ptr(self.bg_box), _lib.MSQ_BG_F32,
                               _dev.ptr(self.roi_box), 0, 0, self.h, self.w, float(self.cfg['min_height']), float(self.cfg['max_height']),
-                              self.flags, _dev.ptr(self.preps[b]), _dev.ptr(self.invs[b]), None, _dev.stream())
+                              self.flags, _dev.ptr(self.preps[b]), _dev.ptr(self.invs[b]), None, _dev.ptr(self.poss[b]), _dev.stream())
                 else:
-                    self.prep(src_host if zero_copy else self.in_f[b], chunk, self.preps[b], self.invs[b], _dev.stream())
+                    self.prep(src_host if zero_copy else self.in_f[b], chunk, self.preps[b], self.invs[b], self.poss[b], _dev.stream())
                 ev_prep = torch.cuda.Event()
                 ev_prep.record(prep_st)
             with torch.cuda.stream(compute):
@@ -349,7 +351,7 @@ class ExtractWorkload:
                 compute.wait_event(ev_prep)
                 if ev_d2h[b] is not None:
                     compute.wait_event(ev_d2h[b])           # output slot drained
-                res = self.engines[b].extract(self.preps[b], self.in_m[b], self.in_k[b], **self.kw)
+                res = self.engines[b].extract(self.preps[b], self.in_m[b], self.in_k[b], positive_bits=self.poss[b], **self.kw)
                 ev_comp[b] = torch.cuda.Event()
                 ev_comp[b].record(compute)
             with torch.cuda.stream(copy_out):
@@ -657,6 +659,7 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
         pred = Predictor.from_random_init(post_nms_topk=topk, scripted=True)
         engine = ChunkEngine()
         prep_buf = [_dev.empty((npool, h, w), torch.uint8) for _ in range(2)]
+        pos_buf = [_dev.positive_bits_like(p) for p in prep_buf]
         invalid = _dev.empty((npool,), torch.int32)
         host_out = {'depth_crops': torch.empty((npool, ch, cw), dtype=torch.uint8).pin_memory(),
                     'mask_crops': torch.empty((npool, ch, cw), dtype=torch.uint8).pin_memory(),
@@ -665,20 +668,21 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
                     'flips': torch.empty((npool,), dtype=torch.uint8).pin_memory()}
         stage_ms = {}
 
-        def prep_chunk(src, dst, stream=None):
-            _lib.call('msq_prep_frames', _dev.ptr(src), npool, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32, _dev.ptr(roi_d), y0, x0, h, w,
-                      float(cfg['min_height']), float(cfg['max_height']), flags, _dev.ptr(dst), _dev.ptr(invalid), None,
-                      stream if stream is not None else _dev.stream())
+        def prep_chunk(src, b, stream=None):
+            _lib.call('msq_prep_frames_bits', _dev.ptr(src), npool, H, W, _dev.ptr(bg_d), _lib.MSQ_BG_F32, _dev.ptr(roi_d), y0, x0, h, w,
+                      float(cfg['min_height']), float(cfg['max_height']), flags, _dev.ptr(prep_buf[b]), _dev.ptr(invalid), None,
+                      _dev.ptr(pos_buf[b]), stream if stream is not None else _dev.stream())
 
-        def infer_and_extract(chunk):
+        def infer_and_extract(b):
+            chunk = prep_buf[b]
             parts = [pred.predict_dense(chunk[i:i + B], cfg['min_height'], cfg['max_height']) for i in range(0, npool, B)]
             masks, kpts = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-            return engine.extract(chunk, masks, kpts, **kw)
+            return engine.extract(chunk, masks, kpts, positive_bits=pos_buf[b], **kw)
 
         def resident_pass():
             for c in range((n + npool - 1) // npool):
-                prep_chunk(dev_pool, prep_buf[0])
-                infer_and_extract(prep_buf[0])
+                prep_chunk(dev_pool, 0)
+                infer_and_extract(0)
 
         prep_st, d2h_st = torch.cuda.Stream(), torch.cuda.Stream()
 
@@ -689,7 +693,7 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
             main = torch.cuda.current_stream()
             ev_prep, ev_free, ev_out = [None, None], [None, None], None
             with torch.cuda.stream(prep_st):
-                prep_chunk(host_pool[0], prep_buf[0], _dev.stream())
+                prep_chunk(host_pool[0], 0, _dev.stream())
                 ev_prep[0] = torch.cuda.Event(); ev_prep[0].record(prep_st)
             for c in range(n_chunks):
                 b = c % 2
@@ -697,12 +701,12 @@ def rcnn_workloads(args, geom, rank, world, barrier, reduce, ops, tensor_peak, p
                     with torch.cuda.stream(prep_st):
                         if ev_free[1 - b] is not None:
                             prep_st.wait_event(ev_free[1 - b])
-                        prep_chunk(host_pool[(c + 1) % n_pool_chunks], prep_buf[1 - b], _dev.stream())
+                        prep_chunk(host_pool[(c + 1) % n_pool_chunks], 1 - b, _dev.stream())
                         ev_prep[1 - b] = torch.cuda.Event(); ev_prep[1 - b].record(prep_st)
                 main.wait_event(ev_prep[b])
                 if ev_out is not None:
                     main.wait_event(ev_out)                 # the engine's result buffers were drained
-                res = infer_and_extract(prep_buf[b])
+                res = infer_and_extract(b)
                 ev_free[b] = torch.cuda.Event(); ev_free[b].record(main)
                 with torch.cuda.stream(d2h_st):
                     d2h_st.wait_event(ev_free[b])

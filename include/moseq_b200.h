@@ -85,6 +85,18 @@ MSQ_API int msq_prep_frames(const int16_t *frames_dev, int n, int H, int W,
                     const void *bground_dev, int bg_dtype, const uint8_t *roi_dev,
                     int y0, int x0, int h, int w, double vmin, double vmax, int flags,
                     uint8_t *out_dev, int32_t *invalid_count_dev, uint8_t *invalid_bits_dev, void *stream);
+/* The same with one more output for the cleaning pass (prep -> clean fusion of the part that can be fused: the prepared frame
+ * itself has to exist, the R-CNN, the masked sums and the crops read it): positive_bits_dev (n, h, ceil(w/32)) uint32 or NULL,
+ * msq_positive_bits_bytes(n,h,w) bytes, bit b of word i of a row = prepared pixel 32i+b is > 0.  msq_extract_chunk_engine /
+ * msq_clean_frames_ws find the rows the 9x9 opening can leave non-zero from these 1-bit rows instead of re-reading and
+ * re-thresholding the 8-bit frame.  Any SUPERSET of the positive pixels keeps the result exact (so the rows stay usable after
+ * msq_inpaint_frames, which only rewrites pixels that were positive); a caller that edits the frames otherwise passes NULL. */
+MSQ_API size_t msq_positive_bits_bytes(int n, int h, int w);
+MSQ_API int msq_prep_frames_bits(const int16_t *frames_dev, int n, int H, int W,
+                    const void *bground_dev, int bg_dtype, const uint8_t *roi_dev,
+                    int y0, int x0, int h, int w, double vmin, double vmax, int flags,
+                    uint8_t *out_dev, int32_t *invalid_count_dev, uint8_t *invalid_bits_dev, uint32_t *positive_bits_dev,
+                    void *stream);
 
 /* Instance masks handed over from the host as bit rows (the reference passes bool images, ref: proc/proc.py:672-684; one bit per
  * pixel is the same information in 1/8 of the PCIe bytes): bits_dev (n, h, ceil(w/8)), bit b of byte B of a row = pixel 8B+b
@@ -239,10 +251,12 @@ MSQ_API int msq_conv_tc(const void *x_dev, int n, int H, int W, int cin, const v
  * 3x3 median (replicate border) then ONE opening with the 9x9 ellipse (SURVEY trap 3). in != out. */
 MSQ_API int msq_clean_frames(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *stream);
 /* The same with scratch memory (msq_clean_scratch_bytes(n,h,w) bytes, 8-byte aligned): the row pre-pass that finds where the
- * opening can be non-zero runs as its own lean launch instead of inside the pipeline kernel (faster; msq_extract_chunk uses it). */
+ * opening can be non-zero runs as its own lean launch instead of inside the pipeline kernel and also writes the zero rows, and
+ * the pipeline kernel gets the remaining rows in equal shares (faster; msq_extract_chunk uses it).  positive_bits_dev: the bit
+ * rows msq_prep_frames_bits wrote for in_dev, or NULL (then the pre-pass thresholds in_dev itself). */
 MSQ_API size_t msq_clean_scratch_bytes(int n, int h, int w);
-MSQ_API int msq_clean_frames_ws(const uint8_t *in_dev, uint8_t *out_dev, int n, int h, int w, void *scratch_dev, size_t scratch_bytes,
-                        void *stream);
+MSQ_API int msq_clean_frames_ws(const uint8_t *in_dev, const uint32_t *positive_bits_dev, uint8_t *out_dev, int n, int h, int w,
+                        void *scratch_dev, size_t scratch_bytes, void *stream);
 
 /* ---- a7  get_frame_features + im_moment_features (ref: proc/proc.py:237-302, 518-549) ----------------
  * fm = (cleaned > frame_threshold) & (mask != 0); polygon moments of the largest outer contour.
@@ -428,14 +442,15 @@ typedef struct msq_chunk_outputs {
 } msq_chunk_outputs;
 
 MSQ_API size_t msq_extract_scratch_bytes(int n, int h, int w);
-/* The side stream + fork / join events msq_extract_chunk runs its general feature kernel on, as an explicit object of the
- * CURRENT device: create once per (thread, GPU), pass to msq_extract_chunk_engine, destroy at the end.  msq_extract_chunk is
- * the same call with an engine the library keeps per (host thread, device) -- the only state the library ever holds. */
+/* The side stream + fork / join events msq_extract_chunk runs its masked sums on (beside the short launches of the main
+ * stream), as an explicit object of the CURRENT device: create once per (thread, GPU), pass to msq_extract_chunk_engine,
+ * destroy at the end.  msq_extract_chunk is the same call with an engine the library keeps per (host thread, device) -- the
+ * only state the library ever holds -- and without positive-pixel rows.  positive_bits_dev: see msq_prep_frames_bits, or NULL. */
 typedef struct msq_engine msq_engine;
 MSQ_API int msq_engine_create(msq_engine **engine);
 MSQ_API int msq_engine_destroy(msq_engine *engine);
-MSQ_API int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *keypoints_dev,
-                      int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
+MSQ_API int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk_dev, const uint32_t *positive_bits_dev,
+                      const uint8_t *mask_dev, const float *keypoints_dev, int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
                       int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch_dev,
                       size_t scratch_bytes, void *stream);
 MSQ_API int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *keypoints_dev,

@@ -64,9 +64,15 @@ def give_back(t: torch.Tensor, like: Any):
     return t.cpu().numpy()
 
 
-def clean_frames_ws(src: torch.Tensor, out: torch.Tensor) -> None:
+def positive_bits_like(chunk: torch.Tensor) -> torch.Tensor:
+    """Room for the positive-pixel bit rows of a (n,h,w) u8 chunk: (n, h, ceil(w/32)) int32 on its device."""
+    n, h, w = (int(v) for v in chunk.shape)
+    return torch.empty((n, h, (w + 31) // 32), dtype=torch.int32, device=chunk.device)
+
+
+def clean_frames_ws(src: torch.Tensor, out: torch.Tensor, positive_bits: Optional[torch.Tensor] = None) -> None:
     """`msq_clean_frames_ws` with a torch-owned scratch buffer (the row pre-pass runs as its own launch)."""
     n, h, w = (int(v) for v in src.shape)
     nbytes = int(_lib.load().msq_clean_scratch_bytes(n, h, w))
     scratch = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=src.device)
-    _lib.call('msq_clean_frames_ws', ptr(src), ptr(out), n, h, w, ptr(scratch), nbytes, stream())
+    _lib.call('msq_clean_frames_ws', ptr(src), ptr(positive_bits), ptr(out), n, h, w, ptr(scratch), nbytes, stream())

@@ -40,6 +40,9 @@ SIGNATURES = {
     'msq_kernel_launches': (ctypes.c_longlong, [c_int]),
     'msq_prep_frames': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                 c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'msq_positive_bits_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'msq_prep_frames_bits': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'msq_unpack_mask_bits': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'msq_copy_roi_rows': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'msq_inpaint_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
@@ -48,7 +51,7 @@ SIGNATURES = {
     'msq_scale_frames_chw3_f32': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int, c_void_p]),
     'msq_clean_frames': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'msq_clean_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
-    'msq_clean_frames_ws': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'msq_clean_frames_ws': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     'msq_frame_features_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_frame_features': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -114,7 +117,7 @@ SIGNATURES = {
     'msq_extract_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_engine_create': (c_int, [POINTER(c_void_p)]),
     'msq_engine_destroy': (c_int, [c_void_p]),
-    'msq_extract_chunk_engine': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
+    'msq_extract_chunk_engine': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                          c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),
     'msq_extract_chunk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                                   c_double, c_int, c_int, POINTER(ChunkOutputs), c_void_p, c_size_t, c_void_p]),

@@ -270,14 +270,20 @@ Geometry make_geometry(int h, int w) {
 
 }  // namespace
 
-size_t clean_scratch_bytes(int n, int w) { return (size_t)(n > 0 ? n : 0) * ((w + 239) / 240) * sizeof(int2); }
+// per (frame, 240-column tile): the band (int2) + one entry of the cost prefix (int, items + 1 of them)
+size_t clean_scratch_bytes(int n, int w) {
+    const size_t items = (size_t)(n > 0 ? n : 0) * ((w + 239) / 240);
+    return items * sizeof(int2) + (items + 1) * sizeof(int);
+}
 
-int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands) {
+int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands, RowBands *written,
+                 const uint32_t *positive_bits) {
+    if (written) *written = {nullptr, 0};
     // fast path: the streaming warp-per-strip kernel (clean_stream.cu); the tiled kernel below serves widths that are
     // not a multiple of 8 / unaligned pointers, and MSQ_CLEAN_TILED=1 forces it for A/B comparisons
     static const bool force_tiled = getenv("MSQ_CLEAN_TILED") != nullptr;
     if (!force_tiled) {
-        const int rc = launch_clean_stream(in, out, n, h, w, st, bands);
+        const int rc = launch_clean_stream(in, out, n, h, w, st, bands, written, positive_bits);
         if (rc != -100) return rc;
     }
     const Geometry G = make_geometry(h, w);
@@ -310,11 +316,13 @@ extern "C" int msq_clean_frames(const uint8_t *in, uint8_t *out, int n, int h, i
 
 extern "C" size_t msq_clean_scratch_bytes(int n, int h, int w) { (void)h; return msq::clean_scratch_bytes(n, w); }
 
-extern "C" int msq_clean_frames_ws(const uint8_t *in, uint8_t *out, int n, int h, int w, void *scratch, size_t scratch_bytes, void *stream) {
+extern "C" int msq_clean_frames_ws(const uint8_t *in, const uint32_t *positive_bits, uint8_t *out, int n, int h, int w, void *scratch,
+                                   size_t scratch_bytes, void *stream) {
+    MSQ_REQUIRE((uintptr_t)positive_bits % 4 == 0, MSQ_EINVAL, "msq_clean_frames_ws: positive_bits must be 4-byte aligned");
     MSQ_REQUIRE(n == 0 || (in && out && in != out), MSQ_EINVAL, "msq_clean_frames_ws: null or aliased pointers");
     MSQ_REQUIRE(n >= 0 && h > 0 && w > 0, MSQ_EINVAL, "msq_clean_frames_ws: bad sizes n=%d h=%d w=%d", n, h, w);
     if (n == 0) return MSQ_OK;
     MSQ_REQUIRE(scratch && (uintptr_t)scratch % 8 == 0 && scratch_bytes >= msq::clean_scratch_bytes(n, w), MSQ_ENOMEM,
                 "msq_clean_frames_ws: scratch must be 8-byte aligned and >= %zu bytes", msq::clean_scratch_bytes(n, w));
-    return msq::launch_clean(in, out, n, h, w, (cudaStream_t)stream, static_cast<int2 *>(scratch));
+    return msq::launch_clean(in, out, n, h, w, (cudaStream_t)stream, static_cast<int2 *>(scratch), nullptr, positive_bits);
 }

@@ -142,12 +142,23 @@ __device__ __forceinline__ void build_scale_lut(uint8_t *lut, double vmin, doubl
 
 // ---- internal launchers shared with the whole-chunk pipeline (pipeline.cu) ---------------------
 namespace msq {
-int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands = nullptr);   // bands: clean_scratch_bytes() or null
-int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands);   // -100: shape not served
+// Rows of a cleaned frame that can hold a non-zero pixel, as left behind by launch_clean() in its scratch: per (frame, 240-column
+// tile) the rows [x, y] on which the opening's erosion is non-zero (y < 0: none); the opened frame is zero outside [x - 4, y + 4].
+// bands == nullptr: not known, every row has to be read.
+struct RowBands {
+    const int2 *bands;
+    int tiles_x;
+};
+int launch_clean(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands = nullptr,
+                 RowBands *written = nullptr, const uint32_t *positive_bits = nullptr);
+// bands: clean_scratch_bytes() or null; *written: what the later kernels may use; positive_bits: msq_prep_frames' bit rows of
+// `in` (a superset of its positive pixels is enough), only used together with bands
+int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cudaStream_t st, int2 *bands, RowBands *written,
+                        const uint32_t *positive_bits);   // -100: shape not served
 size_t clean_scratch_bytes(int n, int w);
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
                           double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
-                          cudaStream_t st, cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join);
+                          cudaStream_t st, cudaEvent_t after_stream = nullptr, RowBands rows = {nullptr, 0});   // after_stream: recorded on st after the streaming pass
 int launch_masked_sums(const uint8_t *chunk_frames, const uint8_t *mask, int n, int h, int w, double min_h, double max_h,
                        int2 *sums_scratch, cudaStream_t st);
 int launch_angles_and_flips(const double *orientation, const double *axis, const double *centroid, const float *kpts,

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "bitrows.cuh"
 #include <algorithm>
+#include <limits.h>
 #include <math.h>
 
 namespace msq {
@@ -481,7 +482,7 @@ template <int LPR>
 __global__ void __launch_bounds__(kStreamWarps * 32, 4)
 features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__ mask, int n, int h, int w, int ge,
                        double *__restrict__ centroid, double *__restrict__ orientation, double *__restrict__ axis_length,
-                       long long *__restrict__ sums24, int *__restrict__ fallback) {
+                       long long *__restrict__ sums24, int *__restrict__ fallback, RowBands rows) {
     constexpr int RPW = 32 / LPR;
     constexpr int kChunkRows = kChunkSteps * RPW;
     constexpr unsigned kAll = 0xffffffffu;
@@ -508,20 +509,42 @@ features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__res
     const int first = blockIdx.x * kStreamWarps + warp, stride = gridDim.x * kStreamWarps;
     const int n_chunks = (h + kChunkRows - 1) / kChunkRows;
     const int my_frames = first < n ? (n - first + stride - 1) / stride : 0;
-    const long long items = (long long)my_frames * n_chunks;            // (frame, chunk) pairs of this warp, in order
-    auto issue = [&](long long item) {                                   // lane 0 only
-        const int fi = (int)(item / n_chunks), c = (int)(item - (long long)fi * n_chunks);
-        const int f = first + fi * stride, st = (int)(item % kStreamStages);
-        const int rows = min(kChunkRows, h - c * kChunkRows);
-        const uint32_t bytes = (uint32_t)rows * w;
-        const size_t off = (size_t)f * h * w + (size_t)c * kChunkRows * w;
-        unsigned char *slot = slots + (size_t)st * slot_bytes;
-        mbar_expect_tx(&bars[warp][st], 2 * bytes);
-        bulk_g2s(slot, cleaned + off, bytes, &bars[warp][st]);
-        bulk_g2s(slot + (size_t)kChunkRows * w, mask + off, bytes, &bars[warp][st]);
+    // Chunks [c0, c1) of frame number fi of this warp that have to be read.  With the row bands of the cleaning pass (the
+    // opened frame is zero outside them, so is the thresholded foreground) that is ~1/3 of the frame; rows of a chunk that lie
+    // outside the band are zero in memory as well, so whole chunks are read as they are.
+    auto chunk_span = [&](int fi, int &c0, int &c1) {
+        c0 = 0; c1 = fi < my_frames ? n_chunks : 0;
+        if (rows.bands == nullptr || fi >= my_frames) return;
+        const int2 *b = rows.bands + (size_t)(first + fi * stride) * rows.tiles_x;
+        int lo = INT_MAX, hi = -1;
+        for (int t = 0; t < rows.tiles_x; ++t) {
+            const int2 v = __ldg(b + t);
+            if (v.y >= 0) { lo = min(lo, v.x); hi = max(hi, v.y); }
+        }
+        if (hi < 0) { c1 = 0; return; }
+        c0 = max(0, lo - 4) / kChunkRows;
+        c1 = (min(h, hi + 5) + kChunkRows - 1) / kChunkRows;
     };
-    if (lane == 0)
-        for (int i = 0; i < kStreamStages && i < items; ++i) issue(i);
+    // the bulk copies run kStreamStages items ahead of the consumer, across frame boundaries (warp-uniform cursor, lane 0 issues)
+    int iss_fi = 0, iss_c, iss_c1;
+    long long iss_item = 0;
+    chunk_span(0, iss_c, iss_c1);
+    auto issue_next = [&]() {
+        while (iss_fi < my_frames && iss_c >= iss_c1) { ++iss_fi; chunk_span(iss_fi, iss_c, iss_c1); }
+        if (iss_fi >= my_frames) return;
+        if (lane == 0) {
+            const int f = first + iss_fi * stride, st = (int)(iss_item % kStreamStages);
+            const int nrows = min(kChunkRows, h - iss_c * kChunkRows);
+            const uint32_t bytes = (uint32_t)nrows * w;
+            const size_t off = (size_t)f * h * w + (size_t)iss_c * kChunkRows * w;
+            unsigned char *slot = slots + (size_t)st * slot_bytes;
+            mbar_expect_tx(&bars[warp][st], 2 * bytes);
+            bulk_g2s(slot, cleaned + off, bytes, &bars[warp][st]);
+            bulk_g2s(slot + (size_t)kChunkRows * w, mask + off, bytes, &bars[warp][st]);
+        }
+        ++iss_c; ++iss_item;
+    };
+    for (int i = 0; i < kStreamStages; ++i) issue_next();
     uint32_t parity = 0u;                                                // bit st: phase of stage st
 
     long long item = 0;
@@ -533,7 +556,9 @@ features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__res
         bool simple = true, started = false, ended = false, prev_ne = false;      // warp-uniform
         int my_starts = 0, ne_rows = 0;                                            // run starts seen by this lane; non-empty rows
         uint32_t prev_bits = 0u;
-        for (int c = 0; c < n_chunks; ++c, ++item) {
+        int c_first, c_end;
+        chunk_span(fi, c_first, c_end);
+        for (int c = c_first; c < c_end; ++c, ++item) {
             const int st = (int)(item % kStreamStages);
             mbar_wait(&bars[warp][st], (parity >> st) & 1u);
             parity ^= 1u << st;
@@ -610,7 +635,7 @@ features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__res
                 }
             }
             __syncwarp();                                                // every lane is done with the slot
-            if (lane == 0 && item + kStreamStages < items) issue(item + kStreamStages);
+            issue_next();
         }
         if (simple) simple = warp_sum(my_starts) == ne_rows;
         if (!simple) {
@@ -648,7 +673,7 @@ features_stream_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__res
 template <int LPR>
 int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, int ge,
                     double *centroid, double *orientation, double *axis, long long *sums24, int *fallback, cudaStream_t st,
-                    cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join) {
+                    cudaEvent_t after_stream, RowBands rows) {
     const size_t smem = (size_t)kFeatWarps * 2 * h * LPR * sizeof(uint32_t);
     MSQ_REQUIRE(smem <= 227 * 1024, MSQ_EUNSUPPORTED,
                 "frame_features: %dx%d frames need %zu B of shared memory per CTA (max 232448)", h, w, smem);
@@ -666,30 +691,18 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
         MSQ_CUDA_OK(cudaFuncSetAttribute(features_stream_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
         const int sgrid = std::min((n + kStreamWarps - 1) / kStreamWarps, sm_count() * 4);
         features_stream_kernel<LPR><<<sgrid, kStreamWarps * 32, ssmem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
-                                                                            axis, sums24, fallback);
+                                                                            axis, sums24, fallback, rows);
         MSQ_LAUNCH_OK("frame_features (streaming)");
     }
-    // The general kernel only has the few frames of the list to do, each a long sequential chain in one warp.  A caller
-    // with independent work (the whole-chunk pipeline: the masked sums) passes a side stream + fork/join events, so that
-    // this latency is hidden; `join` is recorded on the side stream and must be waited for before the features are read.
-    cudaStream_t sg = st;
-    if (stream_ok && st_general != st) {
-        MSQ_CUDA_OK(cudaEventRecord(fork, st));
-        MSQ_CUDA_OK(cudaStreamWaitEvent(st_general, fork, 0));
-        sg = st_general;
-    }
+    // The general kernel only has the few frames of the list to do, each a long sequential chain in one warp: a short,
+    // latency-bound launch.  A caller with independent bandwidth-bound work (the whole-chunk pipeline: the masked sums) passes
+    // an event, recorded here between the two launches, and starts that work on another stream behind it.
+    if (after_stream) MSQ_CUDA_OK(cudaEventRecord(after_stream, st));
     {
-        TimedLaunch timed(K_FEATURES, sg);          // a launch of its own in the counters (and timed on its own stream)
-        features_kernel<LPR><<<grid, kFeatWarps * 32, smem, sg>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
+        TimedLaunch timed(K_FEATURES, st);          // a launch of its own in the counters
+        features_kernel<LPR><<<grid, kFeatWarps * 32, smem, st>>>(cleaned, mask, n, h, w, ge, centroid, orientation,
                                                                 axis, sums24, stream_ok ? fallback : nullptr);
         MSQ_LAUNCH_OK("frame_features");
-    }
-    if (st_general != st) {
-        if (sg == st) {                     // nothing was forked: make the caller's later wait on `join` a no-op
-            MSQ_CUDA_OK(cudaEventRecord(join, st));
-        } else {
-            MSQ_CUDA_OK(cudaEventRecord(join, sg));
-        }
     }
     return MSQ_OK;
 }
@@ -698,7 +711,7 @@ int launch_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, i
 
 int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, int h, int w, double frame_threshold,
                           double *centroid, double *orientation, double *axis, int64_t *sums24, int *fallback,
-                          cudaStream_t st, cudaStream_t st_general, cudaEvent_t fork, cudaEvent_t join) {
+                          cudaStream_t st, cudaEvent_t after_stream, RowBands rows) {
     MSQ_REQUIRE(w <= 1024, MSQ_EUNSUPPORTED, "frame_features: width %d > 1024 is not supported", w);
     // pixel > thr on integers  <=>  pixel >= floor(thr) + 1; clamp to [0, 256] (0: all pass, 256: none)
     int ge;
@@ -707,12 +720,12 @@ int launch_frame_features(const uint8_t *cleaned, const uint8_t *mask, int n, in
     else ge = (int)floor(frame_threshold) + 1;
     const int wpr = (w + 31) / 32;
     long long *s24 = reinterpret_cast<long long *>(sums24);
-    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
-    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
-    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
-    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
-    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
-    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, st_general, fork, join);
+    if (wpr <= 1) return launch_features<1>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, after_stream, rows);
+    if (wpr <= 2) return launch_features<2>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, after_stream, rows);
+    if (wpr <= 4) return launch_features<4>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, after_stream, rows);
+    if (wpr <= 8) return launch_features<8>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, after_stream, rows);
+    if (wpr <= 16) return launch_features<16>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, after_stream, rows);
+    return launch_features<32>(cleaned, mask, n, h, w, ge, centroid, orientation, axis, s24, fallback, st, after_stream, rows);
 }
 
 }  // namespace msq
@@ -730,5 +743,5 @@ extern "C" int msq_frame_features(const uint8_t *cleaned, const uint8_t *mask, i
     int *fallback = (scratch && scratch_bytes >= msq_frame_features_scratch_bytes(n, h, w) && (uintptr_t)scratch % 4 == 0)
                         ? static_cast<int *>(scratch) : nullptr;
     return msq::launch_frame_features(cleaned, mask, n, h, w, frame_threshold, centroid, orientation, axis, sums24, fallback,
-                                      (cudaStream_t)stream, (cudaStream_t)stream, nullptr, nullptr);
+                                      (cudaStream_t)stream);
 }

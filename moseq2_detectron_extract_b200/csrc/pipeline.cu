@@ -13,8 +13,8 @@ extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
            align_up((nn + 1) * sizeof(int), 256) + align_up(clean_scratch_bytes((int)nn, 4096), 256);
 }
 
-// The one piece of state the whole-chunk entry point needs: a side stream + two events on one device, so that the few
-// frames the streaming feature kernel leaves to the general one run beside the masked sums.  Explicit object (create /
+// The one piece of state the whole-chunk entry point needs: a side stream + two events on one device, so that the masked
+// sums run beside the short latency-bound launches (left-over feature frames, angle filter) of the main stream.  Explicit object (create /
 // destroy) for callers that manage their own resources; msq_extract_chunk() keeps one per (host thread, device) for callers
 // that do not.
 struct msq_engine {
@@ -46,12 +46,13 @@ extern "C" int msq_engine_destroy(msq_engine *e) {
     return MSQ_OK;
 }
 
-extern "C" int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev,
-                                        int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
+extern "C" int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk_dev, const uint32_t *positive_bits, const uint8_t *mask_dev,
+                                        const float *kpts_dev, int n, int h, int w, int chunk, double min_height, double max_height, double true_depth,
                                         int crop_w, int crop_h, const msq_chunk_outputs *out, void *scratch, size_t scratch_bytes,
                                         void *stream) {
     MSQ_REQUIRE(engine, MSQ_EINVAL, "msq_extract_chunk_engine: null engine");
     MSQ_REQUIRE(chunk_dev && mask_dev && kpts_dev && out, MSQ_EINVAL, "msq_extract_chunk: null input pointer");
+    MSQ_REQUIRE((uintptr_t)positive_bits % 4 == 0, MSQ_EINVAL, "msq_extract_chunk: positive_bits must be 4-byte aligned");
     MSQ_REQUIRE(out->cleaned && out->centroid && out->angle_deg && out->axis_length && out->flips && out->scalars &&
                     out->kpt_cols && out->depth_crops && out->mask_crops,
                 MSQ_EINVAL, "msq_extract_chunk: null output pointer");
@@ -72,14 +73,19 @@ extern "C" int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk
     int2 *clean_bands = reinterpret_cast<int2 *>(reinterpret_cast<char *>(feature_list) + align_up((size_t)(n + 1) * sizeof(int), 256));
     MSQ_REQUIRE(w <= 4096, MSQ_EUNSUPPORTED, "msq_extract_chunk: frames wider than 4096 pixels (got %d)", w);
     int rc;
-    if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st, clean_bands)) != MSQ_OK) return rc;
-    // frame_threshold = 3 (ref proc/proc.py:716)
+    RowBands rows = {nullptr, 0};          // rows of every cleaned frame that can be non-zero: the feature pass reads only those
+    if ((rc = launch_clean(chunk_dev, out->cleaned, n, h, w, st, clean_bands, &rows, positive_bits)) != MSQ_OK) return rc;
+    // frame_threshold = 3 (ref proc/proc.py:716).  After the streaming feature pass the main stream only has short, latency-bound
+    // work for a while (the general feature kernel on the few frames the fast path left over, then the per-chunk angle filter: a
+    // handful of CTAs each); the bandwidth-bound masked sums, which need none of it, run beside them on the side stream.
     if ((rc = launch_frame_features(out->cleaned, mask_dev, n, h, w, 3.0, out->centroid, orientation, out->axis_length,
-                                    nullptr, feature_list, st, engine->side, engine->fork, engine->join)) != MSQ_OK) return rc;
-    if ((rc = launch_masked_sums(chunk_dev, mask_dev, n, h, w, min_height, max_height, sums, st)) != MSQ_OK) return rc;
-    MSQ_CUDA_OK(cudaStreamWaitEvent(st, engine->join, 0));
+                                    nullptr, feature_list, st, engine->fork, rows)) != MSQ_OK) return rc;
+    MSQ_CUDA_OK(cudaStreamWaitEvent(engine->side, engine->fork, 0));
+    if ((rc = launch_masked_sums(chunk_dev, mask_dev, n, h, w, min_height, max_height, sums, engine->side)) != MSQ_OK) return rc;
+    MSQ_CUDA_OK(cudaEventRecord(engine->join, engine->side));
     if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
                                       out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
+    MSQ_CUDA_OK(cudaStreamWaitEvent(st, engine->join, 0));
     if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,
                                            out->axis_length, kpts_dev, false, n, h, w, chunk, min_height, max_height,
                                            true_depth, out->scalars, out->kpt_cols, sums, st, true)) != MSQ_OK) return rc;
@@ -101,6 +107,6 @@ extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_d
         const int rc = msq_engine_create(&engines[dev]);
         if (rc != MSQ_OK) return rc;
     }
-    return msq_extract_chunk_engine(engines[dev], chunk_dev, mask_dev, kpts_dev, n, h, w, chunk, min_height, max_height, true_depth,
+    return msq_extract_chunk_engine(engines[dev], chunk_dev, nullptr, mask_dev, kpts_dev, n, h, w, chunk, min_height, max_height, true_depth,
                                     crop_w, crop_h, out, scratch, scratch_bytes, stream);
 }

@@ -60,13 +60,29 @@ template <> struct PrepMath<int> {
 __device__ __forceinline__ int s16_lo(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int s16_hi(uint32_t v) { return (int)(short)(v >> 16); }
 
+// Positive-pixel bit rows (optional second output, read by the cleaning pass's row scan instead of the frame itself):
+// per frame and row ceil(w / 32) little-endian words, bit b of word i = prepared pixel 32 i + b is > 0.
+__device__ __host__ __forceinline__ int positive_row_bytes(int w) { return 4 * ((w + 31) >> 5); }
+__device__ __forceinline__ uint32_t nonzero_bytes_to_nibble(uint32_t x) {     // bit k = byte k of x is non-zero
+    return (((bytes_nonzero(x) >> 7) * 0x00204081u) >> 21) & 0xfu;
+}
+
+// bit k = byte k of lo is non-zero, bit 4 + k = byte k of hi is non-zero.  The flags (bit 7 of every byte) of hi and, moved down
+// by 4, of lo share one word; one multiplication by 2^21 + 2^14 + 2^7 + 1 then lines all eight up in the top byte (no two
+// partial products meet below bit 24, so nothing carries into it).
+__device__ __forceinline__ uint8_t nonzero_bytes_to_byte(uint32_t lo, uint32_t hi) {
+    const uint32_t flags = (bytes_nonzero(lo) >> 4) | bytes_nonzero(hi);
+    return (uint8_t)((flags * 0x00204081u) >> 24);
+}
+
 // BG: element type of the background in global memory; ACC: arithmetic type (float/double/int)
 template <typename BG, typename ACC, bool HAS_BG>
 __global__ void __launch_bounds__(kPrepThreads)
 prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
                  const BG *__restrict__ bground, const uint8_t *__restrict__ roi,
                  int y0, int x0, int h, int w, PrepMath<ACC> math, int flags, int frames_per_group,
-                 uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint8_t *__restrict__ invalid_bits) {
+                 uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint8_t *__restrict__ invalid_bits,
+                 uint8_t *__restrict__ positive_bits) {
     const int w8 = w >> 3;
     const int pos = blockIdx.x * kPrepThreads + threadIdx.x;
     if (pos >= h * w8) return;
@@ -74,6 +90,7 @@ prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
     const int c = (pos - r * w8) << 3;
     const size_t in_off = (size_t)(y0 + r) * W + (x0 + c);
     const size_t out_off = (size_t)r * w + c;
+    const int pbr = positive_row_bytes(w);
 
     ACC bg[8], rm[8];
 #pragma unroll
@@ -97,7 +114,7 @@ prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
             const uint32_t words[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
             uint32_t packed[2] = {0u, 0u};
             int bad = 0;
-            uint32_t bad_bits = 0u;
+            uint32_t bad_bits = 0u, pos_bits = 0u;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int v = (k & 1) ? s16_hi(words[k >> 1]) : s16_lo(words[k >> 1]);
@@ -110,10 +127,12 @@ prep_vec8_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
                 else
                     o = math.run(bg[k], v, rm[k], flags);
                 packed[k >> 2] |= o << ((k & 3) * 8);
+                pos_bits |= (uint32_t)(o != 0u) << k;
             }
             stg_stream_u2(out + (size_t)(f + u) * out_stride + out_off, make_uint2(packed[0], packed[1]));
             if (invalid_count && bad) atomicAdd(invalid_count + f + u, bad);
             if (invalid_bits) invalid_bits[((size_t)(f + u) * h + r) * w8 + (c >> 3)] = (uint8_t)bad_bits;
+            if (positive_bits) positive_bits[((size_t)(f + u) * h + r) * pbr + (c >> 3)] = (uint8_t)pos_bits;
         }
     }
 }
@@ -139,7 +158,8 @@ __device__ __forceinline__ uint32_t zero_halfwords(uint32_t w) {        // 0x800
 __global__ void __launch_bounds__(kPrepThreads)
 prep_vec8_f32_fast_kernel(const int16_t *__restrict__ frames, int n, int H, int W, const float *__restrict__ bground,
                           const uint8_t *__restrict__ roi, int y0, int x0, int h, int w, float hi, int frames_per_group,
-                          uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint8_t *__restrict__ invalid_bits) {
+                          uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint8_t *__restrict__ invalid_bits,
+                          uint8_t *__restrict__ positive_bits) {
     const int w8 = w >> 3;
     const int pos = blockIdx.x * kPrepThreads + threadIdx.x;
     if (pos >= h * w8) return;
@@ -147,6 +167,7 @@ prep_vec8_f32_fast_kernel(const int16_t *__restrict__ frames, int n, int H, int 
     const int c = (pos - r * w8) << 3;
     const size_t in_off = (size_t)(y0 + r) * W + (x0 + c);
     const size_t out_off = (size_t)r * w + c;
+    const int pbr = positive_row_bytes(w);
     float bg[8];
     int top[8];                                               // trunc(vmax) inside the ROI, 0 outside
     uint32_t roi_bits = 0u;
@@ -187,8 +208,10 @@ prep_vec8_f32_fast_kernel(const int16_t *__restrict__ frames, int n, int H, int 
             }
             const uint32_t p01 = __byte_perm(t[0], t[1], 0x0040), p23 = __byte_perm(t[2], t[3], 0x0040);
             const uint32_t p45 = __byte_perm(t[4], t[5], 0x0040), p67 = __byte_perm(t[6], t[7], 0x0040);
-            stg_stream_u2(out + (size_t)(f + u) * out_stride + out_off,
-                          make_uint2(__byte_perm(p01, p23, 0x5410), __byte_perm(p45, p67, 0x5410)));
+            const uint2 o8 = make_uint2(__byte_perm(p01, p23, 0x5410), __byte_perm(p45, p67, 0x5410));
+            stg_stream_u2(out + (size_t)(f + u) * out_stride + out_off, o8);
+            if (positive_bits)
+                positive_bits[((size_t)(f + u) * h + r) * pbr + (c >> 3)] = nonzero_bytes_to_byte(o8.x, o8.y);
             const uint32_t z0 = zero_halfwords(words[0]), z1 = zero_halfwords(words[1]), z2 = zero_halfwords(words[2]),
                            z3 = zero_halfwords(words[3]);
             uint32_t bad_bits = 0u;
@@ -210,9 +233,11 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_scalar_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
                    const BG *__restrict__ bground, const uint8_t *__restrict__ roi,
                    int y0, int x0, int h, int w, PrepMath<ACC> math, int flags,
-                   uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint32_t *__restrict__ invalid_bits_words) {
+                   uint8_t *__restrict__ out, int32_t *__restrict__ invalid_count, uint32_t *__restrict__ invalid_bits_words,
+                   uint32_t *__restrict__ positive_words) {
     const size_t total = (size_t)n * h * w;
     const int bytes_per_row = (w + 7) >> 3;
+    const int wpr = (w + 31) >> 5;
     for (size_t i = (size_t)blockIdx.x * kPrepThreads + threadIdx.x; i < total;
          i += (size_t)gridDim.x * kPrepThreads) {
         const int c = (int)(i % w);
@@ -228,6 +253,7 @@ prep_scalar_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
         else
             o = math.run((ACC)bground[pix], v, rm, flags);
         out[i] = (uint8_t)o;
+        if (positive_words && (uint8_t)o != 0) atomicOr(positive_words + ((size_t)f * h + r) * wpr + (c >> 5), 1u << (c & 31));
         if (v == 0 && rm != (ACC)0) {
             if (invalid_count) atomicAdd(invalid_count + f, 1);
             if (invalid_bits_words) {           // byte-packed mask, set with word atomics (buffer zeroed by the launcher)
@@ -241,7 +267,7 @@ prep_scalar_kernel(const int16_t *__restrict__ frames, int n, int H, int W,
 template <typename BG, typename ACC, bool HAS_BG>
 int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground, const uint8_t *roi,
                 int y0, int x0, int h, int w, double vmin, double vmax, int flags, uint8_t *out,
-                int32_t *invalid, uint8_t *invalid_bits, cudaStream_t st) {
+                int32_t *invalid, uint8_t *invalid_bits, uint8_t *positive_bits, cudaStream_t st) {
     PrepMath<ACC> math(vmin, vmax);
     const bool vec_ok = (w % 8 == 0) && (x0 % 8 == 0) && (W % 8 == 0) &&
                         ((uintptr_t)frames % 16 == 0) && ((uintptr_t)out % 8 == 0);
@@ -258,13 +284,13 @@ int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground,
             const float hi = (float)vmax;
             if ((flags & MSQ_PREP_HAS_VMIN) && (flags & MSQ_PREP_HAS_VMAX) && (float)vmin == 0.0f && hi >= 0.0f && hi <= 255.0f) {
                 prep_vec8_f32_fast_kernel<<<grid, kPrepThreads, 0, st>>>(frames, n, H, W, (const float *)bground, roi, y0, x0, h, w,
-                                                                         hi, fpg, out, invalid, invalid_bits);
+                                                                         hi, fpg, out, invalid, invalid_bits, positive_bits);
                 MSQ_LAUNCH_OK("prep_frames (float32 fast path)");
                 return MSQ_OK;
             }
         }
         prep_vec8_kernel<BG, ACC, HAS_BG><<<grid, kPrepThreads, 0, st>>>(
-            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, fpg, out, invalid, invalid_bits);
+            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, fpg, out, invalid, invalid_bits, positive_bits);
     } else {
         const size_t total = (size_t)n * h * w;
         if (invalid_bits) {
@@ -272,10 +298,12 @@ int launch_prep(const int16_t *frames, int n, int H, int W, const void *bground,
             const size_t bytes = align_up((size_t)n * h * ((w + 7) / 8), 4);
             MSQ_CUDA_OK(cudaMemsetAsync(invalid_bits, 0, bytes, st));
         }
+        if (positive_bits) MSQ_CUDA_OK(cudaMemsetAsync(positive_bits, 0, (size_t)n * h * positive_row_bytes(w), st));
         const int blocks = (int)std::min<size_t>((total + kPrepThreads - 1) / kPrepThreads, (size_t)sm_count() * 16);
         TimedLaunch timed(K_PREP, st);
         prep_scalar_kernel<BG, ACC, HAS_BG><<<blocks, kPrepThreads, 0, st>>>(
-            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, out, invalid, reinterpret_cast<uint32_t *>(invalid_bits));
+            frames, n, H, W, (const BG *)bground, roi, y0, x0, h, w, math, flags, out, invalid, reinterpret_cast<uint32_t *>(invalid_bits),
+            reinterpret_cast<uint32_t *>(positive_bits));
     }
     MSQ_LAUNCH_OK("prep_frames");
     return MSQ_OK;
@@ -629,9 +657,10 @@ extern "C" int msq_copy_roi_rows(const int16_t *frames_host, int n, int H, int W
     return MSQ_OK;
 }
 
-extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const void *bground, int bg_dtype,
-                               const uint8_t *roi, int y0, int x0, int h, int w, double vmin, double vmax,
-                               int flags, uint8_t *out, int32_t *invalid, uint8_t *invalid_bits, void *stream) {
+extern "C" int msq_prep_frames_bits(const int16_t *frames, int n, int H, int W, const void *bground, int bg_dtype,
+                                    const uint8_t *roi, int y0, int x0, int h, int w, double vmin, double vmax,
+                                    int flags, uint8_t *out, int32_t *invalid, uint8_t *invalid_bits, uint32_t *positive_bits,
+                                    void *stream) {
     MSQ_REQUIRE(n == 0 || (frames && out), MSQ_EINVAL, "msq_prep_frames: null frames/out pointer");
     MSQ_REQUIRE(n >= 0 && H > 0 && W > 0 && h > 0 && w > 0, MSQ_EINVAL,
                 "msq_prep_frames: bad sizes n=%d H=%d W=%d h=%d w=%d", n, H, W, h, w);
@@ -639,15 +668,28 @@ extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const
                 "msq_prep_frames: box (y0=%d,x0=%d,h=%d,w=%d) outside the %dx%d frame", y0, x0, h, w, H, W);
     MSQ_REQUIRE(bg_dtype >= MSQ_BG_NONE && bg_dtype <= MSQ_BG_U16, MSQ_EINVAL, "msq_prep_frames: bad bg_dtype %d", bg_dtype);
     MSQ_REQUIRE(bg_dtype == MSQ_BG_NONE || bground, MSQ_EINVAL, "msq_prep_frames: bground is null but bg_dtype=%d", bg_dtype);
+    MSQ_REQUIRE((uintptr_t)positive_bits % 4 == 0, MSQ_EINVAL, "msq_prep_frames: positive_bits must be 4-byte aligned");
     if (n == 0) return MSQ_OK;
+    uint8_t *pos = reinterpret_cast<uint8_t *>(positive_bits);
     cudaStream_t st = (cudaStream_t)stream;
     if (invalid) MSQ_CUDA_OK(cudaMemsetAsync(invalid, 0, sizeof(int32_t) * (size_t)n, st));
     switch (bg_dtype) {
-        case MSQ_BG_F32: return launch_prep<float, float, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
-        case MSQ_BG_F64: return launch_prep<double, double, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
-        case MSQ_BG_U16: return launch_prep<uint16_t, int, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
-        default:         return launch_prep<uint16_t, int, false>(frames, n, H, W, nullptr, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, st);
+        case MSQ_BG_F32: return launch_prep<float, float, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, pos, st);
+        case MSQ_BG_F64: return launch_prep<double, double, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, pos, st);
+        case MSQ_BG_U16: return launch_prep<uint16_t, int, true>(frames, n, H, W, bground, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, pos, st);
+        default:         return launch_prep<uint16_t, int, false>(frames, n, H, W, nullptr, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits, pos, st);
     }
+}
+
+extern "C" size_t msq_positive_bits_bytes(int n, int h, int w) {
+    return n > 0 && h > 0 && w > 0 ? (size_t)n * h * msq::positive_row_bytes(w) : 0;
+}
+
+extern "C" int msq_prep_frames(const int16_t *frames, int n, int H, int W, const void *bground, int bg_dtype,
+                               const uint8_t *roi, int y0, int x0, int h, int w, double vmin, double vmax,
+                               int flags, uint8_t *out, int32_t *invalid, uint8_t *invalid_bits, void *stream) {
+    return msq_prep_frames_bits(frames, n, H, W, bground, bg_dtype, roi, y0, x0, h, w, vmin, vmax, flags, out, invalid, invalid_bits,
+                                nullptr, stream);
 }
 
 extern "C" int msq_scale_frames(const uint8_t *in, uint8_t *out, size_t count, double vmin, double vmax,

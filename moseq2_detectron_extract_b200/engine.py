@@ -67,11 +67,16 @@ class ChunkEngine:
 
     # ---- full chunk ----------------------------------------------------------------------------
     def extract(self, chunk: torch.Tensor, masks: torch.Tensor, keypoints: torch.Tensor, *, chunk_size: int,
-                min_height: float, max_height: float, true_depth: float, crop_size=(80, 80)) -> Dict[str, torch.Tensor]:
+                min_height: float, max_height: float, true_depth: float, crop_size=(80, 80),
+                positive_bits: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Run clean -> features -> angles/flips/filter -> scalars + keypoints -> crops on device tensors
         chunk (n,h,w) u8, masks (n,h,w) u8, keypoints (n,8,3) f32.  Returns VIEWS into the engine's workspace
-        (valid until the next call); everything stays on the current stream, nothing synchronises."""
+        (valid until the next call); everything stays on the current stream, nothing synchronises.
+        positive_bits: the bit rows `prep_raw_frames(..., positive_bits_out=)` produced for this chunk (optional)."""
         assert chunk.is_cuda and masks.is_cuda and keypoints.is_cuda
+        if positive_bits is not None:
+            assert positive_bits.is_cuda and positive_bits.is_contiguous() and \
+                tuple(positive_bits.shape) == (chunk.shape[0], chunk.shape[1], (chunk.shape[2] + 31) // 32) and positive_bits.element_size() == 4
         n, h, w = (int(v) for v in chunk.shape)
         cw, ch = int(crop_size[0]), int(crop_size[1])
         n_chunks = (n + chunk_size - 1) // chunk_size
@@ -80,7 +85,8 @@ class ChunkEngine:
         outs = _lib.ChunkOutputs(*(b[k].data_ptr() for k in ('cleaned', 'centroid', 'angle_deg', 'axis_length', 'flips',
                                                              'scalars', 'kpt_cols', 'depth_crops', 'mask_crops',
                                                              'filter_passes')))
-        _lib.call('msq_extract_chunk_engine', self._handle, _dev.ptr(chunk), _dev.ptr(masks), _dev.ptr(keypoints), n, h, w, int(chunk_size),
+        _lib.call('msq_extract_chunk_engine', self._handle, _dev.ptr(chunk), _dev.ptr(positive_bits), _dev.ptr(masks), _dev.ptr(keypoints), n, h, w,
+                  int(chunk_size),
                   float(min_height), float(max_height), float(true_depth), cw, ch, ctypes.byref(outs),
                   _dev.ptr(b['scratch']), b['scratch'].numel(), _dev.stream())
         return {

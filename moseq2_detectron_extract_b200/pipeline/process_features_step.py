@@ -141,7 +141,7 @@ class ProcessFeaturesStep(ProcessPipelineStep):
         else:
             res = self.engine.extract(chunk, masks, kpts, chunk_size=max(n, 1), min_height=self.config['min_height'],
                                       max_height=self.config['max_height'], true_depth=self.config['true_depth'],
-                                      crop_size=self.crop)
+                                      crop_size=self.crop, positive_bits=data.get('positive_bits'))
         for i in np.flatnonzero(np.asarray(ninst) <= 0):
             self.write_message(f"WARN: No instances found for frame {data['frame_idxs'][i]}")
         conv = (lambda t: t.cpu().numpy()) if self.to_host else (lambda t: t.clone())

@@ -22,6 +22,15 @@ class ProduceFramesStep(ProducerPipelineStep):
         self._inflight = collections.deque()
 
         def prep_on_device(frames, **kw):
+            # the prep kernel's second output (one bit per positive pixel) rides along on the chunk tensor to ProcessFeaturesStep
+            bits = []
+            kw = dict(kw, positive_bits_out=bits)
+            out = prep_any(frames, **kw)
+            if bits and isinstance(out, torch.Tensor):
+                out.msq_positive_bits = bits[0]
+            return out
+
+        def prep_any(frames, **kw):
             if isinstance(frames, torch.Tensor):
                 out = prep_raw_frames(frames, **kw)          # CUDA tensor, or pinned host tensor consumed zero-copy
                 if not frames.is_cuda and frames.is_pinned():
@@ -55,6 +64,9 @@ class ProduceFramesStep(ProducerPipelineStep):
             return None
         out = {'batch': i, 'chunk': raw_frames, 'frame_idxs': frame_idxs,
                'offset': self.config['chunk_overlap'] if i > 0 else 0}
+        bits = getattr(raw_frames, 'msq_positive_bits', None)
+        if bits is not None:
+            out['positive_bits'] = bits
         last = getattr(self.session, '_last', None)          # synthetic sessions expose their ground-truth instances
         if last is not None:
             out['synthetic_instances'] = last

@@ -53,9 +53,10 @@ def _bg_code(bground) -> Tuple[int, Optional[torch.Tensor]]:
     return _lib.MSQ_BG_F64, _dev.as_device(arr.astype(np.float64))
 
 
-def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, want_bits: bool = False):
+def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, want_bits: bool = False, positive_bits_out: Optional[list] = None):
     """Launch the fused prep kernel; returns (out_u8 (n,h,w), invalid_count (n) int32 or None) and, with
-    want_bits, additionally the packed invalid-pixel mask (n, h, ceil(w/8)) uint8."""
+    want_bits, additionally the packed invalid-pixel mask (n, h, ceil(w/8)) uint8.  positive_bits_out: a list that receives
+    the positive-pixel bit rows (n, h, ceil(w/32)) int32 the cleaning pass can use instead of re-reading the frames."""
     if isinstance(frames, torch.Tensor) and not frames.is_cuda and frames.dtype == torch.int16 and frames.is_pinned() \
             and frames.is_contiguous():
         _dev.require_cuda()
@@ -87,9 +88,13 @@ def _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid: bool, want_b
     if want_bits:
         row_bytes = (w + 7) // 8
         bits = torch.zeros(((n * h * row_bytes + 3) // 4 * 4,), dtype=torch.uint8, device='cuda')
-    _lib.call('msq_prep_frames', _dev.ptr(raw), n, H, W, _dev.ptr(bg), code, _dev.ptr(roi_dev), y0, x0, h, w,
+    positive = None
+    if positive_bits_out is not None:
+        positive = _dev.positive_bits_like(out)
+        positive_bits_out.append(positive)
+    _lib.call('msq_prep_frames_bits', _dev.ptr(raw), n, H, W, _dev.ptr(bg), code, _dev.ptr(roi_dev), y0, x0, h, w,
               float(vmin if vmin is not None else 0.0), float(vmax if vmax is not None else 0.0), flags,
-              _dev.ptr(out), _dev.ptr(invalid), _dev.ptr(bits), _dev.stream())
+              _dev.ptr(out), _dev.ptr(invalid), _dev.ptr(bits), _dev.ptr(positive), _dev.stream())
     if want_bits:
         return out, invalid, bits
     return out, invalid
@@ -111,17 +116,22 @@ def fill_invalid_pixels_device(frames_u8: torch.Tensor, invalid_count: torch.Ten
 
 
 def prep_raw_frames(frames, bground_im=None, roi=None, vmin: Optional[float] = None, vmax: Optional[float] = None,
-                    dtype='uint8', fix_invalid_pixels: bool = True):
+                    dtype='uint8', fix_invalid_pixels: bool = True, positive_bits_out: Optional[list] = None):
     """Background-subtract, ROI-mask + crop, clamp and cast raw depth frames (ref: proc/proc.py:129-172).
 
     One fused kernel (csrc/prep.cu) replaces find_invalid_pixels + `bground - frames` + apply_roi +
-    the two fancy-index clamps + astype.  Returns (nframes, roi_height, roi_width) uint8."""
+    the two fancy-index clamps + astype.  Returns (nframes, roi_height, roi_width) uint8.
+
+    positive_bits_out (not in the reference): a list; the kernel's second output, one bit per prepared pixel that is > 0, is
+    appended to it for `ChunkEngine.extract(..., positive_bits=)` -- the cleaning pass then finds the rows the opening can leave
+    non-zero from 1/8 of the bytes.  In-painting only rewrites pixels whose bit is set, so the rows stay a valid superset."""
     if np.dtype(dtype) != np.uint8:
         raise NotImplementedError('prep_raw_frames: only dtype=uint8 (the extract path) is implemented')
     if not fix_invalid_pixels:
-        out, _ = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=False)
+        out, _ = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=False, positive_bits_out=positive_bits_out)
         return _dev.give_back(out, frames)
-    out, invalid, bits = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=True, want_bits=True)
+    out, invalid, bits = _prep_device(frames, bground_im, roi, vmin, vmax, want_invalid=True, want_bits=True,
+                                      positive_bits_out=positive_bits_out)
     if invalid is not None and out.numel() > 0:
         fill_invalid_pixels_device(out, invalid, bits)
     return _dev.give_back(out, frames)

@@ -352,5 +352,96 @@ def test_explicit_engine_equals_library_held_engine():
     assert torch.equal(b['depth_crops'][:n], a['depth_crops']) and torch.equal(b['cleaned'][:n], a['cleaned'])
     assert torch.allclose(b['centroid'][:n], a['centroid'], rtol=0, atol=0, equal_nan=True)
     with pytest.raises(_lib.MoseqB200Error):
-        _lib.call('msq_extract_chunk_engine', None, _dev.ptr(prep), _dev.ptr(masks), _dev.ptr(kpts), n, h, w, 1000, 0.0, 100.0, 673.0, 80, 80,
+        _lib.call('msq_extract_chunk_engine', None, _dev.ptr(prep), None, _dev.ptr(masks), _dev.ptr(kpts), n, h, w, 1000, 0.0, 100.0, 673.0, 80, 80,
                   ctypes.byref(outs), _dev.ptr(b['scratch']), b['scratch'].numel(), _dev.stream())
+
+
+@pytest.mark.parametrize('w', [240, 496])
+def test_band_limited_feature_pass_equals_full_frame_pass(w):
+    """msq_extract_chunk hands the cleaning pass's row bands to the streaming feature kernel, which then reads only the chunks of
+    rows that can be non-zero.  Same centroid / axes / cleaned frames as clean + msq_frame_features over whole frames, on the
+    cases that stress the row arithmetic: animal against the top / bottom edge, empty and all-noise frames, a body spanning
+    every row, two bodies, and (w = 496) frames wider than one 240-column cleaning tile."""
+    from moseq2_detectron_extract_b200 import _dev
+    from moseq2_detectron_extract_b200.engine import ChunkEngine
+    h = 240
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:h, 0:w]
+
+    def blob(cy, cx, ry, rx, height=40):
+        return np.where(((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0, height, 0)
+
+    bodies = [blob(10, 60, 18, 30), blob(h - 8, w - 70, 16, 28), np.zeros((h, w), int), blob(120, w // 2, 14, 40),
+              blob(120, 100, 140, 20), blob(40, 50, 15, 25) + blob(190, w - 60, 15, 25), blob(0, 0, 12, 12), blob(h - 1, w - 1, 13, 13),
+              blob(6, w // 2, 5.5, 30), blob(h - 6, 90, 5.5, 30), blob(12, 200, 11, 11), blob(11.5, 30, 12.4, 12.4)]
+    frames = np.stack(bodies * 3).astype(np.int64)
+    noise = rng.integers(-3, 4, size=frames.shape)
+    frames = np.clip(frames + noise, 0, 100).astype(np.uint8)
+    frames[5] = rng.integers(0, 3, size=(h, w))                       # nothing but floor noise
+    masks = (np.stack(bodies * 3) > 0).astype(np.uint8)
+    masks[7] = 1                                                       # mask wider than the animal
+    n = len(frames)
+    kpts = np.full((n, 8, 3), np.nan, np.float32)
+    chunk, m, k = _dev.as_device(frames), _dev.as_device(masks), _dev.as_device(kpts, torch.float32)
+    eng = ChunkEngine()
+    got = eng.extract(chunk, m, k, chunk_size=1000, min_height=0, max_height=100, true_depth=673.0, crop_size=(80, 80))
+    want = eng.clean_and_features(chunk, m)
+    assert torch.equal(got['cleaned'], want['cleaned'])
+    for key in ('centroid', 'axis_length'):
+        assert torch.allclose(got[key], want[key], rtol=0, atol=0, equal_nan=True), key
+    assert (want['cleaned'].flatten(1).max(1).values > 0).sum() >= n - 9     # most frames do carry an animal
+
+
+@pytest.mark.parametrize('geom_name', ['kinect_v2', 'azure'])
+def test_positive_bit_rows_from_prep_give_the_same_chunk_outputs(geom_name):
+    """msq_prep_frames_bits writes, beside the prepared frames, one bit per pixel that is > 0; msq_extract_chunk_engine /
+    msq_clean_frames_ws given those rows return exactly what they return without them (and the rows are what they say).  Also
+    after in-painting (the rows are then a superset), with an odd box width (scalar prep path) and with all-zero bit rows
+    replaced by all-ones rows (the loosest superset)."""
+    from moseq2_detectron_extract_b200 import _dev, synthetic
+    from moseq2_detectron_extract_b200.engine import ChunkEngine
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    geom = synthetic.SessionGeometry() if geom_name == 'kinect_v2' else synthetic.SessionGeometry.azure()
+    ch = synthetic.generate_chunk(14, seed=5, geom=geom, invalid_rate=0.002, missing_every=5)
+    bg, roi = synthetic.make_background(geom), synthetic.make_roi(geom)
+    eng = ChunkEngine()
+    kw = dict(chunk_size=1000, min_height=0, max_height=100, true_depth=673.0, crop_size=(80, 80))
+    for fix in (False, True):
+        bits = []
+        prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=bg, roi=roi, vmin=0, vmax=100, fix_invalid_pixels=fix,
+                               positive_bits_out=bits)
+        pos = bits[0]
+        n, h, w = prep.shape
+        assert pos.shape == (n, h, (w + 31) // 32) and pos.dtype == torch.int32
+        got_bits = np.unpackbits(pos.cpu().numpy().view(np.uint8).reshape(n, h, -1), axis=-1, bitorder='little')[:, :, :w].astype(bool)
+        truth = prep.cpu().numpy() > 0
+        if fix:
+            assert not (truth & ~got_bits).any()             # superset after in-painting
+        else:
+            assert np.array_equal(got_bits, truth)
+        masks, kpts = _dev.as_device(ch.masks), _dev.as_device(ch.keypoints, torch.float32)
+        a = {k: v.clone() for k, v in eng.extract(prep, masks, kpts, **kw).items()}
+        b = {k: v.clone() for k, v in eng.extract(prep, masks, kpts, positive_bits=pos, **kw).items()}
+        c = {k: v.clone() for k, v in eng.extract(prep, masks, kpts, positive_bits=torch.full_like(pos, -1), **kw).items()}
+        for key in a:
+            assert torch.allclose(a[key].double(), b[key].double(), rtol=0, atol=0, equal_nan=True), key
+            assert torch.allclose(a[key].double(), c[key].double(), rtol=0, atol=0, equal_nan=True), key
+        c1, c2 = torch.empty_like(prep), torch.empty_like(prep)
+        _dev.clean_frames_ws(prep, c1)
+        _dev.clean_frames_ws(prep, c2, pos)
+        assert torch.equal(c1, c2) and torch.equal(c1, a['cleaned'])
+    # an odd box (scalar prep kernel; the streaming clean kernel is not used for it): the rows are still exact
+    roi2 = roi.copy()
+    ys, xs = np.nonzero(roi2)
+    roi2[:, xs.max() - 2:] = False
+    bits = []
+    prep = prep_raw_frames(torch.from_numpy(ch.frames).cuda(), bground_im=bg, roi=roi2, vmin=0, vmax=100, fix_invalid_pixels=False,
+                           positive_bits_out=bits)
+    n, h, w = prep.shape
+    assert w % 8 != 0
+    got_bits = np.unpackbits(bits[0].cpu().numpy().view(np.uint8).reshape(n, h, -1), axis=-1, bitorder='little')[:, :, :w].astype(bool)
+    assert np.array_equal(got_bits, prep.cpu().numpy() > 0)
+    masks = _dev.as_device(np.ascontiguousarray(ch.masks[:, :, :w]))
+    a = eng.extract(prep, masks, kpts, **kw)['cleaned'].clone()
+    b = eng.extract(prep, masks, kpts, positive_bits=bits[0], **kw)['cleaned'].clone()
+    assert torch.equal(a, b)
