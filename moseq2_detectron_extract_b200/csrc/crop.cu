@@ -186,7 +186,9 @@ crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__res
             y_lo = min(y_lo, sy); y_hi = max(y_hi, sy + 1);
         }
         const int gx_lo = (x_lo + k.ox) & ~3, gx_hi = x_hi + k.ox;   // frame coordinates, left edge on a 32-bit word
-        const int pitch = ((gx_hi - gx_lo + 1) + 3) & ~3, rows = y_hi - y_lo + 1;
+        // an odd number of 32-bit words per staged row: lanes that walk down a column of the box (crops rotated by ~90 degrees)
+        // then fall on 32 different banks instead of 16
+        const int pitch = ((((gx_hi - gx_lo + 1) + 3) >> 2) | 1) << 2, rows = y_hi - y_lo + 1;
         const bool fits = pitch <= G.pitch_max && rows <= G.rows_max && x_lo > -32000 && x_hi < 32000 && y_lo > -32000 && y_hi < 32000;
         box[0] = gx_lo; box[1] = y_lo + k.oy; box[2] = fits ? pitch : 0; box[3] = rows;
     }
@@ -274,7 +276,7 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
     // fast path: 32-bit staging loads and stores need 4-byte friendly shapes and bases
     const int side = (int)ceil(hypot((double)cw, (double)ch)) + 4;
     StagedGeom G;
-    G.pitch_max = (side + 4 + 3) & ~3;
+    G.pitch_max = ((side + 4 + 3) & ~3) + 4;
     G.rows_max = side;
     const size_t smem = (size_t)2 * (cw + ch) * sizeof(int) + (size_t)(two ? 2 : 1) * G.pitch_max * G.rows_max;
     const bool aligned = (w % 4 == 0) && (cw % 4 == 0) && ((uintptr_t)src % 4 == 0) && ((uintptr_t)out % 4 == 0) &&

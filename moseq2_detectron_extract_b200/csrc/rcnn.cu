@@ -159,9 +159,39 @@ struct RoiPyramid {
 //     out[ph][pw] = sum_rows sum_cols WY[ph][row] * WX[pw][col] * F[row][col]
 // with per-axis weights that already hold the 1 / grid of the average.  Rows touched by one bin are consecutive: (first, count).
 constexpr int kRoiMaxTaps = 12;
-struct AxisTaps {
+struct __align__(16) AxisTaps {
+    float w[kRoiMaxTaps];        // first: the weights of a bin's first four taps are one 16-byte shared-memory load
     int first, count;
-    float w[kRoiMaxTaps];
+    int pad[2];
+};
+static_assert(sizeof(AxisTaps) == 64 && kRoiMaxTaps == 12, "AxisTaps is one 64-byte record");
+
+// acc += wgt * (8 bf16 / fp32 channels held in `raw`)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+    typedef uint4 type;
+    static __device__ __forceinline__ type load(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+    static __device__ __forceinline__ void fma(float (&acc)[8], const type &r, float wgt) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[2 * k] = __fmaf_rn(wgt, __uint_as_float(w[k] << 16), acc[2 * k]);
+            acc[2 * k + 1] = __fmaf_rn(wgt, __uint_as_float(w[k] & 0xffff0000u), acc[2 * k + 1]);
+        }
+    }
+};
+template <> struct Raw8<float> {
+    struct type { float4 a, b; };
+    static __device__ __forceinline__ type load(const float *p) {
+        type r;
+        r.a = __ldg(reinterpret_cast<const float4 *>(p)); r.b = __ldg(reinterpret_cast<const float4 *>(p + 4));
+        return r;
+    }
+    static __device__ __forceinline__ void fma(float (&acc)[8], const type &r, float wgt) {
+        const float v[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = __fmaf_rn(wgt, v[k], acc[k]);
+    }
 };
 
 __device__ __forceinline__ bool build_axis_taps(float start, float bin, int p, int grid, int size, AxisTaps &t) {
@@ -192,6 +222,20 @@ __device__ __forceinline__ bool build_axis_taps(float start, float bin, int p, i
         t.w[y_high - lo] += l * inv;
     }
     return true;
+}
+
+// up to four taps of one feature row (n of them, n >= 1): loads first, then the fused multiply-adds
+template <typename T>
+__device__ __forceinline__ void tap_quad(float (&acc)[8], const T *row, int C, int n, float wy, const float4 &wx) {
+    typename Raw8<T>::type r0, r1, r2, r3;
+    r0 = Raw8<T>::load(row);
+    if (n > 1) r1 = Raw8<T>::load(row + C);
+    if (n > 2) r2 = Raw8<T>::load(row + 2 * C);
+    if (n > 3) r3 = Raw8<T>::load(row + 3 * C);
+    Raw8<T>::fma(acc, r0, wy * wx.x);
+    if (n > 1) Raw8<T>::fma(acc, r1, wy * wx.y);
+    if (n > 2) Raw8<T>::fma(acc, r2, wy * wx.z);
+    if (n > 3) Raw8<T>::fma(acc, r3, wy * wx.w);
 }
 
 template <typename T>
@@ -227,10 +271,9 @@ roi_align_v2_kernel(RoiPyramid pyr, int C, const float *__restrict__ boxes, int 
     if ((int)threadIdx.x < 2 * P) {
         const bool is_y = (int)threadIdx.x < P;
         const int p = is_y ? threadIdx.x : threadIdx.x - P;
-        AxisTaps t;
+        AxisTaps &t = (is_y ? taps_y : taps_x)[p];                   // built in place (dynamic indexing: shared, not local, memory)
         const bool ok = is_y ? build_axis_taps(y0, bin_h, p, gh, H, t) : build_axis_taps(x0, bin_w, p, gw, W, t);
         if (!ok) s_direct = 1;
-        (is_y ? taps_y : taps_x)[p] = t;
     }
     __syncthreads();
     const int bins = P * P, vecs = C >> 3;
@@ -239,19 +282,23 @@ roi_align_v2_kernel(RoiPyramid pyr, int C, const float *__restrict__ boxes, int 
         for (int bin = warp; bin < bins; bin += kRoiThreads / 32) {
             const int ph = bin / P, pw = bin - ph * P;
             const AxisTaps &ty = taps_y[ph], &tx = taps_x[pw];
+            const int cy = ty.count, cx = tx.count;                   // warp-uniform
+            const int row_stride = W * C;                             // elements; a level of one image is far below 2^31
             for (int v = lane; v < vecs; v += 32) {
                 float acc[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-                for (int j = 0; j < ty.count; ++j) {
-                    const float wy = ty.w[j];
-                    const T *row = feat + ((size_t)(ty.first + j) * W + tx.first) * C + v * 8;
-                    for (int i = 0; i < tx.count; ++i) {
-                        const float wgt = wy * tx.w[i];
-                        float val[8];
-                        Ch8<T>::load(row + (size_t)i * C, val);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] = __fmaf_rn(wgt, val[k], acc[k]);
+                const T *p0 = feat + ((size_t)ty.first * W + tx.first) * C + v * 8;
+                if (cx <= 4) {
+                    // the common case (sampling grid <= 3 per bin): the x weights live in registers, the taps of a row are
+                    // loaded together, then accumulated in the order of the general loop (same rounding)
+                    const float4 wx = *reinterpret_cast<const float4 *>(tx.w);
+                    for (int j = 0; j < (cx > 0 ? cy : 0); ++j) tap_quad<T>(acc, p0 + j * row_stride, C, cx, ty.w[j], wx);
+                } else {
+                    for (int j = 0; j < cy; ++j) {
+                        const float wy = ty.w[j];
+                        const T *row = p0 + j * row_stride;
+                        for (int i = 0; i < cx; ++i) Raw8<T>::fma(acc, Raw8<T>::load(row + i * C), wy * tx.w[i]);
                     }
                 }
                 Ch8<T>::store(dst + (size_t)bin * C + v * 8, acc);
