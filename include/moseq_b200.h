@@ -108,6 +108,13 @@ MSQ_API int msq_unpack_mask_bits(const uint8_t *bits_dev, int n, int h, int w, u
  * result to msq_prep_frames with H = h, W = w, y0 = x0 = 0 and the background / ROI cropped to the same box. */
 MSQ_API int msq_copy_roi_rows(const int16_t *frames_host, int n, int H, int W, int y0, int x0, int h, int w, int16_t *out_dev,
                       void *stream);
+/* The same for a ROI that fills only part of its box (the bucket floor is a disc): n_bands horizontal bands, band b = rows
+ * [band_y[b], band_y[b+1]) x columns [band_x0[b], band_x1[b]) relative to the box (HOST int arrays; band_y has n_bands + 1
+ * entries), one strided DMA transfer each into the same dense (n,h,w) array.  Every band must cover the ROI pixels of its rows;
+ * what lies outside the bands is not written and never reaches msq_prep_frames' output (it multiplies by the ROI mask) -- keep
+ * out_dev zero-initialised.  16 bands of a disc: 15 % fewer PCIe bytes than the box. */
+MSQ_API int msq_copy_roi_bands(const int16_t *frames_host, int n, int H, int W, int y0, int x0, int h, int w, const int *band_y,
+                       const int *band_x0, const int *band_x1, int n_bands, int16_t *out_dev, void *stream);
 
 /* ---- a2  fill_invalid_pixels (ref: proc/proc.py:189-210): cv2.inpaint(frame, mask, radius, INPAINT_NS), bit-exact.
  * frames_dev (n_total,h,w) u8 updated IN PLACE; invalid_bits_dev as written by msq_prep_frames; frame_idx_dev (m) int32

@@ -76,3 +76,28 @@ def clean_frames_ws(src: torch.Tensor, out: torch.Tensor, positive_bits: Optiona
     nbytes = int(_lib.load().msq_clean_scratch_bytes(n, h, w))
     scratch = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=src.device)
     _lib.call('msq_clean_frames_ws', ptr(src), ptr(positive_bits), ptr(out), n, h, w, ptr(scratch), nbytes, stream())
+
+
+def roi_bands(roi_box: np.ndarray, n_bands: int = 16, align: int = 8):
+    """Horizontal bands that cover a ROI inside its bounding box, for `msq_copy_roi_bands`: (band_y (n+1), band_x0 (n), band_x1 (n))
+    int32 host arrays; columns rounded outwards to `align` pixels (16-byte DMA rows for int16 frames)."""
+    roi_box = np.asarray(roi_box) > 0
+    h, w = roi_box.shape
+    n_bands = max(1, min(int(n_bands), h))
+    edges = np.linspace(0, h, n_bands + 1).astype(np.int32)
+    x0s, x1s = np.zeros(n_bands, np.int32), np.zeros(n_bands, np.int32)
+    for b in range(n_bands):
+        cols = np.flatnonzero(roi_box[edges[b]:edges[b + 1]].any(axis=0))
+        if cols.size:
+            x0s[b] = cols.min() // align * align
+            x1s[b] = min(w, (cols.max() + align) // align * align)
+    return np.ascontiguousarray(edges), x0s, x1s
+
+
+def copy_roi_bands(frames_host: torch.Tensor, y0: int, x0: int, bands, out: torch.Tensor) -> None:
+    """`msq_copy_roi_bands`: pinned (n,H,W) int16 host frames -> the ROI pixels of the dense (n,h,w) int16 device array `out`."""
+    n, H, W = (int(v) for v in frames_host.shape)
+    _, h, w = (int(v) for v in out.shape)
+    by, bx0, bx1 = bands
+    _lib.call('msq_copy_roi_bands', ptr(frames_host), n, H, W, int(y0), int(x0), h, w, by.ctypes.data_as(ctypes.c_void_p),
+              bx0.ctypes.data_as(ctypes.c_void_p), bx1.ctypes.data_as(ctypes.c_void_p), len(bx0), ptr(out), stream())

@@ -45,6 +45,8 @@ SIGNATURES = {
                                      c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'msq_unpack_mask_bits': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'msq_copy_roi_rows': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'msq_copy_roi_bands': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                   c_void_p]),
     'msq_inpaint_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'msq_inpaint_frames': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     'msq_scale_frames': (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_double, c_int, c_void_p]),

@@ -578,3 +578,42 @@ def test_roi_box_dma_then_prep_equals_prep_of_full_frames(P):
         want = O.prep_frames(ch.frames, bg, roi, 0, 100, fix_invalid=False)
         assert np.array_equal(out.cpu().numpy(), want)
         assert int(inv.sum()) == int(((ch.frames[:, y0:y1, x0:x1] == 0) & roi[y0:y1, x0:x1]).sum())
+
+
+def test_roi_band_dma_then_prep_equals_prep_of_full_frames(P):
+    """msq_copy_roi_bands (the ROI disc as 16 / 5 / 1 horizontal bands, one strided DMA each; pixels outside the bands are never
+    written and hold junk) + msq_prep_frames on the dense box == the oracle's prep of the full frames, bit for bit."""
+    import torch
+    from moseq2_detectron_extract_b200 import _dev, _lib, synthetic
+    for geom in (synthetic.SessionGeometry(), synthetic.SessionGeometry.azure()):
+        ch = synthetic.generate_chunk(7, seed=4, geom=geom, invalid_rate=0.001)
+        roi, bg = synthetic.make_roi(geom), synthetic.make_background(geom)
+        y0, x0, y1, x1 = synthetic.roi_bbox(roi)
+        h, w = y1 - y0, x1 - x0
+        host = torch.from_numpy(ch.frames).pin_memory()
+        bg_box = _dev.as_device(np.ascontiguousarray(bg[y0:y1, x0:x1]))
+        roi_box = _dev.as_device(np.ascontiguousarray(roi[y0:y1, x0:x1].astype(np.uint8)))
+        want = O.prep_frames(ch.frames, bg, roi, 0, 100, fix_invalid=False)
+        for n_bands in (16, 5, 1):
+            bands = _dev.roi_bands(roi[y0:y1, x0:x1], n_bands)
+            covered = np.zeros((h, w), bool)
+            for b in range(len(bands[1])):
+                covered[bands[0][b]:bands[0][b + 1], bands[1][b]:bands[2][b]] = True
+            assert not (roi[y0:y1, x0:x1] & ~covered).any()
+            if n_bands == 16:
+                assert covered.mean() < 0.87
+            box = torch.full((7, h, w), -12345, dtype=torch.int16, device='cuda')      # junk where no band writes
+            _dev.copy_roi_bands(host, y0, x0, bands, box)
+            torch.cuda.synchronize()
+            got = box.cpu().numpy()
+            assert np.array_equal(got[:, covered], ch.frames[:, y0:y1, x0:x1][:, covered])
+            assert (got[:, ~covered] == -12345).all()
+            out = torch.empty((7, h, w), dtype=torch.uint8, device='cuda')
+            inv = torch.empty((7,), dtype=torch.int32, device='cuda')
+            _lib.call('msq_prep_frames', _dev.ptr(box), 7, h, w, _dev.ptr(bg_box), _lib.MSQ_BG_F32, _dev.ptr(roi_box), 0, 0, h, w, 0.0, 100.0,
+                      _lib.MSQ_PREP_HAS_VMIN | _lib.MSQ_PREP_HAS_VMAX, _dev.ptr(out), _dev.ptr(inv), None, _dev.stream())
+            assert np.array_equal(out.cpu().numpy(), want)
+            assert int(inv.sum()) == int(((ch.frames[:, y0:y1, x0:x1] == 0) & roi[y0:y1, x0:x1]).sum())
+    with pytest.raises(_lib.MoseqB200Error):
+        bad = (np.array([0, h + 1], np.int32), np.array([0], np.int32), np.array([w], np.int32))
+        _dev.copy_roi_bands(host, y0, x0, bad, box)
