@@ -563,3 +563,14 @@ def test_sort_tracker_follows_norfair_semantics():
     assert (det_idxs, obj_idxs) == ([0, 1], [0, 1])
     with pytest.raises(ValueError):
         trk._update_objects_in_place(trk.tracked_objects[:1], [Detection(np.array([np.nan, 1.0]))], 1)
+
+
+def test_every_declared_entry_point_is_documented_in_integration_md():
+    """include/moseq_b200.h is the boundary; INTEGRATION.md names, for every entry point, the reference function it replaces."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, 'include', 'moseq_b200.h')).read()
+    names = re.findall(r'MSQ_API\s+[\w\s\*]+?\b(msq_\w+)\s*\(', header)
+    assert len(names) >= 70
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    assert [n for n in names if n not in text] == []
