@@ -239,6 +239,11 @@ MSQ_API int msq_fastrcnn_top1(const float *pred_dev, int pred_stride, const floa
                       int k, int img_h, int img_w, float score_thresh, const float *weights4_host, float *box_dev,
                       float *score_dev, uint8_t *has_dev, int32_t *index_dev, void *stream);
 
+/* The last layer of detectron2's KRCNNConvDeconvUpsampleHead (the reference's keypoint head, model/config.py:84 -> ROI_KEYPOINT_HEAD
+ * defaults): F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) of the deconvolution output.  in_dev
+ * (n,K,H,W) bf16 (in_is_bf16) or fp32 with element strides sN,sC,sH,sW (channels-last or dense) -> out_dev (n,K,2H,2W) fp32 dense. */
+MSQ_API int msq_upsample2x_bilinear(const void *in_dev, int in_is_bf16, long long sN, long long sC, long long sH, long long sW, int n, int K,
+                            int H, int W, float *out_dev, void *stream);
 /* detectron2.structures.keypoints.heatmaps_to_keypoints for a batch: as msq_keypoints_from_heatmaps, but the third column
  * of xyp_dev (R,K,3) is detectron2's score exp(max) / sum(exp(pool-resolution map)); logit_dev (R,K) or NULL receives the
  * heatmap value at the arg-max. */

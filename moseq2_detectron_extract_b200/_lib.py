@@ -108,6 +108,8 @@ SIGNATURES = {
                                  c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     'msq_fastrcnn_top1': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, POINTER(c_float), c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    'msq_upsample2x_bilinear': (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_void_p]),
     'msq_keypoints_from_heatmaps_d2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'msq_sobel_gradient_mask': (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_int, POINTER(c_double), c_int, c_double, c_void_p, c_void_p]),
     'msq_plane_ransac_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -573,6 +573,46 @@ extern "C" int msq_fastrcnn_top1(const float *pred_dev, int pred_stride, const f
     return MSQ_OK;
 }
 
+// torch.nn.functional.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) of the keypoint head's deconvolution
+// output (detectron2 KRCNNConvDeconvUpsampleHead.layers): (R, K, H, W) in any strides, bf16 or fp32 -> (R, K, 2H, 2W) fp32 dense.
+// One thread per output pixel (torch's kernel walks all R * K planes inside every thread: 1 ms for 3 MB of output).
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_bilinear_kernel(const T *__restrict__ in, long long sN, long long sC, long long sH, long long sW, int planes, int K, int H, int W,
+                           float *__restrict__ out) {
+    const int OW = 2 * W, OH = 2 * H;
+    const long long total = (long long)planes * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), pl = (int)(i / ((long long)OW * OH));
+        const int r = pl / K, k = pl - r * K;
+        // area_pixel_compute_source_index(scale = 0.5, align_corners = false): max(0.5 * (dst + 0.5) - 0.5, 0)
+        const float ys = fmaxf(0.5f * ((float)oy + 0.5f) - 0.5f, 0.f), xs = fmaxf(0.5f * ((float)ox + 0.5f) - 0.5f, 0.f);
+        const int y1 = (int)ys, x1 = (int)xs;
+        const int yp = y1 < H - 1 ? 1 : 0, xp = x1 < W - 1 ? 1 : 0;
+        const float ly = ys - (float)y1, hy = 1.f - ly, lx = xs - (float)x1, hx = 1.f - lx;
+        const T *p = in + r * sN + k * sC + y1 * sH + x1 * sW;
+        const float v00 = (float)p[0], v01 = (float)p[xp * sW], v10 = (float)p[yp * sH], v11 = (float)p[yp * sH + xp * sW];
+        out[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    }
+}
+
+extern "C" int msq_upsample2x_bilinear(const void *in, int in_is_bf16, long long sN, long long sC, long long sH, long long sW, int n, int K,
+                                       int H, int W, float *out, void *stream) {
+    MSQ_REQUIRE(n >= 0 && K > 0 && H > 0 && W > 0, MSQ_EINVAL, "msq_upsample2x_bilinear: bad sizes");
+    if (n == 0) return MSQ_OK;
+    MSQ_REQUIRE(in && out, MSQ_EINVAL, "msq_upsample2x_bilinear: null pointer");
+    const long long total = (long long)n * K * 4 * H * W;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+    TimedLaunch timed(K_DETECTOR_GLUE, (cudaStream_t)stream);
+    if (in_is_bf16)
+        upsample2x_bilinear_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16 *>(in), sN, sC, sH, sW,
+                                                                                       n * K, K, H, W, out);
+    else
+        upsample2x_bilinear_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float *>(in), sN, sC, sH, sW, n * K, K, H, W, out);
+    MSQ_LAUNCH_OK("upsample2x_bilinear");
+    return MSQ_OK;
+}
+
 extern "C" int msq_keypoints_from_heatmaps_d2(const float *maps, const float *rois, int n_rois, int K, int Hm, int Wm, float *xyp,
                                               float *logit, void *stream) {
     MSQ_REQUIRE(n_rois >= 0 && K > 0 && Hm > 0 && Wm > 0, MSQ_EINVAL, "msq_keypoints_from_heatmaps_d2: bad sizes");

@@ -34,6 +34,7 @@ _LIB.define('roi_align_v2(Tensor[] feats, float[] scales, Tensor boxes, int rois
 _LIB.define('fastrcnn_top1(Tensor pred, Tensor proposals, Tensor counts, int img_h, int img_w, float score_thresh, float[] weights) '
             '-> (Tensor, Tensor, Tensor)')
 _LIB.define('keypoints_from_heatmaps_d2(Tensor heatmaps, Tensor boxes) -> Tensor')
+_LIB.define('upsample2x_bilinear(Tensor x) -> Tensor')
 
 # implementation switches (bench / tests): which engine runs the dense contractions
 RPN_ENGINE = {'mode': 'fused'}            # 'fused' (msq_rpn_select) | 'torch' (operator by operator)
@@ -363,7 +364,18 @@ def _keypoints_from_heatmaps_d2(heatmaps, boxes):
     return xyp
 
 
-for _name, _fn in (('detector_input', _detector_input), ('stem_conv_pool', _stem_conv_pool), ('stem_conv_pool_tc', _stem_conv_pool_tc), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
+def _upsample2x_bilinear(x):
+    n, k, h, w = (int(v) for v in x.shape)
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        x = x.float()
+    out = torch.empty((n, k, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    if n:
+        sn, sc, sh, sw = (int(v) for v in x.stride())
+        _lib.call('msq_upsample2x_bilinear', _dev.ptr(x), int(x.dtype == torch.bfloat16), sn, sc, sh, sw, n, k, h, w, _dev.ptr(out), _dev.stream())
+    return out
+
+
+for _name, _fn in (('upsample2x_bilinear', _upsample2x_bilinear), ('detector_input', _detector_input), ('stem_conv_pool', _stem_conv_pool), ('stem_conv_pool_tc', _stem_conv_pool_tc), ('conv2d', _conv2d), ('linear', _linear), ('group_norm_nhwc', _group_norm_nhwc),
                    ('rpn_proposals', _rpn_proposals), ('roi_align_v2', _roi_align_v2), ('fastrcnn_top1', _fastrcnn_top1),
                    ('keypoints_from_heatmaps_d2', _keypoints_from_heatmaps_d2)):
     _LIB.impl(_name, _fn, 'CUDA')

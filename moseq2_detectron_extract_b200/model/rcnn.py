@@ -210,8 +210,9 @@ class MoseqRCNN(nn.Module):
         x = torch.ops.msq.roi_align_v2(feats[:4], self.pool_scales, boxes, 1, self.keypoint_pooler, 0, 2, 4, 224.0)
         x = self.kp_fcn(x)
         x = torch.conv_transpose2d(x, self.kp_deconv_w, self.kp_deconv_b, [2, 2], [1, 1])
-        # (n, K, 14, 14) comes out of the deconvolution channels-last: torch's float upsampling kernel is ~40x slower on that layout
-        heat = torch.nn.functional.interpolate(x.float().contiguous(), scale_factor=2.0, mode='bilinear', align_corners=False).contiguous()
+        # F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) in float32: torch's kernel takes 1-2 ms for these
+        # 3 MB (every thread walks all planes); one thread per output pixel, any input strides, takes microseconds
+        heat = torch.ops.msq.upsample2x_bilinear(x)
         return torch.ops.msq.keypoints_from_heatmaps_d2(heat, boxes), heat
 
     def detect(self, x: Tensor, img_h: int, img_w: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:

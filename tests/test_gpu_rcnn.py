@@ -395,3 +395,18 @@ def test_detector_input_matches_torch(bf16, h, w, vmax):
         assert float((got.float() - want.to(torch.bfloat16).float()).abs().max()) <= 2 ** -7 * float(want.abs().max())
     else:
         assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def test_upsample2x_bilinear_matches_torch_interpolate():
+    """msq_upsample2x_bilinear == F.interpolate(x.float(), scale_factor=2, mode='bilinear', align_corners=False) for the layouts the
+    keypoint head produces (bf16 channels-last out of the deconvolution, fp32 dense), edge rows / columns included."""
+    import torch.nn.functional as F
+    msq = _ops()
+    g = torch.Generator().manual_seed(3)
+    for shape in ((5, 8, 14, 14), (3, 2, 7, 9), (1, 1, 1, 1), (0, 8, 14, 14)):
+        x = torch.randn(shape, generator=g).cuda()
+        for t in (x, x.bfloat16(), x.bfloat16().contiguous(memory_format=torch.channels_last), x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)):
+            want = F.interpolate(t.float().contiguous(), scale_factor=2.0, mode='bilinear', align_corners=False) if shape[0] else torch.empty((0, shape[1], 2 * shape[2], 2 * shape[3]), device='cuda')
+            got = msq.upsample2x_bilinear(t)
+            assert got.dtype == torch.float32 and got.shape == want.shape and got.is_contiguous()
+            assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
