@@ -445,3 +445,59 @@ def test_positive_bit_rows_from_prep_give_the_same_chunk_outputs(geom_name):
     a = eng.extract(prep, masks, kpts, **kw)['cleaned'].clone()
     b = eng.extract(prep, masks, kpts, positive_bits=bits[0], **kw)['cleaned'].clone()
     assert torch.equal(a, b)
+
+
+def test_bench_launch_size_properties():
+    """BASELINE configs[1] launches 6 000 frames at a time (six 1000-frame chunks per call).  The oracle cannot follow at that
+    size, so the full-size launch is checked through properties that do not depend on it: (1) every output of the 6 000-frame
+    call equals, bit for bit, the outputs of the same frames processed as six separate 1000-frame calls; (2) the session is the
+    same 1000 distinct frames rolled by 37 per chunk, and every frame-local output follows the roll; (3) a 40-frame window from
+    the middle of the fourth chunk equals the oracle on those frames; (4) with and without the prep kernel's bit rows."""
+    from moseq2_detectron_extract_b200 import _dev, synthetic
+    from moseq2_detectron_extract_b200.engine import ChunkEngine
+    from moseq2_detectron_extract_b200.proc import prep_raw_frames
+    geom = synthetic.SessionGeometry()
+    pool = synthetic.generate_chunk(1000, seed=21, geom=geom, realistic=True, missing_every=97)
+    bg, roi = synthetic.make_background(geom), synthetic.make_roi(geom)
+    n_chunks, C = 6, 1000
+    idx = np.concatenate([(np.arange(C) + 37 * c) % C for c in range(n_chunks)])
+    frames = torch.from_numpy(pool.frames).cuda()[torch.from_numpy(idx).cuda()]
+    masks = _dev.as_device(pool.masks)[torch.from_numpy(idx).cuda()].contiguous()
+    kpts = _dev.as_device(pool.keypoints, torch.float32)[torch.from_numpy(idx).cuda()].contiguous()
+    kw = dict(chunk_size=C, min_height=0, max_height=100, true_depth=673.0, crop_size=(80, 80))
+    eng = ChunkEngine()
+    bits = []
+    prep = prep_raw_frames(frames, bground_im=bg, roi=roi, vmin=0, vmax=100, fix_invalid_pixels=False, positive_bits_out=bits)
+    whole = {k: v.clone() for k, v in eng.extract(prep, masks, kpts, positive_bits=bits[0], **kw).items()}
+    n = n_chunks * C
+    # (4) bit rows or not
+    plain = eng.extract(prep, masks, kpts, **kw)
+    for k in whole:
+        assert torch.allclose(whole[k].double(), plain[k].double(), rtol=0, atol=0, equal_nan=True), k
+    # (1) one launch == six launches
+    per_frame = ('cleaned', 'centroid', 'angle_deg', 'axis_length', 'flips', 'depth_crops', 'mask_crops')
+    for c in range(n_chunks):
+        s = slice(c * C, (c + 1) * C)
+        part = eng.extract(prep_raw_frames(frames[s], bground_im=bg, roi=roi, vmin=0, vmax=100, fix_invalid_pixels=False),
+                           masks[s].contiguous(), kpts[s].contiguous(), **kw)
+        for k in per_frame:
+            assert torch.allclose(whole[k][s].double(), part[k].double(), rtol=0, atol=0, equal_nan=True), (k, c)
+        for k in ('scalars', 'kpt_cols'):
+            assert torch.allclose(whole[k][:, s], part[k], rtol=0, atol=0, equal_nan=True), (k, c)
+        assert int(whole['filter_passes'][c]) == int(part['filter_passes'][0])
+    # (2) frame-local outputs follow the roll
+    for c in range(1, n_chunks):
+        src = torch.from_numpy((np.arange(C) + 37 * c) % C).cuda()
+        for k in ('cleaned', 'centroid', 'axis_length'):
+            assert torch.allclose(whole[k][c * C:(c + 1) * C].double(), whole[k][:C][src].double(), rtol=0, atol=0, equal_nan=True), (k, c)
+    # (3) a window of the fourth chunk against the oracle
+    lo = 3 * C + 480
+    sel = idx[lo:lo + 40]
+    want_prep = O.prep_frames(pool.frames[sel], bg, roi, 0, 100, fix_invalid=False)
+    assert np.array_equal(prep[lo:lo + 40].cpu().numpy(), want_prep)
+    cleaned = O.clean_frames_cv2(want_prep)
+    feats = O.frame_features_cv2(cleaned, pool.masks[sel])
+    assert np.array_equal(whole['cleaned'][lo:lo + 40].cpu().numpy(), cleaned)
+    assert np.allclose(whole['centroid'][lo:lo + 40].cpu().numpy(), feats['centroid'], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.allclose(whole['axis_length'][lo:lo + 40].cpu().numpy(), feats['axis_length'], rtol=1e-10, atol=0, equal_nan=True)
+    assert n == prep.shape[0] and int((whole['cleaned'].flatten(1).amax(1) > 0).sum()) > 0.9 * n
