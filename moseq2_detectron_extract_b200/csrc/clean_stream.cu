@@ -555,7 +555,6 @@ int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cu
     // 20-row lead-in of a strip stays a small part of it
     const long long total_rows = (long long)n * G.tiles_x * h;
     long long ctas = std::min<long long>((long long)sm_count() * resident, std::max<long long>(1, total_rows / 120));
-    if (const char *e = getenv("MSQ_CLEAN_CTAS")) { long long v = atoll(e); if (v >= 1) ctas = v; }
     G.rows_per_cta = (int)((total_rows + ctas - 1) / ctas);
     const int grid = (int)((total_rows + G.rows_per_cta - 1) / G.rows_per_cta);
     TimedLaunch timed(K_CLEAN, st);

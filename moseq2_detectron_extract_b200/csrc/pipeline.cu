@@ -20,7 +20,7 @@ extern "C" size_t msq_extract_scratch_bytes(int n, int /*h*/, int /*w*/) {
 struct msq_engine {
     int device;
     cudaStream_t side;
-    cudaEvent_t fork, join;
+    cudaEvent_t fork, join, angles_done;
 };
 
 extern "C" int msq_engine_create(msq_engine **engine) {
@@ -28,7 +28,8 @@ extern "C" int msq_engine_create(msq_engine **engine) {
     msq_engine *e = new msq_engine();
     if (cudaGetDevice(&e->device) != cudaSuccess || cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->angles_done, cudaEventDisableTiming) != cudaSuccess) {
         set_error("msq_engine_create: %s", cudaGetErrorString(cudaGetLastError()));
         delete e;
         return MSQ_ECUDA;
@@ -41,6 +42,7 @@ extern "C" int msq_engine_destroy(msq_engine *e) {
     if (!e) return MSQ_OK;
     cudaEventDestroy(e->fork);
     cudaEventDestroy(e->join);
+    cudaEventDestroy(e->angles_done);
     cudaStreamDestroy(e->side);
     delete e;
     return MSQ_OK;
@@ -82,15 +84,20 @@ extern "C" int msq_extract_chunk_engine(msq_engine *engine, const uint8_t *chunk
                                     nullptr, feature_list, st, engine->fork, rows)) != MSQ_OK) return rc;
     MSQ_CUDA_OK(cudaStreamWaitEvent(engine->side, engine->fork, 0));
     if ((rc = launch_masked_sums(chunk_dev, mask_dev, n, h, w, min_height, max_height, sums, engine->side)) != MSQ_OK) return rc;
-    MSQ_CUDA_OK(cudaEventRecord(engine->join, engine->side));
     if ((rc = launch_angles_and_flips(orientation, out->axis_length, out->centroid, kpts_dev, n, chunk, out->angle_deg,
                                       out->flips, nullptr, out->filter_passes, st)) != MSQ_OK) return rc;
-    MSQ_CUDA_OK(cudaStreamWaitEvent(st, engine->join, 0));
+    // the scalar / keypoint table (needs the sums and the angles, feeds nothing inside this call) follows the sums on the side
+    // stream and runs beside the crops
+    MSQ_CUDA_OK(cudaEventRecord(engine->angles_done, st));
+    MSQ_CUDA_OK(cudaStreamWaitEvent(engine->side, engine->angles_done, 0));
     if ((rc = launch_scalars_and_keypoints(chunk_dev, mask_dev, out->cleaned, out->centroid, out->angle_deg,
                                            out->axis_length, kpts_dev, false, n, h, w, chunk, min_height, max_height,
-                                           true_depth, out->scalars, out->kpt_cols, sums, st, true)) != MSQ_OK) return rc;
-    return launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
-                              out->depth_crops, out->mask_crops, crop_scratch, st);
+                                           true_depth, out->scalars, out->kpt_cols, sums, engine->side, true)) != MSQ_OK) return rc;
+    MSQ_CUDA_OK(cudaEventRecord(engine->join, engine->side));
+    rc = launch_crop_rotate(chunk_dev, mask_dev, n, h, w, out->centroid, out->angle_deg, crop_w, crop_h,
+                            out->depth_crops, out->mask_crops, crop_scratch, st);
+    MSQ_CUDA_OK(cudaStreamWaitEvent(st, engine->join, 0));          // everything of this call is ordered before what follows on `st`
+    return rc;
 }
 
 extern "C" int msq_extract_chunk(const uint8_t *chunk_dev, const uint8_t *mask_dev, const float *kpts_dev, int n,
