@@ -76,31 +76,35 @@ __device__ __forceinline__ bool is_filter_flip(double after, double before) {
     return fabs(fabs(after - before) - 180.0) <= 1e-8 + 1e-5 * 180.0;    // np.isclose(|cur-angles|, 180)
 }
 
-// one CTA per chunk: degrees + clamp (a8), keypoint flips (a9), iterative filter (a10)
+// degrees + clamp (a8) and keypoint flips (a9) are per-frame float64 work (a dozen double-precision sin / cos per frame): one
+// thread per frame over as many SMs as it takes -- inside the per-chunk filter kernel below the same work sat on the FP64
+// units of ONE SM per chunk (38 us for six 1000-frame chunks, on the critical path of the chunk call).
+__global__ void __launch_bounds__(128)
+angle_votes_kernel(const double *__restrict__ orientation, const double *__restrict__ axis, const double *__restrict__ centroid,
+                   const float *__restrict__ kpts, int n, double *__restrict__ angle_out, uint8_t *__restrict__ flips_out,
+                   double *__restrict__ conf_out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const double length = np_max2(axis[2 * f], axis[2 * f + 1]);
+    double a = -(orientation[f] * k180OverPi);               // ref proc/proc.py:722-724
+    a = (a < 0) ? 360 + a : a;
+    a = fmod(a, 360.0);                                      // a >= 0 here, same as numpy's floor-mod
+    double conf;
+    const bool flip = keypoint_flip_vote(kpts + (size_t)f * 24, centroid[2 * f], centroid[2 * f + 1], a, length, &conf);
+    if (conf_out) conf_out[f] = conf;
+    flips_out[f] = flip ? 1 : 0;
+    if (flip) a += 180;                                      // ref proc/proc.py:834 (no clamp)
+    angle_out[f] = a;                                        // pre-filter angle, needed for the isclose test
+}
+
+// one CTA per chunk: the iterative filter (a10) on the angles angle_votes_kernel left in angle_out
 __global__ void __launch_bounds__(kAngleThreads)
-angles_flips_kernel(const double *__restrict__ orientation, const double *__restrict__ axis,
-                    const double *__restrict__ centroid, const float *__restrict__ kpts, int n, int chunk,
-                    double *__restrict__ angle_out, uint8_t *__restrict__ flips_out, double *__restrict__ conf_out,
-                    int *__restrict__ passes_out) {
+angles_flips_kernel(int n, int chunk, double *__restrict__ angle_out, uint8_t *__restrict__ flips_out, int *__restrict__ passes_out) {
     extern __shared__ __align__(16) double sm_angles[];       // [2][len] ping-pong
     const int begin = blockIdx.x * chunk;
     const int len = min(chunk, n - begin);
     double *buf0 = sm_angles, *buf1 = sm_angles + len;
-
-    for (int i = threadIdx.x; i < len; i += kAngleThreads) {
-        const int f = begin + i;
-        const double length = np_max2(axis[2 * f], axis[2 * f + 1]);
-        double a = -(orientation[f] * k180OverPi);           // ref proc/proc.py:722-724
-        a = (a < 0) ? 360 + a : a;
-        a = fmod(a, 360.0);                                  // a >= 0 here, same as numpy's floor-mod
-        double conf;
-        const bool flip = keypoint_flip_vote(kpts + (size_t)f * 24, centroid[2 * f], centroid[2 * f + 1], a, length, &conf);
-        if (conf_out) conf_out[f] = conf;
-        flips_out[f] = flip ? 1 : 0;
-        if (flip) a += 180;                                  // ref proc/proc.py:834 (no clamp)
-        buf0[i] = a;
-        angle_out[f] = a;                                    // pre-filter angle, needed for the isclose test
-    }
+    for (int i = threadIdx.x; i < len; i += kAngleThreads) buf0[i] = angle_out[begin + i];
     __syncthreads();
     int passes;
     const double *cur = filter_angles_in_smem(buf0, buf1, len, 3, 60.0, 1000, &passes);
@@ -326,8 +330,8 @@ int launch_angles_and_flips(const double *orientation, const double *axis, const
     if (smem > 48 * 1024)
         MSQ_CUDA_OK(cudaFuncSetAttribute(angles_flips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TimedLaunch timed(K_ANGLES, st);
-    angles_flips_kernel<<<chunks, kAngleThreads, smem, st>>>(orientation, axis, centroid, kpts, n, chunk, angle_out,
-                                                            flips, conf, passes);
+    angle_votes_kernel<<<(n + 127) / 128, 128, 0, st>>>(orientation, axis, centroid, kpts, n, angle_out, flips, conf);
+    angles_flips_kernel<<<chunks, kAngleThreads, smem, st>>>(n, chunk, angle_out, flips, passes);
     MSQ_LAUNCH_OK("angles_and_flips");
     return MSQ_OK;
 }
