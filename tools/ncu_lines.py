@@ -1,11 +1,14 @@
 """Join ncu per-SASS-instruction execution counts with source lines (nvdisasm line info).
-usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [top]"""
+usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [top] [nth kernel of the report, default 0]"""
 import sys, csv, subprocess, io, re, os, tempfile, glob, collections
 rep, so, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
+his = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+nth = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+hi = his[nth]
+rows = rows[:his[nth + 1]] if nth + 1 < len(his) else rows
 h = rows[hi]
 ci, si, ss = h.index('Instructions Executed'), h.index('Source'), h.index('# Samples')
 prof = [(r[si].strip(), int(r[ci] or 0), int(r[ss] or 0)) for r in rows[hi + 1:] if len(r) > ci and r[0] != 'Address']
