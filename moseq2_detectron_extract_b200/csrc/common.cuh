@@ -84,6 +84,9 @@ __device__ __forceinline__ void stg_stream_u4(void *p, uint4 v) {
 __device__ __forceinline__ void stg_stream_u2(void *p, uint2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ void stg_stream_u8(void *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void stg_stream_u1(void *p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }

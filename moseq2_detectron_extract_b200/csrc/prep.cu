@@ -168,6 +168,9 @@ prep_vec8_f32_fast_kernel(const int16_t *__restrict__ frames, int n, int H, int 
     const size_t in_off = (size_t)(y0 + r) * W + (x0 + c);
     const size_t out_off = (size_t)r * w + c;
     const int pbr = positive_row_bytes(w);
+    uint8_t *pos_base = positive_bits ? positive_bits + (size_t)r * pbr + (c >> 3) : nullptr;
+    const size_t pos_stride = (size_t)h * pbr;
+    const bool last_group = (c >> 3) == w8 - 1;
     float bg[8];
     int top[8];                                               // trunc(vmax) inside the ROI, 0 outside
     uint32_t roi_bits = 0u;
@@ -214,9 +217,9 @@ prep_vec8_f32_fast_kernel(const int16_t *__restrict__ frames, int n, int H, int 
                 // (measured: the byte store, not the bit gathering, is what this output costs -- ~40 us per 6000 frames; wider
                 // stores through shuffles do not change it.  The last group of a row also writes the row's pad bytes, so that
                 // every 32-byte sector ends up fully written.)
-                uint8_t *dstb = positive_bits + ((size_t)(f + u) * h + r) * pbr + (c >> 3);
-                *dstb = nonzero_bytes_to_byte(o8.x, o8.y);
-                if ((c >> 3) == w8 - 1)
+                uint8_t *dstb = pos_base + (size_t)(f + u) * pos_stride;
+                stg_stream_u8(dstb, nonzero_bytes_to_byte(o8.x, o8.y));
+                if (last_group)
                     for (int q = 1; q <= pbr - w8; ++q) dstb[q] = 0;
             }
             const uint32_t z0 = zero_halfwords(words[0]), z1 = zero_halfwords(words[1]), z2 = zero_halfwords(words[2]),
