@@ -146,7 +146,8 @@ struct StagedGeom {
     int pitch_max, rows_max;      // staging capacity per plane (bytes per row, rows)
 };
 
-__global__ void __launch_bounds__(kCropThreads)
+template <bool kTwo>        // kTwo: a second plane (the mask) shares the transform
+__global__ void __launch_bounds__(kCropThreads, 6)
 crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int H, int W,
                           const double *__restrict__ centroid, const double *__restrict__ angle_deg, int cw, int ch,
                           StagedGeom G, uint8_t *__restrict__ out0, uint8_t *__restrict__ out1) {
@@ -222,31 +223,79 @@ crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__res
     const uint8_t *f1 = src1 ? src1 + (size_t)f * H * W : nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kWarps = kCropThreads / 32;
-    // a warp stages whole rows (lane = 32-bit word), so there is no per-element index arithmetic
-    for (int r = warp; r < rows; r += kWarps) {
-        const int gy = gy_lo + r;
-        const bool row_ok = gy >= ry0 && gy < ry1;
-        const size_t row_off = (size_t)gy * W;
-        for (int c = lane; c < words; c += 32) {
-            const int gx = gx_lo + 4 * c;
-            uint32_t v0 = 0u, v1 = 0u;
-            if (row_ok && gx + 3 >= rx0 && gx < rx1) {
-                uint32_t keep = 0xffffffffu;                     // bytes gx..gx+3, little endian
-                if (gx < rx0) keep &= 0xffffffffu << (8 * (rx0 - gx));
-                if (gx + 4 > rx1) keep &= 0xffffffffu >> (8 * (gx + 4 - rx1));
-                v0 = __ldg(reinterpret_cast<const uint32_t *>(f0 + row_off + gx)) & keep;
-                if (f1) v1 = __ldg(reinterpret_cast<const uint32_t *>(f1 + row_off + gx)) & keep;
+    // a warp stages whole rows, lane = 32-bit word.  Which bytes of a lane's word are readable depends on the column only, so the
+    // byte mask and the lane's pointer are set up once per column block; a row then costs one warp-uniform test, one offset and
+    // a predicated load per plane (the first version redid the 64-bit addressing and the byte masks for every word: 39 % of the
+    // kernel's instructions, ncu source view).
+    uint32_t *s0 = reinterpret_cast<uint32_t *>(plane0), *s1 = reinterpret_cast<uint32_t *>(plane1);
+    for (int cb = 0; cb < words; cb += 32) {
+        const int c = cb + lane;
+        const int gx = gx_lo + 4 * c;
+        uint32_t keep = 0u;                                          // bytes gx..gx+3 (little endian) the reference can read
+        if (c < words && gx + 3 >= rx0 && gx < rx1) {
+            keep = 0xffffffffu;
+            if (gx < rx0) keep &= 0xffffffffu << (8 * (rx0 - gx));
+            if (gx + 4 > rx1) keep &= 0xffffffffu >> (8 * (gx + 4 - rx1));
+        }
+        const uint8_t *p0 = f0 + gx, *p1 = f1 ? f1 + gx : nullptr;  // dereferenced only where keep != 0
+        // four rows per trip: all their loads are in flight before the first store needs its value (a warp has ~15 rows; one row
+        // per trip exposed one global-memory latency per row)
+        constexpr int kRowsPerTrip = 4;
+        for (int r0 = warp; r0 < rows; r0 += kWarps * kRowsPerTrip) {
+            uint32_t v0[kRowsPerTrip], v1[kRowsPerTrip];
+#pragma unroll
+            for (int q = 0; q < kRowsPerTrip; ++q) {
+                const int r = r0 + q * kWarps, gy = gy_lo + r;
+                v0[q] = v1[q] = 0u;
+                if (keep != 0u && r < rows && gy >= ry0 && gy < ry1) {
+                    const int off = gy * W;
+                    v0[q] = __ldg(reinterpret_cast<const uint32_t *>(p0 + off));
+                    if (kTwo) v1[q] = __ldg(reinterpret_cast<const uint32_t *>(p1 + off));
+                }
             }
-            reinterpret_cast<uint32_t *>(plane0)[r * words + c] = v0;
-            if (f1) reinterpret_cast<uint32_t *>(plane1)[r * words + c] = v1;
+#pragma unroll
+            for (int q = 0; q < kRowsPerTrip; ++q) {
+                const int r = r0 + q * kWarps;
+                if (c < words && r < rows) {
+                    s0[r * words + c] = v0[q] & keep;
+                    if (kTwo) s1[r * words + c] = v1[q] & keep;
+                }
+            }
         }
     }
     __syncthreads();
-    // ---- gather: a warp walks output rows, neighbouring lanes take neighbouring output pixels.  (4 pixels per lane
-    // with one 32-bit store was measured first: lanes 4 px apart step through the staged box in multiples of 4 words
-    // along a rotated line, which folds the 32 lanes onto 8 banks -- 60 % of the shared-memory wavefronts conflicted.)
+    // ---- gather: neighbouring lanes take neighbouring output pixels of a row.  (4 pixels per lane with one 32-bit store was
+    // measured first: lanes 4 px apart step through the staged box in multiples of 4 words along a rotated line, which folds the
+    // 32 lanes onto 8 banks -- 60 % of the shared-memory wavefronts conflicted.)  A thread keeps its column: with cw <= 256 the
+    // CTA is kCropThreads / cw row groups of cw threads (80-px crops: 3 x 80 threads, 27 rows each, instead of 32-lane column
+    // strips whose third strip is half empty), the column terms stay in registers and the output pointers advance by a constant.
     const int sh_x = k.ox - gx_lo, sh_y = k.oy - gy_lo;
-    for (int x = lane; x < cw; x += 32) {
+    const int groups = cw <= kCropThreads ? kCropThreads / cw : 0;
+    if (groups > 0) {
+        const int t = threadIdx.x, g = t / cw, x = t - g * cw;
+        if (g >= groups) return;
+        const int ad = adelta[x], bd = bdelta[x];
+        const size_t step = (size_t)groups * cw;
+        uint8_t *o0 = out0 + crop_base + (size_t)g * cw + x;
+        uint8_t *o1 = kTwo ? out1 + crop_base + (size_t)g * cw + x : nullptr;
+        for (int y = g; y < ch; y += groups, o0 += step, o1 += step) {
+            const int X = (X0[y] + ad) >> 5, Y = (Y0[y] + bd) >> 5;
+            const int fx = X & 31, fy = Y & 31, gx = 32 - fx, gy = 32 - fy;
+            const int idx = ((Y >> 5) + sh_y) * pitch + (X >> 5) + sh_x;
+            {
+                const int top = (int)plane0[idx] * gx + (int)plane0[idx + 1] * fx;
+                const int bot = (int)plane0[idx + pitch] * gx + (int)plane0[idx + pitch + 1] * fx;
+                *o0 = (uint8_t)((top * gy + bot * fy + 512) >> 10);
+            }
+            if (kTwo) {
+                const int top = (int)plane1[idx] * gx + (int)plane1[idx + 1] * fx;
+                const int bot = (int)plane1[idx + pitch] * gx + (int)plane1[idx + pitch + 1] * fx;
+                *o1 = (uint8_t)((top * gy + bot * fy + 512) >> 10);
+            }
+        }
+        return;
+    }
+    for (int x = lane; x < cw; x += 32) {                       // crops wider than the CTA: column strips
         const int ad = adelta[x], bd = bdelta[x];
         for (int y = warp; y < ch; y += kWarps) {
             const int X = (X0[y] + ad) >> 5, Y = (Y0[y] + bd) >> 5;
@@ -258,7 +307,7 @@ crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__res
                 const int bot = (int)plane0[idx + pitch] * (32 - fx) + (int)plane0[idx + pitch + 1] * fx;
                 out0[o] = (uint8_t)((top * (32 - fy) + bot * fy + 512) >> 10);
             }
-            if (f1) {
+            if (kTwo) {
                 const int top = (int)plane1[idx] * (32 - fx) + (int)plane1[idx + 1] * fx;
                 const int bot = (int)plane1[idx + pitch] * (32 - fx) + (int)plane1[idx + pitch + 1] * fx;
                 out1[o] = (uint8_t)((top * (32 - fy) + bot * fy + 512) >> 10);
@@ -282,11 +331,10 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
     const bool aligned = (w % 4 == 0) && (cw % 4 == 0) && ((uintptr_t)src % 4 == 0) && ((uintptr_t)out % 4 == 0) &&
                          (!two || (((uintptr_t)src2 % 4 == 0) && ((uintptr_t)out2 % 4 == 0))) && (((size_t)h * w) % 4 == 0);
     if (aligned && smem <= 160 * 1024) {
-        if (smem > 48 * 1024)
-            MSQ_CUDA_OK(cudaFuncSetAttribute(crop_rotate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kernel = two ? crop_rotate_staged_kernel<true> : crop_rotate_staged_kernel<false>;
+        if (smem > 48 * 1024) MSQ_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TimedLaunch timed(K_CROP, st);
-        crop_rotate_staged_kernel<<<n, kCropThreads, smem, st>>>(src, two ? src2 : nullptr, h, w, centroid, angle_deg, cw, ch, G,
-                                                                 out, two ? out2 : nullptr);
+        kernel<<<n, kCropThreads, smem, st>>>(src, two ? src2 : nullptr, h, w, centroid, angle_deg, cw, ch, G, out, two ? out2 : nullptr);
         MSQ_LAUNCH_OK("crop_rotate (staged)");
         return MSQ_OK;
     }

@@ -31,17 +31,25 @@ for vals in rows[2:]:
                 pass
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
-h = rows[hi]
-ci, si, ss = h.index('Instructions Executed'), h.index('Source'), h.index('# Samples')
-ops, samp, tot, tots = collections.Counter(), collections.Counter(), 0, 0
-for r in rows[hi + 1:]:
-    if len(r) <= ci or r[0] == 'Address':
+heads = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 22
+for nth, hi in enumerate(heads):                     # one block of SASS lines per profiled launch, in the order of the kernels above
+    h = rows[hi]
+    ci, si, ss = h.index('Instructions Executed'), h.index('Source'), h.index('# Samples')
+    end = heads[nth + 1] if nth + 1 < len(heads) else len(rows)
+    ops, samp, tot, tots = collections.Counter(), collections.Counter(), 0, 0
+    for r in rows[hi + 1:end]:
+        if len(r) <= ci or not r[si].strip():
+            continue
+        toks = r[si].split()
+        op = toks[1] if toks[0].startswith('@') and len(toks) > 1 else toks[0]
+        try:
+            n = int(r[ci] or 0)
+        except ValueError:
+            continue
+        ops[op] += n; tot += n; samp[op] += int(r[ss] or 0); tots += int(r[ss] or 0)
+    if not tot:
         continue
-    toks = r[si].split()
-    op = toks[1] if toks[0].startswith('@') else toks[0]
-    n = int(r[ci] or 0)
-    ops[op] += n; tot += n; samp[op] += int(r[ss] or 0); tots += int(r[ss] or 0)
-print(f'== executed warp instructions: {tot}')
-for op, n in ops.most_common(int(sys.argv[2]) if len(sys.argv) > 2 else 22):
-    print(f'  {op:26s} {n:12d} {100 * n / tot:5.1f}%   stall samples {100 * samp[op] / max(tots, 1):5.1f}%')
+    print(f'== launch {nth}: executed warp instructions: {tot}')
+    for op, n in ops.most_common(top):
+        print(f'  {op:26s} {n:12d} {100 * n / tot:5.1f}%   stall samples {100 * samp[op] / max(tots, 1):5.1f}%')
