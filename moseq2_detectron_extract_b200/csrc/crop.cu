@@ -147,7 +147,7 @@ struct StagedGeom {
 };
 
 template <bool kTwo>        // kTwo: a second plane (the mask) shares the transform
-__global__ void __launch_bounds__(kCropThreads, 6)
+__global__ void __launch_bounds__(kCropThreads, 5)
 crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int H, int W,
                           const double *__restrict__ centroid, const double *__restrict__ angle_deg, int cw, int ch,
                           StagedGeom G, uint8_t *__restrict__ out0, uint8_t *__restrict__ out1) {
@@ -240,7 +240,7 @@ crop_rotate_staged_kernel(const uint8_t *__restrict__ src0, const uint8_t *__res
         const uint8_t *p0 = f0 + gx, *p1 = f1 ? f1 + gx : nullptr;  // dereferenced only where keep != 0
         // four rows per trip: all their loads are in flight before the first store needs its value (a warp has ~15 rows; one row
         // per trip exposed one global-memory latency per row)
-        constexpr int kRowsPerTrip = 4;
+        constexpr int kRowsPerTrip = 8;
         for (int r0 = warp; r0 < rows; r0 += kWarps * kRowsPerTrip) {
             uint32_t v0[kRowsPerTrip], v1[kRowsPerTrip];
 #pragma unroll
