@@ -15,6 +15,15 @@
 // shared memory allows 16 warps per SM, and with 6-row trips every slot index is a literal.
 // ncu on the tiled kernel showed 52 M shared-memory wavefronts / 1000 frames (LSU pipe 68 % busy) next to a 53 %
 // busy ALU pipe; this formulation needs ~3x fewer wavefronts, no block barriers and no second pass over the raw tile.
+//
+// That pipeline only ever runs where the result can be non-zero.  With scratch memory (msq_clean_frames_ws, msq_extract_chunk)
+// a clean step is three launches:
+//   clean_band_kernel   a 1-bit row scan per (frame, 240-column tile): the exact rows [lo, hi] on which the erosion is non-zero
+//                       (from prep's positive-pixel bit rows when the caller has them, else thresholded from the frame); the
+//                       same CTA stores the zero rows of the output, everything outside [lo - 4, hi + 4];
+//   clean_plan_kernel   prefix sums of (band rows + pipeline lead-in) over the (frame, tile) columns;
+//   clean_stream_kernel the pipeline above on equal-cost shares of those rows, one share per resident CTA.
+// Without scratch (msq_clean_frames) one launch does all of it, strip by strip, at the price of a load-imbalanced tail.
 #include "common.cuh"
 #include <algorithm>
 #include <limits.h>
