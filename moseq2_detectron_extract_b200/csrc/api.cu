@@ -49,8 +49,8 @@ const char *const kKernelNames[K_COUNT] = {"prep_frames", "scale_frames", "clean
                                            "paste_masks", "inpaint", "kalman_tracking", "bground_median", "session_roi", "detector_glue"};
 }  // namespace
 
-TimedLaunch::TimedLaunch(int kernel_id, cudaStream_t stream) : slot(-1), st(stream) {
-    g_timer.launches[kernel_id].fetch_add(1, std::memory_order_relaxed);
+TimedLaunch::TimedLaunch(int kernel_id, cudaStream_t stream, int kernels) : slot(-1), st(stream) {
+    g_timer.launches[kernel_id].fetch_add(kernels, std::memory_order_relaxed);
     if (!g_timer.enabled.load(std::memory_order_acquire)) return;
     const int claimed = g_timer.used.fetch_add(1, std::memory_order_acq_rel);
     if (claimed >= kTimerSlots) { g_timer.dropped.fetch_add(1, std::memory_order_relaxed); return; }

@@ -566,7 +566,7 @@ int launch_clean_stream(const uint8_t *in, uint8_t *out, int n, int h, int w, cu
     long long ctas = std::min<long long>((long long)sm_count() * resident, std::max<long long>(1, total_rows / 120));
     G.rows_per_cta = (int)((total_rows + ctas - 1) / ctas);
     const int grid = (int)((total_rows + G.rows_per_cta - 1) / G.rows_per_cta);
-    TimedLaunch timed(K_CLEAN, st);
+    TimedLaunch timed(K_CLEAN, st, bands ? 3 : 1);
     if (bands) {
         const int items = n * G.tiles_x;
         int *prefix = reinterpret_cast<int *>(bands + items);

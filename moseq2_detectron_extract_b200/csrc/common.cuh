@@ -48,10 +48,10 @@ int sm_count();                                 // api.cu; cached per process (c
 // ---- per-kernel device timing (CUDA events on the launching stream; off by default) ----------
 enum KernelId { K_PREP = 0, K_SCALE, K_CLEAN, K_FEATURES, K_ANGLES, K_MASKED_SUMS, K_SCALARS_KPTS, K_CROP, K_PASTE,
                 K_INPAINT, K_KALMAN, K_BGROUND, K_ROI, K_DETECTOR_GLUE, K_COUNT };
-struct TimedLaunch {                            // RAII: records an event pair around one kernel launch
+struct TimedLaunch {                            // RAII: records an event pair around one step's kernel launch(es)
     int slot;
     cudaStream_t st;
-    TimedLaunch(int kernel_id, cudaStream_t stream);
+    TimedLaunch(int kernel_id, cudaStream_t stream, int kernels = 1);      // kernels: how many launches the scope makes (the counter)
     ~TimedLaunch();
 };
 

@@ -340,7 +340,7 @@ int launch_crop_rotate(const uint8_t *src, const uint8_t *src2, int n, int h, in
     }
     WarpCoeffs *coeffs = reinterpret_cast<WarpCoeffs *>(scratch);
     int *tables = reinterpret_cast<int *>(reinterpret_cast<char *>(scratch) + (size_t)n * sizeof(WarpCoeffs));
-    TimedLaunch timed(K_CROP, st);          // the coefficient kernel is part of the crop step
+    TimedLaunch timed(K_CROP, st, 2);       // the coefficient kernel is part of the crop step
     crop_coeffs_kernel<<<n, 128, 0, st>>>(centroid, angle_deg, n, cw, ch, w, h, coeffs, tables);
     MSQ_LAUNCH_OK("crop_coeffs");
     dim3 grid(n, ((cw + 15) / 16) * ((ch + 15) / 16));

@@ -329,7 +329,7 @@ int launch_angles_and_flips(const double *orientation, const double *axis, const
     MSQ_REQUIRE(smem <= 200 * 1024, MSQ_EUNSUPPORTED, "angles_and_flips: chunk of %d frames is too large", chunk);
     if (smem > 48 * 1024)
         MSQ_CUDA_OK(cudaFuncSetAttribute(angles_flips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TimedLaunch timed(K_ANGLES, st);
+    TimedLaunch timed(K_ANGLES, st, 2);
     angle_votes_kernel<<<(n + 127) / 128, 128, 0, st>>>(orientation, axis, centroid, kpts, n, angle_out, flips, conf);
     angles_flips_kernel<<<chunks, kAngleThreads, smem, st>>>(n, chunk, angle_out, flips, passes);
     MSQ_LAUNCH_OK("angles_and_flips");

@@ -159,7 +159,7 @@ extern "C" int msq_nms_sorted_long(const float *boxes, const uint8_t *valid, int
     MSQ_REQUIRE(scratch_bytes >= msq_nms_scratch_bytes(n, K), MSQ_ENOMEM, "msq_nms_sorted_long: scratch too small");
     const int words = (K + 63) / 64;
     cudaStream_t st = (cudaStream_t)stream;
-    TimedLaunch timed(K_DETECTOR_GLUE, st);
+    TimedLaunch timed(K_DETECTOR_GLUE, st, 2);
     nms_mask_kernel<<<dim3(words, words, n), 64, 0, st>>>(reinterpret_cast<const float4 *>(boxes), valid, K, words, iou_threshold,
                                                           static_cast<unsigned long long *>(scratch));
     nms_scan_kernel<<<(n + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, 0, st>>>(static_cast<const unsigned long long *>(scratch), valid, n, K,

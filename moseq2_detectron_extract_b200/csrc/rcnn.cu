@@ -512,7 +512,7 @@ extern "C" int msq_group_norm_nhwc(const void *x, int is_bf16, int n, int H, int
     double *partial = static_cast<double *>(scratch);
     float *stats = reinterpret_cast<float *>(static_cast<char *>(scratch) + align_up((size_t)n * slabs * vecs * 2 * sizeof(double), 256));
     const size_t smem = (size_t)kGnThreads * 2 * sizeof(double);
-    TimedLaunch timed(K_DETECTOR_GLUE, st);
+    TimedLaunch timed(K_DETECTOR_GLUE, st, 3);
     if (is_bf16) gn_partial_kernel<__nv_bfloat16><<<n * slabs, kGnThreads, smem, st>>>(static_cast<const __nv_bfloat16 *>(x), HW, C, slabs, partial);
     else         gn_partial_kernel<float><<<n * slabs, kGnThreads, smem, st>>>(static_cast<const float *>(x), HW, C, slabs, partial);
     gn_finish_kernel<<<(n * groups + 127) / 128, 128, 0, st>>>(partial, n, slabs, vecs, groups, HW, C, eps, stats);
