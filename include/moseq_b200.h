@@ -177,6 +177,14 @@ MSQ_API int msq_nms_sorted(const float *boxes_dev, const uint8_t *valid_dev, int
 MSQ_API size_t msq_nms_scratch_bytes(int n, int K);
 MSQ_API int msq_nms_sorted_long(const float *boxes_dev, const uint8_t *valid_dev, int n, int K, float iou_threshold, int max_keep,
                         int32_t *keep_dev, int32_t *count_dev, void *scratch_dev, size_t scratch_bytes, void *stream);
+/* The same when the candidates carry their pyramid level: level_valid_dev[i] = 0 (not a candidate) or 1 + level, as
+ * msq_rpn_select writes it.  detectron2's batched_nms never lets levels suppress each other, so the overlap bits are computed per
+ * level (3.4x fewer pairs for 3 x 1000 + 192 + 48 candidates) and every (image, level) is walked by its own warp; at most
+ * max_per_level (<= 2048) candidates per level.  scratch_dev: msq_nms_levels_scratch_bytes(...) bytes, 256-byte aligned. */
+MSQ_API size_t msq_nms_levels_scratch_bytes(int n, int K, int n_levels, int max_per_level);
+MSQ_API int msq_nms_levels_long(const float *boxes_dev, const uint8_t *level_valid_dev, int n, int K, int n_levels, int max_per_level,
+                        float iou_threshold, int max_keep, int32_t *keep_dev, int32_t *count_dev, void *scratch_dev,
+                        size_t scratch_bytes, void *stream);
 
 /* detectron2 find_top_rpn_proposals up to the NMS for a batch of equally sized images, one launch: per-level top-k of the
  * objectness logits (exact k-th largest by radix select; ties in anchor order), Box2BoxTransform decoding of the selected

@@ -64,6 +64,9 @@ SIGNATURES = {
     'msq_stem_conv_pool_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_int, c_float, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
     'msq_nms_scratch_bytes': (c_size_t, [c_int, c_int]),
+    'msq_nms_levels_scratch_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'msq_nms_levels_long': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
     'msq_nms_sorted_long': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'msq_rpn_select': (c_int, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

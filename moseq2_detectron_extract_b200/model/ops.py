@@ -241,8 +241,8 @@ def _rpn_proposals(preds, strides, sizes, ratios, img_h, img_w, pre_topk, post_t
     A = len(ratios)
     fused = _rpn_select_fused(preds, strides, sizes, ratios, img_h, img_w, pre_topk) if RPN_ENGINE['mode'] == 'fused' else None
     if fused is not None:
-        boxes, shifted, scores, valid_u8 = fused
-        return _nms_and_gather(boxes, shifted, scores, valid_u8, post_topk, nms_thresh)
+        boxes, shifted, scores, valid_u8 = fused            # valid_u8 = 1 + pyramid level of every candidate (0: none)
+        return _nms_and_gather(boxes, shifted, scores, valid_u8, post_topk, nms_thresh, levels=len(preds), per_level=int(pre_topk))
     boxes_l, scores_l, level_l = [], [], []
     for lvl, p in enumerate(preds):
         gh, gw = int(p.shape[2]), int(p.shape[3])
@@ -301,12 +301,19 @@ def _rpn_select_fused(preds, strides, sizes, ratios, img_h, img_w, pre_topk):
     return boxes, shifted, scores, valid
 
 
-def _nms_and_gather(boxes, shifted, scores, valid_u8, post_topk, nms_thresh):
+def _nms_and_gather(boxes, shifted, scores, valid_u8, post_topk, nms_thresh, levels=None, per_level=None):
     n, K = int(boxes.shape[0]), int(boxes.shape[1])
     dev = boxes.device
     keep = torch.empty((n, int(post_topk)), dtype=torch.int32, device=dev)
     count = torch.empty((n,), dtype=torch.int32, device=dev)
-    if int(post_topk) > 128 and K <= 6144:       # long keep lists: overlap matrix as bit rows + one ordered walk per image
+    if int(post_topk) > 128 and levels is not None and levels <= 8 and min(K, int(per_level)) <= 2048:
+        # long keep lists, levels known: overlap bits per level only, one walk per (image, level)
+        nbytes = int(_lib.load().msq_nms_levels_scratch_bytes(n, K, int(levels), int(per_level)))
+        scratch = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev)
+        scratch = scratch[(-scratch.data_ptr()) % 256:]
+        _lib.call('msq_nms_levels_long', _dev.ptr(shifted), _dev.ptr(valid_u8), n, K, int(levels), int(per_level), float(nms_thresh),
+                  int(post_topk), _dev.ptr(keep), _dev.ptr(count), _dev.ptr(scratch), nbytes, _dev.stream())
+    elif int(post_topk) > 128 and K <= 6144:       # long keep lists: overlap matrix as bit rows + one ordered walk per image
         nbytes = int(_lib.load().msq_nms_scratch_bytes(n, K))
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         _lib.call('msq_nms_sorted_long', _dev.ptr(shifted), _dev.ptr(valid_u8), n, K, float(nms_thresh), int(post_topk), _dev.ptr(keep),
