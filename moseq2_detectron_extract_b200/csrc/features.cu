@@ -453,7 +453,7 @@ features_kernel(const uint8_t *__restrict__ cleaned, const uint8_t *__restrict__
 // ([0] = count, [1..] = frame indices) and redone by features_kernel.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStreamWarps = 4;
-constexpr int kChunkSteps = 3;         // row steps per bulk copy: 12 rows x 240 B = 2.9 KB contiguous per array (2 and 4 measured: no better)
+constexpr int kChunkSteps = 2;         // row steps per bulk copy: 8 rows x 240 B = 1.9 KB contiguous per array.  (12 rows were as good while whole frames were read; with the row bands of the cleaning pass shorter chunks waste less at the band ends: +2 %; 4 rows: no better)
 constexpr int kStreamStages = 2;       // bulk copies in flight per warp
 
 // ---- mbarrier / bulk-copy (TMA, 1-D) primitives ---------------------------------------------------------------
