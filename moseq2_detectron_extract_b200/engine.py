@@ -8,7 +8,6 @@ from __future__ import annotations
 import ctypes
 from typing import Dict, Optional, Tuple
 
-import numpy as np
 import torch
 
 from . import _dev, _lib

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import warnings
-from typing import Dict, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
