@@ -848,7 +848,6 @@ def secondary_figures(args, geom, cfg, roi, bg):
     # (3) a7 on a less convenient animal: bent body, tail, pasted-28x28 mask outlines.  Which share of the frames does the
     # streaming (row-convex, hole-free) feature kernel settle, and what do both regimes cost?
     try:
-        import ctypes
         from moseq2_detectron_extract_b200 import _lib
         regimes = {}
         for name, kw in (('ellipsoid (headline workload)', {}), ('bent body + tail + pasted 28x28 mask', {'realistic': True})):
